@@ -1,0 +1,1310 @@
+// gmrf_b200.cu -- handle, schedule construction and the C-ABI of libgmrf_b200.so (see include/gmrf_b200.h).
+//
+// Execution model: every numeric phase (factorization+logdet, forward/backward solves, selected inversion) is a
+// static, level-ordered list of kernel launches over task tables that were built on the host at analysis time
+// and live in HBM next to the factor. The factorization and selected-inversion lists are captured into CUDA
+// graphs once per handle, so Newton / hyperparameter loops replay a graph per refactorization.
+#include "../../include/gmrf_b200.h"
+#include "kernels.cuh"
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace gmrf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum LaunchKind : int {
+    K_ASSEMBLE, K_POTRF, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_TRSV0, K_TRSV1, K_GEMV_N, K_GEMV_T
+};
+
+struct Launch {
+    int kind;
+    int aux;            // TRSM: NBT bucket
+    i64 task_off;       // first task in the kind's task array
+    int ntasks;
+    i64 prefix_off;     // offset into the tile-prefix array (ntasks+1 entries) or -1
+    int grid;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Plan {
+    std::vector<Launch> launches;
+};
+
+}  // namespace
+
+struct gmrf_b200_handle {
+    Symbolic S;
+    Options opt;
+    int device = -1;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool factored = false, selinv_valid = false;
+    int fail_col = 0;
+    double logdet = 0.0;
+    double t_ms[5] = {0, 0, 0, 0, 0};
+    size_t device_bytes = 0;
+
+    // device arrays
+    double *d_Lx = nullptr, *d_upd = nullptr, *d_nz = nullptr, *d_Zx = nullptr, *d_zw = nullptr;
+    double *d_y = nullptr, *d_uvec = nullptr, *d_io = nullptr, *d_partial = nullptr, *d_scalars = nullptr;  // scalars: [0]=logdet
+    int *d_fail = nullptr;
+    i64 io_cap = 0;
+    long long *d_qsrc = nullptr, *d_qdst = nullptr, *d_diagpos = nullptr, *d_perm = nullptr;
+    int *d_rowidx = nullptr, *d_relidx = nullptr, *d_child = nullptr, *d_prefix = nullptr, *d_superlist = nullptr;
+    SuperMeta *d_meta = nullptr;
+    GemmTask *d_gemm = nullptr;
+    PotrfTask *d_potrf = nullptr;
+    TrsmTask *d_trsm = nullptr;
+    AsmItem *d_items = nullptr;
+    VecTask *d_vec = nullptr;
+    TrsvTask *d_trsv = nullptr;
+    TransTask *d_trans = nullptr;
+    // selinv task tables are built lazily (they need d_Zx / d_zw)
+    GemmTask *d_gemm_z = nullptr;
+    TrsmTask *d_trsm_z = nullptr;
+    AsmItem *d_items_z = nullptr;
+    int *d_prefix_z = nullptr;
+    // selinv CSC materialisation (lazy)
+    std::vector<i64> z_colptr, z_rowval;
+    long long *d_zpos = nullptr, *d_zdiagpos = nullptr;
+    double *d_zout = nullptr;
+    bool z_pattern_built = false;
+
+    Plan factor_plan, selinv_plan, fwd_plan, bwd_plan;
+    cudaGraphExec_t factor_graph = nullptr, selinv_graph = nullptr;
+    int rhs_block = 8;
+
+    std::vector<void *> owned;   // every cudaMalloc for destroy
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #expr;       \
+            return GMRF_B200_ERR_CUDA;                                                            \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+int dev_alloc(gmrf_b200_handle *h, T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc failed (") + std::to_string(count * sizeof(T)) + " bytes): " + cudaGetErrorString(e);
+        return GMRF_B200_ERR_ALLOC;
+    }
+    h->owned.push_back(*p);
+    h->device_bytes += count * sizeof(T);
+    return 0;
+}
+
+template <class T>
+int dev_upload(gmrf_b200_handle *h, T **p, const std::vector<T> &v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Host-side plan builder
+// ------------------------------------------------------------------------------------------------
+struct Builder {
+    std::vector<GemmTask> gemm;
+    std::vector<PotrfTask> potrf;
+    std::vector<TrsmTask> trsm;
+    std::vector<AsmItem> items;
+    std::vector<VecTask> vec;
+    std::vector<TrsvTask> trsv;
+    std::vector<TransTask> trans;
+    std::vector<int> superlist;
+    std::vector<int> prefix;
+    bool naive = false;
+
+    // GEMM launches: tasks are split into a small-tile and a large-tile launch
+    void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/) {
+        if (tasks.empty()) return;
+        std::vector<GemmTask> small, large;
+        for (auto &t : tasks) {
+            if (t.m <= 0 || t.n <= 0) continue;
+            bool big = !naive && (i64)t.m * t.n >= 256LL * 256LL && t.m >= 128 && t.n >= 96;
+            (big ? large : small).push_back(t);
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            auto &v = pass ? large : small;
+            if (v.empty()) continue;
+            int BM = naive ? 16 : (pass ? 128 : 64), BN = BM;
+            Launch L;
+            L.kind = (variant == 0 ? K_GEMM_NN_S : variant == 1 ? K_GEMM_NT_S : K_GEMM_TT_S) + pass;
+            L.aux = 0;
+            L.task_off = (i64)gemm.size();
+            L.ntasks = (int)v.size();
+            L.prefix_off = (i64)prefix.size();
+            i64 tot = 0;
+            for (auto &t : v) {
+                prefix.push_back((int)tot);
+                tot += (i64)cdiv(t.m, BM) * cdiv(t.n, BN);
+                gemm.push_back(t);
+            }
+            prefix.push_back((int)tot);
+            if (tot > INT_MAX) throw std::runtime_error("too many GEMM tiles in one launch");
+            L.grid = (int)tot;
+            plan.launches.push_back(L);
+        }
+        tasks.clear();
+    }
+    void add_trsm(Plan &plan, std::vector<TrsmTask> &tasks, int var) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = var ? K_TRSM1 : K_TRSM0;
+        int mx = 0;
+        for (auto &t : tasks) mx = std::max(mx, t.nb);
+        L.aux = mx <= 8 ? 8 : mx <= 16 ? 16 : mx <= 32 ? 32 : 64;
+        L.task_off = (i64)trsm.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = (i64)prefix.size();
+        i64 tot = 0;
+        for (auto &t : tasks) {
+            prefix.push_back((int)tot);
+            tot += cdiv(t.m, TRSM_ROWS);
+            trsm.push_back(t);
+        }
+        prefix.push_back((int)tot);
+        L.grid = (int)tot;
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_potrf(Plan &plan, std::vector<PotrfTask> &tasks) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = K_POTRF;
+        L.aux = 0;
+        L.task_off = (i64)potrf.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = -1;
+        L.grid = (int)tasks.size();
+        potrf.insert(potrf.end(), tasks.begin(), tasks.end());
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_items(Plan &plan, std::vector<AsmItem> &its, int kind) {
+        if (its.empty()) return;
+        Launch L;
+        L.kind = kind;
+        L.aux = 0;
+        L.task_off = (i64)items.size();
+        L.ntasks = (int)its.size();
+        L.prefix_off = -1;
+        L.grid = (int)its.size();
+        items.insert(items.end(), its.begin(), its.end());
+        plan.launches.push_back(L);
+        its.clear();
+    }
+    void add_vec(Plan &plan, std::vector<VecTask> &tasks, int kind) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = kind;
+        L.aux = 0;
+        L.task_off = (i64)vec.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = (i64)prefix.size();
+        i64 tot = 0;
+        for (auto &t : tasks) {
+            prefix.push_back((int)tot);
+            tot += (kind == K_GEMV_N) ? cdiv(t.m, 128) : cdiv(t.k, 8);
+            vec.push_back(t);
+        }
+        prefix.push_back((int)tot);
+        L.grid = (int)tot;
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_trsv(Plan &plan, std::vector<TrsvTask> &tasks, int var) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = var ? K_TRSV1 : K_TRSV0;
+        L.aux = 0;
+        L.task_off = (i64)trsv.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = -1;
+        L.grid = (int)tasks.size();
+        trsv.insert(trsv.end(), tasks.begin(), tasks.end());
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_trans(Plan &plan, std::vector<TransTask> &tasks) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = K_TRANSPOSE;
+        L.aux = 0;
+        L.task_off = (i64)trans.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = (i64)prefix.size();
+        i64 tot = 0;
+        for (auto &t : tasks) {
+            prefix.push_back((int)tot);
+            i64 nt = cdiv(t.n, 32);
+            tot += nt * (nt + 1) / 2;
+            trans.push_back(t);
+        }
+        prefix.push_back((int)tot);
+        L.grid = (int)tot;
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_superlist(Plan &plan, std::vector<int> &lst, int kind) {
+        if (lst.empty()) return;
+        Launch L;
+        L.kind = kind;
+        L.aux = 0;
+        L.task_off = (i64)superlist.size();
+        L.ntasks = (int)lst.size();
+        L.prefix_off = -1;
+        L.grid = (int)lst.size();
+        superlist.insert(superlist.end(), lst.begin(), lst.end());
+        plan.launches.push_back(L);
+        lst.clear();
+    }
+};
+
+constexpr int NB = POTRF_NB;
+
+void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
+    const Symbolic &S = h->S;
+    Plan &plan = h->factor_plan;
+    std::vector<AsmItem> its;
+    std::vector<PotrfTask> pt;
+    std::vector<TrsmTask> tt;
+    std::vector<GemmTask> gt;
+    for (i64 l = 0; l < S.nlevels; l++) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp;
+            if (S.child_ptr[s + 1] > S.child_ptr[s])
+                for (i64 c0 = 0; c0 < S.nrow(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
+        }
+        B.add_items(plan, its, K_ASSEMBLE);
+        i64 maxsteps = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        for (i64 j = 0; j < maxsteps; j++) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                i64 k0 = j * NB;
+                if (k0 >= ns) continue;
+                i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                double *P = h->d_Lx + S.panel_off[s];
+                pt.push_back(PotrfTask{P + k0 * ld + k0, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), 0});
+                if (nrow > k1) tt.push_back(TrsmTask{P + k0 * ld + k0, P + k0 * ld + k1, (int)ld, (int)ld, (int)(nrow - k1), (int)nb});
+                if (ns > k1) {
+                    GemmTask g;
+                    g.A = P + k0 * ld + k1;
+                    g.B = P + k0 * ld + k1;
+                    g.C = P + k1 * ld + k1;
+                    g.m = (int)(nrow - k1); g.n = (int)(ns - k1); g.k = (int)nb;
+                    g.lda = g.ldb = g.ldc = (int)ld;
+                    g.flags = GEMM_LOWER; g.pad_ = 0;
+                    gt.push_back(g);
+                }
+            }
+            B.add_potrf(plan, pt);
+            B.add_trsm(plan, tt, 0);
+            B.add_gemm(plan, gt, 0);
+        }
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            if (nr == 0) continue;
+            double *P = h->d_Lx + S.panel_off[s];
+            GemmTask g;
+            g.A = P + ns; g.B = P + ns;
+            g.C = h->d_upd + S.upd_off[s];
+            g.m = g.n = (int)nr; g.k = (int)ns;
+            g.lda = g.ldb = (int)ld; g.ldc = S.upd_ld[s];
+            g.flags = GEMM_LOWER | ((S.child_ptr[s + 1] > S.child_ptr[s]) ? 0 : GEMM_BETA0);
+            g.pad_ = 0;
+            gt.push_back(g);
+        }
+        B.add_gemm(plan, gt, 0);
+    }
+}
+
+void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
+    const Symbolic &S = h->S;
+    std::vector<int> lst;
+    std::vector<TrsvTask> tv;
+    std::vector<VecTask> vt;
+    const i64 n = S.n;
+    // forward: L y = b
+    for (i64 l = 0; l < S.nlevels; l++) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp;
+            if (S.nr(s) > 0 || S.child_ptr[s + 1] > S.child_ptr[s]) lst.push_back((int)s);
+        }
+        B.add_superlist(h->fwd_plan, lst, K_FWD_ASM);
+        i64 maxsteps = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        for (i64 j = 0; j < maxsteps; j++) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+                i64 k0 = j * NB;
+                if (k0 >= ns) continue;
+                i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                const double *P = h->d_Lx + S.panel_off[s];
+                double *yk = h->d_y + S.sfirst[s] + k0;
+                tv.push_back(TrsvTask{P + k0 * ld + k0, yk, (int)ld, (int)n, (int)nb, 0});
+                if (ns > k1) {
+                    VecTask v;
+                    v.A = P + k0 * ld + k1; v.idx = nullptr; v.C = h->d_y + S.sfirst[s] + k1; v.X = yk;
+                    v.m = (int)(ns - k1); v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)n; v.ldx = (int)n; v.pad_ = 0;
+                    vt.push_back(v);
+                }
+                if (nr > 0) {
+                    VecTask v;
+                    v.A = P + k0 * ld + ns; v.idx = nullptr; v.C = h->d_uvec + S.uvec_off[s]; v.X = yk;
+                    v.m = (int)nr; v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)S.uvec_total; v.ldx = (int)n; v.pad_ = 0;
+                    vt.push_back(v);
+                }
+            }
+            B.add_trsv(h->fwd_plan, tv, 0);
+            B.add_vec(h->fwd_plan, vt, K_GEMV_N);
+        }
+    }
+    // backward: L^T x = y
+    for (i64 l = S.nlevels - 1; l >= 0; l--) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        i64 maxsteps = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        for (i64 t = 0; t < maxsteps; t++) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                i64 nblk = cdiv(ns, NB);
+                i64 j = nblk - 1 - t;
+                if (j < 0) continue;
+                i64 k0 = j * NB, nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                const double *P = h->d_Lx + S.panel_off[s];
+                double *yk = h->d_y + S.sfirst[s] + k0;
+                if (nrow > k1) {
+                    VecTask v;
+                    v.A = P + k0 * ld + k1; v.idx = h->d_rowidx + S.rowptr[s] + k1; v.C = yk; v.X = h->d_y;
+                    v.m = (int)(nrow - k1); v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)n; v.ldx = (int)n; v.pad_ = 0;
+                    vt.push_back(v);
+                }
+                tv.push_back(TrsvTask{P + k0 * ld + k0, yk, (int)ld, (int)n, (int)nb, 0});
+            }
+            B.add_vec(h->bwd_plan, vt, K_GEMV_T);
+            B.add_trsv(h->bwd_plan, tv, 1);
+        }
+    }
+}
+
+// Selected inversion (Takahashi), per supernode s with panel L = [L11; L21], W = Z[R,R] gathered from the parent:
+//   T' = -W L21 ;  G = I - L21^T T' = I + L21^T W L21 ;  [H; Z_RS] = [G; T'] L11^-1 ;  Z_SS = H^T L11^-1
+// (Z_SS = L11^-T (I + L21^T W L21) L11^-1, Z_RS = -W L21 L11^-1.)
+void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
+    const Symbolic &S = h->S;
+    Plan &plan = h->selinv_plan;
+    std::vector<AsmItem> its;
+    std::vector<GemmTask> gt;
+    std::vector<TrsmTask> tt;
+    std::vector<TransTask> tr;
+    for (i64 l = S.nlevels - 1; l >= 0; l--) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp;
+            for (i64 c0 = 0; c0 < S.nr(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
+        }
+        B.add_items(plan, its, K_GATHER);
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            if (nr == 0) continue;
+            GemmTask g;
+            g.A = h->d_zw + S.zw_off[s]; g.lda = S.upd_ld[s];
+            g.B = h->d_Lx + S.panel_off[s] + ns; g.ldb = (int)ld;
+            g.C = h->d_Zx + S.panel_off[s] + ns; g.ldc = (int)ld;
+            g.m = (int)nr; g.n = (int)ns; g.k = (int)nr;
+            g.flags = GEMM_BETA0; g.pad_ = 0;
+            gt.push_back(g);
+        }
+        B.add_gemm(plan, gt, 1);
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            GemmTask g;
+            g.A = h->d_Lx + S.panel_off[s] + ns; g.lda = (int)ld;
+            g.B = h->d_Zx + S.panel_off[s] + ns; g.ldb = (int)ld;
+            g.C = h->d_Zx + S.panel_off[s]; g.ldc = (int)ld;
+            g.m = (int)ns; g.n = (int)ns; g.k = (int)nr;
+            g.flags = GEMM_BETA0 | GEMM_ADD_I; g.pad_ = 0;
+            gt.push_back(g);
+        }
+        B.add_gemm(plan, gt, 2);
+        i64 maxsteps = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        for (int pass = 0; pass < 2; pass++) {
+            // pass 0: all nrow rows of [G; T'];  pass 1: the (transposed) ns x ns block only
+            if (pass == 1) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp;
+                    if (S.ns(s) > 1) tr.push_back(TransTask{h->d_Zx + S.panel_off[s], (int)S.ns(s), S.panel_ld[s]});
+                }
+                B.add_trans(plan, tr);
+            }
+            for (i64 t = 0; t < maxsteps; t++) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                    i64 nblk = cdiv(ns, NB);
+                    i64 j = nblk - 1 - t;
+                    if (j < 0) continue;
+                    i64 k0 = j * NB, nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                    i64 m = pass == 0 ? nrow : ns;
+                    double *Z = h->d_Zx + S.panel_off[s];
+                    const double *P = h->d_Lx + S.panel_off[s];
+                    if (ns > k1) {
+                        GemmTask g;
+                        g.A = Z + k1 * ld; g.lda = (int)ld;            // X[:, later]  (m x (ns-k1))
+                        g.B = P + k0 * ld + k1; g.ldb = (int)ld;       // L11[later, K] ((ns-k1) x nb, k-contiguous)
+                        g.C = Z + k0 * ld; g.ldc = (int)ld;
+                        g.m = (int)m; g.n = (int)nb; g.k = (int)(ns - k1);
+                        g.flags = 0; g.pad_ = 0;
+                        gt.push_back(g);
+                    }
+                    tt.push_back(TrsmTask{P + k0 * ld + k0, Z + k0 * ld, (int)ld, (int)ld, (int)m, (int)nb});
+                }
+                B.add_gemm(plan, gt, 1);
+                B.add_trsm(plan, tt, 1);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch dispatch
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
+void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
+    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN>(), st>>>(tasks, prefix, ntasks);
+}
+
+// Opt in to > 48 KB dynamic shared memory for every GEMM instantiation (per device; must run outside stream capture).
+template <int BM, int BN, int WGM, int WGN>
+cudaError_t configure_gemm_tile() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
+    return cudaSuccess;
+}
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    if ((e = configure_gemm_tile<128, 128, 2, 4>())) return e;
+    if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
+    return cudaSuccess;
+}
+
+template <bool TA, bool TB>
+void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
+    if (naive) gemm_naive_kernel<TA, TB><<<grid, 256, 0, st>>>(tasks, prefix, ntasks);
+    else if (large) launch_gemm_t<128, 128, 2, 4, TA, TB>(tasks, prefix, ntasks, grid, st);
+    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
+}
+
+template <int VAR>
+void launch_trsm(int nbt, const TrsmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
+    switch (nbt) {
+        case 8: trsm_strip_kernel<VAR, 8><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
+        case 16: trsm_strip_kernel<VAR, 16><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
+        case 32: trsm_strip_kernel<VAR, 32><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
+        default: trsm_strip_kernel<VAR, 64><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
+    }
+}
+
+struct TableSet {
+    const GemmTask *gemm;
+    const TrsmTask *trsm;
+    const AsmItem *items;
+    const int *prefix;
+};
+
+void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs) {
+    cudaStream_t st = h->stream;
+    const bool naive = h->opt.naive_kernels != 0;
+    const int *pf = L.prefix_off >= 0 ? T.prefix + L.prefix_off : nullptr;
+    if (L.grid <= 0) return;
+    switch (L.kind) {
+        case K_ASSEMBLE:
+            assemble_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd);
+            break;
+        case K_POTRF:
+            potrf_diag_kernel<<<L.grid, 256, 0, st>>>(h->d_potrf + L.task_off, h->d_fail);
+            break;
+        case K_TRSM0: launch_trsm<0>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_TRSM1: launch_trsm<1>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_GEMM_NN_S: case K_GEMM_NN_L:
+            launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_GEMM_NT_S: case K_GEMM_NT_L:
+            launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_GEMM_TT_S: case K_GEMM_TT_L:
+            launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_GATHER:
+            selinv_gather_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_relidx, h->d_Zx, h->d_zw);
+            break;
+        case K_TRANSPOSE:
+            transpose_inplace_kernel<<<L.grid, 256, 0, st>>>(h->d_trans + L.task_off, pf, L.ntasks);
+            break;
+        case K_FWD_ASM: {
+            dim3 g(L.grid, nrhs);
+            fwd_assemble_kernel<<<g, 256, 0, st>>>(h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx,
+                                                   h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
+            break;
+        }
+        case K_TRSV0: case K_TRSV1: {
+            dim3 g(L.grid, (nrhs + 7) / 8);
+            if (L.kind == K_TRSV0) trsv_block_kernel<0><<<g, 256, 0, st>>>(h->d_trsv + L.task_off, nrhs);
+            else trsv_block_kernel<1><<<g, 256, 0, st>>>(h->d_trsv + L.task_off, nrhs);
+            break;
+        }
+        case K_GEMV_N:
+            if (nrhs == 1) gemv_n_kernel<1><<<L.grid, 128, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+            else gemv_n_kernel<8><<<L.grid, 128, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+            break;
+        case K_GEMV_T:
+            if (nrhs == 1) gemv_t_kernel<1><<<L.grid, 256, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+            else gemv_t_kernel<8><<<L.grid, 256, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+            break;
+    }
+}
+
+int check_launch(gmrf_b200_handle *h, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        h->err = std::string("kernel launch failed in ") + what + ": " + cudaGetErrorString(e);
+        return GMRF_B200_ERR_CUDA;
+    }
+    return 0;
+}
+
+void enqueue_factor(gmrf_b200_handle *h) {
+    const Symbolic &S = h->S;
+    cudaStream_t st = h->stream;
+    cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)S.panel_total, st);
+    const int int_max = INT_MAX;
+    (void)int_max;
+    cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);   // 0x7f7f7f7f: "no failure" sentinel
+    i64 cnt = (i64)S.q_src.size();
+    if (cnt > 0) {
+        int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
+        scatter_q_kernel<<<grid, 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+    }
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    for (const Launch &L : h->factor_plan.launches) run_launch(h, L, T, 0);
+    logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
+    logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+}
+
+void enqueue_selinv(gmrf_b200_handle *h) {
+    TableSet T{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z};
+    for (const Launch &L : h->selinv_plan.launches) run_launch(h, L, T, 0);
+}
+
+int ensure_device(gmrf_b200_handle *h) {
+    if (!h) return GMRF_B200_ERR_ARG;
+    if (h->device < 0) {
+        h->err = "numeric call on an analysis-only handle (device < 0): there is no CPU fallback";
+        return GMRF_B200_ERR_NO_DEVICE;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return 0;
+}
+
+int do_factor(gmrf_b200_handle *h) {
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
+    if (h->opt.use_graph) {
+        if (!h->factor_graph) {
+            cudaGraph_t g;
+            CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_factor(h);
+            CUDA_TRY(h, cudaStreamEndCapture(st, &g));
+            CUDA_TRY(h, cudaGraphInstantiate(&h->factor_graph, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CUDA_TRY(h, cudaGraphLaunch(h->factor_graph, st));
+    } else {
+        enqueue_factor(h);
+        int rc = check_launch(h, "factorization");
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
+    double host_logdet = 0;
+    int host_fail = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&host_logdet, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(&host_fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->t_ms[1] = ms;
+    h->logdet = host_logdet;
+    h->fail_col = (host_fail == 0x7f7f7f7f) ? 0 : host_fail;
+    h->factored = true;
+    h->selinv_valid = false;
+    return h->fail_col > 0 ? h->fail_col : 0;
+}
+
+int build_selinv_tables(gmrf_b200_handle *h) {
+    if (h->d_Zx) return 0;
+    const Symbolic &S = h->S;
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_Zx, (size_t)S.panel_total))) return rc;
+    if ((rc = dev_alloc(h, &h->d_zw, (size_t)S.zw_total))) return rc;
+    CUDA_TRY(h, cudaMemset(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total));
+    Builder B;
+    B.naive = h->opt.naive_kernels != 0;
+    try {
+        build_selinv_plan(h, B);
+    } catch (std::exception &e) {
+        h->err = e.what();
+        return GMRF_B200_ERR_ARG;
+    }
+    if ((rc = dev_upload(h, &h->d_gemm_z, B.gemm))) return rc;
+    if ((rc = dev_upload(h, &h->d_trsm_z, B.trsm))) return rc;
+    if ((rc = dev_upload(h, &h->d_items_z, B.items))) return rc;
+    if ((rc = dev_upload(h, &h->d_prefix_z, B.prefix))) return rc;
+    if ((rc = dev_upload(h, &h->d_trans, B.trans))) return rc;
+    std::vector<long long> dp(S.diag_pos.begin(), S.diag_pos.end());
+    // diagonal of Z in ORIGINAL ordering: out[perm[k]] = Z[diag_pos[k]]  ->  pos_orig[i] = diag_pos[iperm[i]]
+    std::vector<long long> zp(S.n);
+    for (i64 i = 0; i < S.n; i++) zp[i] = S.diag_pos[S.iperm[i]];
+    if ((rc = dev_upload(h, &h->d_zdiagpos, zp))) return rc;
+    return 0;
+}
+
+int ensure_io(gmrf_b200_handle *h, i64 count) {
+    if (h->io_cap >= count) return 0;
+    // grow-only staging buffer for host<->device transfers of right-hand sides / results
+    double *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, sizeof(double) * (size_t)count);
+    if (e != cudaSuccess) { h->err = "cudaMalloc failed for the I/O staging buffer"; return GMRF_B200_ERR_ALLOC; }
+    h->owned.push_back(p);
+    h->device_bytes += sizeof(double) * (size_t)count;
+    h->d_io = p;
+    h->io_cap = count;
+    return 0;
+}
+
+// X = Q^-1 B (mode 0) or X = P' L^-T Z (mode 1) on device buffers; nrhs processed in blocks of rhs_block.
+int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
+    const Symbolic &S = h->S;
+    if (!h->factored) { h->err = "solve before the first refactorize"; return GMRF_B200_ERR_STATE; }
+    if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
+    cudaStream_t st = h->stream;
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    const int tpb = 256;
+    const int gridn = (int)((S.n + tpb - 1) / tpb);
+    for (i64 r0 = 0; r0 < nrhs; r0 += h->rhs_block) {
+        int nb = (int)std::min<i64>(h->rhs_block, nrhs - r0);
+        if (S.n == 0) break;
+        if (mode == 0) {
+            permute_rows_kernel<<<gridn, tpb, 0, st>>>(h->d_y, dB + r0 * ld, h->d_perm, S.n, S.n, ld, nb, 0);
+            for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
+        } else {
+            // the half solve takes z in the factor's own ordering (CHOLMOD's `UP \ z`): no input permutation
+            CUDA_TRY(h, cudaMemcpy2DAsync(h->d_y, sizeof(double) * S.n, dB + r0 * ld, sizeof(double) * ld,
+                                          sizeof(double) * S.n, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
+        permute_rows_kernel<<<gridn, tpb, 0, st>>>(dX + r0 * ld, h->d_y, h->d_perm, S.n, ld, S.n, nb, 1);
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
+    int rc = check_launch(h, "solve");
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[2] = ms;
+    return 0;
+}
+
+int do_solve_host(gmrf_b200_handle *h, const double *B, double *X, i64 ld, i64 nrhs, int mode) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    const Symbolic &S = h->S;
+    if (!B || !X) { h->err = "null buffer"; return GMRF_B200_ERR_ARG; }
+    if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
+    if (nrhs == 0 || S.n == 0) return 0;
+    // stage in chunks so the device footprint stays bounded for very wide right-hand sides
+    const i64 chunk = std::max<i64>(h->rhs_block, std::min<i64>(nrhs, (i64)(256LL << 20) / std::max<i64>(S.n, 1)));
+    if ((rc = ensure_io(h, S.n * std::min(chunk, nrhs)))) return rc;
+    for (i64 r0 = 0; r0 < nrhs; r0 += chunk) {
+        i64 nb = std::min(chunk, nrhs - r0);
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->d_io, sizeof(double) * S.n, B + r0 * ld, sizeof(double) * ld, sizeof(double) * S.n,
+                                      nb, cudaMemcpyHostToDevice, h->stream));
+        rc = do_solve_device(h, h->d_io, h->d_io, S.n, nb, mode);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpy2DAsync(X + r0 * ld, sizeof(double) * ld, h->d_io, sizeof(double) * S.n, sizeof(double) * S.n,
+                                      nb, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+void build_z_pattern(gmrf_b200_handle *h) {
+    // full symmetric CSC on the stored factor pattern, original ordering, sorted rows; pos = Z panel position
+    if (h->z_pattern_built) return;
+    const Symbolic &S = h->S;
+    const i64 n = S.n;
+    std::vector<i64> cnt(n + 1, 0);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 ns = S.ns(s), nrow = S.nrow(s);
+        const i32 *rows = S.rowidx.data() + S.rowptr[s];
+        for (i64 lc = 0; lc < ns; lc++) {
+            i64 cj = S.perm[S.sfirst[s] + lc];
+            for (i64 i = lc; i < nrow; i++) {
+                i64 ri = S.perm[rows[i]];
+                cnt[cj + 1]++;
+                if (i != lc) cnt[ri + 1]++;
+            }
+        }
+    }
+    for (i64 j = 0; j < n; j++) cnt[j + 1] += cnt[j];
+    h->z_colptr = cnt;
+    i64 nnz = cnt[n];
+    std::vector<i64> rowv(nnz);
+    std::vector<long long> pos(nnz);
+    std::vector<i64> w(cnt.begin(), cnt.end() - 1);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+        const i32 *rows = S.rowidx.data() + S.rowptr[s];
+        for (i64 lc = 0; lc < ns; lc++) {
+            i64 cj = S.perm[S.sfirst[s] + lc];
+            for (i64 i = lc; i < nrow; i++) {
+                i64 ri = S.perm[rows[i]];
+                long long p = S.panel_off[s] + lc * ld + i;
+                rowv[w[cj]] = ri; pos[w[cj]++] = p;
+                if (i != lc) { rowv[w[ri]] = cj; pos[w[ri]++] = p; }
+            }
+        }
+    }
+    // sort rows within each column
+    std::vector<std::pair<i64, long long>> tmp;
+    for (i64 j = 0; j < n; j++) {
+        i64 a = cnt[j], b = cnt[j + 1];
+        tmp.resize(b - a);
+        for (i64 k = a; k < b; k++) tmp[k - a] = {rowv[k], pos[k]};
+        std::sort(tmp.begin(), tmp.end());
+        for (i64 k = a; k < b; k++) { rowv[k] = tmp[k - a].first; pos[k] = tmp[k - a].second; }
+    }
+    h->z_rowval.swap(rowv);
+    if (h->device >= 0) {
+        dev_upload(h, &h->d_zpos, pos);
+    }
+    h->z_pattern_built = true;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int gmrf_b200_set_option(const char *key, double value) {
+    Options &o = global_options();
+    std::string k = key ? key : "";
+    if (k == "relax_n0") o.relax_n[0] = value;
+    else if (k == "relax_n1") o.relax_n[1] = value;
+    else if (k == "relax_n2") o.relax_n[2] = value;
+    else if (k == "relax_z0") o.relax_z[1] = value;
+    else if (k == "relax_z1") o.relax_z[2] = value;
+    else if (k == "relax_z2") o.relax_z[3] = value;
+    else if (k == "use_graph") o.use_graph = (int)value;
+    else if (k == "naive_kernels") o.naive_kernels = (int)value;
+    else return GMRF_B200_ERR_ARG;
+    return 0;
+}
+
+const char *gmrf_b200_last_error(const gmrf_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
+                     const int64_t *perm, int ordering, int device) {
+    g_create_error.clear();
+    if (!out) { g_create_error = "out is null"; return GMRF_B200_ERR_ARG; }
+    *out = nullptr;
+    if (n < 0 || !colptr || (!rowval && n > 0) || (index_base != 0 && index_base != 1)) {
+        g_create_error = "bad arguments to gmrf_b200_create";
+        return GMRF_B200_ERR_ARG;
+    }
+    std::unique_ptr<gmrf_b200_handle> h(new gmrf_b200_handle());
+    h->opt = global_options();
+    h->device = device;
+    try {
+        std::vector<i64> cp(colptr, colptr + n + 1), rv, pm;
+        for (auto &v : cp) v -= index_base;
+        if (cp[0] != 0) throw std::runtime_error("colptr[0] must equal index_base");
+        i64 nnz = cp[n];
+        if (nnz < 0) throw std::runtime_error("negative nnz");
+        rv.assign(rowval, rowval + nnz);
+        for (auto &v : rv) v -= index_base;
+        if (perm) {
+            pm.assign(perm, perm + n);
+            for (auto &v : pm) v -= index_base;
+        }
+        analyze(h->S, n, cp.data(), rv.data(), perm ? pm.data() : nullptr, ordering, h->opt);
+    } catch (std::exception &e) {
+        g_create_error = e.what();
+        return GMRF_B200_ERR_ARG;
+    }
+    h->t_ms[4] = h->S.analysis_ms;
+    if (device < 0) {
+        *out = h.release();
+        return 0;
+    }
+    // ---- device side -------------------------------------------------------------------------------
+    gmrf_b200_handle *H = h.get();
+    auto fail = [&](int rc) { g_create_error = H->err; gmrf_b200_destroy(h.release()); return rc; };
+    {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device >= ndev) {
+            H->err = "CUDA device " + std::to_string(device) + " is not available (libgmrf_b200 has no CPU fallback)";
+            return fail(GMRF_B200_ERR_NO_DEVICE);
+        }
+        if (cudaSetDevice(device) != cudaSuccess) { H->err = "cudaSetDevice failed"; return fail(GMRF_B200_ERR_CUDA); }
+        if (cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking) != cudaSuccess) { H->err = "stream creation failed"; return fail(GMRF_B200_ERR_CUDA); }
+        for (auto &e2 : H->ev) cudaEventCreate(&e2);
+        if (configure_kernels() != cudaSuccess) { H->err = "cudaFuncSetAttribute failed (is this an sm_100a device?)"; return fail(GMRF_B200_ERR_CUDA); }
+    }
+    const Symbolic &S = H->S;
+    int rc;
+#define TRY_RC(x) do { rc = (x); if (rc) return fail(rc); } while (0)
+    TRY_RC(dev_alloc(H, &H->d_Lx, (size_t)S.panel_total));
+    TRY_RC(dev_alloc(H, &H->d_upd, (size_t)S.upd_total));
+    TRY_RC(dev_alloc(H, &H->d_nz, (size_t)S.nnzA));
+    TRY_RC(dev_alloc(H, &H->d_y, (size_t)(S.n * H->rhs_block)));
+    TRY_RC(dev_alloc(H, &H->d_uvec, (size_t)(S.uvec_total * H->rhs_block)));
+    TRY_RC(dev_alloc(H, &H->d_partial, (size_t)LOGDET_BLOCKS));
+    TRY_RC(dev_alloc(H, &H->d_scalars, (size_t)8));
+    TRY_RC(dev_alloc(H, &H->d_fail, (size_t)2));
+    {
+        std::vector<long long> a(S.q_src.begin(), S.q_src.end()), b(S.q_dst.begin(), S.q_dst.end()),
+            c(S.diag_pos.begin(), S.diag_pos.end()), d(S.perm.begin(), S.perm.end());
+        TRY_RC(dev_upload(H, &H->d_qsrc, a));
+        TRY_RC(dev_upload(H, &H->d_qdst, b));
+        TRY_RC(dev_upload(H, &H->d_diagpos, c));
+        TRY_RC(dev_upload(H, &H->d_perm, d));
+        std::vector<int> ri(S.rowidx.begin(), S.rowidx.end()), rl(S.relidx.begin(), S.relidx.end()),
+            ch(S.child_idx.begin(), S.child_idx.end());
+        TRY_RC(dev_upload(H, &H->d_rowidx, ri));
+        TRY_RC(dev_upload(H, &H->d_relidx, rl));
+        TRY_RC(dev_upload(H, &H->d_child, ch));
+        std::vector<SuperMeta> meta(S.nsuper);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            SuperMeta &m = meta[s];
+            m.panel_off = S.panel_off[s]; m.upd_off = S.upd_off[s]; m.zw_off = S.zw_off[s];
+            m.rowptr = S.rowptr[s]; m.uvec_off = S.uvec_off[s];
+            m.first = (int)S.sfirst[s]; m.ns = (int)S.ns(s); m.nrow = (int)S.nrow(s);
+            m.ld = S.panel_ld[s]; m.uld = S.upd_ld[s]; m.parent = (int)S.sparent[s];
+            m.child_begin = (int)S.child_ptr[s]; m.child_end = (int)S.child_ptr[s + 1];
+        }
+        TRY_RC(dev_upload(H, &H->d_meta, meta));
+    }
+    {
+        Builder B;
+        B.naive = H->opt.naive_kernels != 0;
+        try {
+            build_factor_plan(H, B);
+            build_solve_plans(H, B);
+        } catch (std::exception &e) {
+            H->err = e.what();
+            return fail(GMRF_B200_ERR_ARG);
+        }
+        TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
+        TRY_RC(dev_upload(H, &H->d_potrf, B.potrf));
+        TRY_RC(dev_upload(H, &H->d_trsm, B.trsm));
+        TRY_RC(dev_upload(H, &H->d_items, B.items));
+        TRY_RC(dev_upload(H, &H->d_vec, B.vec));
+        TRY_RC(dev_upload(H, &H->d_trsv, B.trsv));
+        TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
+        TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
+    }
+#undef TRY_RC
+    *out = h.release();
+    return 0;
+}
+
+void gmrf_b200_destroy(gmrf_b200_handle *h) {
+    if (!h) return;
+    if (h->device >= 0) {
+        cudaSetDevice(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->factor_graph) cudaGraphExecDestroy(h->factor_graph);
+        if (h->selinv_graph) cudaGraphExecDestroy(h->selinv_graph);
+        for (void *p : h->owned) cudaFree(p);
+        for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+int gmrf_b200_refactorize_device(gmrf_b200_handle *h, const double *d_nzval, int64_t nnz) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (nnz != h->S.nnzA) {
+        h->err = "nzval holds " + std::to_string(nnz) + " values but the pattern has " + std::to_string(h->S.nnzA) +
+                 " nonzeros; the sparsity pattern must be invariant across refactorizations";
+        return GMRF_B200_ERR_ARG;
+    }
+    if (!d_nzval && nnz > 0) { h->err = "null nzval"; return GMRF_B200_ERR_ARG; }
+    if (d_nzval != h->d_nz && nnz > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_nz, d_nzval, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, h->stream));
+    h->t_ms[0] = 0;
+    return do_factor(h);
+}
+
+int gmrf_b200_refactorize(gmrf_b200_handle *h, const double *nzval, int64_t nnz) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (nnz != h->S.nnzA) {
+        h->err = "nzval holds " + std::to_string(nnz) + " values but the pattern has " + std::to_string(h->S.nnzA) +
+                 " nonzeros; the sparsity pattern must be invariant across refactorizations";
+        return GMRF_B200_ERR_ARG;
+    }
+    if (!nzval && nnz > 0) { h->err = "null nzval"; return GMRF_B200_ERR_ARG; }
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    if (nnz > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_nz, nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    rc = do_factor(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[0] = ms;
+    return rc;
+}
+
+int gmrf_b200_logdet(gmrf_b200_handle *h, double *out) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored) { h->err = "logdet before the first refactorize"; return GMRF_B200_ERR_STATE; }
+    if (!out) { h->err = "null out"; return GMRF_B200_ERR_ARG; }
+    *out = h->logdet;
+    return 0;
+}
+
+int gmrf_b200_solve(gmrf_b200_handle *h, const double *B, double *X, int64_t ld, int64_t nrhs) {
+    return do_solve_host(h, B, X, ld, nrhs, 0);
+}
+int gmrf_b200_solve_Lt(gmrf_b200_handle *h, const double *Z, double *X, int64_t ld, int64_t nrhs) {
+    return do_solve_host(h, Z, X, ld, nrhs, 1);
+}
+int gmrf_b200_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, int64_t ld, int64_t nrhs) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    return do_solve_device(h, dB, dX, ld, nrhs, 0);
+}
+int gmrf_b200_solve_Lt_device(gmrf_b200_handle *h, const double *dZ, double *dX, int64_t ld, int64_t nrhs) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    return do_solve_device(h, dZ, dX, ld, nrhs, 1);
+}
+
+int gmrf_b200_selinv_compute(gmrf_b200_handle *h) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored) { h->err = "selinv before the first refactorize"; return GMRF_B200_ERR_STATE; }
+    if (h->selinv_valid) return 0;
+    if ((rc = build_selinv_tables(h))) return rc;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    if (h->opt.use_graph) {
+        if (!h->selinv_graph) {
+            cudaGraph_t g;
+            CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_selinv(h);
+            CUDA_TRY(h, cudaStreamEndCapture(st, &g));
+            CUDA_TRY(h, cudaGraphInstantiate(&h->selinv_graph, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CUDA_TRY(h, cudaGraphLaunch(h->selinv_graph, st));
+    } else {
+        enqueue_selinv(h);
+        if ((rc = check_launch(h, "selected inversion"))) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[3] = ms;
+    h->selinv_valid = true;
+    return 0;
+}
+
+static int gather_to_host(gmrf_b200_handle *h, const long long *d_pos, i64 cnt, double *out) {
+    int rc;
+    if ((rc = ensure_io(h, std::max<i64>(cnt, 1)))) return rc;
+    if (cnt == 0) return 0;
+    int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
+    gather_values_kernel<<<grid, 256, 0, h->stream>>>(h->d_io, h->d_Zx, d_pos, cnt);
+    if ((rc = check_launch(h, "gather"))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_io, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gmrf_b200_selinv_diag(gmrf_b200_handle *h, double *out) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (!out) { h->err = "null out"; return GMRF_B200_ERR_ARG; }
+    return gather_to_host(h, h->d_zdiagpos, h->S.n, out);
+}
+
+int gmrf_b200_selinv_nnz(gmrf_b200_handle *h, int64_t *nnz) {
+    if (!h || !nnz) return GMRF_B200_ERR_ARG;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    build_z_pattern(h);
+    *nnz = h->z_colptr[h->S.n];
+    return 0;
+}
+
+int gmrf_b200_selinv_pattern(gmrf_b200_handle *h, int64_t *colptr, int64_t *rowval, int index_base) {
+    if (!h || !colptr || !rowval) return GMRF_B200_ERR_ARG;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    build_z_pattern(h);
+    for (i64 j = 0; j <= h->S.n; j++) colptr[j] = h->z_colptr[j] + index_base;
+    for (size_t k = 0; k < h->z_rowval.size(); k++) rowval[k] = h->z_rowval[k] + index_base;
+    return 0;
+}
+
+int gmrf_b200_selinv_values(gmrf_b200_handle *h, double *nzval) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (!nzval) { h->err = "null out"; return GMRF_B200_ERR_ARG; }
+    build_z_pattern(h);
+    if (!h->d_zpos) { h->err = "selinv pattern upload failed"; return GMRF_B200_ERR_ALLOC; }
+    return gather_to_host(h, h->d_zpos, h->z_colptr[h->S.n], nzval);
+}
+
+int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
+                             int index_base, double *out) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    const Symbolic &S = h->S;
+    if (ncol != S.n || !colptr || !out) { h->err = "selinv_extract: pattern must be n x n"; return GMRF_B200_ERR_ARG; }
+    i64 cnt = colptr[ncol] - index_base;
+    std::vector<long long> pos((size_t)std::max<i64>(cnt, 0));
+    for (i64 j = 0; j < ncol; j++)
+        for (i64 p = colptr[j] - index_base; p < colptr[j + 1] - index_base; p++) {
+            i64 i = rowval[p] - index_base;
+            if (i < 0 || i >= S.n) { h->err = "selinv_extract: row index out of range"; return GMRF_B200_ERR_ARG; }
+            i64 a = S.iperm[i], b = S.iperm[j];
+            i64 col = std::min(a, b), row = std::max(a, b);
+            i64 s = S.col2super[col];
+            const i32 *rb = S.rowidx.data() + S.rowptr[s], *re = S.rowidx.data() + S.rowptr[s + 1];
+            const i32 *it = std::lower_bound(rb, re, (i32)row);
+            pos[p] = (it != re && *it == (i32)row) ? (long long)(S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb)) : -1LL;
+        }
+    if (cnt <= 0) return 0;
+    long long *d_pos = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&d_pos, sizeof(long long) * (size_t)cnt));
+    cudaError_t e = cudaMemcpyAsync(d_pos, pos.data(), sizeof(long long) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = gather_to_host(h, d_pos, cnt, out);
+    else { h->err = "H2D copy failed"; rc = GMRF_B200_ERR_CUDA; }
+    cudaFree(d_pos);
+    return rc;
+}
+
+// ---- introspection -------------------------------------------------------------------------------
+int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info) {
+    if (!h || !info) return GMRF_B200_ERR_ARG;
+    const Symbolic &S = h->S;
+    int64_t v[GMRF_B200_INFO_COUNT];
+    v[GMRF_B200_INFO_N] = S.n;
+    v[GMRF_B200_INFO_NNZ_Q] = S.nnzA;
+    v[GMRF_B200_INFO_NNZ_L] = S.nnzL;
+    v[GMRF_B200_INFO_NNZ_L_STORED] = S.panel_total;
+    v[GMRF_B200_INFO_NSUPER] = S.nsuper;
+    v[GMRF_B200_INFO_NLEVELS] = S.nlevels;
+    v[GMRF_B200_INFO_MAX_FRONT] = S.max_front;
+    v[GMRF_B200_INFO_MAX_NS] = S.max_ns;
+    v[GMRF_B200_INFO_UPDATE_POOL] = S.upd_total;
+    v[GMRF_B200_INFO_FLOPS_CHOL] = (int64_t)S.flops;
+    v[GMRF_B200_INFO_FLOPS_CHOL_STORED] = (int64_t)S.flops_stored;
+    v[GMRF_B200_INFO_DEVICE_BYTES] = (int64_t)h->device_bytes;
+    v[GMRF_B200_INFO_GRAPH_NODES] = (int64_t)h->factor_plan.launches.size() + 5;
+    v[GMRF_B200_INFO_SELINV_NODES] = (int64_t)h->selinv_plan.launches.size();
+    for (int i = 0; i < n_info && i < GMRF_B200_INFO_COUNT; i++) info[i] = v[i];
+    return 0;
+}
+
+int gmrf_b200_get_perm(const gmrf_b200_handle *h, int64_t *perm, int index_base) {
+    if (!h || !perm) return GMRF_B200_ERR_ARG;
+    for (i64 k = 0; k < h->S.n; k++) perm[k] = h->S.perm[k] + index_base;
+    return 0;
+}
+int gmrf_b200_get_colcounts(const gmrf_b200_handle *h, int64_t *cc) {
+    if (!h || !cc) return GMRF_B200_ERR_ARG;
+    std::copy(h->S.colcount.begin(), h->S.colcount.end(), cc);
+    return 0;
+}
+int gmrf_b200_get_etree(const gmrf_b200_handle *h, int64_t *parent) {
+    if (!h || !parent) return GMRF_B200_ERR_ARG;
+    std::copy(h->S.parent.begin(), h->S.parent.end(), parent);
+    return 0;
+}
+int gmrf_b200_get_supernodes(const gmrf_b200_handle *h, int64_t *super_ptr, int64_t *super_parent, int64_t *level,
+                             int64_t *row_ptr, int64_t *panel_off, int64_t *panel_ld, int64_t *upd_off, int64_t *upd_ld) {
+    if (!h) return GMRF_B200_ERR_ARG;
+    const Symbolic &S = h->S;
+    if (super_ptr) std::copy(S.sfirst.begin(), S.sfirst.end(), super_ptr);
+    if (super_parent) std::copy(S.sparent.begin(), S.sparent.end(), super_parent);
+    if (level) for (i64 s = 0; s < S.nsuper; s++) level[s] = S.level[s];
+    if (row_ptr) std::copy(S.rowptr.begin(), S.rowptr.end(), row_ptr);
+    if (panel_off) std::copy(S.panel_off.begin(), S.panel_off.end(), panel_off);
+    if (panel_ld) for (i64 s = 0; s < S.nsuper; s++) panel_ld[s] = S.panel_ld[s];
+    if (upd_off) std::copy(S.upd_off.begin(), S.upd_off.end(), upd_off);
+    if (upd_ld) for (i64 s = 0; s < S.nsuper; s++) upd_ld[s] = S.upd_ld[s];
+    return 0;
+}
+int gmrf_b200_get_rows(const gmrf_b200_handle *h, int64_t *row_idx, int64_t *rel_idx) {
+    if (!h) return GMRF_B200_ERR_ARG;
+    const Symbolic &S = h->S;
+    if (row_idx) for (size_t k = 0; k < S.rowidx.size(); k++) row_idx[k] = S.rowidx[k];
+    if (rel_idx) for (size_t k = 0; k < S.relidx.size(); k++) rel_idx[k] = S.relidx[k];
+    return 0;
+}
+int gmrf_b200_get_scatter(const gmrf_b200_handle *h, int64_t *n_entries, int64_t *src, int64_t *dst) {
+    if (!h) return GMRF_B200_ERR_ARG;
+    const Symbolic &S = h->S;
+    if (n_entries) *n_entries = (int64_t)S.q_src.size();
+    if (src) std::copy(S.q_src.begin(), S.q_src.end(), src);
+    if (dst) std::copy(S.q_dst.begin(), S.q_dst.end(), dst);
+    return 0;
+}
+int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n) {
+    if (!h || !ms) return GMRF_B200_ERR_ARG;
+    for (int i = 0; i < n && i < 5; i++) ms[i] = h->t_ms[i];
+    return 0;
+}
+int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored || n_doubles != h->S.panel_total) { h->err = "get_factor_panels: bad state or size"; return GMRF_B200_ERR_ARG; }
+    CUDA_TRY(h, cudaMemcpy(Lx, h->d_Lx, sizeof(double) * (size_t)n_doubles, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (n_doubles != h->S.panel_total) { h->err = "get_selinv_panels: bad size"; return GMRF_B200_ERR_ARG; }
+    CUDA_TRY(h, cudaMemcpy(Zx, h->d_Zx, sizeof(double) * (size_t)n_doubles, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- dense-kernel unit-test hooks (HOST pointers; operands are staged to `device` and back) ------------
+static int test_fail(const char *msg) { g_create_error = msg; return GMRF_B200_ERR_CUDA; }
+
+int gmrf_b200_test_gemm(int device, int transa, int transb, int lower, int m, int n, int k, const double *A, int lda,
+                        const double *B, int ldb, double beta, double *C, int ldc) {
+    if (cudaSetDevice(device) != cudaSuccess || configure_kernels() != cudaSuccess) return test_fail("no usable device");
+    // operand extents in doubles
+    size_t sa = (size_t)lda * (transa ? m : k), sb = (size_t)ldb * (transb ? n : k), sc = (size_t)ldc * n;
+    double *dA, *dB, *dC;
+    GemmTask *dT;
+    int *dP;
+    if (cudaMalloc(&dA, sa * 8 + 16) || cudaMalloc(&dB, sb * 8 + 16) || cudaMalloc(&dC, sc * 8 + 16) ||
+        cudaMalloc(&dT, sizeof(GemmTask)) || cudaMalloc(&dP, 8))
+        return test_fail("alloc");
+    cudaMemcpy(dA, A, sa * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B, sb * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dC, C, sc * 8, cudaMemcpyHostToDevice);
+    GemmTask T;
+    T.A = dA; T.B = dB; T.C = dC; T.m = m; T.n = n; T.k = k; T.lda = lda; T.ldb = ldb; T.ldc = ldc;
+    T.flags = (lower & 1 ? GEMM_LOWER : 0) | (beta == 0.0 ? GEMM_BETA0 : 0) | (lower & 2 ? GEMM_ALPHA_POS : 0) | (lower & 4 ? GEMM_ADD_I : 0);
+    T.pad_ = 0;
+    const bool naive = (lower & 8) != 0, large = (lower & 16) != 0;
+    int BM = naive ? 16 : large ? 128 : 64;
+    int tiles = cdiv(m, BM) * cdiv(n, BM);
+    int pf[2] = {0, tiles};
+    cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
+    if (!transa && !transb) launch_gemm<false, false>(large, naive, dT, dP, 1, tiles, 0);
+    else if (!transa && transb) launch_gemm<false, true>(large, naive, dT, dP, 1, tiles, 0);
+    else if (transa && transb) launch_gemm<true, true>(large, naive, dT, dP, 1, tiles, 0);
+    else return test_fail("unsupported variant");
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(C, dC, sc * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT); cudaFree(dP);
+    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info) {
+    if (cudaSetDevice(device) != cudaSuccess) return test_fail("no device");
+    if (n > POTRF_NB) return GMRF_B200_ERR_ARG;
+    double *dA; PotrfTask *dT; int *dF;
+    if (cudaMalloc(&dA, (size_t)lda * n * 8) || cudaMalloc(&dT, sizeof(PotrfTask)) || cudaMalloc(&dF, 4)) return test_fail("alloc");
+    cudaMemcpy(dA, A, (size_t)lda * n * 8, cudaMemcpyHostToDevice);
+    PotrfTask T{dA, lda, n, 0, 0};
+    cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemset(dF, 0x7f, 4);
+    potrf_diag_kernel<<<1, 256>>>(dT, dF);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(A, dA, (size_t)lda * n * 8, cudaMemcpyDeviceToHost);
+    int f = 0;
+    cudaMemcpy(&f, dF, 4, cudaMemcpyDeviceToHost);
+    if (info) *info = (f == 0x7f7f7f7f) ? 0 : f;
+    cudaFree(dA); cudaFree(dT); cudaFree(dF);
+    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb) {
+    // n <= 64; variant selected by the sign of m: m > 0 -> X L^T = B, m < 0 -> X L = B
+    if (cudaSetDevice(device) != cudaSuccess) return test_fail("no device");
+    int var = m < 0 ? 1 : 0;
+    if (m < 0) m = -m;
+    if (n > POTRF_NB) return GMRF_B200_ERR_ARG;
+    double *dL, *dB; TrsmTask *dT; int *dP;
+    if (cudaMalloc(&dL, (size_t)ldl * n * 8) || cudaMalloc(&dB, (size_t)ldb * n * 8) || cudaMalloc(&dT, sizeof(TrsmTask)) || cudaMalloc(&dP, 8))
+        return test_fail("alloc");
+    cudaMemcpy(dL, L, (size_t)ldl * n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B, (size_t)ldb * n * 8, cudaMemcpyHostToDevice);
+    TrsmTask T{dL, dB, ldl, ldb, m, n};
+    int tiles = cdiv(m, TRSM_ROWS);
+    int pf[2] = {0, tiles};
+    cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
+    int nbt = n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 64;
+    if (var == 0) launch_trsm<0>(nbt, dT, dP, 1, tiles, 0); else launch_trsm<1>(nbt, dT, dP, 1, tiles, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(B, dB, (size_t)ldb * n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dL); cudaFree(dB); cudaFree(dT); cudaFree(dP);
+    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,681 @@
+// kernels.cuh -- hand-written sm_100a device code for the supernodal multifrontal Cholesky, the
+// level-scheduled triangular solves and Takahashi selected inversion. All arithmetic is FP64.
+//
+// B200 facts that shape these kernels (profiles/r01_fp64_probe.json): the FP64 tensor pipe (DMMA.8x8x4,
+// reached through mma.sync.m8n8k4.f64 -- there is no FP64 tcgen05/UMMA) peaks at 37.2 TFLOP/s, the same as
+// the DFMA pipe, but needs 1/8 of the issue slots and 1/4 of the operand traffic, so every GEMM-shaped
+// contraction goes through DMMA with cp.async-staged shared-memory tiles; everything else (assembly,
+// scatter, skinny panel products of the solves) is HBM/L2-bound and written for coalesced streaming.
+//
+// Determinism: no floating-point atomics; every output element has exactly one owner thread and all
+// reductions use a fixed tree, so reruns are bit-identical.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gmrf {
+
+// ------------------------------------------------------------------------------------------------
+// Task descriptors (built on the host at analysis time, resident in HBM)
+// ------------------------------------------------------------------------------------------------
+enum : int {
+    GEMM_LOWER = 1,      // write only entries with local row >= local col
+    GEMM_BETA0 = 2,      // C = alpha*op(A)op(B) (+I) instead of C += ...
+    GEMM_ALPHA_POS = 4,  // alpha = +1 (default alpha = -1)
+    GEMM_ADD_I = 8       // add the identity on the local diagonal
+};
+
+struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
+    const double *A;     // TA=false: element (i,kk) at A[i + kk*lda]   (m-contiguous)
+    const double *B;     // TB=false: element (j,kk) at B[j + kk*ldb]   (n-contiguous)
+    double *C;           // TA/TB=true: element at X[kk + i*ldx]        (k-contiguous)
+    int m, n, k;
+    int lda, ldb, ldc;
+    int flags;
+    int pad_;
+};
+
+struct PotrfTask {       // in-place Cholesky of an nb x nb diagonal block (lower)
+    double *A;
+    int lda, nb;
+    int col0;            // global (permuted) column of the block's first column, for pivot reporting
+    int pad_;
+};
+
+struct TrsmTask {        // B[m x nb] := B * L^-T (variant 0) or B * L^-1 (variant 1), L lower nb x nb
+    const double *L;
+    double *B;
+    int ldl, ldb, m, nb;
+};
+
+struct AsmItem {         // one column tile of one parent front
+    int super;
+    int col0;            // first front column of the tile (0 .. nrow)
+};
+
+struct SuperMeta {
+    long long panel_off;   // doubles
+    long long upd_off;     // doubles (update pool / selinv W pool share the layout fields below)
+    long long zw_off;
+    long long rowptr;      // offset into rowidx / relidx
+    long long uvec_off;    // rows
+    int first, ns, nrow, ld, uld, parent;
+    int child_begin, child_end;   // range in child_idx
+};
+
+struct VecTask {         // skinny panel products of the solves
+    const double *A;     // panel block, element (i,kk) at A[i + kk*lda]
+    const int *idx;      // optional gather/scatter row indices (global permuted rows) or nullptr
+    double *C;           // gemv_n: output rows (contiguous), ldc ; gemv_t: output (k entries)
+    const double *X;     // gemv_n: input block (k x nrhs), ldx ; gemv_t: input rows (gathered via idx)
+    int m, k;            // A is m x k
+    int lda, ldc, ldx, pad_;
+};
+
+struct TrsvTask {        // X[nb x nrhs] := L^-1 X (variant 0) or L^-T X (variant 1)
+    const double *L;
+    double *X;
+    int ldl, ldx, nb, pad_;
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_task(const int *__restrict__ prefix, int ntasks, int bid) {
+    int lo = 0, hi = ntasks;  // prefix has ntasks+1 entries; find t with prefix[t] <= bid < prefix[t+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= bid) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core GEMM:  C (+)= alpha * Aop * Bop^T  over a list of tasks (one launch per schedule step).
+// CTA tile BM x BN, warp grid WGM x WGN, K tile 16, 3-stage cp.async pipeline.
+// smem tiles are stored k-major: As[stage][kk][m] (+4 padding -> conflict-free 8-byte fragment loads).
+// ------------------------------------------------------------------------------------------------
+constexpr int GEMM_KT = 16;
+constexpr int GEMM_STAGES = 3;
+
+template <int BM, int BN>
+constexpr int gemm_smem_bytes() { return GEMM_STAGES * GEMM_KT * ((BM + 4) + (BN + 4)) * (int)sizeof(double); }
+
+// Load a [KT x BX] tile (k-major in smem) of an operand. TR=false: global is x-contiguous; TR=true: k-contiguous.
+template <int BX, int NT, bool TR>
+__device__ __forceinline__ void gemm_load_tile(double *__restrict__ s, const double *__restrict__ g, int ld,
+                                               int x0, int xmax, int k0, int kmax, bool aligned16, int tid) {
+    constexpr int LDS = BX + 4;
+    if (!TR) {
+        if (aligned16) {
+            constexpr int CH = BX / 2;  // 16-byte chunks per k row
+            for (int c = tid; c < CH * GEMM_KT; c += NT) {
+                int kk = c / CH, x = (c - kk * CH) * 2;
+                int gx = x0 + x, gk = k0 + kk;
+                int nb = 0;
+                if (gk < kmax && gx < xmax) nb = (xmax - gx >= 2) ? 16 : 8;
+                const double *src = nb ? (g + gx + (long long)gk * ld) : g;
+                cp_async16(s + kk * LDS + x, src, nb);
+            }
+        } else {
+            for (int c = tid; c < BX * GEMM_KT; c += NT) {
+                int kk = c / BX, x = c - kk * BX;
+                int gx = x0 + x, gk = k0 + kk;
+                int nb = (gk < kmax && gx < xmax) ? 8 : 0;
+                const double *src = nb ? (g + gx + (long long)gk * ld) : g;
+                cp_async8(s + kk * LDS + x, src, nb);
+            }
+        }
+    } else {
+        for (int c = tid; c < BX * GEMM_KT; c += NT) {
+            int x = c / GEMM_KT, kk = c - x * GEMM_KT;
+            int gx = x0 + x, gk = k0 + kk;
+            int nb = (gk < kmax && gx < xmax) ? 8 : 0;
+            const double *src = nb ? (g + gk + (long long)gx * ld) : g;
+            cp_async8(s + kk * LDS + x, src, nb);
+        }
+    }
+}
+
+template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
+__global__ void __launch_bounds__(WGM *WGN * 32)
+gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+    constexpr int NT = WGM * WGN * 32;
+    constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+    constexpr int WM = BM / WGM, WN = BN / WGN;
+    constexpr int MI = WM / 8, NI = WN / 8;
+    extern __shared__ __align__(16) double gemm_smem[];
+    double *As = gemm_smem;
+    double *Bs = gemm_smem + GEMM_STAGES * GEMM_KT * LDA_S;
+
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const GemmTask T = tasks[t];
+    const int local = blockIdx.x - tile_prefix[t];
+    const int mt = (T.m + BM - 1) / BM;
+    const int tm = local % mt, tn = local / mt;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if ((T.flags & GEMM_LOWER) && n0 >= m0 + BM) return;  // tile strictly above the diagonal
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp % WGM) * WM, wn0 = (warp / WGM) * WN;
+    const int grp = lane >> 2, tig = lane & 3;
+    const bool a16 = !TA && ((((uintptr_t)T.A) & 15) == 0) && ((T.lda & 1) == 0);
+    const bool b16 = !TB && ((((uintptr_t)T.B) & 15) == 0) && ((T.ldb & 1) == 0);
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nk = (T.k + GEMM_KT - 1) / GEMM_KT;
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < nk) {
+            gemm_load_tile<BM, NT, TA>(As + s * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, s * GEMM_KT, T.k, a16, tid);
+            gemm_load_tile<BN, NT, TB>(Bs + s * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, s * GEMM_KT, T.k, b16, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = kt + GEMM_STAGES - 1;
+            if (nx < nk) {
+                int st = nx % GEMM_STAGES;
+                gemm_load_tile<BM, NT, TA>(As + st * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, nx * GEMM_KT, T.k, a16, tid);
+                gemm_load_tile<BN, NT, TB>(Bs + st * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, nx * GEMM_KT, T.k, b16, tid);
+            }
+            cp_async_commit();
+        }
+        const double *as = As + (kt % GEMM_STAGES) * GEMM_KT * LDA_S;
+        const double *bs = Bs + (kt % GEMM_STAGES) * GEMM_KT * LDB_S;
+#pragma unroll
+        for (int ks = 0; ks < GEMM_KT / 4; ks++) {
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; i++) a[i] = as[(ks * 4 + tig) * LDA_S + wm0 + 8 * i + grp];
+#pragma unroll
+            for (int j = 0; j < NI; j++) b[j] = bs[(ks * 4 + tig) * LDB_S + wn0 + 8 * j + grp];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const double alpha = (T.flags & GEMM_ALPHA_POS) ? 1.0 : -1.0;
+    const bool beta0 = T.flags & GEMM_BETA0, lower = T.flags & GEMM_LOWER, addi = T.flags & GEMM_ADD_I;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+        const int r = m0 + wm0 + 8 * i + grp;
+        if (r >= T.m) continue;
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = n0 + wn0 + 8 * j + 2 * tig + e;
+                if (c >= T.n) continue;
+                if (lower && r < c) continue;
+                double *p = T.C + r + (long long)c * T.ldc;
+                double v = alpha * acc[i][j][e];
+                if (!beta0) v += *p;
+                if (addi && r == c) v += 1.0;
+                *p = v;
+            }
+        }
+    }
+}
+
+// Debug kernel with the same contract (one thread per output element); selected with the "naive_kernels" option.
+template <bool TA, bool TB>
+__global__ void gemm_naive_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const GemmTask T = tasks[t];
+    const int local = blockIdx.x - tile_prefix[t];
+    const int mt = (T.m + 15) / 16;
+    const int r = (local % mt) * 16 + (threadIdx.x & 15), c = (local / mt) * 16 + (threadIdx.x >> 4);
+    if (r >= T.m || c >= T.n) return;
+    if ((T.flags & GEMM_LOWER) && r < c) return;
+    double s = 0.0;
+    for (int kk = 0; kk < T.k; kk++) {
+        double a = TA ? T.A[kk + (long long)r * T.lda] : T.A[r + (long long)kk * T.lda];
+        double b = TB ? T.B[kk + (long long)c * T.ldb] : T.B[c + (long long)kk * T.ldb];
+        s += a * b;
+    }
+    double *p = T.C + r + (long long)c * T.ldc;
+    double v = ((T.flags & GEMM_ALPHA_POS) ? 1.0 : -1.0) * s;
+    if (!(T.flags & GEMM_BETA0)) v += *p;
+    if ((T.flags & GEMM_ADD_I) && r == c) v += 1.0;
+    *p = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal-block Cholesky: one CTA (256 threads) per nb x nb block (nb <= 64), block staged in smem.
+// Non-positive pivots are recorded with an integer atomicMin (deterministic) and produce NaNs downstream,
+// matching the reference's `check=false` factorization (backend.jl:184).
+// ------------------------------------------------------------------------------------------------
+constexpr int POTRF_NB = 64;
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(const PotrfTask *__restrict__ tasks, int *__restrict__ fail_col) {
+    __shared__ double sA[POTRF_NB][POTRF_NB + 1];
+    const PotrfTask T = tasks[blockIdx.x];
+    const int nb = T.nb, tid = threadIdx.x;
+    for (int e = tid; e < nb * nb; e += 256) {
+        int i = e % nb, j = e / nb;
+        sA[i][j] = (i >= j) ? T.A[i + (long long)j * T.lda] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; j++) {
+        // column j is final up to the scaling: all updates from columns < j were applied by earlier iterations
+        double d = sA[j][j];
+        __syncthreads();
+        if (tid == 0) {
+            if (!(d > 0.0)) atomicMin(fail_col, T.col0 + j + 1);
+            sA[j][j] = sqrt(d);
+        }
+        double inv = 1.0 / sqrt(d);
+        for (int i = j + 1 + tid; i < nb; i += 256) sA[i][j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: A[r][c] -= A[r][j] * A[c][j], j < c <= r < nb
+        const int rem = nb - j - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            int r = j + 1 + e % rem, c = j + 1 + e / rem;
+            if (r >= c) sA[r][c] -= sA[r][j] * sA[c][j];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += 256) {
+        int i = e % nb, j = e / nb;
+        if (i >= j) T.A[i + (long long)j * T.lda] = sA[i][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Right-side triangular solve on row strips: one thread owns one row of B (kept in registers), L staged in smem.
+//   VAR 0: X L^T = B  (x_j = (b_j - sum_{k<j} x_k L_jk) / L_jj, j ascending)      -- factorization panels
+//   VAR 1: X L   = B  (x_j = (b_j - sum_{i>j} x_i L_ij) / L_jj, j descending)     -- selected inversion
+// ------------------------------------------------------------------------------------------------
+constexpr int TRSM_ROWS = 64;   // rows per CTA (= threads per CTA)
+
+template <int VAR, int NBT>
+__global__ void __launch_bounds__(TRSM_ROWS)
+trsm_strip_kernel(const TrsmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+    __shared__ double sL[NBT][NBT + 1];   // sL[i][j] = L_ij, identity-padded beyond nb
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const TrsmTask T = tasks[t];
+    const int strip = blockIdx.x - tile_prefix[t];
+    const int nb = T.nb, tid = threadIdx.x;
+    for (int e = tid; e < NBT * NBT; e += TRSM_ROWS) {
+        int i = e % NBT, j = e / NBT;
+        double v = 0.0;
+        if (i < nb && j < nb && i >= j) v = T.L[i + (long long)j * T.ldl];
+        if (i == j && i >= nb) v = 1.0;
+        sL[i][j] = v;
+    }
+    __syncthreads();
+    const int row = strip * TRSM_ROWS + tid;
+    if (row >= T.m) return;
+    double x[NBT];
+    double *bp = T.B + row;
+#pragma unroll
+    for (int j = 0; j < NBT; j++) x[j] = (j < nb) ? bp[(long long)j * T.ldb] : 0.0;
+    if (VAR == 0) {
+#pragma unroll
+        for (int j = 0; j < NBT; j++) {
+            double s0 = x[j], s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k + 1 < j; k += 2) { s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1]; }
+            if (j & 1) s0 -= x[j - 1] * sL[j][j - 1];
+            x[j] = (s0 + s1) / sL[j][j];
+        }
+    } else {
+#pragma unroll
+        for (int j = NBT - 1; j >= 0; j--) {
+            double s0 = x[j], s1 = 0.0;
+#pragma unroll
+            for (int i = j + 1; i + 1 < NBT; i += 2) { s0 -= x[i] * sL[i][j]; s1 -= x[i + 1] * sL[i + 1][j]; }
+            if ((NBT - 1 - j) & 1) s0 -= x[NBT - 1] * sL[NBT - 1][j];
+            x[j] = (s0 + s1) / sL[j][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NBT; j++)
+        if (j < nb) bp[(long long)j * T.ldb] = x[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q.nzval -> panels (after the panel array has been zeroed): Lx[dst[k]] = nzval[src[k]]
+// ------------------------------------------------------------------------------------------------
+__global__ void scatter_q_kernel(double *__restrict__ Lx, const double *__restrict__ nz,
+                                 const long long *__restrict__ src, const long long *__restrict__ dst, long long cnt) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < cnt; k += stride) Lx[dst[k]] = nz[src[k]];
+}
+
+__global__ void fill_zero_kernel(double *__restrict__ p, long long cnt) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < cnt; k += stride) p[k] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Extend-add ("parent pulls"): each CTA owns a tile of ASM_CW consecutive front columns of one parent and
+// walks the parent's children in fixed order, so every front entry has one owner and one summation order.
+// Columns < ns land in the parent's panel, columns >= ns in its update matrix (zero-filled here first).
+// ------------------------------------------------------------------------------------------------
+constexpr int ASM_CW = 32;
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__ meta,
+                const int *__restrict__ child_idx, const int *__restrict__ relidx,
+                double *__restrict__ Lx, double *__restrict__ upd) {
+    const AsmItem it = items[blockIdx.x];
+    const SuperMeta P = meta[it.super];
+    const int c_lo = it.col0, c_hi = min(it.col0 + ASM_CW, P.nrow);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nr = P.nrow - P.ns;
+    double *Lp = Lx + P.panel_off;
+    double *Up = upd + P.upd_off;
+    // zero-fill the owned columns of the update matrix (lower triangle only)
+    for (int c = max(c_lo, P.ns) + warp; c < c_hi; c += 8) {
+        const int uc = c - P.ns;
+        for (int r = uc + lane; r < nr; r += 32) Up[r + (long long)uc * P.uld] = 0.0;
+    }
+    __syncthreads();
+    for (int ci = P.child_begin; ci < P.child_end; ci++) {
+        const SuperMeta C = meta[child_idx[ci]];
+        const int cnr = C.nrow - C.ns;
+        const int *rel = relidx + C.rowptr + C.ns;   // cnr entries, strictly increasing
+        // child update columns whose parent column falls in [c_lo, c_hi)
+        int a, b;
+        {
+            int lo = 0, hi = cnr;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (rel[mid] < c_lo) lo = mid + 1; else hi = mid; }
+            a = lo;
+            hi = cnr;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (rel[mid] < c_hi) lo = mid + 1; else hi = mid; }
+            b = lo;
+        }
+        const double *Uc = upd + C.upd_off;
+        for (int jc = a + warp; jc < b; jc += 8) {
+            const int pc = rel[jc];
+            const double *src = Uc + (long long)jc * C.uld;
+            if (pc < P.ns) {
+                double *dst = Lp + (long long)pc * P.ld;
+                for (int ic = jc + lane; ic < cnr; ic += 32) dst[rel[ic]] += src[ic];
+            } else {
+                double *dst = Up + (long long)(pc - P.ns) * P.uld - P.ns;
+                for (int ic = jc + lane; ic < cnr; ic += 32) dst[rel[ic]] += src[ic];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// log det Q = 2 * sum_j log L_jj, fused into the factorization graph. Two fixed-shape passes.
+// ------------------------------------------------------------------------------------------------
+constexpr int LOGDET_BLOCKS = 256;
+
+__device__ __forceinline__ double block_sum_256(double v, double *sh) {
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(256)
+logdet_partial_kernel(const double *__restrict__ Lx, const long long *__restrict__ diag_pos, long long n,
+                      double *__restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    // fixed assignment of indices to (block, thread) and fixed sequential order per thread
+    for (long long j = blockIdx.x * 256LL + threadIdx.x; j < n; j += 256LL * LOGDET_BLOCKS) acc += log(Lx[diag_pos[j]]);
+    double s = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) logdet_final_kernel(const double *__restrict__ partial, double *__restrict__ out) {
+    __shared__ double sh[256];
+    double s = block_sum_256(threadIdx.x < LOGDET_BLOCKS ? partial[threadIdx.x] : 0.0, sh);
+    if (threadIdx.x == 0) out[0] = 2.0 * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solve-phase kernels. Right-hand sides live in a permuted n x nrhs column-major work array `y`.
+// ------------------------------------------------------------------------------------------------
+// y[k, r] = b[perm[k], r]  (gather)  /  x[perm[k], r] = y[k, r]  (scatter)
+__global__ void permute_rows_kernel(double *__restrict__ dst, const double *__restrict__ src,
+                                    const long long *__restrict__ perm, long long n, long long ld_dst,
+                                    long long ld_src, int nrhs, int scatter) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long p = perm[k];
+    for (int r = 0; r < nrhs; r++) {
+        if (scatter) dst[p + r * ld_dst] = src[k + r * ld_src];
+        else dst[k + r * ld_dst] = src[p + r * ld_src];
+    }
+}
+
+// Forward-solve assembly: supernode s pulls its children's update vectors (fixed order).
+//   rows that fall inside s's own columns add into y, the others into u_s (zero-filled first).
+__global__ void __launch_bounds__(256)
+fwd_assemble_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
+                    const int *__restrict__ child_idx, const int *__restrict__ relidx,
+                    double *__restrict__ y, long long ldy, double *__restrict__ uvec, long long ldu) {
+    const SuperMeta P = meta[supers[blockIdx.x]];
+    const int nr = P.nrow - P.ns;
+    const int r = blockIdx.y;               // one right-hand side per blockIdx.y
+    double *us = uvec + P.uvec_off + (long long)r * ldu;
+    for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
+    __syncthreads();
+    double *ys = y + P.first + (long long)r * ldy;
+    for (int ci = P.child_begin; ci < P.child_end; ci++) {
+        const SuperMeta C = meta[child_idx[ci]];
+        const int cnr = C.nrow - C.ns;
+        const int *rel = relidx + C.rowptr + C.ns;
+        const double *uc = uvec + C.uvec_off + (long long)r * ldu;
+        for (int i = threadIdx.x; i < cnr; i += 256) {
+            const int p = rel[i];
+            if (p < P.ns) ys[p] += uc[i]; else us[p - P.ns] += uc[i];
+        }
+        __syncthreads();
+    }
+}
+
+// Small triangular solves on nb x nrhs blocks: one warp per right-hand side, rows spread over lanes.
+//   VAR 0: L x = b (forward), VAR 1: L^T x = b (backward). L (nb x nb, lower) staged in smem.
+template <int VAR>
+__global__ void __launch_bounds__(256)
+trsv_block_kernel(const TrsvTask *__restrict__ tasks, int nrhs) {
+    __shared__ double sL[POTRF_NB][POTRF_NB + 1];
+    const TrsvTask T = tasks[blockIdx.x];
+    const int nb = T.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < nb * nb; e += 256) {
+        int i = e % nb, j = e / nb;
+        sL[i][j] = (i >= j) ? T.L[i + (long long)j * T.ldl] : 0.0;
+    }
+    __syncthreads();
+    for (int r = blockIdx.y * 8 + warp; r < nrhs; r += 8 * gridDim.y) {
+        double *xp = T.X + (long long)r * T.ldx;
+        double x0 = lane < nb ? xp[lane] : 0.0;
+        double x1 = lane + 32 < nb ? xp[lane + 32] : 0.0;
+        if (VAR == 0) {
+            for (int j = 0; j < nb; j++) {
+                double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31);
+                xj /= sL[j][j];
+                if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
+                if (lane > j && lane < nb) x0 -= sL[lane][j] * xj;
+                if (lane + 32 > j && lane + 32 < nb) x1 -= sL[lane + 32][j] * xj;
+            }
+        } else {
+            for (int j = nb - 1; j >= 0; j--) {
+                double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31);
+                xj /= sL[j][j];
+                if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
+                if (lane < j) x0 -= sL[j][lane] * xj;
+                if (lane + 32 < j) x1 -= sL[j][lane + 32] * xj;
+            }
+        }
+        if (lane < nb) xp[lane] = x0;
+        if (lane + 32 < nb) xp[lane + 32] = x1;
+    }
+}
+
+// C[m x nrhs] -= A[m x k] * X[k x nrhs]; one thread per row of A, RB right-hand sides in registers.
+// A is streamed exactly once per RB columns with fully coalesced loads.
+template <int RB>
+__global__ void __launch_bounds__(128)
+gemv_n_kernel(const VecTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs) {
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const VecTask T = tasks[t];
+    const int row = (blockIdx.x - tile_prefix[t]) * 128 + threadIdx.x;
+    if (row >= T.m) return;
+    for (int r0 = 0; r0 < nrhs; r0 += RB) {
+        double acc[RB];
+#pragma unroll
+        for (int q = 0; q < RB; q++) acc[q] = 0.0;
+        const double *ap = T.A + row;
+        const double *xp = T.X + (long long)r0 * T.ldx;
+#pragma unroll 4
+        for (int kk = 0; kk < T.k; kk++) {
+            const double a = ap[(long long)kk * T.lda];
+#pragma unroll
+            for (int q = 0; q < RB; q++)
+                if (r0 + q < nrhs) acc[q] += a * xp[kk + (long long)q * T.ldx];
+        }
+#pragma unroll
+        for (int q = 0; q < RB; q++)
+            if (r0 + q < nrhs) T.C[row + (long long)(r0 + q) * T.ldc] -= acc[q];
+    }
+}
+
+// C[kk, r] -= sum_i A[i, kk] * X[idx[i], r]  (A^T times gathered rows); one warp per column kk of A.
+template <int RB>
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const VecTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs) {
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const VecTask T = tasks[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = (blockIdx.x - tile_prefix[t]) * 8 + warp;
+    if (kk >= T.k) return;
+    const double *ap = T.A + (long long)kk * T.lda;
+    for (int r0 = 0; r0 < nrhs; r0 += RB) {
+        double acc[RB];
+#pragma unroll
+        for (int q = 0; q < RB; q++) acc[q] = 0.0;
+        for (int i = lane; i < T.m; i += 32) {
+            const double a = ap[i];
+            const long long xr = T.idx ? (long long)T.idx[i] : (long long)i;
+#pragma unroll
+            for (int q = 0; q < RB; q++)
+                if (r0 + q < nrhs) acc[q] += a * T.X[xr + (long long)(r0 + q) * T.ldx];
+        }
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            double v = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && r0 + q < nrhs) T.C[kk + (long long)(r0 + q) * T.ldc] -= v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Selected inversion kernels
+// ------------------------------------------------------------------------------------------------
+// W_s[a,b] = Z(R_a, R_b), gathered from the parent's front [Z panel of p ; W_p] through the relative
+// indices; written as a full symmetric nr x nr matrix so the following products are plain GEMMs.
+__global__ void __launch_bounds__(256)
+selinv_gather_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__ meta,
+                     const int *__restrict__ relidx, const double *__restrict__ Zx, double *__restrict__ zw) {
+    const AsmItem it = items[blockIdx.x];
+    const SuperMeta S = meta[it.super];
+    const SuperMeta P = meta[S.parent];
+    const int nr = S.nrow - S.ns;
+    const int *rel = relidx + S.rowptr + S.ns;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *Zp = Zx + P.panel_off;
+    const double *Wp = zw + P.zw_off;
+    double *Ws = zw + S.zw_off;
+    const int c_hi = min(it.col0 + ASM_CW, nr);
+    for (int b = it.col0 + warp; b < c_hi; b += 8) {
+        const int pb = rel[b];
+        const double *src = (pb < P.ns) ? (Zp + (long long)pb * P.ld) : (Wp + (long long)(pb - P.ns) * P.uld - P.ns);
+        for (int a = b + lane; a < nr; a += 32) {
+            const double v = src[rel[a]];
+            Ws[a + (long long)b * S.uld] = v;
+            Ws[b + (long long)a * S.uld] = v;
+        }
+    }
+}
+
+// In-place transpose of the leading ns x ns block of a panel (tile pairs swapped through smem).
+struct TransTask { double *A; int n, ld; };
+__global__ void __launch_bounds__(256)
+transpose_inplace_kernel(const TransTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+    __shared__ double s1[32][33], s2[32][33];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const TransTask T = tasks[t];
+    const int nt = (T.n + 31) / 32;
+    // enumerate tile pairs (ti >= tj) from the linear index
+    int local = blockIdx.x - tile_prefix[t];
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= local) ti++;
+    const int tj = local - ti * (ti + 1) / 2;
+    (void)nt;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int yy = ty; yy < 32; yy += 8) {
+        int r = ti * 32 + tx, c = tj * 32 + yy;
+        s1[yy][tx] = (r < T.n && c < T.n) ? T.A[r + (long long)c * T.ld] : 0.0;
+        r = tj * 32 + tx; c = ti * 32 + yy;
+        s2[yy][tx] = (r < T.n && c < T.n) ? T.A[r + (long long)c * T.ld] : 0.0;
+    }
+    __syncthreads();
+    for (int yy = ty; yy < 32; yy += 8) {
+        // block (tj, ti) := transpose of old block (ti, tj): new A[tj*32+tx][ti*32+yy] = old A[ti*32+yy][tj*32+tx] = s1[tx][yy]
+        int r = tj * 32 + tx, c = ti * 32 + yy;
+        if (r < T.n && c < T.n) T.A[r + (long long)c * T.ld] = s1[tx][yy];
+        if (ti != tj) {
+            r = ti * 32 + tx; c = tj * 32 + yy;
+            if (r < T.n && c < T.n) T.A[r + (long long)c * T.ld] = s2[tx][yy];
+        }
+    }
+}
+
+// out[k] = Zx[pos[k]] (pos < 0 -> 0.0): diagonal extraction, CSC materialisation, extract-at-pattern
+__global__ void gather_values_kernel(double *__restrict__ out, const double *__restrict__ Zx,
+                                     const long long *__restrict__ pos, long long cnt) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < cnt; k += stride) {
+        const long long p = pos[k];
+        out[k] = p >= 0 ? Zx[p] : 0.0;
+    }
+}
+
+}  // namespace gmrf

@@ -1,0 +1,647 @@
+// symbolic.cpp -- see symbolic.hpp. Integer graph work only; no floating-point matrix values are touched.
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+
+// METIS ships inside the CUDA toolkit as a static archive without a header
+// (/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a, 64-bit idx_t); prototypes are hand-declared.
+extern "C" {
+int METIS_NodeND(int64_t *nvtxs, int64_t *xadj, int64_t *adjncy, int64_t *vwgt, int64_t *options,
+                 int64_t *perm, int64_t *iperm);
+int METIS_SetDefaultOptions(int64_t *options);
+}
+
+namespace gmrf {
+
+Options &global_options() {
+    static Options o;
+    return o;
+}
+
+void order_metis_nd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm) {
+    perm.resize(n);
+    if (n == 0) return;
+    if (adj.empty()) {
+        std::iota(perm.begin(), perm.end(), 0);
+        return;
+    }
+    std::vector<i64> xa(xadj), ad(adj), ip(n);
+    i64 opts[40];
+    METIS_SetDefaultOptions(opts);
+    i64 nn = n;
+    int rc = METIS_NodeND(&nn, xa.data(), ad.data(), nullptr, opts, perm.data(), ip.data());
+    if (rc != 1) throw std::runtime_error("METIS_NodeND failed");
+    // METIS: A(perm, perm) is the reordered matrix, i.e. perm[k] = original index of the k-th pivot.
+}
+
+// ------------------------------------------------------------------------------------------------
+// Minimum-degree ordering on the quotient graph (elements + variables, external degree updated
+// exactly for the neighbours of each pivot, element absorption, no supervariables). Quality is that
+// of classic MMD without multiple elimination; used when the caller asks for an AMD-family ordering.
+void order_amd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm) {
+    perm.clear();
+    perm.reserve(n);
+    // adjacency of variables: variable neighbours and element neighbours
+    std::vector<std::vector<i64>> vadj(n), eadj(n), elem(n);  // elem[e] = variables of element e
+    for (i64 v = 0; v < n; v++) vadj[v].assign(adj.begin() + xadj[v], adj.begin() + xadj[v + 1]);
+    std::vector<char> eliminated(n, 0), absorbed(n, 0);
+    std::vector<i64> degree(n), mark(n, -1);
+    // bucket lists by degree
+    std::vector<i64> head(n + 1, -1), next(n, -1), prev(n, -1);
+    auto bucket_insert = [&](i64 v) {
+        i64 d = degree[v];
+        prev[v] = -1;
+        next[v] = head[d];
+        if (head[d] != -1) prev[head[d]] = v;
+        head[d] = v;
+    };
+    auto bucket_remove = [&](i64 v) {
+        i64 d = degree[v];
+        if (prev[v] != -1) next[prev[v]] = next[v]; else head[d] = next[v];
+        if (next[v] != -1) prev[next[v]] = prev[v];
+    };
+    for (i64 v = 0; v < n; v++) {
+        degree[v] = (i64)vadj[v].size();
+        bucket_insert(v);
+    }
+    i64 mindeg = 0, stamp = 0, tstamp = 0;
+    std::vector<i64> reach, tag(n, -1);
+    for (i64 step = 0; step < n; step++) {
+        while (mindeg < n && head[mindeg] == -1) mindeg++;
+        i64 p = head[mindeg];
+        bucket_remove(p);
+        eliminated[p] = 1;
+        perm.push_back(p);
+        // reach(p) = variable neighbours + variables of adjacent elements
+        reach.clear();
+        stamp++;
+        mark[p] = stamp;
+        for (i64 u : vadj[p])
+            if (!eliminated[u] && mark[u] != stamp) { mark[u] = stamp; reach.push_back(u); }
+        for (i64 e : eadj[p]) {
+            if (absorbed[e]) continue;
+            for (i64 u : elem[e])
+                if (!eliminated[u] && mark[u] != stamp) { mark[u] = stamp; reach.push_back(u); }
+            absorbed[e] = 1;
+            std::vector<i64>().swap(elem[e]);
+        }
+        elem[p] = reach;  // new element p
+        std::vector<i64>().swap(vadj[p]);
+        std::vector<i64>().swap(eadj[p]);
+        // update the neighbours
+        for (i64 u : reach) {
+            // prune: drop eliminated / reach variables from vadj[u] (they are covered by element p),
+            // drop absorbed elements, add p
+            auto &va = vadj[u];
+            size_t w = 0;
+            for (size_t t = 0; t < va.size(); t++) {
+                i64 x = va[t];
+                if (!eliminated[x] && mark[x] != stamp) va[w++] = x;
+            }
+            va.resize(w);
+            auto &ea = eadj[u];
+            w = 0;
+            for (size_t t = 0; t < ea.size(); t++)
+                if (!absorbed[ea[t]]) ea[w++] = ea[t];
+            ea.resize(w);
+            ea.push_back(p);
+        }
+        for (i64 u : reach) {
+            // exact external degree = |vadj[u] U (union of elem[e], e in eadj[u])| - {u}
+            tstamp++;
+            tag[u] = tstamp;
+            i64 d = 0;
+            for (i64 x : vadj[u])
+                if (tag[x] != tstamp) { tag[x] = tstamp; d++; }
+            for (i64 e : eadj[u])
+                for (i64 x : elem[e])
+                    if (!eliminated[x] && tag[x] != tstamp) { tag[x] = tstamp; d++; }
+            bucket_remove(u);
+            degree[u] = d;
+            bucket_insert(u);
+            if (d < mindeg) mindeg = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct UpperCSC {  // upper triangle (row <= col) of the permuted matrix, column k = row pattern seeds
+    std::vector<i64> ptr, idx;
+};
+
+void build_permuted_upper(i64 n, const i64 *Ap, const i64 *Ai, const std::vector<i64> &iperm, UpperCSC &C) {
+    C.ptr.assign(n + 1, 0);
+    for (i64 j = 0; j < n; j++)
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
+            i64 i = Ai[p];
+            if (i > j) continue;
+            i64 a = iperm[i], b = iperm[j];
+            C.ptr[std::max(a, b) + 1]++;
+        }
+    for (i64 j = 0; j < n; j++) C.ptr[j + 1] += C.ptr[j];
+    C.idx.resize(C.ptr[n]);
+    std::vector<i64> w(C.ptr.begin(), C.ptr.end() - 1);
+    for (i64 j = 0; j < n; j++)
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
+            i64 i = Ai[p];
+            if (i > j) continue;
+            i64 a = iperm[i], b = iperm[j];
+            C.idx[w[std::max(a, b)]++] = std::min(a, b);
+        }
+}
+
+void etree(i64 n, const UpperCSC &C, std::vector<i64> &parent) {
+    parent.assign(n, -1);
+    std::vector<i64> anc(n, -1);
+    for (i64 k = 0; k < n; k++)
+        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++) {
+            i64 i = C.idx[p];
+            while (i != -1 && i < k) {
+                i64 nx = anc[i];
+                anc[i] = k;
+                if (nx == -1) parent[i] = k;
+                i = nx;
+            }
+        }
+}
+
+// Postorder with children visited in the order given by `key` ascending (ties by index).
+void postorder(i64 n, const std::vector<i64> &parent, const std::vector<i64> *key, std::vector<i64> &post) {
+    std::vector<i64> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    if (key) std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) { return (*key)[a] < (*key)[b]; });
+    // build child lists so that popping from head yields ascending key: insert in descending order
+    std::vector<i64> head(n, -1), next(n, -1);
+    std::vector<i64> roots;
+    for (i64 t = n - 1; t >= 0; t--) {
+        i64 v = order[t];
+        if (parent[v] == -1) roots.push_back(v);
+        else { next[v] = head[parent[v]]; head[parent[v]] = v; }
+    }
+    std::reverse(roots.begin(), roots.end());
+    post.clear();
+    post.reserve(n);
+    std::vector<i64> stack;
+    for (i64 r : roots) {
+        stack.push_back(r);
+        while (!stack.empty()) {
+            i64 v = stack.back();
+            i64 c = head[v];
+            if (c == -1) { post.push_back(v); stack.pop_back(); }
+            else { head[v] = next[c]; stack.push_back(c); }
+        }
+    }
+}
+
+// Gilbert-Ng-Peyton column counts; matrix must already be labelled in postorder (parent[j] > j).
+void column_counts(i64 n, const UpperCSC &C, const std::vector<i64> &parent, std::vector<i64> &cc) {
+    // lower-triangular column lists: for column j the rows i > j with A_ij != 0  == transpose of C's strict upper
+    std::vector<i64> lptr(n + 1, 0), lidx;
+    for (i64 k = 0; k < n; k++)
+        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
+            if (C.idx[p] < k) lptr[C.idx[p] + 1]++;
+    for (i64 j = 0; j < n; j++) lptr[j + 1] += lptr[j];
+    lidx.resize(lptr[n]);
+    {
+        std::vector<i64> w(lptr.begin(), lptr.end() - 1);
+        for (i64 k = 0; k < n; k++)
+            for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
+                if (C.idx[p] < k) lidx[w[C.idx[p]]++] = k;
+    }
+    std::vector<i64> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n), delta(n);
+    for (i64 k = 0; k < n; k++) {
+        i64 j = k;
+        delta[j] = (first[j] == -1) ? 1 : 0;
+        for (; j != -1 && first[j] == -1; j = parent[j]) first[j] = k;
+    }
+    std::iota(anc.begin(), anc.end(), 0);
+    for (i64 j = 0; j < n; j++) {
+        if (parent[j] != -1) delta[parent[j]]--;
+        for (i64 p = lptr[j]; p < lptr[j + 1]; p++) {
+            i64 i = lidx[p];
+            if (first[j] <= maxfirst[i]) continue;  // j is not a leaf of the i-th row subtree
+            maxfirst[i] = first[j];
+            i64 jprev = prevleaf[i];
+            prevleaf[i] = j;
+            delta[j]++;
+            if (jprev != -1) {
+                i64 q = jprev;
+                while (q != anc[q]) q = anc[q];
+                for (i64 s = jprev; s != q;) { i64 sp = anc[s]; anc[s] = q; s = sp; }
+                delta[q]--;
+            }
+        }
+        if (parent[j] != -1) anc[j] = parent[j];
+    }
+    cc = delta;
+    for (i64 j = 0; j < n; j++)
+        if (parent[j] != -1) cc[parent[j]] += cc[j];
+}
+
+// First-fit interval packing. Items are (birth, death, size); processed in phase order.
+struct PoolAlloc {
+    std::map<i64, i64> free_;  // offset -> size
+    i64 top = 0;
+    i64 alloc(i64 size) {
+        if (size == 0) return 0;
+        for (auto it = free_.begin(); it != free_.end(); ++it)
+            if (it->second >= size) {
+                i64 off = it->first, rem = it->second - size;
+                free_.erase(it);
+                if (rem > 0) free_[off + size] = rem;
+                return off;
+            }
+        // extend: if the last free block touches the top, grow it
+        if (!free_.empty()) {
+            auto last = std::prev(free_.end());
+            if (last->first + last->second == top) {
+                i64 off = last->first;
+                free_.erase(last);
+                top = off + size;
+                return off;
+            }
+        }
+        i64 off = top;
+        top += size;
+        return off;
+    }
+    void release(i64 off, i64 size) {
+        if (size == 0) return;
+        auto it = free_.emplace(off, size).first;
+        auto nx = std::next(it);
+        if (nx != free_.end() && it->first + it->second == nx->first) { it->second += nx->second; free_.erase(nx); }
+        if (it != free_.begin()) {
+            auto pv = std::prev(it);
+            if (pv->first + pv->second == it->first) { pv->second += it->second; free_.erase(it); }
+        }
+    }
+};
+
+inline i64 round_up(i64 x, i64 m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_perm, int ordering,
+             const Options &opt) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (n < 0) throw std::runtime_error("n must be non-negative");
+    if (n > 2000000000LL) throw std::runtime_error("n exceeds 32-bit row index range");
+    S = Symbolic();
+    S.n = n;
+    S.nnzA = Ap[n];
+    for (i64 j = 0; j < n; j++) {
+        if (Ap[j + 1] < Ap[j]) throw std::runtime_error("colptr must be non-decreasing");
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
+            if (Ai[p] < 0 || Ai[p] >= n) throw std::runtime_error("row index out of range");
+    }
+
+    // ---- 1. ordering ---------------------------------------------------------------------------
+    std::vector<i64> perm0(n);
+    if (user_perm) {
+        std::vector<char> seen(n, 0);
+        for (i64 k = 0; k < n; k++) {
+            i64 v = user_perm[k];
+            if (v < 0 || v >= n || seen[v]) throw std::runtime_error("perm is not a permutation");
+            seen[v] = 1;
+            perm0[k] = v;
+        }
+    } else if (ordering == 0) {
+        std::iota(perm0.begin(), perm0.end(), 0);
+    } else {
+        // adjacency from the upper triangle, symmetrised, no self loops
+        std::vector<i64> xadj(n + 1, 0), adj;
+        for (i64 j = 0; j < n; j++)
+            for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
+                if (Ai[p] < j) { xadj[Ai[p] + 1]++; xadj[j + 1]++; }
+        for (i64 j = 0; j < n; j++) xadj[j + 1] += xadj[j];
+        adj.resize(xadj[n]);
+        std::vector<i64> w(xadj.begin(), xadj.end() - 1);
+        for (i64 j = 0; j < n; j++)
+            for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
+                if (Ai[p] < j) { adj[w[Ai[p]]++] = j; adj[w[j]++] = Ai[p]; }
+        // duplicates are possible if the input repeats entries; METIS tolerates none -> dedupe
+        for (i64 v = 0; v < n; v++) std::sort(adj.begin() + xadj[v], adj.begin() + xadj[v + 1]);
+        {
+            std::vector<i64> xa2(n + 1, 0), ad2;
+            ad2.reserve(adj.size());
+            for (i64 v = 0; v < n; v++) {
+                i64 last = -1;
+                for (i64 p = xadj[v]; p < xadj[v + 1]; p++)
+                    if (adj[p] != last) { ad2.push_back(adj[p]); last = adj[p]; }
+                xa2[v + 1] = (i64)ad2.size();
+            }
+            xadj.swap(xa2);
+            adj.swap(ad2);
+        }
+        if (ordering == 1) order_metis_nd(n, xadj, adj, perm0);
+        else if (ordering == 2) order_amd(n, xadj, adj, perm0);
+        else throw std::runtime_error("unknown ordering");
+    }
+
+    // ---- 2. etree, postorder (children by ascending column count), exact column counts ------------
+    std::vector<i64> iperm0(n);
+    for (i64 k = 0; k < n; k++) iperm0[perm0[k]] = k;
+    UpperCSC C;
+    build_permuted_upper(n, Ap, Ai, iperm0, C);
+    std::vector<i64> parent0, post, cc0;
+    etree(n, C, parent0);
+    // first postorder -> relabel -> counts; then second postorder with the heaviest child last
+    auto relabel = [&](const std::vector<i64> &po) {
+        // po[k] = old label of new label k
+        std::vector<i64> newperm(n);
+        for (i64 k = 0; k < n; k++) newperm[k] = perm0[po[k]];
+        perm0.swap(newperm);
+        for (i64 k = 0; k < n; k++) iperm0[perm0[k]] = k;
+        build_permuted_upper(n, Ap, Ai, iperm0, C);
+        etree(n, C, parent0);
+    };
+    postorder(n, parent0, nullptr, post);
+    relabel(post);
+    column_counts(n, C, parent0, cc0);
+    postorder(n, parent0, &cc0, post);
+    {
+        bool ident = true;
+        for (i64 k = 0; k < n; k++) if (post[k] != k) { ident = false; break; }
+        if (!ident) {
+            relabel(post);
+            column_counts(n, C, parent0, cc0);
+        }
+    }
+    S.perm = perm0;
+    S.iperm = iperm0;
+    S.parent = parent0;
+    S.colcount = cc0;
+    S.nnzL = 0;
+    S.flops = 0;
+    for (i64 j = 0; j < n; j++) {
+        if (parent0[j] != -1 && parent0[j] <= j) throw std::runtime_error("internal: etree not postordered");
+        S.nnzL += cc0[j];
+        S.flops += (double)cc0[j] * (double)cc0[j];
+    }
+
+    // ---- 3. supernodes: maximal chains, then relaxed amalgamation ------------------------------------
+    struct Grp { i64 first, ns, nrow; double exact; i64 last_orig; };
+    std::vector<i64> fund_first;  // first column of each fundamental supernode
+    for (i64 j = 0; j < n; j++) {
+        bool join = j > 0 && parent0[j - 1] == j && cc0[j] == cc0[j - 1] - 1;
+        if (!join) fund_first.push_back(j);
+    }
+    i64 nf = (i64)fund_first.size();
+    fund_first.push_back(n);
+    std::vector<i64> fcol2s(n);
+    for (i64 s = 0; s < nf; s++)
+        for (i64 j = fund_first[s]; j < fund_first[s + 1]; j++) fcol2s[j] = s;
+    std::vector<Grp> stack;
+    auto zfrac_ok = [&](double ns, double nrow, double exact) {
+        double total = ns * nrow - ns * (ns - 1) / 2.0;
+        double z = (total - exact) / total;
+        if (ns <= opt.relax_n[0]) return true;
+        if (ns <= opt.relax_n[1]) return z < opt.relax_z[1];
+        if (ns <= opt.relax_n[2]) return z < opt.relax_z[2];
+        return z < opt.relax_z[3];
+    };
+    for (i64 s = 0; s < nf; s++) {
+        Grp g;
+        g.first = fund_first[s];
+        g.ns = fund_first[s + 1] - fund_first[s];
+        g.nrow = cc0[g.first];
+        g.exact = 0;
+        for (i64 j = g.first; j < g.first + g.ns; j++) g.exact += (double)cc0[j];
+        g.last_orig = s;
+        stack.push_back(g);
+        while (stack.size() >= 2) {
+            Grp &top = stack.back();
+            Grp &ch = stack[stack.size() - 2];
+            // parent (fundamental) supernode of the child group's root
+            i64 lastcol = ch.first + ch.ns - 1;
+            i64 pj = parent0[lastcol];
+            // mergeable only if the child group's root hangs off a column of `top` (it then is the group
+            // immediately preceding `top` in postorder). rows(merged) = cols(ch) U rows(top) exactly.
+            if (pj == -1 || pj < top.first || pj >= top.first + top.ns) break;
+            double ns = (double)(ch.ns + top.ns);
+            double nrow = (double)ch.ns + (double)top.nrow;
+            double exact = ch.exact + top.exact;
+            if (!zfrac_ok(ns, nrow, exact)) break;
+            Grp m;
+            m.first = ch.first;
+            m.ns = ch.ns + top.ns;
+            m.nrow = ch.ns + top.nrow;
+            m.exact = exact;
+            m.last_orig = top.last_orig;
+            stack.pop_back();
+            stack.pop_back();
+            stack.push_back(m);
+        }
+    }
+    S.nsuper = (i64)stack.size();
+    S.sfirst.resize(S.nsuper + 1);
+    for (i64 s = 0; s < S.nsuper; s++) S.sfirst[s] = stack[s].first;
+    S.sfirst[S.nsuper] = n;
+    S.col2super.resize(n);
+    for (i64 s = 0; s < S.nsuper; s++)
+        for (i64 j = S.sfirst[s]; j < S.sfirst[s + 1]; j++) S.col2super[j] = s;
+    S.sparent.assign(S.nsuper, -1);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 pj = parent0[S.sfirst[s + 1] - 1];
+        S.sparent[s] = pj == -1 ? -1 : S.col2super[pj];
+    }
+    // children lists
+    S.child_ptr.assign(S.nsuper + 1, 0);
+    for (i64 s = 0; s < S.nsuper; s++)
+        if (S.sparent[s] != -1) S.child_ptr[S.sparent[s] + 1]++;
+    for (i64 s = 0; s < S.nsuper; s++) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_idx.resize(S.child_ptr[S.nsuper]);
+    {
+        std::vector<i64> w(S.child_ptr.begin(), S.child_ptr.end() - 1);
+        for (i64 s = 0; s < S.nsuper; s++)
+            if (S.sparent[s] != -1) S.child_idx[w[S.sparent[s]]++] = s;
+    }
+
+    // ---- 4. row structures ----------------------------------------------------------------------------
+    // lower-triangular column lists of the permuted matrix
+    std::vector<i64> lptr(n + 1, 0), lidx;
+    for (i64 k = 0; k < n; k++)
+        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
+            if (C.idx[p] < k) lptr[C.idx[p] + 1]++;
+    for (i64 j = 0; j < n; j++) lptr[j + 1] += lptr[j];
+    lidx.resize(lptr[n]);
+    {
+        std::vector<i64> w(lptr.begin(), lptr.end() - 1);
+        for (i64 k = 0; k < n; k++)
+            for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
+                if (C.idx[p] < k) lidx[w[C.idx[p]]++] = k;
+    }
+    S.rowptr.assign(S.nsuper + 1, 0);
+    {
+        std::vector<i64> mark(n, -1);
+        std::vector<std::vector<i32>> rows(S.nsuper);
+        i64 total = 0;
+        for (i64 s = 0; s < S.nsuper; s++) {
+            i64 f = S.sfirst[s], l = S.sfirst[s + 1];
+            std::vector<i32> &r = rows[s];
+            for (i64 j = f; j < l; j++) { mark[j] = s; r.push_back((i32)j); }
+            for (i64 j = f; j < l; j++)
+                for (i64 p = lptr[j]; p < lptr[j + 1]; p++) {
+                    i64 i = lidx[p];
+                    if (mark[i] != s) { mark[i] = s; r.push_back((i32)i); }
+                }
+            for (i64 cp = S.child_ptr[s]; cp < S.child_ptr[s + 1]; cp++) {
+                i64 c = S.child_idx[cp];
+                const std::vector<i32> &cr = rows[c];
+                i64 cns = S.sfirst[c + 1] - S.sfirst[c];
+                for (size_t t = (size_t)cns; t < cr.size(); t++) {
+                    i64 i = cr[t];
+                    if (mark[i] != s) { mark[i] = s; r.push_back((i32)i); }
+                }
+            }
+            std::sort(r.begin() + (l - f), r.end());
+            total += (i64)r.size();
+            S.rowptr[s + 1] = total;
+        }
+        S.rowidx.resize(total);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            std::copy(rows[s].begin(), rows[s].end(), S.rowidx.begin() + S.rowptr[s]);
+            // children's row lists are no longer needed once the parent is built; free eagerly
+        }
+    }
+    // relative indices
+    S.relidx.assign(S.rowidx.size(), -1);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 p = S.sparent[s];
+        if (p == -1) {
+            if (S.nr(s) != 0) throw std::runtime_error("internal: root supernode with rows below");
+            continue;
+        }
+        i64 a = S.rowptr[s] + S.ns(s), ae = S.rowptr[s + 1];
+        i64 b = S.rowptr[p], be = S.rowptr[p + 1];
+        for (; a < ae; a++) {
+            while (b < be && S.rowidx[b] < S.rowidx[a]) b++;
+            if (b == be || S.rowidx[b] != S.rowidx[a]) throw std::runtime_error("internal: child row missing in parent");
+            S.relidx[a] = (i32)(b - S.rowptr[p]);
+        }
+    }
+
+    // ---- 5. panel layout -----------------------------------------------------------------------------
+    S.panel_off.assign(S.nsuper + 1, 0);
+    S.panel_ld.resize(S.nsuper);
+    S.flops_stored = 0;
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 nrow = S.nrow(s), ns = S.ns(s);
+        i64 ld = round_up(nrow, 2);
+        S.panel_ld[s] = (i32)ld;
+        S.panel_off[s + 1] = S.panel_off[s] + round_up(ld * ns, 2);
+        S.max_front = std::max(S.max_front, nrow);
+        S.max_ns = std::max(S.max_ns, ns);
+        for (i64 j = 0; j < ns; j++) S.flops_stored += (double)(nrow - j) * (double)(nrow - j);
+    }
+    S.panel_total = S.panel_off[S.nsuper];
+    S.diag_pos.resize(n);
+    for (i64 s = 0; s < S.nsuper; s++)
+        for (i64 j = S.sfirst[s]; j < S.sfirst[s + 1]; j++) {
+            i64 lc = j - S.sfirst[s];
+            S.diag_pos[j] = S.panel_off[s] + lc * S.panel_ld[s] + lc;
+        }
+
+    // ---- 6. levels ------------------------------------------------------------------------------------
+    S.level.assign(S.nsuper, 0);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        i64 p = S.sparent[s];
+        if (p != -1) S.level[p] = std::max(S.level[p], S.level[s] + 1);
+    }
+    S.nlevels = 0;
+    for (i64 s = 0; s < S.nsuper; s++) S.nlevels = std::max<i64>(S.nlevels, S.level[s] + 1);
+    S.level_ptr.assign(S.nlevels + 1, 0);
+    for (i64 s = 0; s < S.nsuper; s++) S.level_ptr[S.level[s] + 1]++;
+    for (i64 l = 0; l < S.nlevels; l++) S.level_ptr[l + 1] += S.level_ptr[l];
+    S.level_idx.resize(S.nsuper);
+    {
+        std::vector<i64> w(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        for (i64 s = 0; s < S.nsuper; s++) S.level_idx[w[S.level[s]]++] = s;
+    }
+
+    // ---- 7. pools -------------------------------------------------------------------------------------
+    S.upd_off.assign(S.nsuper, 0);
+    S.upd_ld.assign(S.nsuper, 0);
+    S.uvec_off.assign(S.nsuper, 0);
+    S.zw_off.assign(S.nsuper, 0);
+    {
+        PoolAlloc pa, pv;
+        for (i64 l = 0; l < S.nlevels; l++) {
+            for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+                i64 s = S.level_idx[t];
+                i64 nr = S.nr(s);
+                i64 ld = round_up(nr, 2);
+                S.upd_ld[s] = (i32)ld;
+                S.upd_off[s] = pa.alloc(ld * nr);
+                S.uvec_off[s] = pv.alloc(nr);
+            }
+            for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+                i64 s = S.level_idx[t];
+                for (i64 cp = S.child_ptr[s]; cp < S.child_ptr[s + 1]; cp++) {
+                    i64 c = S.child_idx[cp];
+                    pa.release(S.upd_off[c], (i64)S.upd_ld[c] * S.nr(c));
+                    pv.release(S.uvec_off[c], S.nr(c));
+                }
+            }
+        }
+        S.upd_total = pa.top;
+        S.uvec_total = pv.top;
+        // selected inversion, top-down: W_s is born at level(s) and dies after its lowest child level
+        PoolAlloc pz;
+        std::vector<i64> minchild(S.nsuper);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            i64 m = S.level[s];
+            for (i64 cp = S.child_ptr[s]; cp < S.child_ptr[s + 1]; cp++) m = std::min<i64>(m, S.level[S.child_idx[cp]]);
+            minchild[s] = m;
+        }
+        std::vector<std::vector<i64>> dies_at(S.nlevels);
+        for (i64 s = 0; s < S.nsuper; s++) dies_at[minchild[s]].push_back(s);
+        for (i64 l = S.nlevels - 1; l >= 0; l--) {
+            for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+                i64 s = S.level_idx[t];
+                S.zw_off[s] = pz.alloc((i64)S.upd_ld[s] * S.nr(s));
+            }
+            for (i64 s : dies_at[l]) pz.release(S.zw_off[s], (i64)S.upd_ld[s] * S.nr(s));
+        }
+        S.zw_total = pz.top;
+    }
+
+    // ---- 8. scatter map Q.nzval -> panels ------------------------------------------------------------
+    {
+        i64 cnt = 0;
+        for (i64 j = 0; j < n; j++)
+            for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
+                if (Ai[p] <= j) cnt++;
+        S.q_src.resize(cnt);
+        S.q_dst.resize(cnt);
+        i64 k = 0;
+        for (i64 j = 0; j < n; j++)
+            for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
+                i64 i = Ai[p];
+                if (i > j) continue;
+                i64 a = S.iperm[i], b = S.iperm[j];
+                i64 col = std::min(a, b), row = std::max(a, b);
+                i64 s = S.col2super[col];
+                const i32 *rb = S.rowidx.data() + S.rowptr[s];
+                const i32 *re = S.rowidx.data() + S.rowptr[s + 1];
+                const i32 *it = std::lower_bound(rb, re, (i32)row);
+                if (it == re || *it != (i32)row) throw std::runtime_error("internal: Q entry outside factor pattern");
+                S.q_src[k] = p;
+                S.q_dst[k] = S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb);
+                k++;
+            }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    S.analysis_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+
+}  // namespace gmrf

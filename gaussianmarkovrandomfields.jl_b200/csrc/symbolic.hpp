@@ -1,0 +1,89 @@
+// symbolic.hpp -- host-side symbolic analysis for the B200 supernodal multifrontal Cholesky.
+//
+// This is the work the north star leaves on the CPU, done once per sparsity pattern and cached in the
+// handle (reference: the symbolic half of `cholesky(Q; perm)` in src/workspace/backend.jl:147-153 and
+// the "symbolic factorization is computed once and reused" contract of backend.jl:32-50):
+// fill-reducing ordering, elimination tree, exact column counts, supernode partition with relaxed
+// amalgamation, per-supernode row structures, assembly-tree levels, relative indices for extend-add,
+// the Q.nzval -> panel scatter map (cf. _build_full_to_lower_map, cliquetrees_backend.jl:90-123) and the
+// lifetime-packed pools for update matrices.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gmrf {
+
+typedef int64_t i64;
+typedef int32_t i32;
+
+struct Options {
+    // relaxed amalgamation: merge a child into its parent if merged ns <= relax_n[0]; else if the zero
+    // fraction of the merged panel is < relax_z[k] for the first k with ns <= relax_n[k]; relax_z[2]
+    // applies beyond relax_n[2] ... (the shape of CHOLMOD's nrelax/zrelax rule, GPU-tuned values).
+    double relax_n[3] = {8, 32, 96};
+    double relax_z[4] = {0.8, 0.3, 0.1, 0.05};
+    int use_graph = 1;
+    int naive_kernels = 0;
+};
+Options &global_options();
+
+struct Symbolic {
+    i64 n = 0, nnzA = 0;
+    std::vector<i64> perm, iperm;        // final elimination order (ordering o etree postorder)
+    std::vector<i64> parent;             // etree, final order
+    std::vector<i64> colcount;           // exact column counts of L incl. diagonal, final order
+    i64 nnzL = 0;                        // sum colcount
+    double flops = 0;                    // sum colcount^2
+
+    i64 nsuper = 0;
+    std::vector<i64> sfirst;             // [nsuper+1] first column of each supernode
+    std::vector<i64> sparent;            // [nsuper]  parent supernode or -1
+    std::vector<i64> col2super;          // [n]
+    std::vector<i64> rowptr;             // [nsuper+1] offsets into rowidx
+    std::vector<i32> rowidx;             // row structure, sorted; first ns entries are the own columns
+    std::vector<i32> relidx;             // same offsets as rowidx: position of the row in the PARENT's structure
+                                         // (valid for the below-diagonal rows of non-root supernodes)
+    std::vector<i64> panel_off;          // [nsuper+1] offset (doubles) of the nrow x ns panel, column-major
+    std::vector<i32> panel_ld;           // [nsuper]
+    i64 panel_total = 0;
+    double flops_stored = 0;
+
+    std::vector<i64> child_ptr, child_idx;   // children lists (ascending)
+    std::vector<i32> level;                  // height above the leaves
+    i64 nlevels = 0;
+    std::vector<i64> level_ptr, level_idx;   // supernodes grouped by level
+
+    // update-matrix pool (nr x nr, ld = upd_ld), packed by lifetime [level(s), level(parent)]
+    std::vector<i64> upd_off;
+    std::vector<i32> upd_ld;
+    i64 upd_total = 0;
+    // selected-inversion pool: W_s = Z[R_s, R_s] (nr x nr full symmetric), lifetime
+    // [min level of children, level(s)], processed top-down
+    std::vector<i64> zw_off;
+    i64 zw_total = 0;
+    // forward-solve pool in units of rows (u_s has nr_s rows per right-hand side)
+    std::vector<i64> uvec_off;
+    i64 uvec_total = 0;
+
+    // scatter of the upper triangle of Q into the panels: Lx[q_dst[k]] = nzval[q_src[k]]
+    std::vector<i64> q_src, q_dst;
+    std::vector<i64> diag_pos;           // [n] position of L_jj in the panel array
+
+    i64 max_front = 0, max_ns = 0;
+    double analysis_ms = 0;
+
+    inline i64 ns(i64 s) const { return sfirst[s + 1] - sfirst[s]; }
+    inline i64 nrow(i64 s) const { return rowptr[s + 1] - rowptr[s]; }
+    inline i64 nr(i64 s) const { return nrow(s) - ns(s); }
+};
+
+// colptr/rowval: 0-based full symmetric pattern. user_perm may be null. Throws std::runtime_error.
+void analyze(Symbolic &S, i64 n, const i64 *colptr, const i64 *rowval, const i64 *user_perm, int ordering,
+             const Options &opt);
+
+// orderings (0-based adjacency without self loops: xadj[n+1], adj[])
+void order_metis_nd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);
+void order_amd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);
+
+}  // namespace gmrf

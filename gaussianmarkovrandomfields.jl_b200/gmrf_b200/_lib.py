@@ -1,0 +1,120 @@
+"""ctypes binding of libgmrf_b200.so (include/gmrf_b200.h). Fails loudly if the library is missing:
+there is no CPU fallback for the numeric path."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libgmrf_b200.so"))
+
+c_i64 = ctypes.c_int64
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+
+INFO_KEYS = ["n", "nnz_q", "nnz_l", "nnz_l_stored", "nsuper", "nlevels", "max_front", "max_ns", "update_pool",
+             "flops_chol", "flops_chol_stored", "device_bytes", "graph_nodes", "selinv_nodes"]
+
+ORDER_NATURAL, ORDER_ND, ORDER_AMD = 0, 1, 2
+
+EXPORTS = [
+    "gmrf_b200_create", "gmrf_b200_destroy", "gmrf_b200_last_error", "gmrf_b200_refactorize",
+    "gmrf_b200_refactorize_device", "gmrf_b200_logdet", "gmrf_b200_solve", "gmrf_b200_solve_Lt",
+    "gmrf_b200_solve_device", "gmrf_b200_solve_Lt_device", "gmrf_b200_selinv_compute", "gmrf_b200_selinv_diag",
+    "gmrf_b200_selinv_nnz", "gmrf_b200_selinv_pattern", "gmrf_b200_selinv_values", "gmrf_b200_selinv_extract",
+    "gmrf_b200_info", "gmrf_b200_get_perm", "gmrf_b200_get_colcounts", "gmrf_b200_get_etree",
+    "gmrf_b200_get_supernodes", "gmrf_b200_get_rows", "gmrf_b200_get_scatter", "gmrf_b200_last_timings",
+    "gmrf_b200_get_factor_panels", "gmrf_b200_get_selinv_panels", "gmrf_b200_set_option",
+    "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_trsm",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(gmrf_b200 has no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.gmrf_b200_create.restype = ctypes.c_int
+    L.gmrf_b200_create.argtypes = [ctypes.POINTER(c_vp), c_i64, c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int]
+    L.gmrf_b200_destroy.restype = None
+    L.gmrf_b200_destroy.argtypes = [c_vp]
+    L.gmrf_b200_last_error.restype = ctypes.c_char_p
+    L.gmrf_b200_last_error.argtypes = [c_vp]
+    for name in ("gmrf_b200_refactorize", "gmrf_b200_refactorize_device"):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [c_vp, c_vp, c_i64]
+    L.gmrf_b200_logdet.restype = ctypes.c_int
+    L.gmrf_b200_logdet.argtypes = [c_vp, c_f64p]
+    for name in ("gmrf_b200_solve", "gmrf_b200_solve_Lt", "gmrf_b200_solve_device", "gmrf_b200_solve_Lt_device"):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64]
+    L.gmrf_b200_selinv_compute.restype = ctypes.c_int
+    L.gmrf_b200_selinv_compute.argtypes = [c_vp]
+    L.gmrf_b200_selinv_diag.restype = ctypes.c_int
+    L.gmrf_b200_selinv_diag.argtypes = [c_vp, c_vp]
+    L.gmrf_b200_selinv_nnz.restype = ctypes.c_int
+    L.gmrf_b200_selinv_nnz.argtypes = [c_vp, c_i64p]
+    L.gmrf_b200_selinv_pattern.restype = ctypes.c_int
+    L.gmrf_b200_selinv_pattern.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
+    L.gmrf_b200_selinv_values.restype = ctypes.c_int
+    L.gmrf_b200_selinv_values.argtypes = [c_vp, c_vp]
+    L.gmrf_b200_selinv_extract.restype = ctypes.c_int
+    L.gmrf_b200_selinv_extract.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp]
+    L.gmrf_b200_info.restype = ctypes.c_int
+    L.gmrf_b200_info.argtypes = [c_vp, c_vp, ctypes.c_int]
+    L.gmrf_b200_get_perm.restype = ctypes.c_int
+    L.gmrf_b200_get_perm.argtypes = [c_vp, c_vp, ctypes.c_int]
+    for name in ("gmrf_b200_get_colcounts", "gmrf_b200_get_etree"):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [c_vp, c_vp]
+    L.gmrf_b200_get_supernodes.restype = ctypes.c_int
+    L.gmrf_b200_get_supernodes.argtypes = [c_vp] + [c_vp] * 8
+    L.gmrf_b200_get_rows.restype = ctypes.c_int
+    L.gmrf_b200_get_rows.argtypes = [c_vp, c_vp, c_vp]
+    L.gmrf_b200_get_scatter.restype = ctypes.c_int
+    L.gmrf_b200_get_scatter.argtypes = [c_vp, c_i64p, c_vp, c_vp]
+    L.gmrf_b200_last_timings.restype = ctypes.c_int
+    L.gmrf_b200_last_timings.argtypes = [c_vp, c_vp, ctypes.c_int]
+    for name in ("gmrf_b200_get_factor_panels", "gmrf_b200_get_selinv_panels"):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [c_vp, c_vp, c_i64]
+    L.gmrf_b200_set_option.restype = ctypes.c_int
+    L.gmrf_b200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_double]
+    L.gmrf_b200_test_gemm.restype = ctypes.c_int
+    L.gmrf_b200_test_gemm.argtypes = [ctypes.c_int] * 7 + [c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_double, c_vp, ctypes.c_int]
+    L.gmrf_b200_test_potrf.restype = ctypes.c_int
+    L.gmrf_b200_test_potrf.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.gmrf_b200_test_trsm.restype = ctypes.c_int
+    L.gmrf_b200_test_trsm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int]
+    _lib = L
+    return L
+
+
+def ptr(a):
+    """Raw pointer of a numpy array (or None)."""
+    if a is None:
+        return None
+    return a.ctypes.data_as(c_vp)
+
+
+def set_option(key: str, value: float):
+    rc = lib().gmrf_b200_set_option(key.encode(), float(value))
+    if rc != 0:
+        raise ValueError(f"unknown option {key!r}")

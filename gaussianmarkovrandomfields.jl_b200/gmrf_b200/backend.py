@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's `WorkspaceBackend` protocol over the C-ABI.
+
+Reference: src/workspace/backend.jl:8-30 (protocol), :51-61 / :147-284 (CHOLMODBackend, whose caching
+contract the tests pin), src/workspace/cliquetrees_backend.jl:21-150 (second implementation).
+Method names, argument meaning and error behaviour follow the reference (`refactorize!` -> `refactorize`,
+ArgumentError -> ValueError). Julia is not available in this image, so this Python class plays the role of
+the `B200Backend <: WorkspaceBackend` glue in julia/B200Backend.jl; both bind the same entry points.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import ptr
+
+__all__ = ["B200Backend", "PinDenseColumns", "ordering_permutation", "B200Error", "NotPositiveDefinite"]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class NotPositiveDefinite(B200Error):
+    def __init__(self, column):
+        super().__init__(f"matrix is not positive definite: non-positive pivot at column {column} of the factor")
+        self.column = column
+
+
+class PinDenseColumns:
+    """Ordering wrapper: columns with more than frac*n nonzeros are pinned to the END of the elimination
+    order, `inner` orders the remaining sparse block (src/workspace/backend.jl:63-77)."""
+
+    def __init__(self, inner="nd", frac: float = 0.5):
+        self.inner = inner
+        self.frac = frac
+
+
+_ORDER_CODES = {"natural": _lib.ORDER_NATURAL, "nd": _lib.ORDER_ND, "metis": _lib.ORDER_ND, "amd": _lib.ORDER_AMD,
+                "mmd": _lib.ORDER_AMD}
+
+
+def _csc(Q):
+    Q = sp.csc_matrix(Q)
+    if not Q.has_sorted_indices:
+        Q = Q.copy()
+        Q.sort_indices()
+    return Q
+
+
+def ordering_permutation(A, ordering) -> np.ndarray:
+    """Resolve an ordering spec to an explicit 0-based permutation (ordering_permutation, backend.jl:93-133).
+    `ordering` is a permutation vector, one of "nd"/"amd"/"natural", or a PinDenseColumns wrapper."""
+    A = _csc(A)
+    n = A.shape[1]
+    if isinstance(ordering, PinDenseColumns):
+        nnz_col = np.diff(A.indptr)
+        dense = np.flatnonzero(nnz_col > ordering.frac * n)
+        if dense.size == 0:
+            return ordering_permutation(A, ordering.inner)
+        keep = np.flatnonzero(nnz_col <= ordering.frac * n)
+        sub = A[keep][:, keep]
+        inner = ordering_permutation(sub, ordering.inner)
+        return np.concatenate([keep[inner], dense]).astype(np.int64)
+    if isinstance(ordering, str):
+        code = _ORDER_CODES[ordering.lower()]
+        h = _Handle(A.shape[0], A.indptr, A.indices, None, code, device=-1)
+        try:
+            return h.perm()
+        finally:
+            h.close()
+    perm = np.asarray(ordering, dtype=np.int64)
+    if perm.shape != (n,) or not np.array_equal(np.sort(perm), np.arange(n)):
+        raise ValueError("ordering is not a permutation of 0..n-1")
+    return perm
+
+
+class _Handle:
+    """Owns one gmrf_b200_handle*."""
+
+    def __init__(self, n, colptr, rowval, perm, ordering_code, device):
+        L = _lib.lib()
+        self._L = L
+        self._h = ctypes.c_void_p()
+        cp = np.ascontiguousarray(colptr, dtype=np.int64)
+        rv = np.ascontiguousarray(rowval, dtype=np.int64)
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int64)
+        rc = L.gmrf_b200_create(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(pm), int(ordering_code), int(device))
+        if rc != 0:
+            msg = L.gmrf_b200_last_error(None).decode()
+            self._h = None
+            if rc == -1:
+                raise ValueError(msg)
+            raise B200Error(f"gmrf_b200_create failed ({rc}): {msg}")
+        self.n = int(n)
+
+    def check(self, rc, allow_positive=False):
+        if rc == 0 or (allow_positive and rc > 0):
+            return rc
+        msg = self._L.gmrf_b200_last_error(self._h).decode()
+        if rc == -1:
+            raise ValueError(msg)
+        if rc > 0:
+            raise NotPositiveDefinite(rc)
+        raise B200Error(f"libgmrf_b200 error {rc}: {msg}")
+
+    def info(self) -> dict:
+        v = np.zeros(len(_lib.INFO_KEYS), dtype=np.int64)
+        self.check(self._L.gmrf_b200_info(self._h, ptr(v), v.size))
+        return dict(zip(_lib.INFO_KEYS, (int(x) for x in v)))
+
+    def perm(self) -> np.ndarray:
+        p = np.empty(self.n, dtype=np.int64)
+        self.check(self._L.gmrf_b200_get_perm(self._h, ptr(p), 0))
+        return p
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._L.gmrf_b200_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class B200Backend:
+    """B200 sparse-Cholesky backend. `B200Backend(Q; ordering=None, device=0)` performs the symbolic analysis
+    once and the first numeric factorization, like `CHOLMODBackend(Q::Symmetric; ordering)` (backend.jl:147-153).
+
+    Fields mirrored from the reference struct (backend.jl:51-61) because its tests peek at them
+    (test_gmrf_workspace.jl:214,219): `selinv_cache`, `selinv_diag_cache`.
+    """
+
+    def __init__(self, Q, ordering=None, device: int = 0, check: bool = False, factorize: bool = True):
+        Q = _csc(Q)
+        if Q.shape[0] != Q.shape[1]:
+            raise ValueError("Q must be square")
+        self.n = Q.shape[0]
+        self.check_pd = check
+        perm, code = None, _lib.ORDER_ND
+        if ordering is not None:
+            if isinstance(ordering, str) and not isinstance(ordering, PinDenseColumns):
+                code = _ORDER_CODES[ordering.lower()]
+            else:
+                perm = ordering_permutation(Q, ordering)
+        self._colptr = Q.indptr.astype(np.int64)
+        self._rowval = Q.indices.astype(np.int64)
+        self._hd = _Handle(self.n, self._colptr, self._rowval, perm, code, device)
+        self._L = self._hd._L
+        self.device = device
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        self._selinv_pattern = None
+        self.status = 0
+        if factorize and device >= 0:
+            self.refactorize(Q)
+
+    # -- protocol ------------------------------------------------------------------------------------
+    def refactorize(self, Q):
+        """refactorize!(b, Q::Symmetric) (backend.jl:178-189): values only, pattern must be unchanged."""
+        nz = Q.data if sp.issparse(Q) else np.asarray(Q)
+        nz = np.ascontiguousarray(nz, dtype=np.float64)
+        rc = self._L.gmrf_b200_refactorize(self._hd._h, ptr(nz), nz.size)
+        self.status = self._hd.check(rc, allow_positive=not self.check_pd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        return None
+
+    def backend_solve(self, rhs):
+        """backend_solve(b, rhs) (backend.jl:191-209): new array, original ordering; vector or matrix."""
+        rhs = np.asarray(rhs, dtype=np.float64)
+        if rhs.shape[0] != self.n:
+            raise ValueError("right-hand side has the wrong number of rows")
+        B = np.asfortranarray(rhs.reshape(self.n, -1))
+        X = np.empty_like(B, order="F")
+        self._hd.check(self._L.gmrf_b200_solve(self._hd._h, ptr(B), ptr(X), max(self.n, 1), B.shape[1]))
+        return X.reshape(rhs.shape) if rhs.ndim == 1 else X
+
+    def backend_backward_solve(self, x):
+        """backend_backward_solve(b, x) = factor.UP \\ x (backend.jl:281-284)."""
+        x = np.asarray(x, dtype=np.float64)
+        if x.shape[0] != self.n:
+            raise ValueError("vector has the wrong length")
+        Z = np.asfortranarray(x.reshape(self.n, -1))
+        X = np.empty_like(Z, order="F")
+        self._hd.check(self._L.gmrf_b200_solve_Lt(self._hd._h, ptr(Z), ptr(X), max(self.n, 1), Z.shape[1]))
+        return X.reshape(x.shape) if x.ndim == 1 else X
+
+    def compute_logdet(self) -> float:
+        out = ctypes.c_double()
+        self._hd.check(self._L.gmrf_b200_logdet(self._hd._h, ctypes.byref(out)))
+        return float(out.value)
+
+    def compute_selinv(self):
+        """compute_selinv!(b) is lazy in the reference (backend.jl:215-221); the getters trigger the recursion."""
+        return None
+
+    def get_selinv(self):
+        """Full symmetric CSC on the factor's pattern, original ordering, cached (backend.jl:238-246)."""
+        if self.selinv_cache is None:
+            if self._selinv_pattern is None:
+                nnz = ctypes.c_int64()
+                self._hd.check(self._L.gmrf_b200_selinv_nnz(self._hd._h, ctypes.byref(nnz)))
+                cp = np.empty(self.n + 1, dtype=np.int64)
+                rv = np.empty(nnz.value, dtype=np.int64)
+                self._hd.check(self._L.gmrf_b200_selinv_pattern(self._hd._h, ptr(cp), ptr(rv), 0))
+                self._selinv_pattern = (cp, rv)
+            cp, rv = self._selinv_pattern
+            vals = np.empty(rv.size, dtype=np.float64)
+            self._hd.check(self._L.gmrf_b200_selinv_values(self._hd._h, ptr(vals)))
+            self.selinv_cache = sp.csc_matrix((vals, rv, cp), shape=(self.n, self.n))
+        return self.selinv_cache
+
+    def get_selinv_diag(self):
+        """Diagonal of Q^-1, cached until the next refactorize (backend.jl:248-257)."""
+        if self.selinv_diag_cache is None:
+            if self.selinv_cache is not None:
+                self.selinv_diag_cache = self.selinv_cache.diagonal()
+            else:
+                d = np.empty(self.n, dtype=np.float64)
+                self._hd.check(self._L.gmrf_b200_selinv_diag(self._hd._h, ptr(d)))
+                self.selinv_diag_cache = d
+        return self.selinv_diag_cache
+
+    def selinv_extract_at(self, B):
+        """Sigma read at B's pattern (backend.jl:275-279), without materialising the full selected inverse."""
+        B = _csc(B)
+        if B.shape != (self.n, self.n):
+            raise ValueError("pattern matrix has the wrong shape")
+        cp = B.indptr.astype(np.int64)
+        rv = B.indices.astype(np.int64)
+        out = np.empty(rv.size, dtype=np.float64)
+        self._hd.check(self._L.gmrf_b200_selinv_extract(self._hd._h, self.n, ptr(cp), ptr(rv), 0, ptr(out)))
+        return sp.csc_matrix((out, B.indices.copy(), B.indptr.copy()), shape=B.shape)
+
+    def selinv_dot(self, B) -> float:
+        """tr(Q^-1 B) for B on a subset of the factor's pattern (backend.jl:265-267): the values are read on
+        the device at B's pattern, the O(nnz(B)) dot is host work."""
+        B = _csc(B)
+        return float(np.dot(self.selinv_extract_at(B).data, B.data))
+
+    # -- extras --------------------------------------------------------------------------------------
+    def info(self) -> dict:
+        return self._hd.info()
+
+    def permutation(self) -> np.ndarray:
+        return self._hd.perm()
+
+    def colcounts(self) -> np.ndarray:
+        cc = np.empty(self.n, dtype=np.int64)
+        self._hd.check(self._L.gmrf_b200_get_colcounts(self._hd._h, ptr(cc)))
+        return cc
+
+    def timings(self) -> dict:
+        t = np.zeros(5)
+        self._hd.check(self._L.gmrf_b200_last_timings(self._hd._h, ptr(t), 5))
+        return {"h2d_ms": t[0], "factor_ms": t[1], "solve_ms": t[2], "selinv_ms": t[3], "analysis_ms": t[4]}
+
+    def refactorize_device(self, dptr: int, nnz: int):
+        rc = self._L.gmrf_b200_refactorize_device(self._hd._h, ctypes.c_void_p(dptr), int(nnz))
+        self.status = self._hd.check(rc, allow_positive=not self.check_pd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+
+    def selinv_compute(self):
+        self._hd.check(self._L.gmrf_b200_selinv_compute(self._hd._h))
+
+    def solve_device(self, dB: int, dX: int, ld: int, nrhs: int, half: bool = False):
+        f = self._L.gmrf_b200_solve_Lt_device if half else self._L.gmrf_b200_solve_device
+        self._hd.check(f(self._hd._h, ctypes.c_void_p(dB), ctypes.c_void_p(dX), int(ld), int(nrhs)))
+
+    def close(self):
+        self._hd.close()

@@ -1,0 +1,161 @@
+/*
+ * gmrf_b200.h -- C-ABI of libgmrf_b200.so: a B200 (sm_100a) sparse-Cholesky backend that sits
+ * behind GaussianMarkovRandomFields.jl's `WorkspaceBackend` protocol
+ * (reference: src/workspace/backend.jl:8-30; second implementation to imitate:
+ * src/workspace/cliquetrees_backend.jl:21-150).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every output buffer is CALLER-allocated; the library never
+ *     keeps a host pointer after a call returns and never frees caller memory;
+ *   - matrices are column-major Float64; sparse patterns are CSC with Int64 indices, FULL symmetric
+ *     pattern as stored in `GMRFWorkspace.Q` (src/workspace/gmrf_workspace.jl:32); only entries with
+ *     row <= col are read (`Symmetric(ws.Q)`, gmrf_workspace.jl:176). `index_base` is 1 for Julia,
+ *     0 for C/Python callers;
+ *   - return value: 0 = ok, <0 = usage / CUDA error (text via gmrf_b200_last_error), >0 = matrix
+ *     not positive definite, value = 1-based column (in the factor's elimination order) of the
+ *     first non-positive pivot. The reference factorizes with `check=false`
+ *     (backend.jl:184), so the Julia glue ignores >0 unless asked;
+ *   - a handle is bound to one device and one CUDA stream and is NOT thread-safe; distinct handles
+ *     may be used concurrently from different host threads (no global lock; cf. the CHOLMOD lock
+ *     note in src/workspace/workspace_pool.jl:15-21);
+ *   - results are run-to-run bit-reproducible (no floating-point atomics anywhere)
+ *     (test/gaussian_approximation/test_predictive_convergence.jl:20-28).
+ *   - there is NO CPU fallback: every numeric entry point fails with GMRF_B200_ERR_NO_DEVICE on a
+ *     handle created with device < 0 (analysis-only handle).
+ */
+#ifndef GMRF_B200_H
+#define GMRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmrf_b200_handle gmrf_b200_handle;
+
+enum {
+    GMRF_B200_OK = 0,
+    GMRF_B200_ERR_ARG = -1,        /* bad argument (size / pattern / nnz mismatch -> ArgumentError) */
+    GMRF_B200_ERR_CUDA = -2,       /* CUDA runtime error */
+    GMRF_B200_ERR_NO_DEVICE = -3,  /* numeric call on an analysis-only handle */
+    GMRF_B200_ERR_STATE = -4,      /* e.g. solve before the first refactorize */
+    GMRF_B200_ERR_ALLOC = -5
+};
+
+/* Fill-reducing ordering used when `perm` is NULL. The reference resolves `ordering=` on the host
+ * (ordering_permutation, backend.jl:73-133) and may hand over the permutation instead. */
+enum {
+    GMRF_B200_ORDER_NATURAL = 0,
+    GMRF_B200_ORDER_ND = 1,        /* nested dissection (METIS_NodeND), default */
+    GMRF_B200_ORDER_AMD = 2        /* approximate minimum degree (own implementation) */
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------------
+ * replaces  CHOLMODBackend(Q::Symmetric; ordering)   backend.jl:147-153  (symbolic part)
+ *           CliqueTreesBackend(Q; alg)               cliquetrees_backend.jl:28-41
+ * Symbolic analysis on the host (ordering, etree, exact column counts, supernodes, level
+ * schedule, scatter maps), uploaded once to `device`. No numeric work happens here.
+ * perm (optional): perm[k] = index (in `index_base`) of the k-th pivot. device < 0 -> analysis only. */
+int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                     int index_base, const int64_t *perm, int ordering, int device);
+void gmrf_b200_destroy(gmrf_b200_handle *h);
+const char *gmrf_b200_last_error(const gmrf_b200_handle *h);   /* h may be NULL: last create error */
+
+/* ---- numeric factorization -------------------------------------------------------------------
+ * replaces  refactorize!(b, Q::Symmetric)   backend.jl:178-189 (+ _copy_sparse_values! :165-176)
+ * nzval: the nnz values of the full symmetric CSC, positionally matching the pattern given to
+ * create (nnz mismatch -> GMRF_B200_ERR_ARG, like the ArgumentError at backend.jl:168-173).
+ * Invalidates every selected-inverse cache (backend.jl:185-187). The log-determinant is reduced
+ * inside the same pass. `_device` takes nzval already resident in this device's HBM. */
+int gmrf_b200_refactorize(gmrf_b200_handle *h, const double *nzval, int64_t nnz);
+int gmrf_b200_refactorize_device(gmrf_b200_handle *h, const double *d_nzval, int64_t nnz);
+
+/* replaces  compute_logdet(b) = logdet(factor)   backend.jl:211-213 */
+int gmrf_b200_logdet(gmrf_b200_handle *h, double *out);
+
+/* ---- solves ----------------------------------------------------------------------------------
+ * replaces  backend_solve(b, rhs::Vector) / (b, RHS::Matrix)   backend.jl:191-209
+ * X = Q^-1 B, original ordering, B and X are n x nrhs column-major with leading dimension ld
+ * (B == X allowed). */
+int gmrf_b200_solve(gmrf_b200_handle *h, const double *B, double *X, int64_t ld, int64_t nrhs);
+/* replaces  backend_backward_solve(b, x) = factor.UP \ x   backend.jl:281-284
+ * X = P' L^-T Z so that Cov(X) = Q^-1 for Z ~ N(0, I) (sampling). */
+int gmrf_b200_solve_Lt(gmrf_b200_handle *h, const double *Z, double *X, int64_t ld, int64_t nrhs);
+/* Same two operations on buffers resident in this device's HBM. */
+int gmrf_b200_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, int64_t ld, int64_t nrhs);
+int gmrf_b200_solve_Lt_device(gmrf_b200_handle *h, const double *dZ, double *dX, int64_t ld, int64_t nrhs);
+
+/* ---- selected inversion (Takahashi) ----------------------------------------------------------
+ * replaces  compute_selinv! / get_selinv_Z   backend.jl:215-236  (SelectedInversion.selinv(F).Z)
+ * Runs the recursion once per refactorization and caches Z on the device; the getters below call
+ * it on demand (the reference's compute_selinv! is lazy too). */
+int gmrf_b200_selinv_compute(gmrf_b200_handle *h);
+/* replaces  get_selinv_diag(b)   backend.jl:248-257 ; bit-identical to diag of selinv_values */
+int gmrf_b200_selinv_diag(gmrf_b200_handle *h, double *out);
+/* replaces  get_selinv(b) = sparse(Z)   backend.jl:238-246 : full symmetric CSC on the FACTOR's
+ * pattern (superset of Q's), original ordering, sorted rows. Pattern depends on the symbolic
+ * analysis only: fetch it once, then only values after each refactorize. */
+int gmrf_b200_selinv_nnz(gmrf_b200_handle *h, int64_t *nnz);
+int gmrf_b200_selinv_pattern(gmrf_b200_handle *h, int64_t *colptr, int64_t *rowval, int index_base);
+int gmrf_b200_selinv_values(gmrf_b200_handle *h, double *nzval);
+/* replaces  selinv_extract_at(b, B)   backend.jl:275-279 : Sigma read at a caller pattern (CSC,
+ * nnz entries), 0.0 where the position is outside the factor's pattern. */
+int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr,
+                             const int64_t *rowval, int index_base, double *out);
+
+/* ---- introspection (symbolic facts; all host-side, valid on analysis-only handles) -----------*/
+enum {
+    GMRF_B200_INFO_N = 0,
+    GMRF_B200_INFO_NNZ_Q = 1,          /* nnz of the full symmetric input pattern */
+    GMRF_B200_INFO_NNZ_L = 2,          /* exact nnz(L) = sum of column counts */
+    GMRF_B200_INFO_NNZ_L_STORED = 3,   /* doubles in the supernodal panels (incl. relaxation zeros + padding) */
+    GMRF_B200_INFO_NSUPER = 4,
+    GMRF_B200_INFO_NLEVELS = 5,
+    GMRF_B200_INFO_MAX_FRONT = 6,      /* largest front order (ns + nr) */
+    GMRF_B200_INFO_MAX_NS = 7,
+    GMRF_B200_INFO_UPDATE_POOL = 8,    /* doubles in the update-matrix pool */
+    GMRF_B200_INFO_FLOPS_CHOL = 9,     /* sum_j cc_j^2 (exact), the algorithmic factorization flop count */
+    GMRF_B200_INFO_FLOPS_CHOL_STORED = 10, /* flops actually executed on the relaxed panels */
+    GMRF_B200_INFO_DEVICE_BYTES = 11,
+    GMRF_B200_INFO_GRAPH_NODES = 12,   /* kernel launches in one refactorization */
+    GMRF_B200_INFO_SELINV_NODES = 13,  /* kernel launches in one selected inversion */
+    GMRF_B200_INFO_COUNT = 14
+};
+int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info);
+int gmrf_b200_get_perm(const gmrf_b200_handle *h, int64_t *perm, int index_base);       /* final elimination order */
+int gmrf_b200_get_colcounts(const gmrf_b200_handle *h, int64_t *colcount);              /* exact, elimination order */
+int gmrf_b200_get_etree(const gmrf_b200_handle *h, int64_t *parent);                    /* 0-based, -1 = root */
+/* Supernodal schedule tables (0-based), used by the host-side replay test:
+ *   super_ptr[nsuper+1], super_parent[nsuper], level[nsuper], row_ptr[nsuper+1],
+ *   panel_off[nsuper+1], panel_ld[nsuper], upd_off[nsuper], upd_ld[nsuper]. Any pointer may be NULL. */
+int gmrf_b200_get_supernodes(const gmrf_b200_handle *h, int64_t *super_ptr, int64_t *super_parent,
+                             int64_t *level, int64_t *row_ptr, int64_t *panel_off, int64_t *panel_ld,
+                             int64_t *upd_off, int64_t *upd_ld);
+int gmrf_b200_get_rows(const gmrf_b200_handle *h, int64_t *row_idx, int64_t *rel_idx);  /* row_ptr[nsuper] entries each */
+int gmrf_b200_get_scatter(const gmrf_b200_handle *h, int64_t *n_entries, int64_t *src, int64_t *dst);
+/* Wall-clock of the last call's phases in milliseconds (CUDA events on the handle's stream):
+ * [0] h2d of nzval, [1] numeric factorization + logdet, [2] solve, [3] selinv, [4] host analysis. */
+int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n);
+/* Numeric factor / selected inverse panels copied back to the host (tests, CholeskySqrt-style export). */
+int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles);
+int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
+
+/* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
+ * "relax_z0","relax_z1","relax_z2","nd_leaf","use_graph","naive_kernels"}. */
+int gmrf_b200_set_option(const char *key, double value);
+
+/* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`
+ * and back. gemm: C[m x n] = (beta ? C : 0) + alpha * Aop * Bop^T, where transa/transb = 0 means the operand is
+ * stored m x k (resp. n x k), 1 means k x m (resp. k x n); `flags` bits: 1 lower-only, 2 alpha=+1 (default -1),
+ * 4 add identity, 8 naive debug kernel, 16 large (128x128) tile. trsm: m > 0 solves X L^T = B, m < 0 solves
+ * X L = B (|m| rows), L lower n x n, n <= 64. */
+int gmrf_b200_test_gemm(int device, int transa, int transb, int flags, int m, int n, int k,
+                        const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
+int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info);
+int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMRF_B200_H */

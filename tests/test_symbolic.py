@@ -1,0 +1,107 @@
+"""CPU tests (no GPU): symbolic analysis of the library vs the oracle, and a host replay of its schedule tables."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+import replay
+from gmrf_b200 import _lib, spde
+from gmrf_b200.backend import _Handle, PinDenseColumns, ordering_permutation
+
+
+def _handle(Q, perm=None, ordering=_lib.ORDER_ND):
+    Q = sp.csc_matrix(Q)
+    Q.sort_indices()
+    return _Handle(Q.shape[0], Q.indptr, Q.indices, perm, ordering, device=-1)
+
+
+CASES = {
+    "grid_border": lambda: spde.grid_border_fixture(),
+    "grid3d_6": lambda: spde.grid3d_fixture(6, 6, 6),
+    "tridiag10": lambda: spde.tridiag_fixture(10),
+    "rand20": lambda: spde.random_spd_fixture(20),
+    "rand400": lambda: spde.random_spd_fixture(400, 0.02, 1),
+    "matern2d_16": lambda: spde.MaternSPDE(*spde.mesh2d(16), 1).precision(1.0, 0.5),
+    "matern3d_6": lambda: spde.MaternSPDE(*spde.mesh3d(6), 0).precision(1.0, 0.5),
+    "diag": lambda: sp.identity(7, format="csc") * 2.0,
+    "one": lambda: sp.csc_matrix(np.array([[3.0]])),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("ordering", [_lib.ORDER_ND, _lib.ORDER_AMD, _lib.ORDER_NATURAL])
+def test_colcounts_exact_vs_oracle(name, ordering):
+    Q = CASES[name]()
+    h = _handle(Q, ordering=ordering)
+    T = replay.Tables(h)
+    F = oracle.OracleFactor(Q, T.perm)
+    assert np.array_equal(T.colcount, F.colcount)          # bit-exact column counts under the same ordering
+    assert np.array_equal(T.parent, F.parent)
+    assert T.info["nnz_l"] == F.nnzL
+    replay.check_structure(T)
+    h.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_schedule_replay_matches_oracle(name):
+    Q = CASES[name]()
+    n = Q.shape[0]
+    h = _handle(Q)
+    T = replay.Tables(h)
+    F = oracle.OracleFactor(Q, T.perm)
+    Lx = replay.factor(T, Q.data)
+    assert abs(replay.logdet(T, Lx) - F.logdet()) <= 1e-12 * max(1.0, abs(F.logdet()))
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(n)
+    x = replay.solve(T, Lx, b)
+    assert np.linalg.norm(x - F.solve(b)) <= 1e-10 * np.linalg.norm(x)
+    z = rng.standard_normal(n)
+    assert np.linalg.norm(replay.solve(T, Lx, z, half=True) - F.backward_solve(z)) <= 1e-10 * np.linalg.norm(z)
+    Zx = replay.selinv(T, Lx)
+    d = replay.selinv_diag(T, Zx)
+    assert np.max(np.abs(d - F.selinv_diag()) / F.selinv_diag()) <= 1e-9
+    h.close()
+
+
+def test_user_permutation_and_errors():
+    Q = spde.grid_border_fixture()
+    n = Q.shape[0]
+    perm = np.arange(n)[::-1].copy()
+    h = _handle(Q, perm=perm)
+    T = replay.Tables(h)
+    # the final order is the user's order composed with an etree postorder: column counts are a permutation of the oracle's
+    F = oracle.OracleFactor(Q, perm)
+    assert sorted(T.colcount) == sorted(F.colcount)
+    h.close()
+    with pytest.raises(ValueError):
+        _handle(Q, perm=np.zeros(n, dtype=np.int64))
+
+
+def test_pin_dense_columns():
+    Q = spde.grid_border_fixture()
+    n = Q.shape[0]
+    p = ordering_permutation(Q, PinDenseColumns("nd"))
+    assert np.array_equal(np.sort(p), np.arange(n))
+    assert p[-1] == n - 1                       # the dense border column goes last
+    p2 = ordering_permutation(Q[: n - 1][:, : n - 1], PinDenseColumns("nd"))
+    assert np.array_equal(np.sort(p2), np.arange(n - 1))
+
+
+def test_numeric_calls_fail_without_device():
+    Q = spde.tridiag_fixture(10)
+    h = _handle(Q)
+    nz = np.ascontiguousarray(Q.data)
+    rc = h._L.gmrf_b200_refactorize(h._h, _lib.ptr(nz), nz.size)
+    assert rc == -3                             # GMRF_B200_ERR_NO_DEVICE: no CPU fallback
+    assert b"no CPU fallback" in h._L.gmrf_b200_last_error(h._h)
+    h.close()
+
+
+def test_library_exports_every_declared_symbol():
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "gmrf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gmrf_b200_[a-zA-Z_0-9]+)\s*\(", hdr)))
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert set(declared) == set(_lib.EXPORTS)
