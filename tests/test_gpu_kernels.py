@@ -1,0 +1,94 @@
+"""GPU unit tests of the dense FP64 building blocks through the C-ABI test hooks (host pointers in/out)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from gmrf_b200 import _lib
+from gmrf_b200._lib import ptr
+
+pytestmark = pytest.mark.gpu
+
+LOWER, ALPHA_POS, ADD_I, NAIVE, LARGE = 1, 2, 4, 8, 16
+
+
+def _gemm(ta, tb, flags, m, n, k, beta, rng, lda_pad=0, ldb_pad=0, ldc_pad=0, offset=0):
+    """C = (beta? C:0) + alpha * Aop Bop^T ; returns (got, want)."""
+    L = _lib.lib()
+    Aop = rng.standard_normal((m, k))
+    Bop = rng.standard_normal((n, k))
+    C0 = rng.standard_normal((m, n))
+    A = np.asfortranarray(Aop.T if ta else Aop)
+    B = np.asfortranarray(Bop.T if tb else Bop)
+    lda = A.shape[0] + lda_pad
+    ldb = B.shape[0] + ldb_pad
+    ldc = m + ldc_pad
+    Ab = np.zeros((lda, A.shape[1]), order="F"); Ab[: A.shape[0]] = A
+    Bb = np.zeros((ldb, B.shape[1]), order="F"); Bb[: B.shape[0]] = B
+    Cb = np.full((ldc, n), 7.0, order="F"); Cb[:m] = C0
+    rc = L.gmrf_b200_test_gemm(0, ta, tb, flags, m, n, k, ptr(Ab), lda, ptr(Bb), ldb, float(beta), ptr(Cb), ldc)
+    assert rc == 0, L.gmrf_b200_last_error(None)
+    alpha = 1.0 if flags & ALPHA_POS else -1.0
+    want = (C0 if beta else 0.0) + alpha * Aop @ Bop.T
+    if flags & ADD_I:
+        want = want + np.eye(m, n)
+    got = Cb[:m].copy()
+    if flags & LOWER:
+        iu = np.triu_indices(m, 1, n)
+        want = np.asarray(want).copy()
+        want[iu] = C0[iu]
+    assert np.all(Cb[m:] == 7.0)   # padding rows untouched
+    return got, want
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("size", [LARGE, 0, NAIVE])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 128, 16), (200, 136, 77), (1, 1, 1), (5, 3, 0), (257, 130, 33),
+                                   (300, 300, 300), (63, 65, 17)])
+def test_gemm_variants(ta, tb, size, shape):
+    rng = np.random.default_rng(hash((ta, tb, size, shape)) % 2**32)
+    m, n, k = shape
+    for beta, flags, pads in [(1.0, size, (0, 0, 0)), (0.0, size | ALPHA_POS, (1, 3, 1)), (1.0, size | LOWER, (2, 0, 5)),
+                              (0.0, size | ADD_I, (1, 1, 1))]:
+        got, want = _gemm(ta, tb, flags, m, n, k, beta, rng, *pads)
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(got - want).max() <= 1e-12 * scale * max(k, 1), (shape, flags, pads)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 31, 32, 33, 63, 64])
+def test_potrf_diag(n):
+    L = _lib.lib()
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    A = M @ M.T + n * np.eye(n)
+    lda = n + 3
+    Ab = np.zeros((lda, n), order="F"); Ab[:n] = A
+    info = ctypes.c_int(-1)
+    assert L.gmrf_b200_test_potrf(0, n, ptr(Ab), lda, ctypes.byref(info)) == 0
+    assert info.value == 0
+    got = np.tril(Ab[:n])
+    want = np.linalg.cholesky(A)
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max() * n
+    # not positive definite: the failing column (1-based) is reported
+    if n >= 3:
+        A2 = A.copy(); A2[2, 2] = -1.0
+        Ab = np.zeros((lda, n), order="F"); Ab[:n] = A2
+        assert L.gmrf_b200_test_potrf(0, n, ptr(Ab), lda, ctypes.byref(info)) == 0
+        assert info.value == 3
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 16, 24, 32, 50, 64])
+@pytest.mark.parametrize("m", [1, 63, 64, 65, 300])
+@pytest.mark.parametrize("var", [0, 1])
+def test_trsm_strip(n, m, var):
+    L = _lib.lib()
+    rng = np.random.default_rng(n * 1000 + m)
+    Lm = np.tril(rng.standard_normal((n, n))) + n * np.eye(n)
+    B = rng.standard_normal((m, n))
+    ldl, ldb = n + 1, m + 2
+    Lb = np.zeros((ldl, n), order="F"); Lb[:n] = Lm + np.triu(rng.standard_normal((n, n)), 1)   # junk above the diagonal
+    Bb = np.zeros((ldb, n), order="F"); Bb[:m] = B
+    assert L.gmrf_b200_test_trsm(0, -m if var else m, n, ptr(Lb), ldl, ptr(Bb), ldb) == 0
+    want = np.linalg.solve(Lm, B.T).T if var == 0 else np.linalg.solve(Lm.T, B.T).T
+    # var 0: X L^T = B -> X = B L^-T ; var 1: X L = B -> X = B L^-1
+    assert np.abs(Bb[:m] - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
