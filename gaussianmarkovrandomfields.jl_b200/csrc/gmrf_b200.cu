@@ -27,7 +27,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_POTRF, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_TRSV0, K_TRSV1, K_GEMV_N, K_GEMV_T
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_TRSV0, K_TRSV1, K_GEMV_N, K_GEMV_T, K_PANEL
 };
 
 struct Launch {
@@ -75,6 +75,8 @@ struct gmrf_b200_handle {
     SuperMeta *d_meta = nullptr;
     GemmTask *d_gemm = nullptr;
     PotrfTask *d_potrf = nullptr;
+    PanelTask *d_panel = nullptr;
+    int *d_panel_cnt = nullptr;   // per-launch reader counters of the fused panel kernel (self-resetting)
     TrsmTask *d_trsm = nullptr;
     AsmItem *d_items = nullptr;
     VecTask *d_vec = nullptr;
@@ -139,6 +141,7 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 struct Builder {
     std::vector<GemmTask> gemm;
     std::vector<PotrfTask> potrf;
+    std::vector<PanelTask> panel;
     std::vector<TrsmTask> trsm;
     std::vector<AsmItem> items;
     std::vector<VecTask> vec;
@@ -195,6 +198,27 @@ struct Builder {
             prefix.push_back((int)tot);
             tot += cdiv(t.m, TRSM_ROWS);
             trsm.push_back(t);
+        }
+        prefix.push_back((int)tot);
+        L.grid = (int)tot;
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_panel(Plan &plan, std::vector<PanelTask> &tasks) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = K_PANEL;
+        int mx = 0;
+        for (auto &t : tasks) mx = std::max(mx, t.nb);
+        L.aux = mx <= 8 ? 8 : mx <= 16 ? 16 : mx <= 32 ? 32 : 64;
+        L.task_off = (i64)panel.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = (i64)prefix.size();
+        i64 tot = 0;
+        for (auto &t : tasks) {
+            prefix.push_back((int)tot);
+            tot += std::max(1, cdiv(t.m, 64));
+            panel.push_back(t);
         }
         prefix.push_back((int)tot);
         L.grid = (int)tot;
@@ -296,12 +320,16 @@ struct Builder {
 
 constexpr int NB = POTRF_NB;
 
+// Panel factorization of a supernode (nrow x ns, column-major, in place), two-level blocking:
+//   outer blocks of OB columns: left-looking update with ALL previous columns in one large-k DMMA GEMM,
+//   inner blocks of NB=64 columns: fused potrf+trsm step, then a k=64 trailing update confined to the outer block.
+// All supernodes of a level advance in lockstep, so one launch serves every front of the level.
 void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
     const Symbolic &S = h->S;
     Plan &plan = h->factor_plan;
+    const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
     std::vector<AsmItem> its;
-    std::vector<PotrfTask> pt;
-    std::vector<TrsmTask> tt;
+    std::vector<PanelTask> pt;
     std::vector<GemmTask> gt;
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
@@ -311,31 +339,45 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                 for (i64 c0 = 0; c0 < S.nrow(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
         }
         B.add_items(plan, its, K_ASSEMBLE);
-        i64 maxsteps = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
-        for (i64 j = 0; j < maxsteps; j++) {
-            for (const i64 *sp = sb; sp < se; sp++) {
-                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
-                i64 k0 = j * NB;
-                if (k0 >= ns) continue;
-                i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
-                double *P = h->d_Lx + S.panel_off[s];
-                pt.push_back(PotrfTask{P + k0 * ld + k0, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), 0});
-                if (nrow > k1) tt.push_back(TrsmTask{P + k0 * ld + k0, P + k0 * ld + k1, (int)ld, (int)ld, (int)(nrow - k1), (int)nb});
-                if (ns > k1) {
+        i64 maxouter = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
+        for (i64 J = 0; J < maxouter; J++) {
+            const i64 J0 = J * OB;
+            if (J0 > 0) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                    if (J0 >= ns) continue;
+                    i64 J1 = std::min(J0 + OB, ns);
+                    double *P = h->d_Lx + S.panel_off[s];
                     GemmTask g;
-                    g.A = P + k0 * ld + k1;
-                    g.B = P + k0 * ld + k1;
-                    g.C = P + k1 * ld + k1;
-                    g.m = (int)(nrow - k1); g.n = (int)(ns - k1); g.k = (int)nb;
+                    g.A = P + J0; g.B = P + J0; g.C = P + J0 * ld + J0;
+                    g.m = (int)(nrow - J0); g.n = (int)(J1 - J0); g.k = (int)J0;
                     g.lda = g.ldb = g.ldc = (int)ld;
                     g.flags = GEMM_LOWER; g.pad_ = 0;
                     gt.push_back(g);
                 }
+                B.add_gemm(plan, gt, 0);
             }
-            B.add_potrf(plan, pt);
-            B.add_trsm(plan, tt, 0);
-            B.add_gemm(plan, gt, 0);
+            for (i64 jj = 0; jj < OB / NB; jj++) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                    i64 k0 = J0 + jj * NB;
+                    if (k0 >= ns) continue;
+                    i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb, J1 = std::min(J0 + OB, ns);
+                    double *P = h->d_Lx + S.panel_off[s];
+                    pt.push_back(PanelTask{P + k0 * ld + k0, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), (int)(nrow - k1)});
+                    if (J1 > k1) {
+                        GemmTask g;
+                        g.A = P + k0 * ld + k1; g.B = P + k0 * ld + k1; g.C = P + k1 * ld + k1;
+                        g.m = (int)(nrow - k1); g.n = (int)(J1 - k1); g.k = (int)nb;
+                        g.lda = g.ldb = g.ldc = (int)ld;
+                        g.flags = GEMM_LOWER; g.pad_ = 0;
+                        gt.push_back(g);
+                    }
+                }
+                B.add_panel(plan, pt);
+                B.add_gemm(plan, gt, 0);
+            }
         }
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
@@ -464,8 +506,10 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
             gt.push_back(g);
         }
         B.add_gemm(plan, gt, 2);
-        i64 maxsteps = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        // X := X L11^-1 by block back-substitution, two-level blocking (outer OB, inner NB), lockstep over the level
+        const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
+        i64 maxouter = 0;
+        for (const i64 *sp = sb; sp < se; sp++) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
         for (int pass = 0; pass < 2; pass++) {
             // pass 0: all nrow rows of [G; T'];  pass 1: the (transposed) ns x ns block only
             if (pass == 1) {
@@ -475,29 +519,51 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
                 }
                 B.add_trans(plan, tr);
             }
-            for (i64 t = 0; t < maxsteps; t++) {
+            for (i64 tJ = 0; tJ < maxouter; tJ++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
                     i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
-                    i64 nblk = cdiv(ns, NB);
-                    i64 j = nblk - 1 - t;
-                    if (j < 0) continue;
-                    i64 k0 = j * NB, nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                    i64 J = cdiv(ns, OB) - 1 - tJ;
+                    if (J < 0) continue;
+                    i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                    if (J1 >= ns) continue;
                     i64 m = pass == 0 ? nrow : ns;
                     double *Z = h->d_Zx + S.panel_off[s];
                     const double *P = h->d_Lx + S.panel_off[s];
-                    if (ns > k1) {
-                        GemmTask g;
-                        g.A = Z + k1 * ld; g.lda = (int)ld;            // X[:, later]  (m x (ns-k1))
-                        g.B = P + k0 * ld + k1; g.ldb = (int)ld;       // L11[later, K] ((ns-k1) x nb, k-contiguous)
-                        g.C = Z + k0 * ld; g.ldc = (int)ld;
-                        g.m = (int)m; g.n = (int)nb; g.k = (int)(ns - k1);
-                        g.flags = 0; g.pad_ = 0;
-                        gt.push_back(g);
-                    }
-                    tt.push_back(TrsmTask{P + k0 * ld + k0, Z + k0 * ld, (int)ld, (int)ld, (int)m, (int)nb});
+                    GemmTask g;
+                    g.A = Z + J1 * ld; g.lda = (int)ld;             // X[:, J1:ns]
+                    g.B = P + J0 * ld + J1; g.ldb = (int)ld;        // L11[J1:ns, J0:J1]  (k-contiguous)
+                    g.C = Z + J0 * ld; g.ldc = (int)ld;
+                    g.m = (int)m; g.n = (int)(J1 - J0); g.k = (int)(ns - J1);
+                    g.flags = 0; g.pad_ = 0;
+                    gt.push_back(g);
                 }
                 B.add_gemm(plan, gt, 1);
-                B.add_trsm(plan, tt, 1);
+                for (i64 tj = 0; tj < OB / NB; tj++) {
+                    for (const i64 *sp = sb; sp < se; sp++) {
+                        i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                        i64 J = cdiv(ns, OB) - 1 - tJ;
+                        if (J < 0) continue;
+                        i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                        i64 jj = cdiv(J1 - J0, NB) - 1 - tj;
+                        if (jj < 0) continue;
+                        i64 k0 = J0 + jj * NB, nb = std::min<i64>(NB, J1 - k0), k1 = k0 + nb;
+                        i64 m = pass == 0 ? nrow : ns;
+                        double *Z = h->d_Zx + S.panel_off[s];
+                        const double *P = h->d_Lx + S.panel_off[s];
+                        if (J1 > k1) {
+                            GemmTask g;
+                            g.A = Z + k1 * ld; g.lda = (int)ld;          // X[:, k1:J1]
+                            g.B = P + k0 * ld + k1; g.ldb = (int)ld;     // L11[k1:J1, K]
+                            g.C = Z + k0 * ld; g.ldc = (int)ld;
+                            g.m = (int)m; g.n = (int)nb; g.k = (int)(J1 - k1);
+                            g.flags = 0; g.pad_ = 0;
+                            gt.push_back(g);
+                        }
+                        tt.push_back(TrsmTask{P + k0 * ld + k0, Z + k0 * ld, (int)ld, (int)ld, (int)m, (int)nb});
+                    }
+                    B.add_gemm(plan, gt, 1);
+                    B.add_trsm(plan, tt, 1);
+                }
             }
         }
     }
@@ -562,6 +628,14 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_POTRF:
             potrf_diag_kernel<<<L.grid, 256, 0, st>>>(h->d_potrf + L.task_off, h->d_fail);
+            break;
+        case K_PANEL:
+            switch (L.aux) {
+                case 8: panel_factor_kernel<8><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
+                case 16: panel_factor_kernel<16><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
+                case 32: panel_factor_kernel<32><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
+                default: panel_factor_kernel<64><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
+            }
             break;
         case K_TRSM0: launch_trsm<0>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
         case K_TRSM1: launch_trsm<1>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
@@ -844,6 +918,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "relax_z1") o.relax_z[2] = value;
     else if (k == "relax_z2") o.relax_z[3] = value;
     else if (k == "use_graph") o.use_graph = (int)value;
+    else if (k == "outer_block") o.outer_block = (int)value;
     else if (k == "naive_kernels") o.naive_kernels = (int)value;
     else return GMRF_B200_ERR_ARG;
     return 0;
@@ -946,6 +1021,9 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         }
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
         TRY_RC(dev_upload(H, &H->d_potrf, B.potrf));
+        TRY_RC(dev_upload(H, &H->d_panel, B.panel));
+        TRY_RC(dev_alloc(H, &H->d_panel_cnt, B.panel.size() + 1));
+        if (cudaMemset(H->d_panel_cnt, 0, sizeof(int) * (B.panel.size() + 1)) != cudaSuccess) { H->err = "memset failed"; return fail(GMRF_B200_ERR_CUDA); }
         TRY_RC(dev_upload(H, &H->d_trsm, B.trsm));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
         TRY_RC(dev_upload(H, &H->d_vec, B.vec));
@@ -1304,6 +1382,46 @@ int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, doub
     cudaMemcpy(B, dB, (size_t)ldb * n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dL); cudaFree(dB); cudaFree(dT); cudaFree(dP);
     if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+// Device-timed GEMM micro-benchmark of the library's own kernel (tests/ and profiling only): operands are
+// allocated and filled on the device; returns the best-of-reps time in ms (CUDA events on the default stream).
+int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, int n, int k, int reps, double *ms_out) {
+    if (cudaSetDevice(device) != cudaSuccess || configure_kernels() != cudaSuccess) return test_fail("no usable device");
+    const int lda = (transa ? k : m) + 2, ldb = (transb ? k : n) + 2, ldc = m + 2;
+    size_t sa = (size_t)lda * (transa ? m : k), sb = (size_t)ldb * (transb ? n : k), sc = (size_t)ldc * n;
+    double *dA, *dB, *dC; GemmTask *dT; int *dP;
+    if (cudaMalloc(&dA, sa * 8) || cudaMalloc(&dB, sb * 8) || cudaMalloc(&dC, sc * 8) || cudaMalloc(&dT, sizeof(GemmTask)) || cudaMalloc(&dP, 8))
+        return test_fail("alloc");
+    cudaMemset(dA, 0, sa * 8); cudaMemset(dB, 0, sb * 8); cudaMemset(dC, 0, sc * 8);
+    GemmTask T;
+    T.A = dA; T.B = dB; T.C = dC; T.m = m; T.n = n; T.k = k; T.lda = lda; T.ldb = ldb; T.ldc = ldc;
+    T.flags = (flags & 1 ? GEMM_LOWER : 0); T.pad_ = 0;
+    const bool large = (flags & 16) != 0;
+    int BM = large ? 128 : 64;
+    int tiles = cdiv(m, BM) * cdiv(n, BM);
+    int pf[2] = {0, tiles};
+    cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaEventRecord(e0, 0);
+        if (!transa && !transb) launch_gemm<false, false>(large, false, dT, dP, 1, tiles, 0);
+        else if (!transa && transb) launch_gemm<false, true>(large, false, dT, dP, 1, tiles, 0);
+        else launch_gemm<true, true>(large, false, dT, dP, 1, tiles, 0);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) best = std::min(best, ms);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT); cudaFree(dP);
+    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    if (ms_out) *ms_out = best;
     return 0;
 }
 

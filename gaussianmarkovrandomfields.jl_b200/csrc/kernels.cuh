@@ -48,6 +48,13 @@ struct TrsmTask {        // B[m x nb] := B * L^-T (variant 0) or B * L^-1 (varia
     int ldl, ldb, m, nb;
 };
 
+struct PanelTask {       // fused block-column step: D := chol(D) (nb x nb), rows below := rows * D^-T
+    double *D;           // diagonal block; the m rows below start at D + nb, same leading dimension
+    int ld, nb;
+    int col0;            // global (permuted) column of the block's first column, for pivot reporting
+    int m;               // rows below the diagonal block
+};
+
 struct AsmItem {         // one column tile of one parent front
     int super;
     int col0;            // first front column of the tile (0 .. nrow)
@@ -324,12 +331,13 @@ trsm_strip_kernel(const TrsmTask *__restrict__ tasks, const int *__restrict__ ti
     const TrsmTask T = tasks[t];
     const int strip = blockIdx.x - tile_prefix[t];
     const int nb = T.nb, tid = threadIdx.x;
-    for (int e = tid; e < NBT * NBT; e += TRSM_ROWS) {
-        int i = e % NBT, j = e / NBT;
-        double v = 0.0;
-        if (i < nb && j < nb && i >= j) v = T.L[i + (long long)j * T.ldl];
-        if (i == j && i >= nb) v = 1.0;
-        sL[i][j] = v;
+    if (tid < NBT) {   // one row of L per thread: NBT independent loads in flight (static unroll), identity padding
+#pragma unroll
+        for (int k = 0; k < NBT; k++) {
+            double v = (k == tid) ? 1.0 : 0.0;
+            if (tid < nb && k < nb && k <= tid) v = T.L[tid + (long long)k * T.ldl];
+            sL[tid][k] = v;
+        }
     }
     __syncthreads();
     const int row = strip * TRSM_ROWS + tid;
@@ -360,6 +368,92 @@ trsm_strip_kernel(const TrsmTask *__restrict__ tasks, const int *__restrict__ ti
 #pragma unroll
     for (int j = 0; j < NBT; j++)
         if (j < nb) bp[(long long)j * T.ldb] = x[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused block-column step of the panel factorization (latency-critical: one launch per 64 columns of a chain):
+// every CTA re-factors the nb x nb diagonal block redundantly (identical arithmetic -> identical bits), one row
+// per thread held in registers, then solves its own 64-row strip X L^T = B by forward substitution.
+// CTA 0 of a task writes the factored diagonal block back and reports non-positive pivots.
+// ------------------------------------------------------------------------------------------------
+template <int NBT>
+__global__ void __launch_bounds__(64)
+panel_factor_kernel(const PanelTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks,
+                    int *__restrict__ fail_col, int *__restrict__ readers) {
+    __shared__ double sL[NBT][NBT + 1];
+    __shared__ double scol[64];
+    __shared__ double s_piv;
+    __shared__ int s_writer;
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const PanelTask T = tasks[t];
+    const int strip = blockIdx.x - tile_prefix[t];
+    const int ntiles = tile_prefix[t + 1] - tile_prefix[t];
+    const int nb = T.nb, tid = threadIdx.x;
+    {
+        double a[NBT];   // row `tid` of the diagonal block (identity-padded beyond nb)
+#pragma unroll
+        for (int k = 0; k < NBT; k++) {
+            double v = (k == tid) ? 1.0 : 0.0;
+            if (tid < nb && k < nb && k <= tid) v = T.D[tid + (long long)k * T.ld];
+            a[k] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < NBT; j++) {
+            if (tid == j) {
+                const double d = a[j];
+                if (!(d > 0.0) && strip == 0 && j < nb) atomicMin(fail_col, T.col0 + j + 1);
+                s_piv = sqrt(d);
+            }
+            __syncthreads();
+            const double piv = s_piv;
+            double lij = 0.0;
+            if (tid == j) a[j] = piv;
+            else if (tid > j && tid < NBT) { lij = a[j] / piv; a[j] = lij; scol[tid] = lij; }
+            __syncthreads();
+#pragma unroll
+            for (int k = j + 1; k < NBT; k++)
+                if (k <= tid) a[k] -= lij * scol[k];
+        }
+        if (tid < NBT) {
+#pragma unroll
+            for (int k = 0; k < NBT; k++) sL[tid][k] = (k <= tid) ? a[k] : 0.0;
+        }
+        // In-place write-back of the factored diagonal block: only the LAST CTA of this task to get here writes,
+        // because every other CTA has then finished reading the unfactored block (all CTAs hold identical bits).
+        __syncthreads();
+        if (tid == 0) {
+            int last = 1;
+            if (ntiles > 1) {
+                __threadfence();
+                last = (atomicAdd(readers + t, 1) == ntiles - 1);
+                if (last) readers[t] = 0;   // re-arm for the next replay of the graph
+            }
+            s_writer = last;
+        }
+        __syncthreads();
+        if (s_writer && tid < nb) {
+#pragma unroll
+            for (int k = 0; k < NBT; k++)
+                if (k <= tid) T.D[tid + (long long)k * T.ld] = a[k];
+        }
+    }
+    const int row = strip * 64 + tid;
+    if (row >= T.m) return;
+    double x[NBT];
+    double *bp = T.D + nb + row;
+#pragma unroll
+    for (int j = 0; j < NBT; j++) x[j] = (j < nb) ? bp[(long long)j * T.ld] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NBT; j++) {
+        double s0 = x[j], s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) { s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1]; }
+        if (j & 1) s0 -= x[j - 1] * sL[j][j - 1];
+        x[j] = (s0 + s1) / sL[j][j];
+    }
+#pragma unroll
+    for (int j = 0; j < NBT; j++)
+        if (j < nb) bp[(long long)j * T.ld] = x[j];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ struct Options {
     double relax_n[3] = {8, 32, 96};
     double relax_z[4] = {0.8, 0.3, 0.1, 0.05};
     int use_graph = 1;
+    int outer_block = 256;   // outer panel block (columns) of the two-level blocked factorization
     int naive_kernels = 0;
 };
 Options &global_options();

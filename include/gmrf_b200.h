@@ -142,7 +142,7 @@ int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubl
 int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","nd_leaf","use_graph","naive_kernels"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`
@@ -154,6 +154,9 @@ int gmrf_b200_test_gemm(int device, int transa, int transb, int flags, int m, in
                         const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
 int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info);
 int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb);
+/* Device-timed micro-benchmark of the library's own FP64 GEMM kernel (zero-filled device operands, best of
+ * `reps`, CUDA events): used to compare against the measured cuBLAS DGEMM peak in profiles/. */
+int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, int n, int k, int reps, double *ms_out);
 
 #ifdef __cplusplus
 }
