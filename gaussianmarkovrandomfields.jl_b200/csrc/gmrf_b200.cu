@@ -157,13 +157,15 @@ struct Builder {
         std::vector<GemmTask> small, large;
         for (auto &t : tasks) {
             if (t.m <= 0 || t.n <= 0) continue;
-            bool big = !naive && (i64)t.m * t.n >= 256LL * 256LL && t.m >= 128 && t.n >= 96;
+            // measured on B200 (profiles/r01_gemm_variants.log): the 64x64 tile (4 CTAs/SM) wins everywhere except very
+            // large square-ish products, where the 128x64 tile (warp tile 64x32) is ~4% faster
+            bool big = !naive && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024;
             (big ? large : small).push_back(t);
         }
         for (int pass = 0; pass < 2; pass++) {
             auto &v = pass ? large : small;
             if (v.empty()) continue;
-            int BM = naive ? 16 : (pass ? 128 : 64), BN = BM;
+            int BM = naive ? 16 : (pass ? 128 : 64), BN = naive ? 16 : 64;
             Launch L;
             L.kind = (variant == 0 ? K_GEMM_NN_S : variant == 1 ? K_GEMM_NT_S : K_GEMM_TT_S) + pass;
             L.aux = 0;
@@ -588,7 +590,7 @@ cudaError_t configure_gemm_tile() {
 }
 cudaError_t configure_kernels() {
     cudaError_t e;
-    if ((e = configure_gemm_tile<128, 128, 2, 4>())) return e;
+    if ((e = configure_gemm_tile<128, 64, 2, 2>())) return e;
     if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
     return cudaSuccess;
 }
@@ -596,7 +598,7 @@ cudaError_t configure_kernels() {
 template <bool TA, bool TB>
 void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
     if (naive) gemm_naive_kernel<TA, TB><<<grid, 256, 0, st>>>(tasks, prefix, ntasks);
-    else if (large) launch_gemm_t<128, 128, 2, 4, TA, TB>(tasks, prefix, ntasks, grid, st);
+    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
     else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
 }
 
@@ -608,6 +610,13 @@ void launch_trsm(int nbt, const TrsmTask *tasks, const int *prefix, int ntasks, 
         case 32: trsm_strip_kernel<VAR, 32><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
         default: trsm_strip_kernel<VAR, 64><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
     }
+}
+
+template <int BM, int BN, int WGM, int WGN, int KT, int ST>
+void launch_gemm_exp(const GemmTask *tasks, const int *prefix, int grid) {
+    auto kern = gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, KT, ST>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, KT, ST>());
+    kern<<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, KT, ST>()>>>(tasks, prefix, 1);
 }
 
 struct TableSet {
@@ -1324,8 +1333,8 @@ int gmrf_b200_test_gemm(int device, int transa, int transb, int lower, int m, in
     T.flags = (lower & 1 ? GEMM_LOWER : 0) | (beta == 0.0 ? GEMM_BETA0 : 0) | (lower & 2 ? GEMM_ALPHA_POS : 0) | (lower & 4 ? GEMM_ADD_I : 0);
     T.pad_ = 0;
     const bool naive = (lower & 8) != 0, large = (lower & 16) != 0;
-    int BM = naive ? 16 : large ? 128 : 64;
-    int tiles = cdiv(m, BM) * cdiv(n, BM);
+    int BM = naive ? 16 : large ? 128 : 64, BN = naive ? 16 : 64;
+    int tiles = cdiv(m, BM) * cdiv(n, BN);
     int pf[2] = {0, tiles};
     cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
     cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
@@ -1399,8 +1408,20 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
     T.A = dA; T.B = dB; T.C = dC; T.m = m; T.n = n; T.k = k; T.lda = lda; T.ldb = ldb; T.ldc = ldc;
     T.flags = (flags & 1 ? GEMM_LOWER : 0); T.pad_ = 0;
     const bool large = (flags & 16) != 0;
-    int BM = large ? 128 : 64;
-    int tiles = cdiv(m, BM) * cdiv(n, BM);
+    const int variant = (flags >> 8) & 0xff;   // experimental tile configurations (NN only)
+    int BM = large ? 128 : 64, BN = 64;
+    switch (variant) {
+        case 1: BM = 128; BN = 64; break;
+        case 2: BM = 128; BN = 128; break;
+        case 3: BM = 64; BN = 64; break;
+        case 4: BM = 128; BN = 64; break;
+        case 5: BM = 64; BN = 128; break;
+        case 6: BM = 128; BN = 128; break;
+        case 7: BM = 64; BN = 64; break;
+        case 8: BM = 128; BN = 64; break;
+        default: break;
+    }
+    int tiles = cdiv(m, BM) * cdiv(n, BN);
     int pf[2] = {0, tiles};
     cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
     cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
@@ -1409,7 +1430,15 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
     float best = 1e30f;
     for (int r = 0; r < reps + 1; r++) {
         cudaEventRecord(e0, 0);
-        if (!transa && !transb) launch_gemm<false, false>(large, false, dT, dP, 1, tiles, 0);
+        if (variant == 1) launch_gemm_exp<128, 64, 2, 2, 16, 3>(dT, dP, tiles);        // 4 warps, warp tile 64x32
+        else if (variant == 2) launch_gemm_exp<128, 128, 4, 4, 16, 3>(dT, dP, tiles);  // 16 warps, warp tile 32x32
+        else if (variant == 3) launch_gemm_exp<64, 64, 2, 2, 32, 3>(dT, dP, tiles);    // deeper K tile
+        else if (variant == 4) launch_gemm_exp<128, 64, 4, 2, 16, 3>(dT, dP, tiles);   // 8 warps, warp tile 32x32
+        else if (variant == 5) launch_gemm_exp<64, 128, 2, 4, 16, 3>(dT, dP, tiles);   // 8 warps, warp tile 32x32
+        else if (variant == 6) launch_gemm_exp<128, 128, 2, 4, 16, 4>(dT, dP, tiles);  // production large + 4 stages
+        else if (variant == 7) launch_gemm_exp<64, 64, 2, 2, 16, 4>(dT, dP, tiles);    // production small + 4 stages
+        else if (variant == 8) launch_gemm_exp<128, 64, 4, 2, 32, 3>(dT, dP, tiles);
+        else if (!transa && !transb) launch_gemm<false, false>(large, false, dT, dP, 1, tiles, 0);
         else if (!transa && transb) launch_gemm<false, true>(large, false, dT, dP, 1, tiles, 0);
         else launch_gemm<true, true>(large, false, dT, dP, 1, tiles, 0);
         cudaEventRecord(e1, 0);

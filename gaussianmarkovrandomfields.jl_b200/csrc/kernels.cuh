@@ -118,14 +118,11 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // CTA tile BM x BN, warp grid WGM x WGN, K tile 16, 3-stage cp.async pipeline.
 // smem tiles are stored k-major: As[stage][kk][m] (+4 padding -> conflict-free 8-byte fragment loads).
 // ------------------------------------------------------------------------------------------------
-constexpr int GEMM_KT = 16;
-constexpr int GEMM_STAGES = 3;
-
-template <int BM, int BN>
-constexpr int gemm_smem_bytes() { return GEMM_STAGES * GEMM_KT * ((BM + 4) + (BN + 4)) * (int)sizeof(double); }
+template <int BM, int BN, int KT = 16, int ST = 3>
+constexpr int gemm_smem_bytes() { return ST * KT * ((BM + 4) + (BN + 4)) * (int)sizeof(double); }
 
 // Load a [KT x BX] tile (k-major in smem) of an operand. TR=false: global is x-contiguous; TR=true: k-contiguous.
-template <int BX, int NT, bool TR>
+template <int BX, int NT, bool TR, int GEMM_KT>
 __device__ __forceinline__ void gemm_load_tile(double *__restrict__ s, const double *__restrict__ g, int ld,
                                                int x0, int xmax, int k0, int kmax, bool aligned16, int tid) {
     constexpr int LDS = BX + 4;
@@ -160,7 +157,7 @@ __device__ __forceinline__ void gemm_load_tile(double *__restrict__ s, const dou
     }
 }
 
-template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
+template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, int GEMM_STAGES = 3>
 __global__ void __launch_bounds__(WGM *WGN * 32)
 gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
     constexpr int NT = WGM * WGN * 32;
@@ -195,8 +192,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; s++) {
         if (s < nk) {
-            gemm_load_tile<BM, NT, TA>(As + s * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, s * GEMM_KT, T.k, a16, tid);
-            gemm_load_tile<BN, NT, TB>(Bs + s * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, s * GEMM_KT, T.k, b16, tid);
+            gemm_load_tile<BM, NT, TA, GEMM_KT>(As + s * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, s * GEMM_KT, T.k, a16, tid);
+            gemm_load_tile<BN, NT, TB, GEMM_KT>(Bs + s * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, s * GEMM_KT, T.k, b16, tid);
         }
         cp_async_commit();
     }
@@ -207,8 +204,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
             int nx = kt + GEMM_STAGES - 1;
             if (nx < nk) {
                 int st = nx % GEMM_STAGES;
-                gemm_load_tile<BM, NT, TA>(As + st * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, nx * GEMM_KT, T.k, a16, tid);
-                gemm_load_tile<BN, NT, TB>(Bs + st * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, nx * GEMM_KT, T.k, b16, tid);
+                gemm_load_tile<BM, NT, TA, GEMM_KT>(As + st * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, nx * GEMM_KT, T.k, a16, tid);
+                gemm_load_tile<BN, NT, TB, GEMM_KT>(Bs + st * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, nx * GEMM_KT, T.k, b16, tid);
             }
             cp_async_commit();
         }
@@ -382,6 +379,7 @@ panel_factor_kernel(const PanelTask *__restrict__ tasks, const int *__restrict__
                     int *__restrict__ fail_col, int *__restrict__ readers) {
     __shared__ double sL[NBT][NBT + 1];
     __shared__ double scol[64];
+    __shared__ double sinv[64];
     __shared__ double s_piv;
     __shared__ int s_writer;
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
@@ -399,16 +397,18 @@ panel_factor_kernel(const PanelTask *__restrict__ tasks, const int *__restrict__
         }
 #pragma unroll
         for (int j = 0; j < NBT; j++) {
+            // critical path per step: rsqrt of the pivot -> scale column j -> update column j+1 (no divisions)
             if (tid == j) {
                 const double d = a[j];
                 if (!(d > 0.0) && strip == 0 && j < nb) atomicMin(fail_col, T.col0 + j + 1);
-                s_piv = sqrt(d);
+                const double r = rsqrt(d);
+                s_piv = r;
+                a[j] = d * r;          // sqrt(d)
+                sinv[j] = r;           // 1 / L_jj, reused by the strip solve below
             }
             __syncthreads();
-            const double piv = s_piv;
             double lij = 0.0;
-            if (tid == j) a[j] = piv;
-            else if (tid > j && tid < NBT) { lij = a[j] / piv; a[j] = lij; scol[tid] = lij; }
+            if (tid > j && tid < NBT) { lij = a[j] * s_piv; a[j] = lij; scol[tid] = lij; }
             __syncthreads();
 #pragma unroll
             for (int k = j + 1; k < NBT; k++)
@@ -445,11 +445,15 @@ panel_factor_kernel(const PanelTask *__restrict__ tasks, const int *__restrict__
     for (int j = 0; j < NBT; j++) x[j] = (j < nb) ? bp[(long long)j * T.ld] : 0.0;
 #pragma unroll
     for (int j = 0; j < NBT; j++) {
-        double s0 = x[j], s1 = 0.0;
+        double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) { s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1]; }
-        if (j & 1) s0 -= x[j - 1] * sL[j][j - 1];
-        x[j] = (s0 + s1) / sL[j][j];
+        for (int k = 0; k + 3 < j; k += 4) {
+            s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1];
+            s2 -= x[k + 2] * sL[j][k + 2]; s3 -= x[k + 3] * sL[j][k + 3];
+        }
+#pragma unroll
+        for (int k = (j / 4) * 4; k < j; k++) s0 -= x[k] * sL[j][k];
+        x[j] = ((s0 + s1) + (s2 + s3)) * sinv[j];
     }
 #pragma unroll
     for (int j = 0; j < NBT; j++)

@@ -110,7 +110,24 @@ def gemm_bench():
                 print(f"   gemm [{nm}] tile={'128' if large else '64'} m={m} n={n} k={k}: {ms.value:.3f} ms  {2.0 * m * n * k / ms.value / 1e9:.2f} TFLOP/s", flush=True)
 
 
+def gemm_variants():
+    import ctypes
+    L = _lib.lib()
+    names = {0: "prod 64x64 2x2 KT16 ST3", 1: "128x64 2x2(w64x32) KT16 ST3", 2: "128x128 4x4(w32x32) KT16 ST3", 3: "64x64 2x2 KT32 ST3",
+             4: "128x64 4x2(w32x32) KT16 ST3", 5: "64x128 2x4(w32x32) KT16 ST3", 6: "128x128 2x4 KT16 ST4", 7: "64x64 2x2 KT16 ST4",
+             8: "128x64 4x2 KT32 ST3", 99: "prod 128x128 2x4 KT16 ST3"}
+    for (m, n, k) in [(8192, 8192, 8192), (16384, 256, 8192), (8192, 8192, 256), (16384, 192, 64), (12000, 12000, 64)]:
+        for v in (0, 99, 1, 2, 3, 4, 5, 6, 7, 8):
+            flags = 16 if v == 99 else (v << 8)
+            ms = ctypes.c_double()
+            rc = L.gmrf_b200_bench_gemm(0, 0, 0, flags, m, n, k, 3, ctypes.byref(ms))
+            assert rc == 0, L.gmrf_b200_last_error(None)
+            print(f"   variant {names[v]:32s} m={m} n={n} k={k}: {ms.value:8.3f} ms  {2.0 * m * n * k / ms.value / 1e9:6.2f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
+    if "--gemm-variants" in sys.argv:
+        gemm_variants()
     if "--gemm" in sys.argv:
         gemm_bench()
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
