@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 sparse-Cholesky hot path (BASELINE.json metric).
+
+Workload (N = 1, default): BASELINE.json configs[3] -- 3D Matern SPDE (smoothness 0 => alpha = 2) on a structured
+100^3-cell tetrahedral mesh of [-1,1]^3, n = 1,030,301 latent dofs, nnz(Q) = 65.0 M; one STEP = one numeric
+refactorization (values -> supernodal LL^T) with the fused log-determinant, same sparsity pattern, new
+hyperparameters (tau, range) every step. Selected inversion (marginal variances) is timed separately and reported
+in `selinv_ms`.  N > 1: the path does not shard a single factorization (north star: "a single factorization stays
+on one GPU"); the ranks evaluate independent hyperparameter points of the same model (one handle per GPU, same
+symbolic analysis) and all-gather the log-determinants over NCCL -- weak scaling, no data-path collective.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells 100] [--selinv-reps 1]
+
+`value`      factorizations (+logdet) per second, nzval resident in HBM (gmrf_b200_refactorize_device), whole job.
+`e2e`        same through the public API (GMRFWorkspace.update_precision_values + logdet) from HOST buffers:
+             host copy into ws.Q.nzval, H2D of nnz(Q) doubles, factorization, D2H of the scalar.
+`roofline`   the DMMA GEMM kernel (dominant): algorithmic GEMM flops / summed launch time (CUDA events around every
+             launch of one extra refactorization) against the measured cuBLAS FP64 peak of this pool's B200.
+`cpu_baseline` multithreaded BLAS-3 supernodal Cholesky on the host cores (oracle/cpu_baseline.py, "port"): bounded
+             sample (a smaller mesh of the same recipe), scaled to the full problem by the algorithmic flop count.
+--impl reference  times that CPU port alone (all host threads) and prints the same JSON line with impl=reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Cholesky+logdet/s, 1M-dof 3D Matern SPDE Q (selinv ms and FP64 TFLOP/s alongside)"
+UNIT = "factorizations/s"
+FP64_PEAK_TFLOPS = 36.09      # cuBLAS DGEMM 16384^3 measured on this pool's B200: profiles/r01_fp64_probe.json
+FP64_PEAK_SOURCE = ("profiles/r01_fp64_probe.json (cuBLAS DGEMM 16384^3, this pool's B200); MEASURED_PEAKS.json "
+                    "carries only HBM and bf16, so the FP64 denominator is this repo's own probe")
+
+
+def _peak():
+    p = os.path.join(ROOT, "profiles", "r01_fp64_probe.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["cublas_dgemm_nt_16384_tflops"])
+    except Exception:
+        return FP64_PEAK_TFLOPS
+
+
+def theta_for(step: int, rank: int):
+    """Hyperparameter point (tau, range) of the sweep evaluated at (step, rank): a 16x16 log grid."""
+    i = (step * 7 + rank * 3) % 16
+    j = (step * 5 + rank * 11) % 16
+    tau = 10.0 ** (-1.0 + 2.0 * i / 15.0)
+    rng = 10.0 ** (-1.3 + 1.3 * j / 15.0)
+    return tau, max(rng, 0.12)
+
+
+def build_model(cells: int):
+    from gmrf_b200 import spde
+    coords, tets = spde.mesh3d(cells)
+    model = spde.MaternSPDE(coords, tets, smoothness=0)
+    perm = spde.geometric_nd_perm((cells + 1,) * 3, leaf=64, width=2)
+    return model, perm
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                out = [o.strip() for o in out]
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for nm, v in zip(names, out[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_baseline_run(sample_cells: int, full_flops: float, reps: int = 1):
+    """Time the CPU supernodal port on a smaller mesh of the same recipe; scale to the full problem by flops."""
+    import oracle  # noqa: F401  (test/bench infrastructure -- the only place bench.py touches oracle/)
+    from oracle.cpu_baseline import CpuSupernodalCholesky
+    from gmrf_b200 import _lib
+    from gmrf_b200.backend import _Handle
+    from gmrf_b200.introspect import Tables
+    model, perm = build_model(sample_cells)
+    Q = model.precision(*theta_for(0, 0))
+    h = _Handle(Q.shape[0], Q.indptr, Q.indices, perm, _lib.ORDER_ND, device=-1)   # host-only symbolic analysis
+    T = Tables(h)
+    cpu = CpuSupernodalCholesky(T)
+    cpu.refactorize(Q.data)                       # warm-up (page faults, thread pools)
+    best = min(cpu.refactorize(model.values(*theta_for(r + 1, 0))) for r in range(max(1, reps)))
+    flops = float(T.info["flops_chol"])
+    gflops = flops / best / 1e9
+    value = (gflops * 1e9) / full_flops
+    sample = (f"3D Matern alpha=2, {sample_cells}^3 cells (n={Q.shape[0]}, {flops:.3g} flop) factorized in {best:.2f} s "
+              f"= {gflops:.0f} GFLOP/s on {cpu.threads} threads; scaled to the {full_flops:.3g}-flop workload")
+    h.close()
+    return {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port", "sample": sample,
+            "gflops": gflops, "sample_seconds": best}
+
+
+def full_flops_estimate(cells: int) -> float:
+    """Algorithmic flop count of the full workload without a GPU (host-only symbolic analysis)."""
+    from gmrf_b200 import _lib
+    from gmrf_b200.backend import _Handle
+    model, perm = build_model(cells)
+    h = _Handle(model.n, model.colptr, model.rowval, perm, _lib.ORDER_ND, device=-1)
+    fl = float(h.info()["flops_chol"])
+    h.close()
+    return fl
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    full = full_flops_estimate(args.cells)
+    sample_cells = min(args.cells, args.cpu_sample_cells)
+    # every step is one bounded-sample factorization
+    import oracle  # noqa: F401
+    from oracle.cpu_baseline import CpuSupernodalCholesky
+    from gmrf_b200 import _lib
+    from gmrf_b200.backend import _Handle
+    from gmrf_b200.introspect import Tables
+    model, perm = build_model(sample_cells)
+    h = _Handle(model.n, model.colptr, model.rowval, perm, _lib.ORDER_ND, device=-1)
+    T = Tables(h)
+    cpu = CpuSupernodalCholesky(T)
+    flops = float(T.info["flops_chol"])
+    for w in range(args.warmup):
+        cpu.refactorize(model.values(*theta_for(w, 0)))
+    t = 0.0
+    for k in range(args.steps):
+        t += cpu.refactorize(model.values(*theta_for(args.warmup + k, 0)))
+    per = t / args.steps
+    value = (flops / per) / full
+    sample = (f"each step = one numeric Cholesky+logdet of the same recipe at {sample_cells}^3 cells (n={model.n}, {flops:.3g} flop, "
+              f"{per:.2f} s/step = {flops / per / 1e9:.0f} GFLOP/s on {cpu.threads} threads), scaled by flops to the {full:.3g}-flop workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D Matern SPDE alpha=2, {args.cells}^3-cell tetrahedral mesh, n={(args.cells + 1) ** 3}, numeric Cholesky+logdet",
+                   "cpu_path": "oracle/supernodal_cpu.c (BLAS-3 supernodal multifrontal, OpenBLAS from SciPy, OpenMP): the reference's CHOLMOD "
+                               "path cannot run here (no Julia / libcholmod in the image)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gmrf_b200.workspace import GMRFWorkspace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgmrf_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    t0 = time.time()
+    model, perm = build_model(args.cells)
+    # two hyperparameter points are kept resident and alternated; every step re-factorizes different values
+    nz_host = [np.ascontiguousarray(model.values(*theta_for(k, rank))) for k in range(2)]
+    Q0 = model.precision(*theta_for(0, rank))
+    ws = GMRFWorkspace(Q0, ordering=perm, device=local)           # symbolic analysis + first factorization
+    be = ws.backend
+    info = be.info()
+    setup_s = time.time() - t0
+    nnz = nz_host[0].size
+    nz_dev = [torch.from_numpy(a).cuda() for a in nz_host]
+    flops = float(info["flops_chol"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: nzval resident in HBM ------------------------------------------------------------------
+    logdets = []
+    for w in range(args.warmup):
+        be.refactorize_device(nz_dev[w % 2].data_ptr(), nnz)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms = 0.0
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        be.refactorize_device(nz_dev[k % 2].data_ptr(), nnz)
+        dev_ms += be.timings()["factor_ms"]                     # CUDA events on the handle's stream
+        logdets.append(be.compute_logdet())
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
+    status = be.status
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = t.tolist()
+        # the only exchange of the sharded sweep: gather the per-point log-determinants
+        mine = torch.tensor(logdets, device="cuda", dtype=torch.float64)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+    ms_per_step = dev_ms / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- e2e: public API from host buffers -----------------------------------------------------------------
+    for w in range(max(1, args.warmup // 2)):
+        ws.update_precision_values(nz_host[w % 2]); ws.logdet()
+    barrier()
+    t_e = time.perf_counter()
+    for k in range(args.steps):
+        ws.update_precision_values(nz_host[k % 2])
+        ws.logdet()
+    barrier()
+    e2e_s = time.perf_counter() - t_e
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * args.steps / e2e_s
+    h2d_ms = be.timings()["h2d_ms"]
+
+    # ---- selected inversion (marginal variances) ---------------------------------------------------------------
+    selinv_ms = None
+    if args.selinv_reps > 0:
+        ts = []
+        for r in range(args.selinv_reps + 1):
+            be.refactorize_device(nz_dev[r % 2].data_ptr(), nnz)
+            be.selinv_compute()
+            ts.append(be.timings()["selinv_ms"])
+        selinv_ms = min(ts[1:]) if len(ts) > 1 else ts[0]
+        if world > 1:
+            t = torch.tensor([selinv_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            selinv_ms = float(t.item())
+
+    # ---- roofline of the dominant kernel (live CUDA events around every launch of one more refactorization) ------
+    prof = be.profile_refactorize()
+    gemm_ms, gemm_launches, gemm_flops = prof["ms"]["gemm"], prof["launches"]["gemm"], prof["gemm_flops"]
+    peak = _peak()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_run(min(args.cells, args.cpu_sample_cells), flops)
+            except Exception as e:  # the baseline is reporting only; never let it sink the GPU number
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"3D Matern SPDE alpha=2 (smoothness 0), {args.cells}^3-cell tetrahedral mesh of [-1,1]^3, "
+                            f"n={info['n']}, nnz(Q)={info['nnz_q']}: numeric supernodal Cholesky + fused logdet per step "
+                            f"(BASELINE.json configs[3])",
+                "ordering": "geometric nested dissection passed as ordering=perm (host side, once per pattern)",
+                "nnz_L": info["nnz_l"], "nnz_L_stored": info["nnz_l_stored"], "flops_per_step": flops,
+                "supernodes": info["nsuper"], "levels": info["nlevels"], "max_front": info["max_front"],
+                "device_GiB": round(info["device_bytes"] / 2 ** 30, 2),
+                "l2": "inputs larger than L2 (nzval 0.5 GB, factor 39 GB stream through the 126 MB L2 every step)",
+                "parallelism": "1 factorization per GPU" if world == 1 else
+                               f"{world} independent hyperparameter points, one per GPU, all_gather of logdets (NCCL)",
+                "setup_seconds": round(setup_s, 1), "analysis_ms": round(be.timings()["analysis_ms"], 1),
+            },
+            "fp64_tflops": flops / (ms_per_step * 1e-3) / 1e12,
+            "selinv_ms": selinv_ms,
+            "selinv_fp64_tflops_equiv": (2.0 * flops / (selinv_ms * 1e-3) / 1e12) if selinv_ms else None,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "logdet": logdets[-1], "factor_status": status,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nnz * 8), "d2h_bytes_per_step": 12,
+                    "h2d_ms": h2d_ms, "api": "GMRFWorkspace.update_precision_values(nzval_host); logdet(ws)"},
+            "gpu_launches": int(args.steps * info["graph_nodes"]),
+            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 via mma.sync.m8n8k4.f64)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "peak_source": FP64_PEAK_SOURCE,
+                         "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
+                         "share_of_step": gemm_ms / sum(prof["ms"].values()) if sum(prof["ms"].values()) > 0 else None,
+                         "other_kernels_ms": {k: v for k, v in prof["ms"].items() if k != "gemm"}},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=100, help="cells per axis of the 3D mesh (100 -> 1,030,301 dofs)")
+    ap.add_argument("--selinv-reps", type=int, default=1)
+    ap.add_argument("--cpu-sample-cells", type=int, default=56)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,7 @@ struct gmrf_b200_handle {
     double logdet = 0.0;
     double t_ms[5] = {0, 0, 0, 0, 0};
     size_t device_bytes = 0;
+    double gemm_flops_factor = 0, gemm_flops_selinv = 0;
 
     // device arrays
     double *d_Lx = nullptr, *d_upd = nullptr, *d_nz = nullptr, *d_Zx = nullptr, *d_zw = nullptr;
@@ -150,6 +151,7 @@ struct Builder {
     std::vector<int> superlist;
     std::vector<int> prefix;
     bool naive = false;
+    double gemm_flops = 0;
 
     // GEMM launches: tasks are split into a small-tile and a large-tile launch
     void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/) {
@@ -157,6 +159,7 @@ struct Builder {
         std::vector<GemmTask> small, large;
         for (auto &t : tasks) {
             if (t.m <= 0 || t.n <= 0) continue;
+            gemm_flops += 2.0 * t.m * (double)t.n * t.k * ((t.flags & GEMM_LOWER) ? 0.5 * (1.0 + 1.0 / std::max(1, t.m)) * ((double)t.n <= t.m ? (2.0 - (double)t.n / t.m) : 1.0) : 1.0);
             // measured on B200 (profiles/r01_gemm_variants.log): the 64x64 tile (4 CTAs/SM) wins everywhere except very
             // large square-ish products, where the 128x64 tile (warp tile 64x32) is ~4% faster
             bool big = !naive && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024;
@@ -764,7 +767,7 @@ int build_selinv_tables(gmrf_b200_handle *h) {
     const Symbolic &S = h->S;
     int rc;
     if ((rc = dev_alloc(h, &h->d_Zx, (size_t)S.panel_total))) return rc;
-    if ((rc = dev_alloc(h, &h->d_zw, (size_t)S.zw_total))) return rc;
+    h->d_zw = h->d_upd;
     CUDA_TRY(h, cudaMemset(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total));
     Builder B;
     B.naive = h->opt.naive_kernels != 0;
@@ -988,7 +991,9 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
     int rc;
 #define TRY_RC(x) do { rc = (x); if (rc) return fail(rc); } while (0)
     TRY_RC(dev_alloc(H, &H->d_Lx, (size_t)S.panel_total));
-    TRY_RC(dev_alloc(H, &H->d_upd, (size_t)S.upd_total));
+    // one pool serves the update matrices of the factorization and, afterwards, the gathered Z[R,R] blocks of the
+    // selected inversion (the two phases never overlap)
+    TRY_RC(dev_alloc(H, &H->d_upd, (size_t)std::max(S.upd_total, S.zw_total)));
     TRY_RC(dev_alloc(H, &H->d_nz, (size_t)S.nnzA));
     TRY_RC(dev_alloc(H, &H->d_y, (size_t)(S.n * H->rhs_block)));
     TRY_RC(dev_alloc(H, &H->d_uvec, (size_t)(S.uvec_total * H->rhs_block)));
@@ -1028,6 +1033,7 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
             H->err = e.what();
             return fail(GMRF_B200_ERR_ARG);
         }
+        H->gemm_flops_factor = B.gemm_flops;
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
         TRY_RC(dev_upload(H, &H->d_potrf, B.potrf));
         TRY_RC(dev_upload(H, &H->d_panel, B.panel));
@@ -1451,6 +1457,68 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT); cudaFree(dP);
     if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
     if (ms_out) *ms_out = best;
+    return 0;
+}
+
+// Live per-kernel-family profile of ONE refactorization (graphs off, a CUDA event pair around every launch on the
+// handle's stream). kinds: 0 gemm (DMMA), 1 fused panel (potrf+trsm), 2 assemble (extend-add), 3 scatter/memset/logdet.
+// ms[k] = summed device time, count[k] = launches, flops[0] = algorithmic GEMM flops issued (lower-only tasks count half).
+int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *count, double *flops) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored) { h->err = "profile_refactorize needs a previous refactorize (values resident)"; return GMRF_B200_ERR_STATE; }
+    const Symbolic &S = h->S;
+    cudaStream_t st = h->stream;
+    for (int k = 0; k < 4; k++) { ms[k] = 0; count[k] = 0; }
+    std::vector<cudaEvent_t> evs;
+    std::vector<int> kinds;
+    auto mark = [&](int kind) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+        kinds.push_back(kind);
+    };
+    mark(3);
+    cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)S.panel_total, st);
+    cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
+    i64 cnt = (i64)S.q_src.size();
+    if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    for (const Launch &L : h->factor_plan.launches) {
+        int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0 : L.kind == K_PANEL ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
+        mark(kind);
+        run_launch(h, L, T, 0);
+    }
+    mark(3);
+    logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
+    logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+    mark(-1);
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (size_t i = 0; i + 1 < evs.size(); i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
+        ms[kinds[i]] += t;
+        count[kinds[i]] += 1;
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+    if (flops) *flops = h->gemm_flops_factor;
+    if ((rc = check_launch(h, "profile_refactorize"))) return rc;
+    return 0;
+}
+
+// Page-lock / unlock a caller-owned host buffer (e.g. the workspace's nzval array) so refactorize() copies it with
+// a true asynchronous DMA instead of a staged pageable copy. Purely an optimisation; the buffer stays caller-owned.
+int gmrf_b200_host_register(void *ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return GMRF_B200_ERR_ARG;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = cudaGetErrorString(e); return GMRF_B200_ERR_CUDA; }
+    return 0;
+}
+int gmrf_b200_host_unregister(void *ptr) {
+    if (!ptr) return GMRF_B200_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return GMRF_B200_ERR_CUDA; }
     return 0;
 }
 

@@ -156,6 +156,7 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
         self._selinv_pattern = None
+        self._pinned = []
         self.status = 0
         if factorize and device >= 0:
             self.refactorize(Q)
@@ -274,5 +275,26 @@ class B200Backend:
         f = self._L.gmrf_b200_solve_Lt_device if half else self._L.gmrf_b200_solve_device
         self._hd.check(f(self._hd._h, ctypes.c_void_p(dB), ctypes.c_void_p(dX), int(ld), int(nrhs)))
 
+    def profile_refactorize(self) -> dict:
+        """Per-kernel-family device time of one refactorization (CUDA events around every launch)."""
+        ms = np.zeros(4)
+        cnt = np.zeros(4, dtype=np.int64)
+        fl = ctypes.c_double()
+        self._hd.check(self._L.gmrf_b200_profile_refactorize(self._hd._h, ptr(ms), ptr(cnt), ctypes.byref(fl)))
+        names = ("gemm", "panel", "assemble", "other")
+        return {"ms": dict(zip(names, ms.tolist())), "launches": dict(zip(names, cnt.tolist())), "gemm_flops": fl.value}
+
+    def pin_host_buffer(self, arr: np.ndarray) -> bool:
+        """Page-lock a caller-owned numpy buffer for asynchronous H2D copies (no-op without a device)."""
+        if self.device < 0 or arr.size == 0:
+            return False
+        rc = self._L.gmrf_b200_host_register(ptr(arr), arr.nbytes)
+        if rc == 0:
+            self._pinned.append(arr)
+        return rc == 0
+
     def close(self):
+        for a in self._pinned:
+            self._L.gmrf_b200_host_unregister(ptr(a))
+        self._pinned = []
         self._hd.close()

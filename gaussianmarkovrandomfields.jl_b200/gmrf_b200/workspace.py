@@ -24,6 +24,8 @@ class GMRFWorkspace:
             raise ValueError("Q must be square")
         self.Q = Q.copy()
         self.backend = backend_type(self.Q, **backend_kwargs)
+        if hasattr(self.backend, "pin_host_buffer"):
+            self.backend.pin_host_buffer(self.Q.data)   # ws.Q.nzval is the H2D source of every refactorization
         n = Q.shape[0]
         self.rhs = np.zeros(n)
         self.solution = np.zeros(n)

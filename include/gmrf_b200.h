@@ -137,9 +137,18 @@ int gmrf_b200_get_scatter(const gmrf_b200_handle *h, int64_t *n_entries, int64_t
 /* Wall-clock of the last call's phases in milliseconds (CUDA events on the handle's stream):
  * [0] h2d of nzval, [1] numeric factorization + logdet, [2] solve, [3] selinv, [4] host analysis. */
 int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n);
+/* Live per-kernel-family profile of one refactorization with the values of the previous refactorize (graphs off,
+ * CUDA event pairs around every launch on the handle's stream): ms[4]/count[4] for {0: DMMA GEMM, 1: fused panel
+ * potrf+trsm, 2: extend-add assembly, 3: memset+scatter+logdet}; *gemm_flops = algorithmic flops of the GEMM tasks. */
+int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *count, double *gemm_flops);
 /* Numeric factor / selected inverse panels copied back to the host (tests, CholeskySqrt-style export). */
 int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles);
 int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
+
+/* Page-lock / unlock a caller-owned host buffer (typically the workspace's nzval array, `ws.Q.nzval`) so that
+ * gmrf_b200_refactorize moves it with an asynchronous DMA. Optional; ownership stays with the caller. */
+int gmrf_b200_host_register(void *ptr, int64_t bytes);
+int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
  * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels"}. */

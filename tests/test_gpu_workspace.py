@@ -1,0 +1,308 @@
+"""GPU parity tests through the C-ABI (ctypes -> libgmrf_b200.so), written to read like the reference's
+test/workspace/test_gmrf_workspace.jl, test_backend_ordering.jl and test_cliquetrees_backend.jl. The checker is the
+CPU oracle and the golden dense-LinearAlgebra vectors; tolerances are the reference's (logdet 1e-10, solve 1e-10,
+selinv diag 1e-8, selinv entries 1e-6, cached/bit-identical paths exact)."""
+import importlib.util
+import os
+import threading
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from gmrf_b200 import spde
+from gmrf_b200.backend import B200Backend, NotPositiveDefinite, PinDenseColumns, ordering_permutation
+from gmrf_b200.workspace import (GMRFWorkspace, WorkspacePool, backward_solve, dimension, logdet, selinv, selinv_diag,
+                                 selinv_dot, selinv_extract_at, update_precision, update_precision_values,
+                                 workspace_solve)
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "fixtures.npz"))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(make_golden)
+FIX = make_golden.fixtures()
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+# ---------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", list(FIX))
+@pytest.mark.parametrize("ordering", [None, "amd", "natural"])
+def test_golden_fixtures(name, ordering):
+    Q = FIX[name]
+    ws = GMRFWorkspace(Q, ordering=ordering)
+    assert dimension(ws) == Q.shape[0]
+    assert abs(logdet(ws) - GOLD[name + "/logdet"]) <= 1e-10 * max(1.0, abs(GOLD[name + "/logdet"]))
+    assert _rel(workspace_solve(ws, GOLD[name + "/b"]), GOLD[name + "/x"]) <= 1e-10
+    d = selinv_diag(ws)
+    assert np.max(np.abs(d - GOLD[name + "/diag_inv"]) / GOLD[name + "/diag_inv"]) <= 1e-8
+    S = selinv(ws)
+    got = np.asarray(S[GOLD[name + "/inv_rows"], GOLD[name + "/inv_cols"]]).ravel()
+    assert np.allclose(got, GOLD[name + "/inv_vals"], rtol=1e-6, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------- test_gmrf_workspace.jl
+class TestGMRFWorkspace:
+    n = 20
+    Q = FIX["rand20"]
+    Qd = FIX["rand20"].toarray()
+    Qinv = np.linalg.inv(FIX["rand20"].toarray())
+
+    def test_solve_vector_and_matrix(self):
+        ws = GMRFWorkspace(self.Q)
+        rng = np.random.default_rng(0)
+        b = rng.standard_normal(self.n)
+        assert _rel(workspace_solve(ws, b), np.linalg.solve(self.Qd, b)) <= 1e-10
+        B = rng.standard_normal((self.n, 13))
+        X = workspace_solve(ws, B)
+        assert X.shape == B.shape and _rel(X, np.linalg.solve(self.Qd, B)) <= 1e-10
+
+    def test_selinv_dot(self):
+        ws = GMRFWorkspace(self.Q)
+        assert abs(selinv_dot(ws, self.Q) - self.n) <= 1e-8 * self.n         # tr(Q^-1 Q) = n
+        B = self.Q.copy()
+        B.data = np.random.default_rng(1).standard_normal(B.nnz)
+        S = selinv(ws)
+        want = float(S.multiply(B).sum())
+        assert abs(selinv_dot(ws, B) - want) <= 1e-10 * abs(want)
+
+    @pytest.mark.parametrize("name", ["rand20", "rand400"])
+    def test_selinv_extract_at_bit_identical(self, name):
+        Qt = FIX[name]
+        ws = GMRFWorkspace(Qt)
+        Se = selinv_extract_at(ws, Qt)
+        Sf = selinv(ws)
+        assert np.array_equal(Se.indptr, Qt.indptr) and np.array_equal(Se.indices, Qt.indices)
+        full = np.asarray(Sf[Qt.tocoo().row, Qt.tocoo().col]).ravel()
+        assert np.array_equal(Se.tocoo().data, full)                          # bit-identical
+
+    def test_selinv_extract_outside_pattern_is_zero(self):
+        Q = FIX["tridiag10"]
+        ws = GMRFWorkspace(Q, ordering="natural")
+        B = sp.csc_matrix(np.ones((10, 10)))
+        S = selinv_extract_at(ws, B).toarray()
+        inv = np.linalg.inv(Q.toarray())
+        tri = np.abs(np.subtract.outer(np.arange(10), np.arange(10))) <= 1
+        assert np.allclose(S[tri], inv[tri], rtol=1e-10)
+        assert np.all(S[~tri] == 0.0)
+
+    def test_backward_solve_is_a_sampler(self):
+        ws = GMRFWorkspace(self.Q)
+        M = backward_solve(ws, np.eye(self.n))                                # columns = P' L^-T e_i
+        assert np.allclose(M @ M.T, self.Qinv, rtol=1e-10, atol=1e-14)        # exact covariance identity
+        rng = np.random.default_rng(123)
+        Z = rng.standard_normal((self.n, 50000))
+        X = backward_solve(ws, Z)
+        emp = (X * X).mean(axis=1)
+        assert np.allclose(emp, np.diag(self.Qinv), rtol=0.1)                 # test_gmrf_workspace.jl:85-100
+
+    def test_update_precision_and_values(self):
+        ws = GMRFWorkspace(self.Q)
+        Q2 = self.Q.copy(); Q2.data *= 2.0
+        update_precision(ws, Q2)
+        b = np.random.default_rng(2).standard_normal(self.n)
+        assert _rel(workspace_solve(ws, b), np.linalg.solve(Q2.toarray(), b)) <= 1e-10
+        assert abs(logdet(ws) - np.linalg.slogdet(Q2.toarray())[1]) <= 1e-10 * abs(logdet(ws))
+        assert np.allclose(selinv_diag(ws), np.diag(np.linalg.inv(Q2.toarray())), rtol=1e-8)
+        update_precision_values(ws, self.Q.data * 3.0)
+        assert abs(logdet(ws) - np.linalg.slogdet(3.0 * self.Qd)[1]) <= 1e-10 * abs(logdet(ws))
+
+    def test_persistent_buffers_across_many_updates(self):
+        ws = GMRFWorkspace(self.Q)
+        rng = np.random.default_rng(7)
+        for k in range(1, 7):
+            Qk = self.Q.copy().tolil()
+            Qk = sp.csc_matrix(Qk) * (0.5 + k)
+            Qk = Qk + sp.diags(0.3 * k * np.arange(1, self.n + 1) / self.n)
+            Qk = sp.csc_matrix(Qk); Qk.sort_indices()
+            update_precision(ws, Qk)
+            b = rng.standard_normal(self.n)
+            D = Qk.toarray()
+            assert _rel(workspace_solve(ws, b), np.linalg.solve(D, b)) <= 1e-10
+            assert abs(logdet(ws) - np.linalg.slogdet(D)[1]) <= 1e-10 * abs(logdet(ws))
+            assert np.allclose(selinv_diag(ws), np.diag(np.linalg.inv(D)), rtol=1e-8)
+
+    def test_pattern_mismatch_error(self):
+        ws = GMRFWorkspace(self.Q)
+        with pytest.raises(ValueError):
+            update_precision(ws, spde.random_spd_fixture(self.n, 0.1, 99))
+        with pytest.raises(ValueError):
+            update_precision_values(ws, np.ones(3))
+        with pytest.raises(ValueError):
+            ws.backend.refactorize(np.ones(5))                                 # nnz mismatch inside the backend
+
+    def test_lazy_invalidation_and_caches(self):
+        ws = GMRFWorkspace(self.Q)
+        d1 = selinv_diag(ws).copy()
+        Q2 = self.Q.copy(); Q2.data *= 2.0
+        update_precision(ws, Q2)
+        d2 = selinv_diag(ws)
+        assert np.allclose(d2, 0.5 * d1, rtol=1e-8) and not np.allclose(d1, d2)
+        s1, s2 = selinv(ws), selinv(ws)
+        assert s1 is s2                                                        # cached object
+        assert selinv_diag(ws) is selinv_diag(ws)
+
+    def test_selinv_lazy_materialisation_and_bit_equality(self):
+        ws = GMRFWorkspace(self.Q)
+        d = selinv_diag(ws)
+        assert ws.backend.selinv_cache is None                                 # diagonal-only path builds no CSC
+        ws2 = GMRFWorkspace(self.Q)
+        S = selinv(ws2)
+        assert ws2.backend.selinv_cache is not None
+        assert np.array_equal(selinv_diag(ws2), S.diagonal())
+        assert np.array_equal(d, S.diagonal())                                 # bit-for-bit (test_gmrf_workspace.jl:220-223)
+
+
+# ---------------------------------------------------------------------------------------------- test_backend_ordering.jl
+def test_backend_ordering_override():
+    Q = FIX["grid_border"]
+    N = Q.shape[0]
+    rhs = np.random.default_rng(0).standard_normal(N)
+    ws0 = GMRFWorkspace(Q)
+    x0, ld0 = ws0.backend.backend_solve(rhs), ws0.backend.compute_logdet()
+    d0 = ws0.selinv_diag()
+    for ordering in (np.arange(N)[::-1].copy(), "amd", PinDenseColumns("amd"), PinDenseColumns("nd")):
+        ws = GMRFWorkspace(Q, ordering=ordering)
+        assert _rel(ws.backend.backend_solve(rhs), x0) <= 1e-10
+        assert abs(ws.backend.compute_logdet() - ld0) <= 1e-10 * abs(ld0)
+        assert np.allclose(ws.selinv_diag(), d0, rtol=1e-8)
+    p = ordering_permutation(Q, PinDenseColumns("amd"))
+    assert p[-1] == N - 1
+    ws = GMRFWorkspace(Q, ordering="amd")
+    update_precision(ws, 2.0 * Q)
+    ws.ensure_numeric()
+    assert abs(ws.backend.compute_logdet() - (ld0 + N * np.log(2.0))) <= 1e-9 * abs(ld0)
+
+
+def test_pool_shares_one_ordering_and_threads():
+    Q = FIX["grid_border"]
+    N = Q.shape[0]
+    pool = WorkspacePool(Q, size=4, ordering="amd")
+    perms = [ws.backend.permutation() for ws in pool.workspaces]
+    assert all(np.array_equal(perms[0], p) for p in perms)
+    D = Q.toarray()
+    rng = np.random.default_rng(3)
+    rhs = rng.standard_normal((N, 20))
+    out, errs = [None] * 20, []
+
+    def work(i):                     # 20 tasks over 4 workspaces (test_cliquetrees_backend.jl:77-108)
+        try:
+            with pool.with_workspace() as ws:
+                scale = 1.0 + 0.1 * i
+                ws.update_precision_values(Q.data * scale)
+                out[i] = (ws.workspace_solve(rhs[:, i]), ws.logdet(), scale)
+        except Exception as e:       # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(20)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for i, (x, ld, scale) in enumerate(out):
+        assert _rel(x, np.linalg.solve(D * scale, rhs[:, i])) <= 1e-10
+        assert abs(ld - np.linalg.slogdet(D * scale)[1]) <= 1e-10 * abs(ld)
+
+
+# ---------------------------------------------------------------------------------------------- vs the oracle on SPDE inputs
+@pytest.mark.parametrize("kind,cells,smooth", [("2d", 40, 1), ("3d", 12, 0), ("3d", 8, 1), ("2d", 64, 0)])
+def test_spde_parity_with_oracle(kind, cells, smooth):
+    mesh = spde.mesh2d(cells) if kind == "2d" else spde.mesh3d(cells)
+    model = spde.MaternSPDE(*mesh, smooth)
+    Q = model.precision(0.7, 0.45)
+    n = Q.shape[0]
+    be = B200Backend(Q, device=0)
+    F = oracle.OracleFactor(Q, be.permutation())
+    assert np.array_equal(be.colcounts(), F.colcount)            # nnz(L) / column counts bit-exact under the same ordering
+    assert be.info()["nnz_l"] == F.nnzL
+    assert abs(be.compute_logdet() - F.logdet()) <= 1e-10 * abs(F.logdet())
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal((n, 3))
+    x = be.backend_solve(b)
+    assert np.linalg.norm(Q @ x - b) <= 1e-10 * np.linalg.norm(b) * max(1.0, np.linalg.norm(x) * abs(Q).max() / np.linalg.norm(b) * 1e-3)
+    assert _rel(x, F.solve(b)) <= 1e-8
+    z = rng.standard_normal(n)
+    assert _rel(be.backend_backward_solve(z), F.backward_solve(z)) <= 1e-8
+    assert np.max(np.abs(be.get_selinv_diag() - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
+    # new hyperparameters, same pattern: refactorize only (Newton / theta loops)
+    Q2 = model.precision(2.5, 0.2)
+    be.refactorize(Q2)
+    F.refactorize(Q2.data)
+    assert abs(be.compute_logdet() - F.logdet()) <= 1e-10 * abs(F.logdet())
+    assert np.max(np.abs(be.get_selinv_diag() - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
+    be.close()
+
+
+def test_run_to_run_bit_reproducible():
+    model = spde.MaternSPDE(*spde.mesh3d(10), 0)
+    Q = model.precision(1.0, 0.3)
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(Q.shape[0])
+    res = []
+    for _ in range(2):
+        be = B200Backend(Q, device=0)
+        for _ in range(2):
+            be.refactorize(Q)
+        res.append((be.compute_logdet(), be.backend_solve(b), be.get_selinv_diag().copy(), be.backend_backward_solve(b)))
+        be.close()
+    assert res[0][0] == res[1][0]
+    for a, c in zip(res[0][1:], res[1][1:]):
+        assert np.array_equal(a, c)
+
+
+def test_not_positive_definite_is_reported():
+    Q = FIX["grid_border"].copy()
+    be = B200Backend(Q, device=0)
+    assert be.status == 0
+    Qb = Q.copy()
+    Qb.data[:] = -Q.data
+    be.refactorize(Qb)                       # silent like `check=false` (backend.jl:184) ...
+    assert be.status > 0                      # ... but the failing column is reported
+    strict = B200Backend(Q, device=0, check=True)
+    with pytest.raises(NotPositiveDefinite):
+        strict.refactorize(Qb)
+    be.refactorize(Q)                        # the handle recovers on the next valid refactorization
+    assert be.status == 0 and abs(be.compute_logdet() - GOLD["grid_border/logdet"]) <= 1e-10 * abs(GOLD["grid_border/logdet"])
+
+
+def test_edge_cases():
+    be = B200Backend(sp.csc_matrix(np.array([[4.0]])), device=0)
+    assert abs(be.compute_logdet() - np.log(4.0)) < 1e-15
+    assert np.allclose(be.backend_solve(np.array([2.0])), [0.5])
+    assert np.allclose(be.get_selinv_diag(), [0.25])
+    D = sp.identity(37, format="csc") * 2.0
+    be = B200Backend(D, device=0)
+    assert abs(be.compute_logdet() - 37 * np.log(2.0)) < 1e-13
+    assert np.allclose(be.backend_backward_solve(np.ones(37)), np.ones(37) / np.sqrt(2.0))
+    with pytest.raises(ValueError):
+        be.backend_solve(np.ones(5))
+    with pytest.raises(ValueError):
+        B200Backend(sp.csc_matrix(np.ones((2, 3))), device=0)
+
+
+def test_full_size_config1_properties():
+    """BASELINE config 1 size (50,625 dofs): size-independent properties instead of the (slow) oracle."""
+    model = spde.MaternSPDE(*spde.mesh2d(224), 1)
+    Q = model.precision(1.0, 0.3)
+    n = Q.shape[0]
+    ws = GMRFWorkspace(Q)
+    ld = ws.logdet()
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(n)
+    x = ws.workspace_solve(b)
+    # normwise backward error (cond(Q) ~ 1e8 here; the residual relative to |b| alone is conditioning-limited)
+    assert np.linalg.norm(Q @ x - b) <= 1e-10 * (np.linalg.norm(b) + abs(Q).sum(axis=1).max() * np.linalg.norm(x))
+    idx = rng.choice(n, 5, replace=False)
+    E = np.zeros((n, 5)); E[idx, np.arange(5)] = 1.0
+    ref = ws.workspace_solve(E)[idx, np.arange(5)]
+    assert np.allclose(ws.selinv_diag()[idx], ref, rtol=1e-8)
+    update_precision_values(ws, 2.0 * Q.data)
+    assert abs(ws.logdet() - (ld + n * np.log(2.0))) <= 1e-10 * abs(ld)
+    z = rng.standard_normal(n)
+    s = ws.backward_solve(z)                  # x = P' L^-T z  =>  x' (2Q) x = z' z
+    assert abs(s @ (2.0 * (Q @ s)) - z @ z) <= 1e-9 * (z @ z)

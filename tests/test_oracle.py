@@ -1,0 +1,86 @@
+"""CPU tests: the oracle (oracle/gmrf_oracle.c) pinned against the golden dense-LinearAlgebra vectors of the
+reference's own deterministic fixtures (tests/golden/fixtures.npz) with the reference's tolerances, plus the CPU
+supernodal baseline against the oracle."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gmrf_b200 import _lib, spde
+from gmrf_b200.backend import _Handle
+from gmrf_b200.introspect import Tables
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "fixtures.npz"))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(make_golden)
+FIX = make_golden.fixtures()
+
+
+@pytest.mark.parametrize("name", list(FIX))
+@pytest.mark.parametrize("order", ["natural", "reverse", "random"])
+def test_oracle_against_golden(name, order):
+    Q = FIX[name]
+    n = Q.shape[0]
+    perm = {"natural": None, "reverse": np.arange(n)[::-1].copy(),
+            "random": np.random.default_rng(5).permutation(n)}[order]
+    F = oracle.OracleFactor(Q, perm)
+    assert F.status == 0
+    # tolerances of the reference's tests: logdet rtol 1e-10, solve ~ dense \, selinv diag rtol 1e-8, entries 1e-6
+    assert abs(F.logdet() - GOLD[name + "/logdet"]) <= 1e-10 * max(1.0, abs(GOLD[name + "/logdet"]))
+    x = F.solve(GOLD[name + "/b"])
+    assert np.linalg.norm(x - GOLD[name + "/x"]) <= 1e-10 * np.linalg.norm(GOLD[name + "/x"])
+    d = F.selinv_diag()
+    assert np.max(np.abs(d - GOLD[name + "/diag_inv"]) / np.abs(GOLD[name + "/diag_inv"])) <= 1e-8
+    S = F.selinv()
+    got = np.asarray(S[GOLD[name + "/inv_rows"], GOLD[name + "/inv_cols"]]).ravel()
+    assert np.allclose(got, GOLD[name + "/inv_vals"], rtol=1e-6, atol=0)
+
+
+def test_oracle_sampling_half_solve_covariance():
+    # backward_solve maps z ~ N(0, I) to N(0, Q^-1): (P' L^-T)(P' L^-T)' = Q^-1 exactly (test_gmrf_workspace.jl:85-100)
+    Q = FIX["rand20"]
+    n = Q.shape[0]
+    F = oracle.OracleFactor(Q, np.random.default_rng(1).permutation(n))
+    M = F.backward_solve(np.eye(n))
+    assert np.allclose(M @ M.T, np.linalg.inv(Q.toarray()), rtol=1e-10, atol=1e-14)
+
+
+def test_oracle_logdet_scaling_and_not_pd():
+    Q = FIX["grid_border"]
+    n = Q.shape[0]
+    F = oracle.OracleFactor(Q)
+    ld = F.logdet()
+    F.refactorize(2.0 * Q.data)
+    assert abs(F.logdet() - (ld + n * np.log(2.0))) <= 1e-9 * abs(ld)      # test_backend_ordering.jl:61-67
+    Qb = Q.copy()
+    Qb.data[Qb.indptr[3]:Qb.indptr[4]][Qb.indices[Qb.indptr[3]:Qb.indptr[4]] == 3] = -5.0
+    assert oracle.OracleFactor(Qb).status > 0
+
+
+def test_oracle_empty_and_ragged():
+    import scipy.sparse as sp
+    F = oracle.OracleFactor(sp.csc_matrix((0, 0)))
+    assert F.nnzL == 0 and F.logdet() == 0.0
+    F = oracle.OracleFactor(sp.identity(5, format="csc") * 4.0)
+    assert abs(F.logdet() - 5 * np.log(4.0)) < 1e-14
+    with pytest.raises(ValueError):
+        F.refactorize(np.ones(3))
+
+
+@pytest.mark.parametrize("cells", [6, 10])
+def test_cpu_supernodal_baseline_matches_oracle(cells):
+    from oracle.cpu_baseline import CpuSupernodalCholesky
+    model = spde.MaternSPDE(*spde.mesh3d(cells), 0)
+    Q = model.precision(1.3, 0.4)
+    h = _Handle(Q.shape[0], Q.indptr, Q.indices, None, _lib.ORDER_ND, device=-1)
+    T = Tables(h)
+    cpu = CpuSupernodalCholesky(T, threads=2)
+    cpu.refactorize(Q.data)
+    F = oracle.OracleFactor(Q, T.perm)
+    assert cpu.status == 0
+    assert abs(cpu.logdet - F.logdet()) <= 1e-11 * abs(F.logdet())
+    h.close()
