@@ -286,7 +286,9 @@ class B200Backend:
 
     def pin_host_buffer(self, arr: np.ndarray) -> bool:
         """Page-lock a caller-owned numpy buffer for asynchronous H2D copies (no-op without a device)."""
-        if self.device < 0 or arr.size == 0:
+        # Only large buffers are registered: they are mmap-backed (own pages), whereas page-locking a small heap
+        # array would also pin its neighbours' pages and make later pageable copies of those fail.
+        if self.device < 0 or arr.nbytes < (64 << 20):
             return False
         rc = self._L.gmrf_b200_host_register(ptr(arr), arr.nbytes)
         if rc == 0:
@@ -298,3 +300,9 @@ class B200Backend:
             self._L.gmrf_b200_host_unregister(ptr(a))
         self._pinned = []
         self._hd.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -83,14 +83,22 @@ class TestGMRFWorkspace:
         assert np.array_equal(Se.tocoo().data, full)                          # bit-identical
 
     def test_selinv_extract_outside_pattern_is_zero(self):
-        Q = FIX["tridiag10"]
-        ws = GMRFWorkspace(Q, ordering="natural")
-        B = sp.csc_matrix(np.ones((10, 10)))
-        S = selinv_extract_at(ws, B).toarray()
+        # positions outside the (supernodal, relaxed) factor pattern read as 0.0; inside they are Q^-1 entries
+        Q = FIX["grid3d_12"]
+        n = Q.shape[0]
+        ws = GMRFWorkspace(Q)
+        rng = np.random.default_rng(4)
+        B = sp.random(n, n, density=0.002, random_state=rng, format="csc") + sp.identity(n, format="csc")
+        B = sp.csc_matrix(B); B.sort_indices()
+        Se = selinv_extract_at(ws, B).tocoo()
+        Sf = selinv(ws)
+        pat = sp.csc_matrix((np.ones(Sf.nnz), Sf.indices, Sf.indptr), shape=Sf.shape)
+        inside = np.asarray(pat[Se.row, Se.col]).ravel() > 0
+        assert inside.any() and (~inside).any()
+        assert np.all(Se.data[~inside] == 0.0)
+        assert np.array_equal(Se.data[inside], np.asarray(Sf[Se.row[inside], Se.col[inside]]).ravel())
         inv = np.linalg.inv(Q.toarray())
-        tri = np.abs(np.subtract.outer(np.arange(10), np.arange(10))) <= 1
-        assert np.allclose(S[tri], inv[tri], rtol=1e-10)
-        assert np.all(S[~tri] == 0.0)
+        assert np.allclose(Se.data[inside], inv[Se.row[inside], Se.col[inside]], rtol=1e-6)
 
     def test_backward_solve_is_a_sampler(self):
         ws = GMRFWorkspace(self.Q)
