@@ -1,0 +1,168 @@
+# B200Backend.jl -- Julia glue a maintainer adds to GaussianMarkovRandomFields.jl (e.g. as a package extension
+# `ext/GaussianMarkovRandomFieldsB200.jl`) to put libgmrf_b200.so behind the existing `WorkspaceBackend` protocol
+# (src/workspace/backend.jl:8-30). It mirrors `CliqueTreesBackend` (src/workspace/cliquetrees_backend.jl:21-150)
+# method by method; everything above it (GMRFWorkspace, WorkspaceGMRF, gaussian_approximation, autodiff rules) runs
+# unchanged.  NOT executed in this repository's CI: the image has no Julia. The Python class
+# gmrf_b200/backend.py binds exactly the same entry points and is what the parity tests drive.
+
+module GaussianMarkovRandomFieldsB200
+
+using GaussianMarkovRandomFields
+using LinearAlgebra, SparseArrays
+import GaussianMarkovRandomFields: WorkspaceBackend, GMRFWorkspace, refactorize!, backend_solve, compute_logdet,
+    compute_selinv!, get_selinv, get_selinv_diag, backend_backward_solve, selinv_dot, selinv_extract_at,
+    ordering_permutation, AbstractLatentWorkspacePool, checkout, checkin
+
+const libgmrf = get(ENV, "GMRF_B200_LIB", "libgmrf_b200.so")
+
+export B200Backend, B200WorkspacePool
+
+mutable struct B200Backend <: WorkspaceBackend
+    handle::Ptr{Cvoid}
+    n::Int
+    nnz::Int
+    device::Int
+    check::Bool
+    # field names mirrored from CHOLMODBackend because tests/benchmarks peek at them
+    # (test/workspace/test_gmrf_workspace.jl:214,219; benchmarks/benchmarks.jl:185-190)
+    selinv_cache::Union{Nothing, SparseMatrixCSC{Float64, Int}}
+    selinv_diag_cache::Union{Nothing, Vector{Float64}}
+    selinv_pattern::Union{Nothing, Tuple{Vector{Int}, Vector{Int}}}
+end
+
+_errmsg(h) = unsafe_string(ccall((:gmrf_b200_last_error, libgmrf), Cstring, (Ptr{Cvoid},), h))
+
+function _check(b::B200Backend, rc::Cint)
+    rc == 0 && return nothing
+    rc == -1 && throw(ArgumentError(_errmsg(b.handle)))
+    rc > 0 && (b.check ? throw(PosDefException(Int(rc))) : return nothing)   # reference uses check=false (backend.jl:184)
+    error("libgmrf_b200 error $rc: " * _errmsg(b.handle))
+end
+
+"""
+    B200Backend(Q::SparseMatrixCSC{Float64,Int}; ordering = nothing, device = 0, check = false)
+
+Symbolic analysis once (host) + first numeric factorization on `device`. `ordering` accepts what
+`CHOLMODBackend` accepts (backend.jl:147-153): `nothing` (library default: nested dissection), a permutation
+vector, a CliqueTrees elimination algorithm, or `PinDenseColumns(...)` -- resolved on the host by the package's
+own `ordering_permutation` and handed over as a 1-based permutation.
+"""
+function B200Backend(Q::SparseMatrixCSC{Float64, Int}; ordering = nothing, device::Integer = 0, check::Bool = false)
+    n = size(Q, 1)
+    permvec = ordering === nothing ? Int[] : ordering_permutation(Q, ordering)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = GC.@preserve Q permvec ccall((:gmrf_b200_create, libgmrf), Cint,
+        (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Cint),
+        href, n, SparseArrays.getcolptr(Q), rowvals(Q), 1, isempty(permvec) ? C_NULL : pointer(permvec), 1, device)
+    rc == 0 || throw(ArgumentError(unsafe_string(ccall((:gmrf_b200_last_error, libgmrf), Cstring, (Ptr{Cvoid},), C_NULL))))
+    b = B200Backend(href[], n, nnz(Q), device, check, nothing, nothing, nothing)
+    finalizer(x -> ccall((:gmrf_b200_destroy, libgmrf), Cvoid, (Ptr{Cvoid},), x.handle), b)
+    refactorize!(b, Symmetric(Q))
+    return b
+end
+
+function refactorize!(b::B200Backend, Q::Symmetric)
+    nz = nonzeros(Q.data)                                    # positional, same pattern (gmrf_workspace.jl:131-143)
+    _check(b, GC.@preserve nz ccall((:gmrf_b200_refactorize, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64),
+        b.handle, nz, length(nz)))
+    b.selinv_cache = nothing                                 # backend.jl:185-187
+    b.selinv_diag_cache = nothing
+    return nothing
+end
+
+function backend_solve(b::B200Backend, rhs::AbstractVector)
+    B = Vector{Float64}(rhs); X = similar(B)
+    _check(b, ccall((:gmrf_b200_solve, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+        b.handle, B, X, b.n, 1))
+    return X
+end
+
+function backend_solve(b::B200Backend, RHS::Matrix{Float64})   # blocked multi-RHS (backend.jl:207-209)
+    X = similar(RHS)
+    _check(b, ccall((:gmrf_b200_solve, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+        b.handle, RHS, X, b.n, size(RHS, 2)))
+    return X
+end
+
+function backend_backward_solve(b::B200Backend, x::AbstractVector)   # factor.UP \ x (backend.jl:281-284)
+    Z = Vector{Float64}(x); X = similar(Z)
+    _check(b, ccall((:gmrf_b200_solve_Lt, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+        b.handle, Z, X, b.n, 1))
+    return X
+end
+
+function compute_logdet(b::B200Backend)
+    out = Ref{Float64}(0.0)
+    _check(b, ccall((:gmrf_b200_logdet, libgmrf), Cint, (Ptr{Cvoid}, Ref{Float64}), b.handle, out))
+    return out[]
+end
+
+compute_selinv!(b::B200Backend) = nothing                      # lazy, like backend.jl:215-221
+
+function get_selinv_diag(b::B200Backend)
+    if b.selinv_diag_cache === nothing
+        if b.selinv_cache !== nothing
+            b.selinv_diag_cache = diag(b.selinv_cache)
+        else
+            d = Vector{Float64}(undef, b.n)
+            _check(b, ccall((:gmrf_b200_selinv_diag, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.handle, d))
+            b.selinv_diag_cache = d
+        end
+    end
+    return b.selinv_diag_cache
+end
+
+function get_selinv(b::B200Backend)
+    if b.selinv_cache === nothing
+        if b.selinv_pattern === nothing
+            nz = Ref{Int64}(0)
+            _check(b, ccall((:gmrf_b200_selinv_nnz, libgmrf), Cint, (Ptr{Cvoid}, Ref{Int64}), b.handle, nz))
+            cp = Vector{Int}(undef, b.n + 1); rv = Vector{Int}(undef, nz[])
+            _check(b, ccall((:gmrf_b200_selinv_pattern, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint),
+                b.handle, cp, rv, 1))
+            b.selinv_pattern = (cp, rv)
+        end
+        cp, rv = b.selinv_pattern
+        vals = Vector{Float64}(undef, length(rv))
+        _check(b, ccall((:gmrf_b200_selinv_values, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.handle, vals))
+        b.selinv_cache = SparseMatrixCSC(b.n, b.n, copy(cp), copy(rv), vals)
+    end
+    return b.selinv_cache
+end
+
+function selinv_extract_at(b::B200Backend, B::SparseMatrixCSC)
+    out = Vector{Float64}(undef, nnz(B))
+    cp = Vector{Int64}(SparseArrays.getcolptr(B)); rv = Vector{Int64}(rowvals(B))
+    _check(b, ccall((:gmrf_b200_selinv_extract, libgmrf), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Float64}), b.handle, b.n, cp, rv, 1, out))
+    return SparseMatrixCSC(size(B)..., copy(SparseArrays.getcolptr(B)), copy(rowvals(B)), out)
+end
+
+# tr(Q^-1 B): values are read on the device at B's pattern, the O(nnz(B)) dot stays generic so that
+# ForwardDiff.Dual-valued B keeps working (ext/forwarddiff/logdetcov.jl:23)
+selinv_dot(b::B200Backend, B::SparseMatrixCSC) = dot(nonzeros(selinv_extract_at(b, B)), nonzeros(B))
+
+# GMRFWorkspace(Q, B200Backend; ...) -- copy of cliquetrees_backend.jl:132-150
+function GMRFWorkspace(Q::SparseMatrixCSC{T}, ::Type{B200Backend}; kw...) where {T}
+    n = size(Q, 1)
+    size(Q, 1) == size(Q, 2) || throw(ArgumentError("Q must be square"))
+    backend = B200Backend(SparseMatrixCSC{Float64, Int}(Q); kw...)
+    return GMRFWorkspace{T, typeof(backend)}(copy(Q), backend, zeros(T, n), zeros(T, n), true, false, false, zero(T), 1, 0)
+end
+
+# One workspace per GPU, ordering resolved once (workspace_pool.jl:53-67); protocol of src/workspace/workspace.jl:25-41
+struct B200WorkspacePool <: AbstractLatentWorkspacePool
+    channel::Channel{Any}
+end
+function B200WorkspacePool(Q::SparseMatrixCSC; devices = 0:0, ordering = nothing)
+    perm = ordering === nothing ? nothing : ordering_permutation(Q, ordering)
+    ch = Channel{Any}(length(devices))
+    for d in devices
+        put!(ch, GMRFWorkspace(Q, B200Backend; ordering = perm, device = d))
+    end
+    return B200WorkspacePool(ch)
+end
+checkout(p::B200WorkspacePool) = take!(p.channel)
+checkin(p::B200WorkspacePool, ws) = put!(p.channel, ws)
+
+end # module
