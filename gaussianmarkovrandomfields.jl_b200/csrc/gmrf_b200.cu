@@ -6,6 +6,7 @@
 // graphs once per handle, so Newton / hyperparameter loops replay a graph per refactorization.
 #include "../../include/gmrf_b200.h"
 #include "kernels.cuh"
+#include "solve_kernels.cuh"
 #include "symbolic.hpp"
 
 #include <algorithm>
@@ -27,7 +28,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_POTRF, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_TRSV0, K_TRSV1, K_GEMV_N, K_GEMV_T, K_PANEL
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL
 };
 
 struct Launch {
@@ -80,8 +81,15 @@ struct gmrf_b200_handle {
     int *d_panel_cnt = nullptr;   // per-launch reader counters of the fused panel kernel (self-resetting)
     TrsmTask *d_trsm = nullptr;
     AsmItem *d_items = nullptr;
-    VecTask *d_vec = nullptr;
-    TrsvTask *d_trsv = nullptr;
+    FwdStepTask *d_fwd = nullptr;
+    BwdGatherTask *d_bwdg = nullptr;
+    BwdStepTask *d_bwds = nullptr;
+    InvTask *d_invtasks = nullptr;
+    double *d_Linv = nullptr;          // explicitly inverted 64-column diagonal blocks (solve phase)
+    long long *d_invbase = nullptr;    // per supernode: offset of its first inverted block in d_Linv
+    i64 n_invtasks = 0;
+    bool inv_valid = false;
+    std::map<int, cudaGraphExec_t> solve_graphs;   // key = nrhs * 2 + mode
     TransTask *d_trans = nullptr;
     // selinv task tables are built lazily (they need d_Zx / d_zw)
     GemmTask *d_gemm_z = nullptr;
@@ -145,8 +153,11 @@ struct Builder {
     std::vector<PanelTask> panel;
     std::vector<TrsmTask> trsm;
     std::vector<AsmItem> items;
-    std::vector<VecTask> vec;
-    std::vector<TrsvTask> trsv;
+    std::vector<FwdStepTask> fwd;
+    std::vector<BwdGatherTask> bwdg;
+    std::vector<BwdStepTask> bwds;
+    std::vector<InvTask> inv;
+    std::vector<long long> inv_base;
     std::vector<TransTask> trans;
     std::vector<int> superlist;
     std::vector<int> prefix;
@@ -256,35 +267,25 @@ struct Builder {
         plan.launches.push_back(L);
         its.clear();
     }
-    void add_vec(Plan &plan, std::vector<VecTask> &tasks, int kind) {
+    // solve-phase launches: `tiles(t)` CTAs per task, tasks appended to the kind's table
+    template <class Task, class TilesFn>
+    void add_tiled(Plan &plan, std::vector<Task> &tasks, std::vector<Task> &table, int kind, TilesFn tiles) {
         if (tasks.empty()) return;
         Launch L;
         L.kind = kind;
         L.aux = 0;
-        L.task_off = (i64)vec.size();
+        L.task_off = (i64)table.size();
         L.ntasks = (int)tasks.size();
         L.prefix_off = (i64)prefix.size();
         i64 tot = 0;
         for (auto &t : tasks) {
             prefix.push_back((int)tot);
-            tot += (kind == K_GEMV_N) ? cdiv(t.m, 128) : cdiv(t.k, 8);
-            vec.push_back(t);
+            tot += tiles(t);
+            table.push_back(t);
         }
         prefix.push_back((int)tot);
+        if (tot > INT_MAX) throw std::runtime_error("too many tiles in one solve launch");
         L.grid = (int)tot;
-        plan.launches.push_back(L);
-        tasks.clear();
-    }
-    void add_trsv(Plan &plan, std::vector<TrsvTask> &tasks, int var) {
-        if (tasks.empty()) return;
-        Launch L;
-        L.kind = var ? K_TRSV1 : K_TRSV0;
-        L.aux = 0;
-        L.task_off = (i64)trsv.size();
-        L.ntasks = (int)tasks.size();
-        L.prefix_off = -1;
-        L.grid = (int)tasks.size();
-        trsv.insert(trsv.end(), tasks.begin(), tasks.end());
         plan.launches.push_back(L);
         tasks.clear();
     }
@@ -401,72 +402,96 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
     }
 }
 
+// Solve plans (few right-hand sides; kernels in solve_kernels.cuh). Per level: forward = children assembly + first
+// block solve, then one launch per 64-column step of the level's supernode chains (lockstep); backward = gather
+// phase (t_S = y_S - L21' x_R, last block solve), then one launch per block step, descending.
 void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     const Symbolic &S = h->S;
     std::vector<int> lst;
-    std::vector<TrsvTask> tv;
-    std::vector<VecTask> vt;
-    const i64 n = S.n;
+    std::vector<FwdStepTask> ft;
+    std::vector<BwdGatherTask> gt;
+    std::vector<BwdStepTask> bt;
+    const i64 BB = (i64)SOLVE_NB * SOLVE_NB;
+    // inverted diagonal blocks
+    B.inv_base.assign(S.nsuper, 0);
+    i64 inv_total = 0;
+    for (i64 s = 0; s < S.nsuper; s++) {
+        B.inv_base[s] = inv_total;
+        i64 ns = S.ns(s), ld = S.panel_ld[s];
+        const double *P = h->d_Lx + S.panel_off[s];
+        for (i64 k0 = 0; k0 < ns; k0 += SOLVE_NB) {
+            i64 nb = std::min<i64>(SOLVE_NB, ns - k0);
+            B.inv.push_back(InvTask{P + k0 * ld + k0, h->d_Linv + inv_total, (int)ld, (int)nb});
+            inv_total += (nb == SOLVE_NB) ? BB : nb * nb;
+        }
+    }
+    auto inv_ptr = [&](i64 s, i64 j) { return (const double *)(h->d_Linv + B.inv_base[s] + j * BB); };
     // forward: L y = b
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
-        for (const i64 *sp = sb; sp < se; sp++) {
-            i64 s = *sp;
-            if (S.nr(s) > 0 || S.child_ptr[s + 1] > S.child_ptr[s]) lst.push_back((int)s);
-        }
+        for (const i64 *sp = sb; sp < se; sp++) lst.push_back((int)*sp);
         B.add_superlist(h->fwd_plan, lst, K_FWD_ASM);
         i64 maxsteps = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
+        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), SOLVE_NB));
         for (i64 j = 0; j < maxsteps; j++) {
             for (const i64 *sp = sb; sp < se; sp++) {
-                i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
-                i64 k0 = j * NB;
+                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                i64 k0 = j * SOLVE_NB;
                 if (k0 >= ns) continue;
-                i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                i64 nb = std::min<i64>(SOLVE_NB, ns - k0), k1 = k0 + nb;
+                if (nrow == k1) continue;
                 const double *P = h->d_Lx + S.panel_off[s];
-                double *yk = h->d_y + S.sfirst[s] + k0;
-                tv.push_back(TrsvTask{P + k0 * ld + k0, yk, (int)ld, (int)n, (int)nb, 0});
-                if (ns > k1) {
-                    VecTask v;
-                    v.A = P + k0 * ld + k1; v.idx = nullptr; v.C = h->d_y + S.sfirst[s] + k1; v.X = yk;
-                    v.m = (int)(ns - k1); v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)n; v.ldx = (int)n; v.pad_ = 0;
-                    vt.push_back(v);
-                }
-                if (nr > 0) {
-                    VecTask v;
-                    v.A = P + k0 * ld + ns; v.idx = nullptr; v.C = h->d_uvec + S.uvec_off[s]; v.X = yk;
-                    v.m = (int)nr; v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)S.uvec_total; v.ldx = (int)n; v.pad_ = 0;
-                    vt.push_back(v);
-                }
+                FwdStepTask t;
+                t.L = P + k0 * ld + k1;
+                t.x = h->d_y + S.sfirst[s] + k0;
+                t.y = h->d_y + S.sfirst[s] + k1;
+                t.u = h->d_uvec + S.uvec_off[s];
+                t.ld = (int)ld; t.nb = (int)nb; t.ms = (int)(ns - k1); t.m = (int)(nrow - k1);
+                t.nb_next = (int)std::min<i64>(SOLVE_NB, ns - k1);
+                t.inv_next = t.nb_next > 0 ? inv_ptr(s, j + 1) : nullptr;
+                t.pad_ = 0;
+                ft.push_back(t);
             }
-            B.add_trsv(h->fwd_plan, tv, 0);
-            B.add_vec(h->fwd_plan, vt, K_GEMV_N);
+            B.add_tiled(h->fwd_plan, ft, B.fwd, K_FWD_STEP, [](const FwdStepTask &t) { return (i64)cdiv(t.m, SOLVE_NB); });
         }
     }
     // backward: L^T x = y
     for (i64 l = S.nlevels - 1; l >= 0; l--) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
         i64 maxsteps = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), NB));
-        for (i64 t = 0; t < maxsteps; t++) {
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            i64 nblk = cdiv(ns, SOLVE_NB);
+            maxsteps = std::max(maxsteps, nblk);
+            BwdGatherTask t;
+            t.L21 = h->d_Lx + S.panel_off[s] + ns;
+            t.idx = h->d_rowidx + S.rowptr[s] + ns;
+            t.inv_last = inv_ptr(s, nblk - 1);
+            t.y = h->d_y + S.sfirst[s];
+            t.ld = (int)ld; t.ns = (int)ns; t.nr = (int)nr; t.nb_last = (int)(ns - (nblk - 1) * SOLVE_NB);
+            t.tile0 = nr > 0 ? 0 : (int)(nblk - 1);
+            t.pad_ = 0;
+            gt.push_back(t);
+        }
+        B.add_tiled(h->bwd_plan, gt, B.bwdg, K_BWD_GATHER, [](const BwdGatherTask &t) {
+            return (i64)(cdiv(t.ns, SOLVE_NB) - t.tile0);
+        });
+        for (i64 tt = 0; tt + 1 < maxsteps; tt++) {
             for (const i64 *sp = sb; sp < se; sp++) {
-                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
-                i64 nblk = cdiv(ns, NB);
-                i64 j = nblk - 1 - t;
-                if (j < 0) continue;
-                i64 k0 = j * NB, nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
-                const double *P = h->d_Lx + S.panel_off[s];
-                double *yk = h->d_y + S.sfirst[s] + k0;
-                if (nrow > k1) {
-                    VecTask v;
-                    v.A = P + k0 * ld + k1; v.idx = h->d_rowidx + S.rowptr[s] + k1; v.C = yk; v.X = h->d_y;
-                    v.m = (int)(nrow - k1); v.k = (int)nb; v.lda = (int)ld; v.ldc = (int)n; v.ldx = (int)n; v.pad_ = 0;
-                    vt.push_back(v);
-                }
-                tv.push_back(TrsvTask{P + k0 * ld + k0, yk, (int)ld, (int)n, (int)nb, 0});
+                i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
+                i64 nblk = cdiv(ns, SOLVE_NB);
+                i64 j = nblk - 1 - tt;
+                if (j < 1) continue;
+                i64 k0 = j * SOLVE_NB, nb = std::min<i64>(SOLVE_NB, ns - k0);
+                BwdStepTask t;
+                t.L = h->d_Lx + S.panel_off[s] + k0;
+                t.inv_prev = inv_ptr(s, j - 1);
+                t.x = h->d_y + S.sfirst[s] + k0;
+                t.y = h->d_y + S.sfirst[s];
+                t.ld = (int)ld; t.nb = (int)nb; t.ncols = (int)k0; t.pad_ = 0;
+                bt.push_back(t);
             }
-            B.add_vec(h->bwd_plan, vt, K_GEMV_T);
-            B.add_trsv(h->bwd_plan, tv, 1);
+            B.add_tiled(h->bwd_plan, bt, B.bwds, K_BWD_STEP, [](const BwdStepTask &t) { return (i64)(t.ncols / SOLVE_NB); });
         }
     }
 }
@@ -665,24 +690,27 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_FWD_ASM: {
             dim3 g(L.grid, nrhs);
-            fwd_assemble_kernel<<<g, 256, 0, st>>>(h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx,
-                                                   h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
+            fwd_assemble_x0_kernel<<<g, 256, 0, st>>>(h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
+                                                      h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
             break;
         }
-        case K_TRSV0: case K_TRSV1: {
-            dim3 g(L.grid, (nrhs + 7) / 8);
-            if (L.kind == K_TRSV0) trsv_block_kernel<0><<<g, 256, 0, st>>>(h->d_trsv + L.task_off, nrhs);
-            else trsv_block_kernel<1><<<g, 256, 0, st>>>(h->d_trsv + L.task_off, nrhs);
+#define SOLVE_RB_DISPATCH(KERNEL, ...)                                                         \
+    do {                                                                                       \
+        if (nrhs <= 1) KERNEL<1><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                         \
+        else if (nrhs <= 2) KERNEL<2><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                    \
+        else if (nrhs <= 4) KERNEL<4><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                    \
+        else KERNEL<8><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                                   \
+    } while (0)
+        case K_FWD_STEP:
+            SOLVE_RB_DISPATCH(fwd_step_kernel, h->d_fwd + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
             break;
-        }
-        case K_GEMV_N:
-            if (nrhs == 1) gemv_n_kernel<1><<<L.grid, 128, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
-            else gemv_n_kernel<8><<<L.grid, 128, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+        case K_BWD_GATHER:
+            SOLVE_RB_DISPATCH(bwd_gather_kernel, h->d_bwdg + L.task_off, pf, L.ntasks, nrhs, h->d_y, (long long)h->S.n);
             break;
-        case K_GEMV_T:
-            if (nrhs == 1) gemv_t_kernel<1><<<L.grid, 256, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
-            else gemv_t_kernel<8><<<L.grid, 256, 0, st>>>(h->d_vec + L.task_off, pf, L.ntasks, nrhs);
+        case K_BWD_STEP:
+            SOLVE_RB_DISPATCH(bwd_step_kernel, h->d_bwds + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
             break;
+#undef SOLVE_RB_DISPATCH
     }
 }
 
@@ -759,6 +787,7 @@ int do_factor(gmrf_b200_handle *h) {
     h->fail_col = (host_fail == 0x7f7f7f7f) ? 0 : host_fail;
     h->factored = true;
     h->selinv_valid = false;
+    h->inv_valid = false;
     return h->fail_col > 0 ? h->fail_col : 0;
 }
 
@@ -803,14 +832,27 @@ int ensure_io(gmrf_b200_handle *h, i64 count) {
     return 0;
 }
 
+// Enqueue the level-scheduled sweeps on the permuted work array d_y (mode 0: forward + backward, 1: backward only).
+void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    if (mode == 0)
+        for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
+    for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
+}
+
 // X = Q^-1 B (mode 0) or X = P' L^-T Z (mode 1) on device buffers; nrhs processed in blocks of rhs_block.
+// The sweeps of one block are a static launch list on fixed buffers -> captured once per (block width, mode) into a
+// CUDA graph and replayed (thousands of dependent micro-launches on the chains of the top supernodes).
 int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
     const Symbolic &S = h->S;
     if (!h->factored) { h->err = "solve before the first refactorize"; return GMRF_B200_ERR_STATE; }
     if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
     cudaStream_t st = h->stream;
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
     CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    if (!h->inv_valid && h->n_invtasks > 0) {
+        diag_inv_kernel<<<(unsigned)h->n_invtasks, SOLVE_NB, 0, st>>>(h->d_invtasks);
+        h->inv_valid = true;
+    }
     const int tpb = 256;
     const int gridn = (int)((S.n + tpb - 1) / tpb);
     for (i64 r0 = 0; r0 < nrhs; r0 += h->rhs_block) {
@@ -818,13 +860,28 @@ int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i
         if (S.n == 0) break;
         if (mode == 0) {
             permute_rows_kernel<<<gridn, tpb, 0, st>>>(h->d_y, dB + r0 * ld, h->d_perm, S.n, S.n, ld, nb, 0);
-            for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
         } else {
             // the half solve takes z in the factor's own ordering (CHOLMOD's `UP \ z`): no input permutation
             CUDA_TRY(h, cudaMemcpy2DAsync(h->d_y, sizeof(double) * S.n, dB + r0 * ld, sizeof(double) * ld,
                                           sizeof(double) * S.n, nb, cudaMemcpyDeviceToDevice, st));
         }
-        for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
+        if (h->opt.use_graph) {
+            const int key = nb * 2 + mode;
+            auto it = h->solve_graphs.find(key);
+            if (it == h->solve_graphs.end()) {
+                cudaGraph_t g;
+                cudaGraphExec_t ge;
+                CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                enqueue_sweeps(h, nb, mode);
+                CUDA_TRY(h, cudaStreamEndCapture(st, &g));
+                CUDA_TRY(h, cudaGraphInstantiate(&ge, g, 0));
+                cudaGraphDestroy(g);
+                it = h->solve_graphs.emplace(key, ge).first;
+            }
+            CUDA_TRY(h, cudaGraphLaunch(it->second, st));
+        } else {
+            enqueue_sweeps(h, nb, mode);
+        }
         permute_rows_kernel<<<gridn, tpb, 0, st>>>(dX + r0 * ld, h->d_y, h->d_perm, S.n, ld, S.n, nb, 1);
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
@@ -1024,6 +1081,15 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         TRY_RC(dev_upload(H, &H->d_meta, meta));
     }
     {
+        i64 inv_total = 0;   // doubles in the inverted diagonal blocks (nb x nb each, 64-column blocks)
+        for (i64 s = 0; s < S.nsuper; s++)
+            for (i64 k0 = 0; k0 < S.ns(s); k0 += SOLVE_NB) {
+                i64 nb = std::min<i64>(SOLVE_NB, S.ns(s) - k0);
+                inv_total += nb * nb;
+            }
+        TRY_RC(dev_alloc(H, &H->d_Linv, (size_t)inv_total));
+    }
+    {
         Builder B;
         B.naive = H->opt.naive_kernels != 0;
         try {
@@ -1041,8 +1107,12 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         if (cudaMemset(H->d_panel_cnt, 0, sizeof(int) * (B.panel.size() + 1)) != cudaSuccess) { H->err = "memset failed"; return fail(GMRF_B200_ERR_CUDA); }
         TRY_RC(dev_upload(H, &H->d_trsm, B.trsm));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
-        TRY_RC(dev_upload(H, &H->d_vec, B.vec));
-        TRY_RC(dev_upload(H, &H->d_trsv, B.trsv));
+        TRY_RC(dev_upload(H, &H->d_fwd, B.fwd));
+        TRY_RC(dev_upload(H, &H->d_bwdg, B.bwdg));
+        TRY_RC(dev_upload(H, &H->d_bwds, B.bwds));
+        TRY_RC(dev_upload(H, &H->d_invtasks, B.inv));
+        TRY_RC(dev_upload(H, &H->d_invbase, B.inv_base));
+        H->n_invtasks = (i64)B.inv.size();
         TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
     }
@@ -1058,6 +1128,7 @@ void gmrf_b200_destroy(gmrf_b200_handle *h) {
         if (h->stream) cudaStreamSynchronize(h->stream);
         if (h->factor_graph) cudaGraphExecDestroy(h->factor_graph);
         if (h->selinv_graph) cudaGraphExecDestroy(h->selinv_graph);
+        for (auto &kv : h->solve_graphs) cudaGraphExecDestroy(kv.second);
         for (void *p : h->owned) cudaFree(p);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);

@@ -70,21 +70,6 @@ struct SuperMeta {
     int child_begin, child_end;   // range in child_idx
 };
 
-struct VecTask {         // skinny panel products of the solves
-    const double *A;     // panel block, element (i,kk) at A[i + kk*lda]
-    const int *idx;      // optional gather/scatter row indices (global permuted rows) or nullptr
-    double *C;           // gemv_n: output rows (contiguous), ldc ; gemv_t: output (k entries)
-    const double *X;     // gemv_n: input block (k x nrhs), ldx ; gemv_t: input rows (gathered via idx)
-    int m, k;            // A is m x k
-    int lda, ldc, ldx, pad_;
-};
-
-struct TrsvTask {        // X[nb x nrhs] := L^-1 X (variant 0) or L^-T X (variant 1)
-    const double *L;
-    double *X;
-    int ldl, ldx, nb, pad_;
-};
-
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int find_task(const int *__restrict__ prefix, int ntasks, int bid) {
     int lo = 0, hi = ntasks;  // prefix has ntasks+1 entries; find t with prefix[t] <= bid < prefix[t+1]
@@ -564,7 +549,7 @@ __global__ void __launch_bounds__(256) logdet_final_kernel(const double *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solve-phase kernels. Right-hand sides live in a permuted n x nrhs column-major work array `y`.
+// Solve phase: right-hand sides live in a permuted n x nrhs column-major work array `y` (sweeps: solve_kernels.cuh).
 // ------------------------------------------------------------------------------------------------
 // y[k, r] = b[perm[k], r]  (gather)  /  x[perm[k], r] = y[k, r]  (scatter)
 __global__ void permute_rows_kernel(double *__restrict__ dst, const double *__restrict__ src,
@@ -576,130 +561,6 @@ __global__ void permute_rows_kernel(double *__restrict__ dst, const double *__re
     for (int r = 0; r < nrhs; r++) {
         if (scatter) dst[p + r * ld_dst] = src[k + r * ld_src];
         else dst[k + r * ld_dst] = src[p + r * ld_src];
-    }
-}
-
-// Forward-solve assembly: supernode s pulls its children's update vectors (fixed order).
-//   rows that fall inside s's own columns add into y, the others into u_s (zero-filled first).
-__global__ void __launch_bounds__(256)
-fwd_assemble_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
-                    const int *__restrict__ child_idx, const int *__restrict__ relidx,
-                    double *__restrict__ y, long long ldy, double *__restrict__ uvec, long long ldu) {
-    const SuperMeta P = meta[supers[blockIdx.x]];
-    const int nr = P.nrow - P.ns;
-    const int r = blockIdx.y;               // one right-hand side per blockIdx.y
-    double *us = uvec + P.uvec_off + (long long)r * ldu;
-    for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
-    __syncthreads();
-    double *ys = y + P.first + (long long)r * ldy;
-    for (int ci = P.child_begin; ci < P.child_end; ci++) {
-        const SuperMeta C = meta[child_idx[ci]];
-        const int cnr = C.nrow - C.ns;
-        const int *rel = relidx + C.rowptr + C.ns;
-        const double *uc = uvec + C.uvec_off + (long long)r * ldu;
-        for (int i = threadIdx.x; i < cnr; i += 256) {
-            const int p = rel[i];
-            if (p < P.ns) ys[p] += uc[i]; else us[p - P.ns] += uc[i];
-        }
-        __syncthreads();
-    }
-}
-
-// Small triangular solves on nb x nrhs blocks: one warp per right-hand side, rows spread over lanes.
-//   VAR 0: L x = b (forward), VAR 1: L^T x = b (backward). L (nb x nb, lower) staged in smem.
-template <int VAR>
-__global__ void __launch_bounds__(256)
-trsv_block_kernel(const TrsvTask *__restrict__ tasks, int nrhs) {
-    __shared__ double sL[POTRF_NB][POTRF_NB + 1];
-    const TrsvTask T = tasks[blockIdx.x];
-    const int nb = T.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < nb * nb; e += 256) {
-        int i = e % nb, j = e / nb;
-        sL[i][j] = (i >= j) ? T.L[i + (long long)j * T.ldl] : 0.0;
-    }
-    __syncthreads();
-    for (int r = blockIdx.y * 8 + warp; r < nrhs; r += 8 * gridDim.y) {
-        double *xp = T.X + (long long)r * T.ldx;
-        double x0 = lane < nb ? xp[lane] : 0.0;
-        double x1 = lane + 32 < nb ? xp[lane + 32] : 0.0;
-        if (VAR == 0) {
-            for (int j = 0; j < nb; j++) {
-                double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31);
-                xj /= sL[j][j];
-                if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-                if (lane > j && lane < nb) x0 -= sL[lane][j] * xj;
-                if (lane + 32 > j && lane + 32 < nb) x1 -= sL[lane + 32][j] * xj;
-            }
-        } else {
-            for (int j = nb - 1; j >= 0; j--) {
-                double xj = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31);
-                xj /= sL[j][j];
-                if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-                if (lane < j) x0 -= sL[j][lane] * xj;
-                if (lane + 32 < j) x1 -= sL[j][lane + 32] * xj;
-            }
-        }
-        if (lane < nb) xp[lane] = x0;
-        if (lane + 32 < nb) xp[lane + 32] = x1;
-    }
-}
-
-// C[m x nrhs] -= A[m x k] * X[k x nrhs]; one thread per row of A, RB right-hand sides in registers.
-// A is streamed exactly once per RB columns with fully coalesced loads.
-template <int RB>
-__global__ void __launch_bounds__(128)
-gemv_n_kernel(const VecTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs) {
-    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const VecTask T = tasks[t];
-    const int row = (blockIdx.x - tile_prefix[t]) * 128 + threadIdx.x;
-    if (row >= T.m) return;
-    for (int r0 = 0; r0 < nrhs; r0 += RB) {
-        double acc[RB];
-#pragma unroll
-        for (int q = 0; q < RB; q++) acc[q] = 0.0;
-        const double *ap = T.A + row;
-        const double *xp = T.X + (long long)r0 * T.ldx;
-#pragma unroll 4
-        for (int kk = 0; kk < T.k; kk++) {
-            const double a = ap[(long long)kk * T.lda];
-#pragma unroll
-            for (int q = 0; q < RB; q++)
-                if (r0 + q < nrhs) acc[q] += a * xp[kk + (long long)q * T.ldx];
-        }
-#pragma unroll
-        for (int q = 0; q < RB; q++)
-            if (r0 + q < nrhs) T.C[row + (long long)(r0 + q) * T.ldc] -= acc[q];
-    }
-}
-
-// C[kk, r] -= sum_i A[i, kk] * X[idx[i], r]  (A^T times gathered rows); one warp per column kk of A.
-template <int RB>
-__global__ void __launch_bounds__(256)
-gemv_t_kernel(const VecTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs) {
-    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const VecTask T = tasks[t];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kk = (blockIdx.x - tile_prefix[t]) * 8 + warp;
-    if (kk >= T.k) return;
-    const double *ap = T.A + (long long)kk * T.lda;
-    for (int r0 = 0; r0 < nrhs; r0 += RB) {
-        double acc[RB];
-#pragma unroll
-        for (int q = 0; q < RB; q++) acc[q] = 0.0;
-        for (int i = lane; i < T.m; i += 32) {
-            const double a = ap[i];
-            const long long xr = T.idx ? (long long)T.idx[i] : (long long)i;
-#pragma unroll
-            for (int q = 0; q < RB; q++)
-                if (r0 + q < nrhs) acc[q] += a * T.X[xr + (long long)(r0 + q) * T.ldx];
-        }
-#pragma unroll
-        for (int q = 0; q < RB; q++) {
-            double v = acc[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && r0 + q < nrhs) T.C[kk + (long long)(r0 + q) * T.ldc] -= v;
-        }
     }
 }
 

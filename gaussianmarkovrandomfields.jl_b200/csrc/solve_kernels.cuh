@@ -1,0 +1,398 @@
+// solve_kernels.cuh -- level-scheduled supernodal triangular solves for a few right-hand sides (nrhs <= 8).
+//
+// The solves are HBM-bound: the factor panels are streamed exactly once per direction, everything else (the
+// right-hand sides, the 64x64 inverted diagonal blocks) lives in L2. Design points, all driven by the first B200
+// measurements (profiles/r01_perf_1m_first.log: 242 GB/s with the one-thread-per-row / one-warp-per-column kernels):
+//   * ONE launch per 64-column block step of a supernode chain, no cross-CTA reductions:
+//       forward  (L y = b)  is right-looking over row tiles   : b[rows below] -= L[rows, K_j] x_j
+//       backward (L' x = y) is right-looking over column tiles: t[cols left]  -= L[K_j, cols]' x_j
+//     so every output element has one owner CTA and a fixed summation order (bit-reproducible).
+//   * the small triangular solves with the diagonal blocks are replaced by products with explicitly inverted
+//     64x64 blocks (diag_inv_kernel, run once per factorization, lazily before the first solve); the CTA that owns
+//     the tile holding the NEXT block of the chain applies that inverse right after its update ("look-ahead"), so
+//     the block solve never needs a launch of its own.
+//   * a CTA owns a 64 x 64 tile (32 KB of L): 8 warps x 8 columns, every thread issues its 16 independent 8-byte
+//     loads before the first use -> ~32 KB in flight per CTA, several CTAs per SM.
+#pragma once
+#include "kernels.cuh"
+
+namespace gmrf {
+
+constexpr int SOLVE_NB = 64;
+
+struct InvTask {          // one diagonal block of the factor to invert
+    const double *L;      // nb x nb lower triangle at L, leading dimension ldl
+    double *inv;          // nb x nb, leading dimension nb, zeros above the diagonal
+    int ldl, nb;
+};
+
+struct FwdStepTask {      // block column K_j = [k0, k1) of a supernode, x_j final in `x`
+    const double *L;      // first row below the diagonal block: panel + k0*ld + k1
+    const double *inv_next;   // inverse of the next diagonal block (nb_next x nb_next) or nullptr
+    const double *x;      // x_j (nb entries per right-hand side, stride ldy)
+    double *y;            // rows k1.. of the supernode's own columns (ms of them), stride ldy
+    double *u;            // update vector of the supernode (rows beyond ns), stride ldu
+    int ld, nb, ms, m;    // m = rows below the block (ms own-column rows + nr update rows)
+    int nb_next, pad_;
+};
+
+struct BwdGatherTask {    // t_S = y_S - L21' x_R for one supernode, then x of the LAST block of its chain
+    const double *L21;    // panel + ns (nr x ns, leading dimension ld)
+    const int *idx;       // global (permuted) rows of R (nr entries)
+    const double *inv_last;   // inverse of the last diagonal block (nb_last x nb_last)
+    double *y;            // own columns of the supernode (ns entries), stride ldy
+    int ld, ns, nr, nb_last;
+    int tile0, pad_;      // first 64-column tile this task launches (nr == 0: only the last one)
+};
+
+struct BwdStepTask {      // block row K_j = [k0, k1) of L11, x_j final in `x`
+    const double *L;      // panel + k0 (row k0, column 0), leading dimension ld
+    const double *inv_prev;   // inverse of diagonal block j-1 (64 x 64)
+    const double *x;      // x_j (nb entries), stride ldy
+    double *y;            // own columns 0.. of the supernode, stride ldy
+    int ld, nb, ncols, pad_;  // ncols = k0 (a multiple of 64)
+};
+
+// ------------------------------------------------------------------------------------------------
+// inv(L_jj) for every 64-column diagonal block: thread c builds column c by forward substitution.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SOLVE_NB) diag_inv_kernel(const InvTask *__restrict__ tasks) {
+    __shared__ double sL[SOLVE_NB][SOLVE_NB + 1];   // identity-padded beyond nb
+    const InvTask T = tasks[blockIdx.x];
+    const int nb = T.nb, c = threadIdx.x;
+#pragma unroll 8
+    for (int k = 0; k < SOLVE_NB; k++) {                // coalesced column loads, thread = row
+        double v = (k == c) ? 1.0 : 0.0;
+        if (c < nb && k <= c && k < nb) v = T.L[c + (long long)k * T.ldl];
+        sL[c][k] = v;
+    }
+    __syncthreads();
+    double v[SOLVE_NB];                                 // column c of the inverse, fully unrolled -> registers
+#pragma unroll
+    for (int i = 0; i < SOLVE_NB; i++) {
+        double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= sL[i][k] * v[k];   // v[k] == 0 for k < c
+        v[i] = (i >= c) ? s / sL[i][i] : 0.0;
+    }
+    if (c < nb) {
+#pragma unroll
+        for (int i = 0; i < SOLVE_NB; i++)
+            if (i < nb) T.inv[i + (long long)c * nb] = v[i];
+    }
+}
+
+// Fixed-tree reduction of 8 per-lane values over the 32 lanes of a warp with 9 shuffles (instead of 40):
+// three transposing rounds halve the number of live values while folding lane bits 4, 3, 2, two plain rounds fold
+// bits 1, 0. On return every lane holds the full sum of value index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1).
+__device__ __forceinline__ double warp_reduce8(double (&v)[8], int lane) {
+    const unsigned full = 0xffffffffu;
+    double a[4];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double send = hi ? v[i] : v[i + 4];
+            const double keep = hi ? v[i + 4] : v[i];
+            a[i] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    double b[2];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double send = hi ? a[i] : a[i + 2];
+            const double keep = hi ? a[i + 2] : a[i];
+            b[i] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    double c;
+    {
+        const bool hi = lane & 4;
+        const double send = hi ? b[0] : b[1];
+        const double keep = hi ? b[1] : b[0];
+        c = keep + __shfl_xor_sync(full, send, 4);
+    }
+    c += __shfl_xor_sync(full, c, 2);
+    c += __shfl_xor_sync(full, c, 1);
+    return c;
+}
+__device__ __forceinline__ int warp_reduce8_index(int lane) {
+    return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
+// The inverted diagonal block is fetched into registers at the START of the kernel by the one CTA that will need it
+// (16 independent loads per thread, overlapped with the tile loads), and applied from registers afterwards.
+//   lower   : x[r, q] = sum_c inv[r + c*nb] * b[c][q]    thread (r = tid & 63, part = tid >> 6) owns 16 columns
+//   lower^T : x[c, q] = sum_r inv[r + c*nb] * t[r][q]    warp owns 8 columns, lanes own rows lane, lane + 32
+__device__ __forceinline__ void load_inv_lower(double (&g)[16], const double *__restrict__ inv, int nb, int tid) {
+    const int r = tid & 63, part = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int c = part * 16 + i;
+        g[i] = (r < nb && c <= r) ? inv[r + (long long)c * nb] : 0.0;
+    }
+}
+template <int RB>
+__device__ __forceinline__ void apply_inv_lower(const double (&g)[16], int nb, const double (*sb)[RB], double (*sp)[SOLVE_NB][RB],
+                                                double *__restrict__ out, long long ldo, int nrhs, int tid) {
+    const int r = tid & 63, part = tid >> 6;
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            s0 += g[i] * sb[part * 16 + i][q];
+            s1 += g[i + 1] * sb[part * 16 + i + 1][q];
+        }
+        sp[part][r][q] = s0 + s1;
+    }
+    __syncthreads();
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+        if (rr < nb && q < nrhs) out[rr + q * ldo] = (sp[0][rr][q] + sp[1][rr][q]) + (sp[2][rr][q] + sp[3][rr][q]);
+    }
+}
+
+__device__ __forceinline__ void load_inv_lower_t(double (&g)[16], const double *__restrict__ inv, int nb, int warp, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = warp * 8 + i;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = lane + 32 * h;
+            g[2 * i + h] = (c < nb && r < nb && r >= c) ? inv[r + (long long)c * nb] : 0.0;
+        }
+    }
+}
+template <int RB>
+__device__ __forceinline__ void apply_inv_lower_t(const double (&g)[16], int nb, const double (*st)[RB],
+                                                  double *__restrict__ out, long long ldo, int nrhs, int warp, int lane) {
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        if (q >= nrhs) break;
+        double p[8];
+        const double t0 = lane < nb ? st[lane][q] : 0.0, t1 = lane + 32 < nb ? st[lane + 32][q] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = g[2 * i] * t0 + g[2 * i + 1] * t1;
+        const double s = warp_reduce8(p, lane);
+        const int c = warp * 8 + warp_reduce8_index(lane);
+        if ((lane & 3) == 0 && c < nb) out[c + q * ldo] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward assembly of one level: supernode s pulls its children's update vectors (fixed order) into its own
+// rows of y and into u_s, then the first block of its chain is solved: x_0 = inv(L_00) b_0.
+// One CTA per (supernode, right-hand side).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
+                       const int *__restrict__ child_idx, const int *__restrict__ relidx,
+                       const double *__restrict__ Linv, const long long *__restrict__ inv_base,
+                       double *__restrict__ y, long long ldy, double *__restrict__ uvec, long long ldu) {
+    __shared__ double sb[SOLVE_NB][1];
+    __shared__ double sp[4][SOLVE_NB][1];
+    const int s = supers[blockIdx.x];
+    const SuperMeta P = meta[s];
+    const int nr = P.nrow - P.ns;
+    const int r = blockIdx.y;
+    const int nb0 = min(P.ns, SOLVE_NB);
+    double g[16];
+    load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
+    double *us = uvec + P.uvec_off + (long long)r * ldu;
+    for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
+    __syncthreads();
+    double *ys = y + P.first + (long long)r * ldy;
+    for (int ci = P.child_begin; ci < P.child_end; ci++) {
+        const SuperMeta C = meta[child_idx[ci]];
+        const int cnr = C.nrow - C.ns;
+        const int *rel = relidx + C.rowptr + C.ns;
+        const double *uc = uvec + C.uvec_off + (long long)r * ldu;
+        for (int i = threadIdx.x; i < cnr; i += 256) {
+            const int p = rel[i];
+            if (p < P.ns) ys[p] += uc[i]; else us[p - P.ns] += uc[i];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < SOLVE_NB) sb[threadIdx.x][0] = threadIdx.x < nb0 ? ys[threadIdx.x] : 0.0;
+    __syncthreads();
+    apply_inv_lower<1>(g, nb0, sb, sp, ys, 0, 1, threadIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward block step: rows below block column K_j:  b[r] -= sum_k L[r, k] x_j[k]; the tile that holds the next
+// diagonal block then solves it (x_{j+1} = inv(L_{j+1,j+1}) b_{j+1}) and stores x in place of b.
+// ------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(256)
+fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
+                long long ldy, long long ldu) {
+    __shared__ double xs[SOLVE_NB][RB];
+    __shared__ double part[8][SOLVE_NB][RB];
+    __shared__ double sb[SOLVE_NB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const FwdStepTask T = tasks[t];
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = tile * SOLVE_NB;
+    const bool head = (tile == 0 && T.nb_next > 0);
+    double g[16];
+    if (head) load_inv_lower(g, T.inv_next, T.nb_next, tid);
+    // issue the tile loads first: 8 columns x 2 rows per thread
+    double l[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int kk = warp * 8 + i;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = row0 + lane + 32 * h;
+            l[i][h] = (kk < T.nb && r < T.m) ? T.L[r + (long long)kk * T.ld] : 0.0;
+        }
+    }
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
+        xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double xv = xs[warp * 8 + i][q];
+            a0 += l[i][0] * xv;
+            a1 += l[i][1] * xv;
+        }
+        part[warp][lane][q] = a0;
+        part[warp][lane + 32][q] = a1;
+    }
+    __syncthreads();
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+        const int r = row0 + rr;
+        if (head && rr >= T.nb_next) sb[rr][q] = 0.0;
+        if (r >= T.m || q >= nrhs) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += part[w][rr][q];
+        double *dst = (r < T.ms) ? (T.y + r + q * ldy) : (T.u + (r - T.ms) + q * ldu);
+        const double v = *dst - s;
+        if (head && rr < T.nb_next) sb[rr][q] = v; else *dst = v;
+    }
+    if (!head) return;
+    __syncthreads();
+    apply_inv_lower<RB>(g, T.nb_next, sb, (double (*)[SOLVE_NB][RB])part, T.y, ldy, nrhs, tid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward, first phase of a level: t_S = y_S - L21' x_R with x_R gathered through the row structure; the tile
+// that holds the last block of the chain then solves it: x_last = inv(L_last)' t_last.
+// One CTA per 64 own columns, one warp per 8 columns, lanes stride the nr rows (coalesced column reads).
+// ------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(256)
+bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
+                  const double *__restrict__ xg, long long ldy) {
+    __shared__ double st[SOLVE_NB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const BwdGatherTask T = tasks[t];
+    const int tile = T.tile0 + (blockIdx.x - tile_prefix[t]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = tile * SOLVE_NB + warp * 8;
+    const int nblk = (T.ns + SOLVE_NB - 1) / SOLVE_NB;
+    const bool tail = (tile == nblk - 1);
+    double g[16];
+    if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
+    double acc[8][RB];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int q = 0; q < RB; q++) acc[i][q] = 0.0;
+    if (c0 < T.ns) {
+#pragma unroll 2
+        for (int r = lane; r < T.nr; r += 32) {
+            const long long gr = T.idx[r];
+            double xv[RB];
+#pragma unroll
+            for (int q = 0; q < RB; q++) xv[q] = (q < nrhs) ? xg[gr + q * ldy] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double lv = (c0 + i < T.ns) ? T.L21[r + (long long)(c0 + i) * T.ld] : 0.0;
+#pragma unroll
+                for (int q = 0; q < RB; q++) acc[i][q] += lv * xv[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        double p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = acc[i][q];
+        const double s = warp_reduce8(p, lane);
+        const int cl = warp * 8 + warp_reduce8_index(lane);      // column within the tile
+        const int c = tile * SOLVE_NB + cl;
+        if ((lane & 3) == 0 && c < T.ns && q < nrhs) {
+            const double v = T.y[c + q * ldy] - s;
+            if (tail) st[cl][q] = v; else T.y[c + q * ldy] = v;
+        }
+    }
+    if (!tail) return;
+    __syncthreads();
+    apply_inv_lower_t<RB>(g, T.nb_last, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward block step: columns left of block row K_j:  t[c] -= sum_{r in K_j} L[r, c] x_j[r]; the tile that
+// holds block j-1 then solves it: x_{j-1} = inv(L_{j-1,j-1})' t_{j-1}.
+// ------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(256)
+bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
+                long long ldy) {
+    __shared__ double xs[SOLVE_NB][RB];
+    __shared__ double st[SOLVE_NB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const BwdStepTask T = tasks[t];
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = tile * SOLVE_NB + warp * 8;
+    const int ntiles = T.ncols / SOLVE_NB;
+    const bool tail = (tile == ntiles - 1);
+    double g[16];
+    if (tail) load_inv_lower_t(g, T.inv_prev, SOLVE_NB, warp, lane);
+    double l[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = lane + 32 * h;
+            l[i][h] = (r < T.nb) ? T.L[r + (long long)(c0 + i) * T.ld] : 0.0;
+        }
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
+        xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        if (q >= nrhs) break;
+        const double x0 = xs[lane][q], x1 = xs[lane + 32][q];
+        double p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = l[i][0] * x0 + l[i][1] * x1;
+        const double s = warp_reduce8(p, lane);
+        const int cl = warp * 8 + warp_reduce8_index(lane);
+        if ((lane & 3) == 0) {
+            double *dst = T.y + (long long)tile * SOLVE_NB + cl + q * ldy;
+            const double v = *dst - s;
+            if (tail) st[cl][q] = v; else *dst = v;
+        }
+    }
+    if (!tail) return;
+    __syncthreads();
+    apply_inv_lower_t<RB>(g, SOLVE_NB, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
+}
+
+}  // namespace gmrf
