@@ -27,7 +27,7 @@ namespace {
 thread_local std::string g_create_error;
 
 enum LaunchKind : int {
-    K_ASSEMBLE, K_POTRF, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
+    K_ASSEMBLE, K_POTRF_UNUSED, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
     K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL
 };
 
@@ -76,19 +76,16 @@ struct gmrf_b200_handle {
     int *d_rowidx = nullptr, *d_relidx = nullptr, *d_child = nullptr, *d_prefix = nullptr, *d_superlist = nullptr;
     SuperMeta *d_meta = nullptr;
     GemmTask *d_gemm = nullptr;
-    PotrfTask *d_potrf = nullptr;
     PanelTask *d_panel = nullptr;
-    int *d_panel_cnt = nullptr;   // per-launch reader counters of the fused panel kernel (self-resetting)
     TrsmTask *d_trsm = nullptr;
     AsmItem *d_items = nullptr;
     FwdStepTask *d_fwd = nullptr;
     BwdGatherTask *d_bwdg = nullptr;
     BwdStepTask *d_bwds = nullptr;
-    InvTask *d_invtasks = nullptr;
-    double *d_Linv = nullptr;          // explicitly inverted 64-column diagonal blocks (solve phase)
+    double *d_Linv = nullptr;          // inverted 64-column diagonal blocks: written by the factorization (TRSM by
+                                       // GEMM), reused by the solve phase
     long long *d_invbase = nullptr;    // per supernode: offset of its first inverted block in d_Linv
-    i64 n_invtasks = 0;
-    bool inv_valid = false;
+    std::vector<long long> inv_base;   // host copy
     std::map<int, cudaGraphExec_t> solve_graphs;   // key = nrhs * 2 + mode
     TransTask *d_trans = nullptr;
     // selinv task tables are built lazily (they need d_Zx / d_zw)
@@ -149,15 +146,12 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 // ------------------------------------------------------------------------------------------------
 struct Builder {
     std::vector<GemmTask> gemm;
-    std::vector<PotrfTask> potrf;
     std::vector<PanelTask> panel;
     std::vector<TrsmTask> trsm;
     std::vector<AsmItem> items;
     std::vector<FwdStepTask> fwd;
     std::vector<BwdGatherTask> bwdg;
     std::vector<BwdStepTask> bwds;
-    std::vector<InvTask> inv;
-    std::vector<long long> inv_base;
     std::vector<TransTask> trans;
     std::vector<int> superlist;
     std::vector<int> prefix;
@@ -165,15 +159,15 @@ struct Builder {
     double gemm_flops = 0;
 
     // GEMM launches: tasks are split into a small-tile and a large-tile launch
-    void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/) {
+    void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/, bool force_small = false, double flop_weight = 1.0) {
         if (tasks.empty()) return;
         std::vector<GemmTask> small, large;
         for (auto &t : tasks) {
             if (t.m <= 0 || t.n <= 0) continue;
-            gemm_flops += 2.0 * t.m * (double)t.n * t.k * ((t.flags & GEMM_LOWER) ? 0.5 * (1.0 + 1.0 / std::max(1, t.m)) * ((double)t.n <= t.m ? (2.0 - (double)t.n / t.m) : 1.0) : 1.0);
+            gemm_flops += flop_weight * 2.0 * t.m * (double)t.n * t.k * ((t.flags & GEMM_LOWER) ? 0.5 * (1.0 + 1.0 / std::max(1, t.m)) * ((double)t.n <= t.m ? (2.0 - (double)t.n / t.m) : 1.0) : 1.0);
             // measured on B200 (profiles/r01_gemm_variants.log): the 64x64 tile (4 CTAs/SM) wins everywhere except very
             // large square-ish products, where the 128x64 tile (warp tile 64x32) is ~4% faster
-            bool big = !naive && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024;
+            bool big = !naive && !force_small && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024;
             (big ? large : small).push_back(t);
         }
         for (int pass = 0; pass < 2; pass++) {
@@ -229,28 +223,9 @@ struct Builder {
         L.aux = mx <= 8 ? 8 : mx <= 16 ? 16 : mx <= 32 ? 32 : 64;
         L.task_off = (i64)panel.size();
         L.ntasks = (int)tasks.size();
-        L.prefix_off = (i64)prefix.size();
-        i64 tot = 0;
-        for (auto &t : tasks) {
-            prefix.push_back((int)tot);
-            tot += std::max(1, cdiv(t.m, 64));
-            panel.push_back(t);
-        }
-        prefix.push_back((int)tot);
-        L.grid = (int)tot;
-        plan.launches.push_back(L);
-        tasks.clear();
-    }
-    void add_potrf(Plan &plan, std::vector<PotrfTask> &tasks) {
-        if (tasks.empty()) return;
-        Launch L;
-        L.kind = K_POTRF;
-        L.aux = 0;
-        L.task_off = (i64)potrf.size();
-        L.ntasks = (int)tasks.size();
         L.prefix_off = -1;
         L.grid = (int)tasks.size();
-        potrf.insert(potrf.end(), tasks.begin(), tasks.end());
+        panel.insert(panel.end(), tasks.begin(), tasks.end());
         plan.launches.push_back(L);
         tasks.clear();
     }
@@ -336,7 +311,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
     const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
     std::vector<AsmItem> its;
     std::vector<PanelTask> pt;
-    std::vector<GemmTask> gt;
+    std::vector<GemmTask> gt, st;
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
         for (const i64 *sp = sb; sp < se; sp++) {
@@ -371,7 +346,16 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                     if (k0 >= ns) continue;
                     i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb, J1 = std::min(J0 + OB, ns);
                     double *P = h->d_Lx + S.panel_off[s];
-                    pt.push_back(PanelTask{P + k0 * ld + k0, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), (int)(nrow - k1)});
+                    double *inv = h->d_Linv + h->inv_base[s] + (k0 / NB) * (i64)NB * NB;
+                    pt.push_back(PanelTask{P + k0 * ld + k0, inv, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), 0});
+                    if (nrow > k1) {   // rows below the block: X = B * inv(L_kk)^T, in place (one 64-wide tile per row strip)
+                        GemmTask g;
+                        g.A = P + k0 * ld + k1; g.B = inv; g.C = P + k0 * ld + k1;
+                        g.m = (int)(nrow - k1); g.n = (int)nb; g.k = (int)nb;
+                        g.lda = g.ldc = (int)ld; g.ldb = (int)nb;
+                        g.flags = GEMM_BETA0 | GEMM_ALPHA_POS; g.pad_ = 0;
+                        st.push_back(g);
+                    }
                     if (J1 > k1) {
                         GemmTask g;
                         g.A = P + k0 * ld + k1; g.B = P + k0 * ld + k1; g.C = P + k1 * ld + k1;
@@ -382,6 +366,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                     }
                 }
                 B.add_panel(plan, pt);
+                B.add_gemm(plan, st, 0, /*force_small=*/true, /*triangular operand: half the flops are algorithmic*/ 0.5);
                 B.add_gemm(plan, gt, 0);
             }
         }
@@ -412,20 +397,7 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     std::vector<BwdGatherTask> gt;
     std::vector<BwdStepTask> bt;
     const i64 BB = (i64)SOLVE_NB * SOLVE_NB;
-    // inverted diagonal blocks
-    B.inv_base.assign(S.nsuper, 0);
-    i64 inv_total = 0;
-    for (i64 s = 0; s < S.nsuper; s++) {
-        B.inv_base[s] = inv_total;
-        i64 ns = S.ns(s), ld = S.panel_ld[s];
-        const double *P = h->d_Lx + S.panel_off[s];
-        for (i64 k0 = 0; k0 < ns; k0 += SOLVE_NB) {
-            i64 nb = std::min<i64>(SOLVE_NB, ns - k0);
-            B.inv.push_back(InvTask{P + k0 * ld + k0, h->d_Linv + inv_total, (int)ld, (int)nb});
-            inv_total += (nb == SOLVE_NB) ? BB : nb * nb;
-        }
-    }
-    auto inv_ptr = [&](i64 s, i64 j) { return (const double *)(h->d_Linv + B.inv_base[s] + j * BB); };
+    auto inv_ptr = [&](i64 s, i64 j) { return (const double *)(h->d_Linv + h->inv_base[s] + j * BB); };
     // forward: L y = b
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
@@ -498,24 +470,143 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
 
 // Selected inversion (Takahashi), per supernode s with panel L = [L11; L21], W = Z[R,R] gathered from the parent:
 //   T' = -W L21 ;  G = I - L21^T T' = I + L21^T W L21 ;  [H; Z_RS] = [G; T'] L11^-1 ;  Z_SS = H^T L11^-1
-// (Z_SS = L11^-T (I + L21^T W L21) L11^-1, Z_RS = -W L21 L11^-1.)
+// (Z_SS = L11^-T (I + L21^T W L21) L11^-1, Z_RS = -W L21 L11^-1.) Right solves with the 64-column diagonal blocks are
+// GEMMs with the inverted blocks the factorization left in d_Linv (in place: one 64-wide tile owns a whole row strip).
+//
+// Root supernodes of the top level (nr == 0, nothing to gather) take a cheaper route that exploits triangularity:
+//   H = L11^-1 is built as a LOWER TRIANGULAR matrix in the (then empty) update pool, restricted to its nonzero rows
+//   and, per row block, to its nonzero k-range (trtri, ~ns^3/3 flops instead of ns^3), and
+//   Z_SS = H^T H is one triangular product written straight into the Z panel (lauum, ~ns^3/3 instead of ns^3).
+// At 1 M dofs the root (ns = 30,502) was half of the selected-inversion time with the generic path.
 void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
     const Symbolic &S = h->S;
     Plan &plan = h->selinv_plan;
     std::vector<AsmItem> its;
-    std::vector<GemmTask> gt;
-    std::vector<TrsmTask> tt;
+    std::vector<GemmTask> gt, st;
     std::vector<TransTask> tr;
+    const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
+    const i64 BBLK = (i64)NB * NB;
+    auto inv_ptr = [&](i64 s, i64 k0) { return (const double *)(h->d_Linv + h->inv_base[s] + (k0 / NB) * BBLK); };
+    // X[row0:, K] := X[row0:, K] * inv(L_KK) (in place), K = [k0, k0 + nb)
+    auto push_block_solve = [&](double *X, i64 ldx, i64 s, i64 k0, i64 nb, i64 m) {
+        if (m <= 0) return;
+        GemmTask g;
+        g.A = X; g.lda = (int)ldx;
+        g.B = inv_ptr(s, k0); g.ldb = (int)nb;             // Bop[j][kk] = inv[kk + j*nb]  (k-contiguous)
+        g.C = X; g.ldc = (int)ldx;
+        g.m = (int)m; g.n = (int)nb; g.k = (int)nb;
+        g.flags = GEMM_BETA0 | GEMM_ALPHA_POS; g.pad_ = 0;
+        st.push_back(g);
+    };
+    std::vector<char> fast(S.nsuper, 0);
+    std::vector<i64> scratch_off(S.nsuper, 0);
+    if (S.nlevels > 0 && h->opt.selinv_fast_root) {
+        i64 l = S.nlevels - 1, used = 0;
+        const i64 pool = std::max(S.upd_total, S.zw_total);
+        for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+            i64 s = S.level_idx[t], ns = S.ns(s);
+            i64 need = (i64)S.panel_ld[s] * ns;
+            if (S.nr(s) == 0 && ns >= 4 * NB && used + need <= pool) { fast[s] = 1; scratch_off[s] = used; used += need; }
+        }
+    }
     for (i64 l = S.nlevels - 1; l >= 0; l--) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        // ---- fast roots -------------------------------------------------------------------------------------
+        {
+            const i64 RBK = 2048;   // row block of the triangular products (k-range is cut per row block)
+            i64 maxouter = 0;
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp;
+                if (!fast[s]) continue;
+                i64 ns = S.ns(s), ld = S.panel_ld[s];
+                maxouter = std::max<i64>(maxouter, cdiv(ns, OB));
+                GemmTask g;   // scratch := I
+                g.A = h->d_Lx; g.B = h->d_Lx; g.lda = g.ldb = 1;
+                g.C = h->d_zw + scratch_off[s]; g.ldc = (int)ld;
+                g.m = g.n = (int)ns; g.k = 0;
+                g.flags = GEMM_BETA0 | GEMM_ADD_I; g.pad_ = 0;
+                gt.push_back(g);
+            }
+            B.add_gemm(plan, gt, 1, true);
+            for (i64 tJ = 0; tJ < maxouter; tJ++) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp;
+                    if (!fast[s]) continue;
+                    i64 ns = S.ns(s), ld = S.panel_ld[s];
+                    i64 J = cdiv(ns, OB) - 1 - tJ;
+                    if (J < 0) continue;
+                    i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                    double *X = h->d_zw + scratch_off[s];
+                    const double *P = h->d_Lx + S.panel_off[s];
+                    for (i64 a = J1; a < ns; a += RBK) {     // X[a:b, J] -= X[a:b, J1:b] L[J1:b, J]
+                        i64 b = std::min(a + RBK, ns);
+                        GemmTask g;
+                        g.A = X + J1 * ld + a; g.lda = (int)ld;
+                        g.B = P + J0 * ld + J1; g.ldb = (int)ld;
+                        g.C = X + J0 * ld + a; g.ldc = (int)ld;
+                        g.m = (int)(b - a); g.n = (int)(J1 - J0); g.k = (int)(b - J1);
+                        g.flags = 0; g.pad_ = 0;
+                        gt.push_back(g);
+                    }
+                }
+                B.add_gemm(plan, gt, 1);
+                for (i64 tj = 0; tj < OB / NB; tj++) {
+                    for (const i64 *sp = sb; sp < se; sp++) {
+                        i64 s = *sp;
+                        if (!fast[s]) continue;
+                        i64 ns = S.ns(s), ld = S.panel_ld[s];
+                        i64 J = cdiv(ns, OB) - 1 - tJ;
+                        if (J < 0) continue;
+                        i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                        i64 jj = cdiv(J1 - J0, NB) - 1 - tj;
+                        if (jj < 0) continue;
+                        i64 k0 = J0 + jj * NB, nb = std::min<i64>(NB, J1 - k0), k1 = k0 + nb;
+                        double *X = h->d_zw + scratch_off[s];
+                        const double *P = h->d_Lx + S.panel_off[s];
+                        if (J1 > k1) {                        // X[k1:, K] -= X[k1:, k1:J1] L[k1:J1, K]
+                            GemmTask g;
+                            g.A = X + k1 * ld + k1; g.lda = (int)ld;
+                            g.B = P + k0 * ld + k1; g.ldb = (int)ld;
+                            g.C = X + k0 * ld + k1; g.ldc = (int)ld;
+                            g.m = (int)(ns - k1); g.n = (int)nb; g.k = (int)(J1 - k1);
+                            g.flags = 0; g.pad_ = 0;
+                            gt.push_back(g);
+                        }
+                        push_block_solve(X + k0 * ld + k0, ld, s, k0, nb, ns - k0);
+                    }
+                    B.add_gemm(plan, gt, 1);
+                    B.add_gemm(plan, st, 1, true, 0.5);
+                }
+            }
+            for (const i64 *sp = sb; sp < se; sp++) {       // Z_SS (lower) = H^T H, one task per row block
+                i64 s = *sp;
+                if (!fast[s]) continue;
+                i64 ns = S.ns(s), ld = S.panel_ld[s];
+                const double *X = h->d_zw + scratch_off[s];
+                double *Z = h->d_Zx + S.panel_off[s];
+                for (i64 a = 0; a < ns; a += RBK) {
+                    i64 b = std::min(a + RBK, ns);
+                    GemmTask g;
+                    g.A = X + a * ld + a; g.lda = (int)ld;     // Aop[i][kk] = H[a + kk, a + i]
+                    g.B = X + a; g.ldb = (int)ld;              // Bop[j][kk] = H[a + kk, j]
+                    g.C = Z + a; g.ldc = (int)ld;
+                    g.m = (int)(b - a); g.n = (int)b; g.k = (int)(ns - a);
+                    g.flags = GEMM_BETA0 | GEMM_ALPHA_POS; g.pad_ = 0;
+                    gt.push_back(g);
+                }
+            }
+            B.add_gemm(plan, gt, 2);
+        }
+        // ---- generic path -----------------------------------------------------------------------------------
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp;
+            if (fast[s]) continue;
             for (i64 c0 = 0; c0 < S.nr(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
         }
         B.add_items(plan, its, K_GATHER);
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
-            if (nr == 0) continue;
+            if (nr == 0 || fast[s]) continue;
             GemmTask g;
             g.A = h->d_zw + S.zw_off[s]; g.lda = S.upd_ld[s];
             g.B = h->d_Lx + S.panel_off[s] + ns; g.ldb = (int)ld;
@@ -527,6 +618,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
         B.add_gemm(plan, gt, 1);
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            if (fast[s]) continue;
             GemmTask g;
             g.A = h->d_Lx + S.panel_off[s] + ns; g.lda = (int)ld;
             g.B = h->d_Zx + S.panel_off[s] + ns; g.ldb = (int)ld;
@@ -537,21 +629,22 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
         }
         B.add_gemm(plan, gt, 2);
         // X := X L11^-1 by block back-substitution, two-level blocking (outer OB, inner NB), lockstep over the level
-        const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
         i64 maxouter = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
+        for (const i64 *sp = sb; sp < se; sp++)
+            if (!fast[*sp]) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
         for (int pass = 0; pass < 2; pass++) {
             // pass 0: all nrow rows of [G; T'];  pass 1: the (transposed) ns x ns block only
             if (pass == 1) {
                 for (const i64 *sp = sb; sp < se; sp++) {
                     i64 s = *sp;
-                    if (S.ns(s) > 1) tr.push_back(TransTask{h->d_Zx + S.panel_off[s], (int)S.ns(s), S.panel_ld[s]});
+                    if (S.ns(s) > 1 && !fast[s]) tr.push_back(TransTask{h->d_Zx + S.panel_off[s], (int)S.ns(s), S.panel_ld[s]});
                 }
                 B.add_trans(plan, tr);
             }
             for (i64 tJ = 0; tJ < maxouter; tJ++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
                     i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                    if (fast[s]) continue;
                     i64 J = cdiv(ns, OB) - 1 - tJ;
                     if (J < 0) continue;
                     i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
@@ -571,6 +664,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
                 for (i64 tj = 0; tj < OB / NB; tj++) {
                     for (const i64 *sp = sb; sp < se; sp++) {
                         i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                        if (fast[s]) continue;
                         i64 J = cdiv(ns, OB) - 1 - tJ;
                         if (J < 0) continue;
                         i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
@@ -589,10 +683,10 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
                             g.flags = 0; g.pad_ = 0;
                             gt.push_back(g);
                         }
-                        tt.push_back(TrsmTask{P + k0 * ld + k0, Z + k0 * ld, (int)ld, (int)ld, (int)m, (int)nb});
+                        push_block_solve(Z + k0 * ld, ld, s, k0, nb, m);
                     }
                     B.add_gemm(plan, gt, 1);
-                    B.add_trsm(plan, tt, 1);
+                    B.add_gemm(plan, st, 1, true, 0.5);
                 }
             }
         }
@@ -663,15 +757,12 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
         case K_ASSEMBLE:
             assemble_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd);
             break;
-        case K_POTRF:
-            potrf_diag_kernel<<<L.grid, 256, 0, st>>>(h->d_potrf + L.task_off, h->d_fail);
-            break;
         case K_PANEL:
             switch (L.aux) {
-                case 8: panel_factor_kernel<8><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
-                case 16: panel_factor_kernel<16><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
-                case 32: panel_factor_kernel<32><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
-                default: panel_factor_kernel<64><<<L.grid, 64, 0, st>>>(h->d_panel + L.task_off, pf, L.ntasks, h->d_fail, h->d_panel_cnt + L.task_off); break;
+                case 8: potrf_inv_kernel<8><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
+                case 16: potrf_inv_kernel<16><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
+                case 32: potrf_inv_kernel<32><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
+                default: potrf_inv64_kernel<<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
             }
             break;
         case K_TRSM0: launch_trsm<0>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
@@ -787,7 +878,6 @@ int do_factor(gmrf_b200_handle *h) {
     h->fail_col = (host_fail == 0x7f7f7f7f) ? 0 : host_fail;
     h->factored = true;
     h->selinv_valid = false;
-    h->inv_valid = false;
     return h->fail_col > 0 ? h->fail_col : 0;
 }
 
@@ -848,11 +938,30 @@ int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i
     if (!h->factored) { h->err = "solve before the first refactorize"; return GMRF_B200_ERR_STATE; }
     if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
     cudaStream_t st = h->stream;
-    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
-    if (!h->inv_valid && h->n_invtasks > 0) {
-        diag_inv_kernel<<<(unsigned)h->n_invtasks, SOLVE_NB, 0, st>>>(h->d_invtasks);
-        h->inv_valid = true;
+    // graphs for the block widths this call needs are built before the timed region starts
+    auto sweep_graph = [&](int nb, cudaGraphExec_t *out) -> int {
+        const int key = nb * 2 + mode;
+        auto it = h->solve_graphs.find(key);
+        if (it == h->solve_graphs.end()) {
+            cudaGraph_t g;
+            cudaGraphExec_t ge;
+            CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_sweeps(h, nb, mode);
+            CUDA_TRY(h, cudaStreamEndCapture(st, &g));
+            CUDA_TRY(h, cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            it = h->solve_graphs.emplace(key, ge).first;
+        }
+        *out = it->second;
+        return 0;
+    };
+    cudaGraphExec_t g_full = nullptr, g_tail = nullptr;
+    if (h->opt.use_graph && S.n > 0 && nrhs > 0) {
+        int rc;
+        if (nrhs >= h->rhs_block && (rc = sweep_graph(h->rhs_block, &g_full))) return rc;
+        if (nrhs % h->rhs_block && (rc = sweep_graph((int)(nrhs % h->rhs_block), &g_tail))) return rc;
     }
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
     const int tpb = 256;
     const int gridn = (int)((S.n + tpb - 1) / tpb);
     for (i64 r0 = 0; r0 < nrhs; r0 += h->rhs_block) {
@@ -865,23 +974,8 @@ int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i
             CUDA_TRY(h, cudaMemcpy2DAsync(h->d_y, sizeof(double) * S.n, dB + r0 * ld, sizeof(double) * ld,
                                           sizeof(double) * S.n, nb, cudaMemcpyDeviceToDevice, st));
         }
-        if (h->opt.use_graph) {
-            const int key = nb * 2 + mode;
-            auto it = h->solve_graphs.find(key);
-            if (it == h->solve_graphs.end()) {
-                cudaGraph_t g;
-                cudaGraphExec_t ge;
-                CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                enqueue_sweeps(h, nb, mode);
-                CUDA_TRY(h, cudaStreamEndCapture(st, &g));
-                CUDA_TRY(h, cudaGraphInstantiate(&ge, g, 0));
-                cudaGraphDestroy(g);
-                it = h->solve_graphs.emplace(key, ge).first;
-            }
-            CUDA_TRY(h, cudaGraphLaunch(it->second, st));
-        } else {
-            enqueue_sweeps(h, nb, mode);
-        }
+        if (h->opt.use_graph) CUDA_TRY(h, cudaGraphLaunch(nb == h->rhs_block ? g_full : g_tail, st));
+        else enqueue_sweeps(h, nb, mode);
         permute_rows_kernel<<<gridn, tpb, 0, st>>>(dX + r0 * ld, h->d_y, h->d_perm, S.n, ld, S.n, nb, 1);
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
@@ -989,6 +1083,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "use_graph") o.use_graph = (int)value;
     else if (k == "outer_block") o.outer_block = (int)value;
     else if (k == "naive_kernels") o.naive_kernels = (int)value;
+    else if (k == "selinv_fast_root") o.selinv_fast_root = (int)value;
     else return GMRF_B200_ERR_ARG;
     return 0;
 }
@@ -1082,12 +1177,16 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
     }
     {
         i64 inv_total = 0;   // doubles in the inverted diagonal blocks (nb x nb each, 64-column blocks)
-        for (i64 s = 0; s < S.nsuper; s++)
+        H->inv_base.assign(S.nsuper, 0);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            H->inv_base[s] = inv_total;
             for (i64 k0 = 0; k0 < S.ns(s); k0 += SOLVE_NB) {
                 i64 nb = std::min<i64>(SOLVE_NB, S.ns(s) - k0);
                 inv_total += nb * nb;
             }
+        }
         TRY_RC(dev_alloc(H, &H->d_Linv, (size_t)inv_total));
+        TRY_RC(dev_upload(H, &H->d_invbase, H->inv_base));
     }
     {
         Builder B;
@@ -1101,18 +1200,12 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         }
         H->gemm_flops_factor = B.gemm_flops;
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
-        TRY_RC(dev_upload(H, &H->d_potrf, B.potrf));
         TRY_RC(dev_upload(H, &H->d_panel, B.panel));
-        TRY_RC(dev_alloc(H, &H->d_panel_cnt, B.panel.size() + 1));
-        if (cudaMemset(H->d_panel_cnt, 0, sizeof(int) * (B.panel.size() + 1)) != cudaSuccess) { H->err = "memset failed"; return fail(GMRF_B200_ERR_CUDA); }
         TRY_RC(dev_upload(H, &H->d_trsm, B.trsm));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
         TRY_RC(dev_upload(H, &H->d_fwd, B.fwd));
         TRY_RC(dev_upload(H, &H->d_bwdg, B.bwdg));
         TRY_RC(dev_upload(H, &H->d_bwds, B.bwds));
-        TRY_RC(dev_upload(H, &H->d_invtasks, B.inv));
-        TRY_RC(dev_upload(H, &H->d_invbase, B.inv_base));
-        H->n_invtasks = (i64)B.inv.size();
         TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
     }
@@ -1426,24 +1519,32 @@ int gmrf_b200_test_gemm(int device, int transa, int transb, int lower, int m, in
     return 0;
 }
 
-int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info) {
+int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv, int *info) {
     if (cudaSetDevice(device) != cudaSuccess) return test_fail("no device");
-    if (n > POTRF_NB) return GMRF_B200_ERR_ARG;
-    double *dA; PotrfTask *dT; int *dF;
-    if (cudaMalloc(&dA, (size_t)lda * n * 8) || cudaMalloc(&dT, sizeof(PotrfTask)) || cudaMalloc(&dF, 4)) return test_fail("alloc");
+    if (n > POTRF_NB || n < 1) return GMRF_B200_ERR_ARG;
+    double *dA, *dI; PanelTask *dT; int *dF;
+    if (cudaMalloc(&dA, (size_t)lda * n * 8) || cudaMalloc(&dI, (size_t)n * n * 8) || cudaMalloc(&dT, sizeof(PanelTask)) || cudaMalloc(&dF, 4))
+        return test_fail("alloc");
     cudaMemcpy(dA, A, (size_t)lda * n * 8, cudaMemcpyHostToDevice);
-    PotrfTask T{dA, lda, n, 0, 0};
+    PanelTask T{dA, dI, lda, n, 0, 0};
     cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
     cudaMemset(dF, 0x7f, 4);
-    potrf_diag_kernel<<<1, 256>>>(dT, dF);
+    if (n <= 8) potrf_inv_kernel<8><<<1, 256>>>(dT, dF);
+    else if (n <= 16) potrf_inv_kernel<16><<<1, 256>>>(dT, dF);
+    else if (n <= 32) potrf_inv_kernel<32><<<1, 256>>>(dT, dF);
+    else potrf_inv64_kernel<<<1, 256>>>(dT, dF);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(A, dA, (size_t)lda * n * 8, cudaMemcpyDeviceToHost);
+    if (inv) cudaMemcpy(inv, dI, (size_t)n * n * 8, cudaMemcpyDeviceToHost);
     int f = 0;
     cudaMemcpy(&f, dF, 4, cudaMemcpyDeviceToHost);
     if (info) *info = (f == 0x7f7f7f7f) ? 0 : f;
-    cudaFree(dA); cudaFree(dT); cudaFree(dF);
+    cudaFree(dA); cudaFree(dI); cudaFree(dT); cudaFree(dF);
     if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
     return 0;
+}
+int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info) {
+    return gmrf_b200_test_potrf_inv(device, n, A, lda, nullptr, info);
 }
 
 int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb) {
@@ -1576,6 +1677,63 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     if (flops) *flops = h->gemm_flops_factor;
     if ((rc = check_launch(h, "profile_refactorize"))) return rc;
     return 0;
+}
+
+// Per-launch device times of one phase (graphs off, a CUDA event pair around every launch on the handle's stream):
+// phase 0 = factorization plan, 1 = selected-inversion plan, 2 = forward sweep, 3 = backward sweep (nrhs columns of
+// whatever the work array holds). Fills up to `cap` entries of kind[] (LaunchKind), grid[] (CTAs), ms[]; *count = launches.
+// Profiling/diagnostics only: phases 0 and 1 recompute from the resident values, phases 2/3 leave the work array dirty.
+int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap, int *kind, int *grid, double *ms, int64_t *count) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored) { h->err = "profile_plan needs a previous refactorize"; return GMRF_B200_ERR_STATE; }
+    const Plan *plan = nullptr;
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    cudaStream_t st = h->stream;
+    if (phase == 0) {
+        plan = &h->factor_plan;
+        cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)h->S.panel_total, st);
+        cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
+        i64 cnt = (i64)h->S.q_src.size();
+        if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+        h->selinv_valid = false;
+    } else if (phase == 1) {
+        if ((rc = build_selinv_tables(h))) return rc;
+        plan = &h->selinv_plan;
+        T = TableSet{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z};
+    } else if (phase == 2 || phase == 3) {
+        plan = phase == 2 ? &h->fwd_plan : &h->bwd_plan;
+        if (nrhs < 1 || nrhs > h->rhs_block) { h->err = "profile_plan: 1 <= nrhs <= 8"; return GMRF_B200_ERR_ARG; }
+    } else {
+        h->err = "profile_plan: phase must be 0..3";
+        return GMRF_B200_ERR_ARG;
+    }
+    const size_t nl = plan->launches.size();
+    std::vector<cudaEvent_t> evs(nl + 1);
+    for (auto &e : evs) cudaEventCreate(&e);
+    for (size_t i = 0; i < nl; i++) {
+        cudaEventRecord(evs[i], st);
+        run_launch(h, plan->launches[i], T, nrhs);
+    }
+    cudaEventRecord(evs[nl], st);
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < nl; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
+        if ((int64_t)i < cap) {
+            if (kind) kind[i] = plan->launches[i].kind;
+            if (grid) grid[i] = plan->launches[i].grid;
+            if (ms) ms[i] = t;
+        }
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+    if (count) *count = (int64_t)nl;
+    if (phase == 0) {
+        logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, h->S.n, h->d_partial);
+        logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+    return check_launch(h, "profile_plan");
 }
 
 // Page-lock / unlock a caller-owned host buffer (e.g. the workspace's nzval array) so refactorize() copies it with

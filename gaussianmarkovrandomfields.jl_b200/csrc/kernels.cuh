@@ -35,24 +35,18 @@ struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
     int pad_;
 };
 
-struct PotrfTask {       // in-place Cholesky of an nb x nb diagonal block (lower)
-    double *A;
-    int lda, nb;
-    int col0;            // global (permuted) column of the block's first column, for pivot reporting
-    int pad_;
-};
-
 struct TrsmTask {        // B[m x nb] := B * L^-T (variant 0) or B * L^-1 (variant 1), L lower nb x nb
     const double *L;
     double *B;
     int ldl, ldb, m, nb;
 };
 
-struct PanelTask {       // fused block-column step: D := chol(D) (nb x nb), rows below := rows * D^-T
-    double *D;           // diagonal block; the m rows below start at D + nb, same leading dimension
+struct PanelTask {       // diagonal block step: D := chol(D) (nb x nb, in place, lower) and inv := D^-1
+    double *D;           // diagonal block, leading dimension ld
+    double *inv;         // nb x nb, leading dimension nb, zeros above the diagonal (reused by the solve phase)
     int ld, nb;
     int col0;            // global (permuted) column of the block's first column, for pivot reporting
-    int m;               // rows below the diagonal block
+    int pad_;
 };
 
 struct AsmItem {         // one column tile of one parent front
@@ -156,8 +150,15 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const GemmTask T = tasks[t];
     const int local = blockIdx.x - tile_prefix[t];
-    const int mt = (T.m + BM - 1) / BM;
-    const int tm = local % mt, tn = local / mt;
+    const int mt = (T.m + BM - 1) / BM, nt = (T.n + BN - 1) / BN;
+    // L2-friendly rasterisation: consecutive CTAs sweep bands of GEMM_BAND row tiles column by column, so one wave of
+    // resident CTAs covers a roughly square patch of C and every operand strip it streams is shared by many CTAs
+    // (ncu, 8192^2 x 2048 with the plain column-major order: 15 GB of DRAM reads for 0.27 GB of operands).
+    constexpr int GEMM_BAND = 16;
+    const int band = local / (GEMM_BAND * nt);
+    const int rem = local - band * GEMM_BAND * nt;
+    const int bh = min(GEMM_BAND, mt - band * GEMM_BAND);
+    const int tm = band * GEMM_BAND + rem % bh, tn = rem / bh;
     const int m0 = tm * BM, n0 = tn * BN;
     if ((T.flags & GEMM_LOWER) && n0 >= m0 + BM) return;  // tile strictly above the diagonal
 
@@ -257,46 +258,7 @@ __global__ void gemm_naive_kernel(const GemmTask *__restrict__ tasks, const int 
     *p = v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Diagonal-block Cholesky: one CTA (256 threads) per nb x nb block (nb <= 64), block staged in smem.
-// Non-positive pivots are recorded with an integer atomicMin (deterministic) and produce NaNs downstream,
-// matching the reference's `check=false` factorization (backend.jl:184).
-// ------------------------------------------------------------------------------------------------
 constexpr int POTRF_NB = 64;
-
-__global__ void __launch_bounds__(256) potrf_diag_kernel(const PotrfTask *__restrict__ tasks, int *__restrict__ fail_col) {
-    __shared__ double sA[POTRF_NB][POTRF_NB + 1];
-    const PotrfTask T = tasks[blockIdx.x];
-    const int nb = T.nb, tid = threadIdx.x;
-    for (int e = tid; e < nb * nb; e += 256) {
-        int i = e % nb, j = e / nb;
-        sA[i][j] = (i >= j) ? T.A[i + (long long)j * T.lda] : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < nb; j++) {
-        // column j is final up to the scaling: all updates from columns < j were applied by earlier iterations
-        double d = sA[j][j];
-        __syncthreads();
-        if (tid == 0) {
-            if (!(d > 0.0)) atomicMin(fail_col, T.col0 + j + 1);
-            sA[j][j] = sqrt(d);
-        }
-        double inv = 1.0 / sqrt(d);
-        for (int i = j + 1 + tid; i < nb; i += 256) sA[i][j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: A[r][c] -= A[r][j] * A[c][j], j < c <= r < nb
-        const int rem = nb - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            int r = j + 1 + e % rem, c = j + 1 + e / rem;
-            if (r >= c) sA[r][c] -= sA[r][j] * sA[c][j];
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < nb * nb; e += 256) {
-        int i = e % nb, j = e / nb;
-        if (i >= j) T.A[i + (long long)j * T.lda] = sA[i][j];
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Right-side triangular solve on row strips: one thread owns one row of B (kept in registers), L staged in smem.
@@ -353,96 +315,191 @@ trsm_strip_kernel(const TrsmTask *__restrict__ tasks, const int *__restrict__ ti
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused block-column step of the panel factorization (latency-critical: one launch per 64 columns of a chain):
-// every CTA re-factors the nb x nb diagonal block redundantly (identical arithmetic -> identical bits), one row
-// per thread held in registers, then solves its own 64-row strip X L^T = B by forward substitution.
-// CTA 0 of a task writes the factored diagonal block back and reports non-positive pivots.
+// Diagonal-block step of the panel factorization (latency-critical: one launch per 64 columns of a chain):
+// ONE CTA factors the nb x nb block in shared memory (right-looking, 256 threads on the trailing update) and then
+// inverts the triangular factor (thread c builds column c of L^-1 by forward substitution, registers only).
+// The rows below the block are then solved by a DMMA GEMM with the inverted block (X = B * L^-T, in place), and
+// the same inverted blocks serve the triangular solves later (solve_kernels.cuh), so they cost nothing extra there.
+// Non-positive pivots are recorded with an integer atomicMin (deterministic) and produce NaNs downstream,
+// matching the reference's `check=false` factorization (backend.jl:184).
 // ------------------------------------------------------------------------------------------------
 template <int NBT>
-__global__ void __launch_bounds__(64)
-panel_factor_kernel(const PanelTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks,
-                    int *__restrict__ fail_col, int *__restrict__ readers) {
-    __shared__ double sL[NBT][NBT + 1];
-    __shared__ double scol[64];
-    __shared__ double sinv[64];
-    __shared__ double s_piv;
-    __shared__ int s_writer;
-    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const PanelTask T = tasks[t];
-    const int strip = blockIdx.x - tile_prefix[t];
-    const int ntiles = tile_prefix[t + 1] - tile_prefix[t];
+__global__ void __launch_bounds__(256)
+potrf_inv_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col) {
+    __shared__ double sA[NBT][NBT + 1];   // identity-padded beyond nb
+    const PanelTask T = tasks[blockIdx.x];
     const int nb = T.nb, tid = threadIdx.x;
-    {
-        double a[NBT];   // row `tid` of the diagonal block (identity-padded beyond nb)
-#pragma unroll
-        for (int k = 0; k < NBT; k++) {
-            double v = (k == tid) ? 1.0 : 0.0;
-            if (tid < nb && k < nb && k <= tid) v = T.D[tid + (long long)k * T.ld];
-            a[k] = v;
-        }
-#pragma unroll
-        for (int j = 0; j < NBT; j++) {
-            // critical path per step: rsqrt of the pivot -> scale column j -> update column j+1 (no divisions)
-            if (tid == j) {
-                const double d = a[j];
-                if (!(d > 0.0) && strip == 0 && j < nb) atomicMin(fail_col, T.col0 + j + 1);
-                const double r = rsqrt(d);
-                s_piv = r;
-                a[j] = d * r;          // sqrt(d)
-                sinv[j] = r;           // 1 / L_jj, reused by the strip solve below
-            }
-            __syncthreads();
-            double lij = 0.0;
-            if (tid > j && tid < NBT) { lij = a[j] * s_piv; a[j] = lij; scol[tid] = lij; }
-            __syncthreads();
-#pragma unroll
-            for (int k = j + 1; k < NBT; k++)
-                if (k <= tid) a[k] -= lij * scol[k];
-        }
-        if (tid < NBT) {
-#pragma unroll
-            for (int k = 0; k < NBT; k++) sL[tid][k] = (k <= tid) ? a[k] : 0.0;
-        }
-        // In-place write-back of the factored diagonal block: only the LAST CTA of this task to get here writes,
-        // because every other CTA has then finished reading the unfactored block (all CTAs hold identical bits).
-        __syncthreads();
-        if (tid == 0) {
-            int last = 1;
-            if (ntiles > 1) {
-                __threadfence();
-                last = (atomicAdd(readers + t, 1) == ntiles - 1);
-                if (last) readers[t] = 0;   // re-arm for the next replay of the graph
-            }
-            s_writer = last;
-        }
-        __syncthreads();
-        if (s_writer && tid < nb) {
-#pragma unroll
-            for (int k = 0; k < NBT; k++)
-                if (k <= tid) T.D[tid + (long long)k * T.ld] = a[k];
-        }
+    for (int e = tid; e < NBT * NBT; e += 256) {
+        const int i = e % NBT, j = e / NBT;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j <= i) v = T.D[i + (long long)j * T.ld];
+        sA[i][j] = v;
     }
-    const int row = strip * 64 + tid;
-    if (row >= T.m) return;
-    double x[NBT];
-    double *bp = T.D + nb + row;
-#pragma unroll
-    for (int j = 0; j < NBT; j++) x[j] = (j < nb) ? bp[(long long)j * T.ld] : 0.0;
-#pragma unroll
+    __syncthreads();
+    const int ti = tid % NBT, tk = tid / NBT;        // trailing update: thread owns row ti, columns tk, tk + KS, ...
+    constexpr int KS = 256 / NBT;
     for (int j = 0; j < NBT; j++) {
-        double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double d = sA[j][j];
+        if (tid == 0 && !(d > 0.0) && j < nb) atomicMin(fail_col, T.col0 + j + 1);
+        const double r = rsqrt(d);
+        __syncthreads();                              // everyone has read the pivot
+        if (tid == j) sA[j][j] = d * r;
+        else if (tid > j && tid < NBT) sA[tid][j] *= r;
+        __syncthreads();
+        const double lij = sA[ti][j];
+        for (int k = j + 1 + tk; k <= ti; k += KS) sA[ti][k] -= lij * sA[k][j];
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int i = e % nb, j = e / nb;
+        if (i >= j) T.D[i + (long long)j * T.ld] = sA[i][j];
+    }
+    if (tid >= NBT) return;
+    // column c = tid of L^-1: v_i = (delta_ic - sum_{k<i} L_ik v_k) / L_ii, four partial sums to shorten the chain
+    double v[NBT];
 #pragma unroll
-        for (int k = 0; k + 3 < j; k += 4) {
-            s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1];
-            s2 -= x[k + 2] * sL[j][k + 2]; s3 -= x[k + 3] * sL[j][k + 3];
+    for (int i = 0; i < NBT; i++) {
+        double s0 = (i == tid) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 3 < i; k += 4) {
+            s0 -= sA[i][k] * v[k]; s1 -= sA[i][k + 1] * v[k + 1];
+            s2 -= sA[i][k + 2] * v[k + 2]; s3 -= sA[i][k + 3] * v[k + 3];
         }
 #pragma unroll
-        for (int k = (j / 4) * 4; k < j; k++) s0 -= x[k] * sL[j][k];
-        x[j] = ((s0 + s1) + (s2 + s3)) * sinv[j];
+        for (int k = (i / 4) * 4; k < i; k++) s0 -= sA[i][k] * v[k];
+        v[i] = (i >= tid) ? ((s0 + s1) + (s2 + s3)) / sA[i][i] : 0.0;
     }
+    if (tid < nb) {
 #pragma unroll
-    for (int j = 0; j < NBT; j++)
-        if (j < nb) bp[(long long)j * T.ld] = x[j];
+        for (int i = 0; i < NBT; i++)
+            if (i < nb) T.inv[i + (long long)tid * nb] = v[i];
+    }
+}
+
+// 64 x 64 variant with register tiling: the block is held as 4 x 4 tiles in the registers of a 16 x 16 thread grid
+// (thread (ty, tx), ty >= tx, owns rows 4ty.., columns 4tx..). 16 panel steps, two barriers each:
+//   (a) the diagonal thread factors its 4 x 4 tile (scalar code, 4 dependent rsqrt) and publishes it,
+//   (b) the threads below it solve their tiles against it and publish the 64 x 4 column panel,
+//   (c) everybody to the right applies the rank-4 update to its own tile from the published panel.
+// Then the factor sits in shared memory and the first 64 threads invert it column by column as above.
+__global__ void __launch_bounds__(256)
+potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col) {
+    constexpr int N = 64, LDS_ = 66;                  // even leading dimension: 16-byte aligned row pairs
+    __shared__ __align__(16) double sA[N * LDS_];     // sA[i * LDS_ + j]
+    __shared__ double sdiag[16];                      // published 4 x 4 diagonal tile (lower) ...
+    __shared__ double srinv[4];                       // ... and the reciprocals of its diagonal
+    __shared__ __align__(16) double spanel2[2][N][4];  // published column panel (rows 0..63 of the current 4 columns),
+                                                       // double-buffered: step P+1 publishes while step P is still read
+    const PanelTask T = tasks[blockIdx.x];
+    const int nb = T.nb, tid = threadIdx.x;
+    for (int e = tid; e < N * N; e += 256) {
+        const int i = e % N, j = e / N;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j <= i) v = T.D[i + (long long)j * T.ld];
+        sA[i * LDS_ + j] = v;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    const bool active = ty >= tx;
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[r][c] = active ? sA[(4 * ty + r) * LDS_ + 4 * tx + c] : 0.0;
+#pragma unroll 1
+    for (int P = 0; P < 16; P++) {
+        double (*spanel)[4] = spanel2[P & 1];
+        if (ty == P && tx == P) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double d = a[c][c];
+                if (!(d > 0.0) && 4 * P + c < nb) atomicMin(fail_col, T.col0 + 4 * P + c + 1);
+                const double r = rsqrt(d);
+                a[c][c] = d * r;
+                srinv[c] = r;
+#pragma unroll
+                for (int r2 = c + 1; r2 < 4; r2++) a[r2][c] *= r;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 4; c2++)
+#pragma unroll
+                    for (int r2 = c2; r2 < 4; r2++) a[r2][c2] -= a[r2][c] * a[c2][c];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    sdiag[r * 4 + c] = (c <= r) ? a[r][c] : 0.0;
+                    spanel[4 * P + r][c] = (c <= r) ? a[r][c] : 0.0;
+                }
+        }
+        __syncthreads();
+        if (tx == P && ty > P) {
+            // X * L_PP^T = B on the 4 x 4 tile, column by column
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    double s = a[r][c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) s -= a[r][k] * sdiag[c * 4 + k];
+                    a[r][c] = s * srinv[c];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) spanel[4 * ty + r][c] = a[r][c];
+        }
+        __syncthreads();
+        if (tx > P && active) {
+            double pr[4][4], pc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) { pr[r][k] = spanel[4 * ty + r][k]; pc[r][k] = spanel[4 * tx + r][k]; }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) a[r][c] -= pr[r][k] * pc[c][k];
+        }
+        // the next step's (a) works on registers and publishes into the other panel buffer
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) sA[(4 * ty + r) * LDS_ + 4 * tx + c] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int i = e % nb, j = e / nb;
+        if (i >= j) T.D[i + (long long)j * T.ld] = sA[i * LDS_ + j];
+    }
+    if (tid < N) {
+        // column c = tid of L^-1 by forward substitution; rows of L are read as 16-byte pairs (broadcast)
+        double v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            double s0 = (i == tid) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const double2 *row = reinterpret_cast<const double2 *>(sA + i * LDS_);
+#pragma unroll
+            for (int k = 0; k + 3 < i; k += 4) {
+                const double2 l0 = row[k / 2], l1 = row[k / 2 + 1];
+                s0 -= l0.x * v[k]; s1 -= l0.y * v[k + 1];
+                s2 -= l1.x * v[k + 2]; s3 -= l1.y * v[k + 3];
+            }
+#pragma unroll
+            for (int k = (i / 4) * 4; k < i; k++) s0 -= sA[i * LDS_ + k] * v[k];
+            v[i] = (i >= tid) ? ((s0 + s1) + (s2 + s3)) / sA[i * LDS_ + i] : 0.0;
+        }
+        if (tid < nb) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (i < nb) T.inv[i + (long long)tid * nb] = v[i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,8 +7,8 @@
 //       forward  (L y = b)  is right-looking over row tiles   : b[rows below] -= L[rows, K_j] x_j
 //       backward (L' x = y) is right-looking over column tiles: t[cols left]  -= L[K_j, cols]' x_j
 //     so every output element has one owner CTA and a fixed summation order (bit-reproducible).
-//   * the small triangular solves with the diagonal blocks are replaced by products with explicitly inverted
-//     64x64 blocks (diag_inv_kernel, run once per factorization, lazily before the first solve); the CTA that owns
+//   * the small triangular solves with the diagonal blocks are replaced by products with the explicitly inverted
+//     64x64 blocks that the factorization already produced (potrf_inv_kernel, kernels.cuh); the CTA that owns
 //     the tile holding the NEXT block of the chain applies that inverse right after its update ("look-ahead"), so
 //     the block solve never needs a launch of its own.
 //   * a CTA owns a 64 x 64 tile (32 KB of L): 8 warps x 8 columns, every thread issues its 16 independent 8-byte
@@ -19,12 +19,6 @@
 namespace gmrf {
 
 constexpr int SOLVE_NB = 64;
-
-struct InvTask {          // one diagonal block of the factor to invert
-    const double *L;      // nb x nb lower triangle at L, leading dimension ldl
-    double *inv;          // nb x nb, leading dimension nb, zeros above the diagonal
-    int ldl, nb;
-};
 
 struct FwdStepTask {      // block column K_j = [k0, k1) of a supernode, x_j final in `x`
     const double *L;      // first row below the diagonal block: panel + k0*ld + k1
@@ -52,35 +46,6 @@ struct BwdStepTask {      // block row K_j = [k0, k1) of L11, x_j final in `x`
     double *y;            // own columns 0.. of the supernode, stride ldy
     int ld, nb, ncols, pad_;  // ncols = k0 (a multiple of 64)
 };
-
-// ------------------------------------------------------------------------------------------------
-// inv(L_jj) for every 64-column diagonal block: thread c builds column c by forward substitution.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SOLVE_NB) diag_inv_kernel(const InvTask *__restrict__ tasks) {
-    __shared__ double sL[SOLVE_NB][SOLVE_NB + 1];   // identity-padded beyond nb
-    const InvTask T = tasks[blockIdx.x];
-    const int nb = T.nb, c = threadIdx.x;
-#pragma unroll 8
-    for (int k = 0; k < SOLVE_NB; k++) {                // coalesced column loads, thread = row
-        double v = (k == c) ? 1.0 : 0.0;
-        if (c < nb && k <= c && k < nb) v = T.L[c + (long long)k * T.ldl];
-        sL[c][k] = v;
-    }
-    __syncthreads();
-    double v[SOLVE_NB];                                 // column c of the inverse, fully unrolled -> registers
-#pragma unroll
-    for (int i = 0; i < SOLVE_NB; i++) {
-        double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; k++) s -= sL[i][k] * v[k];   // v[k] == 0 for k < c
-        v[i] = (i >= c) ? s / sL[i][i] : 0.0;
-    }
-    if (c < nb) {
-#pragma unroll
-        for (int i = 0; i < SOLVE_NB; i++)
-            if (i < nb) T.inv[i + (long long)c * nb] = v[i];
-    }
-}
 
 // Fixed-tree reduction of 8 per-lane values over the 32 lanes of a warp with 9 shuffles (instead of 40):
 // three transposing rounds halve the number of live values while folding lane bits 4, 3, 2, two plain rounds fold

@@ -28,7 +28,7 @@ EXPORTS = [
     "gmrf_b200_info", "gmrf_b200_get_perm", "gmrf_b200_get_colcounts", "gmrf_b200_get_etree",
     "gmrf_b200_get_supernodes", "gmrf_b200_get_rows", "gmrf_b200_get_scatter", "gmrf_b200_last_timings",
     "gmrf_b200_get_factor_panels", "gmrf_b200_get_selinv_panels", "gmrf_b200_set_option",
-    "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_trsm", "gmrf_b200_bench_gemm", "gmrf_b200_profile_refactorize", "gmrf_b200_host_register", "gmrf_b200_host_unregister",
+    "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_potrf_inv", "gmrf_b200_test_trsm", "gmrf_b200_bench_gemm", "gmrf_b200_profile_refactorize", "gmrf_b200_profile_plan", "gmrf_b200_host_register", "gmrf_b200_host_unregister",
 ]
 
 _lib = None
@@ -101,12 +101,16 @@ def lib():
     L.gmrf_b200_test_gemm.argtypes = [ctypes.c_int] * 7 + [c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_double, c_vp, ctypes.c_int]
     L.gmrf_b200_test_potrf.restype = ctypes.c_int
     L.gmrf_b200_test_potrf.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.gmrf_b200_test_potrf_inv.restype = ctypes.c_int
+    L.gmrf_b200_test_potrf_inv.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(ctypes.c_int)]
     L.gmrf_b200_test_trsm.restype = ctypes.c_int
     L.gmrf_b200_test_trsm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int]
     L.gmrf_b200_bench_gemm.restype = ctypes.c_int
     L.gmrf_b200_bench_gemm.argtypes = [ctypes.c_int] * 8 + [c_f64p]
     L.gmrf_b200_profile_refactorize.restype = ctypes.c_int
     L.gmrf_b200_profile_refactorize.argtypes = [c_vp, c_vp, c_vp, c_f64p]
+    L.gmrf_b200_profile_plan.restype = ctypes.c_int
+    L.gmrf_b200_profile_plan.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.gmrf_b200_host_register.restype = ctypes.c_int
     L.gmrf_b200_host_register.argtypes = [c_vp, c_i64]
     L.gmrf_b200_host_unregister.restype = ctypes.c_int

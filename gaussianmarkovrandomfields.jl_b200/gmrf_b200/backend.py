@@ -284,6 +284,18 @@ class B200Backend:
         names = ("gemm", "panel", "assemble", "other")
         return {"ms": dict(zip(names, ms.tolist())), "launches": dict(zip(names, cnt.tolist())), "gemm_flops": fl.value}
 
+    LAUNCH_KINDS = ("assemble", "potrf", "trsm0", "trsm1", "gemm_nn_s", "gemm_nn_l", "gemm_nt_s", "gemm_nt_l", "gemm_tt_s",
+                    "gemm_tt_l", "gather", "transpose", "fwd_asm", "fwd_step", "bwd_gather", "bwd_step", "panel")
+
+    def profile_plan(self, phase: int, nrhs: int = 1):
+        """Per-launch (kind, grid, ms) of one phase: 0 factorization, 1 selinv, 2 forward sweep, 3 backward sweep."""
+        cnt = ctypes.c_int64()
+        self._hd.check(self._L.gmrf_b200_profile_plan(self._hd._h, phase, nrhs, 0, None, None, None, ctypes.byref(cnt)))
+        n = cnt.value
+        kind = np.zeros(n, dtype=np.int32); grid = np.zeros(n, dtype=np.int32); ms = np.zeros(n)
+        self._hd.check(self._L.gmrf_b200_profile_plan(self._hd._h, phase, nrhs, n, ptr(kind), ptr(grid), ptr(ms), ctypes.byref(cnt)))
+        return [(self.LAUNCH_KINDS[k], int(g), float(t)) for k, g, t in zip(kind, grid, ms)]
+
     def pin_host_buffer(self, arr: np.ndarray) -> bool:
         """Page-lock a caller-owned numpy buffer for asynchronous H2D copies (no-op without a device)."""
         # Only large buffers are registered: they are mmap-backed (own pages), whereas page-locking a small heap

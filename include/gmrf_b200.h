@@ -141,6 +141,11 @@ int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n);
  * CUDA event pairs around every launch on the handle's stream): ms[4]/count[4] for {0: DMMA GEMM, 1: fused panel
  * potrf+trsm, 2: extend-add assembly, 3: memset+scatter+logdet}; *gemm_flops = algorithmic flops of the GEMM tasks. */
 int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *count, double *gemm_flops);
+/* Per-launch device times of one phase (diagnostics; graphs off, event pair around every launch): phase 0 = numeric
+ * factorization, 1 = selected inversion, 2 = forward sweep, 3 = backward sweep with `nrhs` (<= 8) columns. Up to `cap`
+ * entries of kind[] (internal launch kind), grid[] (CTAs) and ms[] are filled; *count = launches in the phase. */
+int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap, int *kind, int *grid, double *ms,
+                           int64_t *count);
 /* Numeric factor / selected inverse panels copied back to the host (tests, CholeskySqrt-style export). */
 int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles);
 int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
@@ -162,6 +167,8 @@ int gmrf_b200_set_option(const char *key, double value);
 int gmrf_b200_test_gemm(int device, int transa, int transb, int flags, int m, int n, int k,
                         const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
 int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info);
+/* same kernel, also returning inv(L) (n x n, leading dimension n, zeros above the diagonal) */
+int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv, int *info);
 int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb);
 /* Device-timed micro-benchmark of the library's own FP64 GEMM kernel (zero-filled device operands, best of
  * `reps`, CUDA events): used to compare against the measured cuBLAS DGEMM peak in profiles/. */

@@ -1,0 +1,41 @@
+"""Per-launch profile of one phase on the GPU box (diagnostics, not a pytest file):
+    python tests/gpu_plan_profile.py 3d:100 --phase=3 [--order=geo] [--top=40]
+phase 0 factorization, 1 selinv, 2 forward sweep, 3 backward sweep."""
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200"), os.path.join(ROOT, "tests")]
+from gmrf_b200 import spde  # noqa: E402
+from gmrf_b200.backend import B200Backend  # noqa: E402
+from gpu_perf import build_problem  # noqa: E402
+
+spec = [a for a in sys.argv[1:] if not a.startswith("--")][0]
+opt = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--") and "=" in a)
+phases = [int(p) for p in opt.get("phase", "3").split(",")]
+top = int(opt.get("top", "30"))
+Q, dims, width, _ = build_problem(spec)
+ordering = spde.geometric_nd_perm(dims, leaf=64, width=width) if opt.get("order", "geo") == "geo" else "nd"
+b = B200Backend(Q, ordering=ordering, device=0)
+for phase in phases:
+    b.profile_plan(phase)                       # warm-up
+    rows = b.profile_plan(phase)
+    tot = sum(r[2] for r in rows)
+    print(f"== {spec} phase {phase}: {len(rows)} launches, {tot:.3f} ms summed")
+    agg = collections.OrderedDict()
+    for k, g, t in rows:
+        c, tt, gg = agg.get(k, (0, 0.0, 0))
+        agg[k] = (c + 1, tt + t, gg + g)
+    for k, (c, tt, gg) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"   {k:12s} {c:6d} launches {tt:10.3f} ms ({100 * tt / tot:5.1f}%)  avg {1e3 * tt / c:9.1f} us  avg grid {gg / c:9.1f}")
+    print("   slowest launches (index kind grid ms):")
+    for i in sorted(range(len(rows)), key=lambda i: -rows[i][2])[:top]:
+        print(f"     {i:6d} {rows[i][0]:12s} {rows[i][1]:8d} {rows[i][2]:9.4f}")
+    # cumulative time by position (coarse timeline in 20 buckets)
+    nb = 20
+    step = max(1, len(rows) // nb)
+    line = []
+    for a in range(0, len(rows), step):
+        line.append(f"{sum(r[2] for r in rows[a:a + step]):.1f}")
+    print("   timeline (ms per 1/20 of the launch list):", " ".join(line))

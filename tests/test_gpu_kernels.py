@@ -64,11 +64,15 @@ def test_potrf_diag(n):
     lda = n + 3
     Ab = np.zeros((lda, n), order="F"); Ab[:n] = A
     info = ctypes.c_int(-1)
-    assert L.gmrf_b200_test_potrf(0, n, ptr(Ab), lda, ctypes.byref(info)) == 0
+    inv = np.full((n, n), np.nan, order="F")
+    assert L.gmrf_b200_test_potrf_inv(0, n, ptr(Ab), lda, ptr(inv), ctypes.byref(info)) == 0
     assert info.value == 0
     got = np.tril(Ab[:n])
     want = np.linalg.cholesky(A)
     assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max() * n
+    # the same kernel also returns inv(L) (dense n x n, zeros above the diagonal): used for TRSM-by-GEMM and the solves
+    assert np.array_equal(np.triu(inv, 1), np.zeros((n, n)))
+    assert np.abs(inv @ want - np.eye(n)).max() <= 1e-13 * n * np.linalg.cond(want)
     # not positive definite: the failing column (1-based) is reported
     if n >= 3:
         A2 = A.copy(); A2[2, 2] = -1.0
