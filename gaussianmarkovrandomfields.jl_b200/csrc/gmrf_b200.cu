@@ -28,7 +28,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_POTRF_UNUSED, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE
 };
 
 struct Launch {
@@ -88,6 +88,9 @@ struct gmrf_b200_handle {
     std::vector<long long> inv_base;   // host copy
     std::map<int, cudaGraphExec_t> solve_graphs;   // key = nrhs * 2 + mode
     TransTask *d_trans = nullptr;
+    SplitTask *d_split = nullptr, *d_split_z = nullptr;
+    double *d_splitk = nullptr;        // scratch for split-K partial products
+    i64 splitk_cap = 0;                // doubles
     // selinv task tables are built lazily (they need d_Zx / d_zw)
     GemmTask *d_gemm_z = nullptr;
     TrsmTask *d_trsm_z = nullptr;
@@ -153,14 +156,57 @@ struct Builder {
     std::vector<BwdGatherTask> bwdg;
     std::vector<BwdStepTask> bwds;
     std::vector<TransTask> trans;
+    std::vector<SplitTask> split;
+    double *splitk_base = nullptr;     // device scratch for split-K partial products
+    i64 splitk_cap = 0;
+    int splitk_min_k = 1024;
     std::vector<int> superlist;
     std::vector<int> prefix;
     bool naive = false;
     double gemm_flops = 0;
 
     // GEMM launches: tasks are split into a small-tile and a large-tile launch
-    void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/, bool force_small = false, double flop_weight = 1.0) {
+    // GEMM launches: tasks are split into a small-tile and a large-tile launch. With allow_split, products that leave
+    // the GPU under-filled (few output tiles, very long k) are cut along k into slices that write partial products to
+    // the split-K scratch, folded afterwards in fixed order by splitk_reduce_kernel.
+    void add_gemm(Plan &plan, std::vector<GemmTask> &tasks, int variant /*0=NN,1=NT,2=TT*/, bool force_small = false,
+                  double flop_weight = 1.0, bool allow_split = false) {
         if (tasks.empty()) return;
+        std::vector<SplitTask> reduce;
+        if (allow_split && !naive && splitk_base) {
+            const i64 slots = 148 * 4;                       // resident 64 x 64-tile CTAs on a B200
+            i64 tiles = 0;
+            for (auto &t : tasks) tiles += (i64)cdiv(t.m, 64) * cdiv(t.n, 64);
+            if (tiles < 4 * slots) {
+                std::vector<GemmTask> out;
+                i64 used = 0;
+                for (auto &t : tasks) {
+                    int S = (int)std::min<i64>({8, (4 * slots + tiles - 1) / std::max<i64>(tiles, 1), (i64)t.k / splitk_min_k});
+                    const i64 ldp = (t.m + 1) & ~1LL;
+                    const bool plain = (t.flags & ~GEMM_LOWER) == 0;          // C -= A B^T, optionally lower-only
+                    if (S < 2 || !plain || t.m <= 0 || t.n <= 0 || used + (i64)S * ldp * t.n > splitk_cap) { out.push_back(t); continue; }
+                    const int kslice = ((t.k + S - 1) / S + 15) & ~15;
+                    S = (t.k + kslice - 1) / kslice;
+                    double *part = splitk_base + used;
+                    const long long stride = ldp * t.n;
+                    used += (i64)S * stride;
+                    const bool ta = variant == 2, tb = variant >= 1;
+                    for (int q = 0; q < S; q++) {
+                        GemmTask g = t;
+                        const int kk0 = q * kslice;
+                        g.k = std::min(kslice, t.k - kk0);
+                        g.A = t.A + (ta ? (long long)kk0 : (long long)kk0 * t.lda);
+                        g.B = t.B + (tb ? (long long)kk0 : (long long)kk0 * t.ldb);
+                        g.C = part + q * stride;
+                        g.ldc = (int)ldp;
+                        g.flags = (t.flags & GEMM_LOWER) | GEMM_BETA0 | GEMM_ALPHA_POS;
+                        out.push_back(g);
+                    }
+                    reduce.push_back(SplitTask{t.C, part, stride, t.m, t.n, t.ldc, (int)ldp, S, (t.flags & GEMM_LOWER) ? 1 : 0});
+                }
+                tasks.swap(out);
+            }
+        }
         std::vector<GemmTask> small, large;
         for (auto &t : tasks) {
             if (t.m <= 0 || t.n <= 0) continue;
@@ -192,6 +238,23 @@ struct Builder {
             plan.launches.push_back(L);
         }
         tasks.clear();
+        if (!reduce.empty()) {
+            Launch L;
+            L.kind = K_SPLIT_REDUCE;
+            L.aux = 0;
+            L.task_off = (i64)split.size();
+            L.ntasks = (int)reduce.size();
+            L.prefix_off = (i64)prefix.size();
+            i64 tot = 0;
+            for (auto &t : reduce) {
+                prefix.push_back((int)tot);
+                tot += (i64)cdiv(t.m, 256) * cdiv(t.n, 4);
+                split.push_back(t);
+            }
+            prefix.push_back((int)tot);
+            L.grid = (int)tot;
+            plan.launches.push_back(L);
+        }
     }
     void add_trsm(Plan &plan, std::vector<TrsmTask> &tasks, int var) {
         if (tasks.empty()) return;
@@ -337,7 +400,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                     g.flags = GEMM_LOWER; g.pad_ = 0;
                     gt.push_back(g);
                 }
-                B.add_gemm(plan, gt, 0);
+                B.add_gemm(plan, gt, 0, false, 1.0, /*allow_split=*/true);
             }
             for (i64 jj = 0; jj < OB / NB; jj++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
@@ -549,7 +612,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
                         gt.push_back(g);
                     }
                 }
-                B.add_gemm(plan, gt, 1);
+                B.add_gemm(plan, gt, 1, false, 1.0, /*allow_split=*/true);
                 for (i64 tj = 0; tj < OB / NB; tj++) {
                     for (const i64 *sp = sb; sp < se; sp++) {
                         i64 s = *sp;
@@ -660,7 +723,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
                     g.flags = 0; g.pad_ = 0;
                     gt.push_back(g);
                 }
-                B.add_gemm(plan, gt, 1);
+                B.add_gemm(plan, gt, 1, false, 1.0, /*allow_split=*/true);
                 for (i64 tj = 0; tj < OB / NB; tj++) {
                     for (const i64 *sp = sb; sp < se; sp++) {
                         i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
@@ -746,6 +809,7 @@ struct TableSet {
     const TrsmTask *trsm;
     const AsmItem *items;
     const int *prefix;
+    const SplitTask *split;
 };
 
 void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs) {
@@ -773,6 +837,9 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
         case K_GEMM_TT_S: case K_GEMM_TT_L:
             launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+        case K_SPLIT_REDUCE:
+            splitk_reduce_kernel<<<L.grid, 256, 0, st>>>(T.split + L.task_off, pf, L.ntasks);
+            break;
         case K_GATHER:
             selinv_gather_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_relidx, h->d_Zx, h->d_zw);
             break;
@@ -826,14 +893,14 @@ void enqueue_factor(gmrf_b200_handle *h) {
         int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
         scatter_q_kernel<<<grid, 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
     }
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) run_launch(h, L, T, 0);
     logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
     logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
 }
 
 void enqueue_selinv(gmrf_b200_handle *h) {
-    TableSet T{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z};
+    TableSet T{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
     for (const Launch &L : h->selinv_plan.launches) run_launch(h, L, T, 0);
 }
 
@@ -890,6 +957,7 @@ int build_selinv_tables(gmrf_b200_handle *h) {
     CUDA_TRY(h, cudaMemset(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total));
     Builder B;
     B.naive = h->opt.naive_kernels != 0;
+    B.splitk_base = h->d_splitk; B.splitk_cap = h->splitk_cap; B.splitk_min_k = h->opt.splitk_min_k;
     try {
         build_selinv_plan(h, B);
     } catch (std::exception &e) {
@@ -901,6 +969,7 @@ int build_selinv_tables(gmrf_b200_handle *h) {
     if ((rc = dev_upload(h, &h->d_items_z, B.items))) return rc;
     if ((rc = dev_upload(h, &h->d_prefix_z, B.prefix))) return rc;
     if ((rc = dev_upload(h, &h->d_trans, B.trans))) return rc;
+    if ((rc = dev_upload(h, &h->d_split_z, B.split))) return rc;
     std::vector<long long> dp(S.diag_pos.begin(), S.diag_pos.end());
     // diagonal of Z in ORIGINAL ordering: out[perm[k]] = Z[diag_pos[k]]  ->  pos_orig[i] = diag_pos[iperm[i]]
     std::vector<long long> zp(S.n);
@@ -924,7 +993,7 @@ int ensure_io(gmrf_b200_handle *h, i64 count) {
 
 // Enqueue the level-scheduled sweeps on the permuted work array d_y (mode 0: forward + backward, 1: backward only).
 void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
     if (mode == 0)
         for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
     for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
@@ -1084,6 +1153,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "outer_block") o.outer_block = (int)value;
     else if (k == "naive_kernels") o.naive_kernels = (int)value;
     else if (k == "selinv_fast_root") o.selinv_fast_root = (int)value;
+    else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else return GMRF_B200_ERR_ARG;
     return 0;
 }
@@ -1188,9 +1258,12 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         TRY_RC(dev_alloc(H, &H->d_Linv, (size_t)inv_total));
         TRY_RC(dev_upload(H, &H->d_invbase, H->inv_base));
     }
+    H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
+    TRY_RC(dev_alloc(H, &H->d_splitk, (size_t)H->splitk_cap));
     {
         Builder B;
         B.naive = H->opt.naive_kernels != 0;
+        B.splitk_base = H->d_splitk; B.splitk_cap = H->splitk_cap; B.splitk_min_k = H->opt.splitk_min_k;
         try {
             build_factor_plan(H, B);
             build_solve_plans(H, B);
@@ -1208,6 +1281,7 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         TRY_RC(dev_upload(H, &H->d_bwds, B.bwds));
         TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
+        TRY_RC(dev_upload(H, &H->d_split, B.split));
     }
 #undef TRY_RC
     *out = h.release();
@@ -1656,7 +1730,7 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
     i64 cnt = (i64)S.q_src.size();
     if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) {
         int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0 : L.kind == K_PANEL ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
         mark(kind);
@@ -1688,7 +1762,7 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     if (rc) return rc;
     if (!h->factored) { h->err = "profile_plan needs a previous refactorize"; return GMRF_B200_ERR_STATE; }
     const Plan *plan = nullptr;
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix};
+    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
     cudaStream_t st = h->stream;
     if (phase == 0) {
         plan = &h->factor_plan;
@@ -1700,7 +1774,7 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     } else if (phase == 1) {
         if ((rc = build_selinv_tables(h))) return rc;
         plan = &h->selinv_plan;
-        T = TableSet{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z};
+        T = TableSet{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
     } else if (phase == 2 || phase == 3) {
         plan = phase == 2 ? &h->fwd_plan : &h->bwd_plan;
         if (nrhs < 1 || nrhs > h->rhs_block) { h->err = "profile_plan: 1 <= nrhs <= 8"; return GMRF_B200_ERR_ARG; }

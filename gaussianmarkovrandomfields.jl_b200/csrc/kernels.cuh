@@ -503,6 +503,38 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split-K epilogue: C -= part_0 + part_1 + ... (fixed order -> bit-reproducible). The k-range of a product with too
+// few output tiles to fill the GPU (the left-looking block-column updates of the top supernodes: m x 256 outputs,
+// k up to 30,000) is cut into `nsplit` slices whose partial products go to a scratch buffer; this kernel folds them.
+// ------------------------------------------------------------------------------------------------
+struct SplitTask {
+    double *C;
+    const double *part;      // nsplit slabs of ldp x n doubles, slab stride `stride`
+    long long stride;
+    int m, n, ldc, ldp, nsplit, lower;
+};
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const SplitTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const SplitTask T = tasks[t];
+    const int local = blockIdx.x - tile_prefix[t];
+    const int mt = (T.m + 255) / 256;                 // a CTA owns 256 rows x 4 columns
+    const int r = (local % mt) * 256 + threadIdx.x;
+    const int c0 = (local / mt) * 4;
+    if (r >= T.m) return;
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+        const int c = c0 + cc;
+        if (c >= T.n || (T.lower && r < c)) continue;
+        const double *p = T.part + r + (long long)c * T.ldp;
+        double s = p[0];
+        for (int q = 1; q < T.nsplit; q++) s += p[q * T.stride];
+        T.C[r + (long long)c * T.ldc] -= s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Q.nzval -> panels (after the panel array has been zeroed): Lx[dst[k]] = nzval[src[k]]
 // ------------------------------------------------------------------------------------------------
 __global__ void scatter_q_kernel(double *__restrict__ Lx, const double *__restrict__ nz,

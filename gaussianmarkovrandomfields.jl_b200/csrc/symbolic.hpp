@@ -26,6 +26,7 @@ struct Options {
     int use_graph = 1;
     int outer_block = 256;   // outer panel block (columns) of the two-level blocked factorization
     int naive_kernels = 0;
+    int splitk_min_k = 1024;  // split-K: a k-slice is at least this long (tests lower it to reach the path on small inputs)
     int selinv_fast_root = 1; // triangular (trtri + lauum) route for top-level root supernodes in the selected inversion
 };
 Options &global_options();

@@ -11,7 +11,7 @@ import pytest
 import scipy.sparse as sp
 
 import oracle
-from gmrf_b200 import spde
+from gmrf_b200 import _lib, spde
 from gmrf_b200.backend import B200Backend, NotPositiveDefinite, PinDenseColumns, ordering_permutation
 from gmrf_b200.workspace import (GMRFWorkspace, WorkspacePool, backward_solve, dimension, logdet, selinv, selinv_diag,
                                  selinv_dot, selinv_extract_at, update_precision, update_precision_values,
@@ -244,6 +244,38 @@ def test_spde_parity_with_oracle(kind, cells, smooth):
     assert abs(be.compute_logdet() - F.logdet()) <= 1e-10 * abs(F.logdet())
     assert np.max(np.abs(be.get_selinv_diag() - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
     be.close()
+
+
+def test_schedule_variants_agree():
+    """The scheduling options change the launch lists, never the mathematics: split-K with tiny k-slices (the path the
+    top supernodes of the 1 M-dof problem take), a small outer block, the generic selected-inversion route for roots and
+    stream launches instead of graphs must all reproduce the default answers and the oracle's."""
+    model = spde.MaternSPDE(*spde.mesh3d(12), 0)
+    Q = model.precision(0.9, 0.5)
+    n = Q.shape[0]
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((n, 2))
+    base = B200Backend(Q, device=0)
+    perm = base.permutation()
+    F = oracle.OracleFactor(Q, perm)
+    ref = (base.compute_logdet(), base.backend_solve(b), base.get_selinv_diag())
+    base.close()
+    assert np.max(np.abs(ref[2] - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
+    variants = [{"splitk_min_k": 32}, {"splitk_min_k": 16, "outer_block": 128}, {"selinv_fast_root": 0}, {"use_graph": 0}]
+    defaults = {"splitk_min_k": 1024, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1}
+    try:
+        for v in variants:
+            for k, val in {**defaults, **v}.items():
+                _lib.set_option(k, val)
+            be = B200Backend(Q, ordering=perm, device=0)
+            ld, x, d = be.compute_logdet(), be.backend_solve(b), be.get_selinv_diag()
+            assert abs(ld - ref[0]) <= 1e-12 * abs(ref[0]), v
+            assert _rel(x, ref[1]) <= 1e-10, v
+            assert np.max(np.abs(d - ref[2]) / ref[2]) <= 1e-10, v
+            be.close()
+    finally:
+        for k, val in defaults.items():
+            _lib.set_option(k, val)
 
 
 def test_run_to_run_bit_reproducible():
