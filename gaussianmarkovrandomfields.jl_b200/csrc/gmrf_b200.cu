@@ -28,7 +28,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_POTRF_UNUSED, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER
 };
 
 struct Launch {
@@ -87,6 +87,14 @@ struct gmrf_b200_handle {
     long long *d_invbase = nullptr;    // per supernode: offset of its first inverted block in d_Linv
     std::vector<long long> inv_base;   // host copy
     std::map<int, cudaGraphExec_t> solve_graphs;   // key = nrhs * 2 + mode
+    // wide right-hand-side path (blocks of MULTI_W columns, DMMA GEMM sweeps), built lazily
+    bool multi_built = false;
+    double *d_ym = nullptr, *d_um = nullptr;
+    GemmTask *d_gemm_m = nullptr;
+    RowGatherTask *d_rg_m = nullptr;
+    int *d_prefix_m = nullptr, *d_superlist_m = nullptr;
+    Plan multi_fwd_plan, multi_bwd_plan;
+    cudaGraphExec_t multi_graph[2] = {nullptr, nullptr};
     TransTask *d_trans = nullptr;
     SplitTask *d_split = nullptr, *d_split_z = nullptr;
     double *d_splitk = nullptr;        // scratch for split-K partial products
@@ -157,6 +165,7 @@ struct Builder {
     std::vector<BwdStepTask> bwds;
     std::vector<TransTask> trans;
     std::vector<SplitTask> split;
+    std::vector<RowGatherTask> rowgather;
     double *splitk_base = nullptr;     // device scratch for split-K partial products
     i64 splitk_cap = 0;
     int splitk_min_k = 1024;
@@ -531,6 +540,116 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     }
 }
 
+// Wide right-hand-side sweeps (blocks of MULTI_W = 64 columns): every step is a DMMA GEMM on the 64-column block.
+// Two-level blocking like the factorization: inside an outer block of OB columns the 64-column diagonal blocks are
+// applied through their inverses (one 64 x 64-tile GEMM each, in place) with small k = 64 updates confined to the outer
+// block; the rows below / columns left of the outer block get ONE k = OB update (forward: right-looking over rows,
+// backward: right-looking over columns, exactly the dependency structure of the few-RHS kernels).
+void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
+    const Symbolic &S = h->S;
+    const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
+    const i64 BBLK = (i64)NB * NB;
+    const int W = MULTI_W;
+    const int ldy = (int)S.n, ldu = (int)S.uvec_total;
+    std::vector<int> lst;
+    std::vector<GemmTask> st, gt;
+    std::vector<RowGatherTask> rg;
+    auto inv_ptr = [&](i64 s, i64 k0) { return (const double *)(h->d_Linv + h->inv_base[s] + (k0 / NB) * BBLK); };
+    auto task = [](const double *A, int lda, const double *Bm, int ldb, double *C, int ldc, i64 m, i64 n, i64 k, int flags) {
+        GemmTask g;
+        g.A = A; g.B = Bm; g.C = C; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+        g.m = (int)m; g.n = (int)n; g.k = (int)k; g.flags = flags; g.pad_ = 0;
+        return g;
+    };
+    // ---- forward: L y = b ------------------------------------------------------------------------------------
+    for (i64 l = 0; l < S.nlevels; l++) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        i64 maxouter = 0;
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp;
+            if (S.nr(s) > 0 || S.child_ptr[s + 1] > S.child_ptr[s]) lst.push_back((int)s);
+            maxouter = std::max<i64>(maxouter, cdiv(S.ns(s), OB));
+        }
+        B.add_superlist(h->multi_fwd_plan, lst, K_FWD_ASM_M);
+        for (i64 J = 0; J < maxouter; J++) {
+            for (i64 jj = 0; jj < OB / NB; jj++) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
+                    i64 J0 = J * OB, k0 = J0 + jj * NB;
+                    if (k0 >= ns) continue;
+                    i64 J1 = std::min(J0 + OB, ns), nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb;
+                    const double *P = h->d_Lx + S.panel_off[s];
+                    double *ys = h->d_ym + S.sfirst[s];
+                    // x_K = inv(L_KK) y_K : C[nb x W] = inv * y_K, in place (one tile)
+                    st.push_back(task(inv_ptr(s, k0), (int)nb, ys + k0, ldy, ys + k0, ldy, nb, W, nb, GEMM_BETA0 | GEMM_ALPHA_POS));
+                    // y[k1:J1] -= L[k1:J1, K] x_K
+                    if (J1 > k1) gt.push_back(task(P + k0 * ld + k1, (int)ld, ys + k0, ldy, ys + k1, ldy, J1 - k1, W, nb, 0));
+                }
+                B.add_gemm(h->multi_fwd_plan, st, 1, true, 0.5);
+                B.add_gemm(h->multi_fwd_plan, gt, 1);
+            }
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+                i64 J0 = J * OB;
+                if (J0 >= ns) continue;
+                i64 J1 = std::min(J0 + OB, ns);
+                const double *P = h->d_Lx + S.panel_off[s];
+                double *ys = h->d_ym + S.sfirst[s];
+                if (ns > J1) gt.push_back(task(P + J0 * ld + J1, (int)ld, ys + J0, ldy, ys + J1, ldy, ns - J1, W, J1 - J0, 0));
+                if (nr > 0) gt.push_back(task(P + J0 * ld + ns, (int)ld, ys + J0, ldy, h->d_um + S.uvec_off[s], ldu, nr, W, J1 - J0, 0));
+            }
+            B.add_gemm(h->multi_fwd_plan, gt, 1);
+        }
+    }
+    // ---- backward: L^T x = y ---------------------------------------------------------------------------------
+    for (i64 l = S.nlevels - 1; l >= 0; l--) {
+        const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        i64 maxouter = 0;
+        for (const i64 *sp = sb; sp < se; sp++) {
+            i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
+            maxouter = std::max<i64>(maxouter, cdiv(ns, OB));
+            if (nr == 0) continue;
+            rg.push_back(RowGatherTask{h->d_rowidx + S.rowptr[s] + ns, h->d_um + S.uvec_off[s], (int)nr, 0});
+            // y_S -= L21^T u_s
+            gt.push_back(task(h->d_Lx + S.panel_off[s] + ns, (int)ld, h->d_um + S.uvec_off[s], ldu, h->d_ym + S.sfirst[s], ldy, ns, W, nr, 0));
+        }
+        B.add_tiled(h->multi_bwd_plan, rg, B.rowgather, K_ROWS_GATHER, [](const RowGatherTask &t) { return (i64)cdiv(t.nr, 256); });
+        B.add_gemm(h->multi_bwd_plan, gt, 2);
+        for (i64 tJ = 0; tJ < maxouter; tJ++) {
+            for (i64 tj = 0; tj < OB / NB; tj++) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
+                    i64 J = cdiv(ns, OB) - 1 - tJ;
+                    if (J < 0) continue;
+                    i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                    i64 jj = cdiv(J1 - J0, NB) - 1 - tj;
+                    if (jj < 0) continue;
+                    i64 k0 = J0 + jj * NB, nb = std::min<i64>(NB, J1 - k0);
+                    const double *P = h->d_Lx + S.panel_off[s];
+                    double *ys = h->d_ym + S.sfirst[s];
+                    // x_K = inv(L_KK)^T t_K : Aop[c][r] = inv[r + c*nb]
+                    st.push_back(task(inv_ptr(s, k0), (int)nb, ys + k0, ldy, ys + k0, ldy, nb, W, nb, GEMM_BETA0 | GEMM_ALPHA_POS));
+                    // t[J0:k0] -= L[K, J0:k0]^T x_K
+                    if (k0 > J0) gt.push_back(task(P + J0 * ld + k0, (int)ld, ys + k0, ldy, ys + J0, ldy, k0 - J0, W, nb, 0));
+                }
+                B.add_gemm(h->multi_bwd_plan, st, 2, true, 0.5);
+                B.add_gemm(h->multi_bwd_plan, gt, 2);
+            }
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
+                i64 J = cdiv(ns, OB) - 1 - tJ;
+                if (J < 1) continue;
+                i64 J0 = J * OB, J1 = std::min(J0 + OB, ns);
+                const double *P = h->d_Lx + S.panel_off[s];
+                double *ys = h->d_ym + S.sfirst[s];
+                // t[0:J0] -= L[J, 0:J0]^T x_J
+                gt.push_back(task(P + J0, (int)ld, ys + J0, ldy, ys, ldy, J0, W, J1 - J0, 0));
+            }
+            B.add_gemm(h->multi_bwd_plan, gt, 2);
+        }
+    }
+}
+
 // Selected inversion (Takahashi), per supernode s with panel L = [L11; L21], W = Z[R,R] gathered from the parent:
 //   T' = -W L21 ;  G = I - L21^T T' = I + L21^T W L21 ;  [H; Z_RS] = [G; T'] L11^-1 ;  Z_SS = H^T L11^-1
 // (Z_SS = L11^-T (I + L21^T W L21) L11^-1, Z_RS = -W L21 L11^-1.) Right solves with the 64-column diagonal blocks are
@@ -810,6 +929,9 @@ struct TableSet {
     const AsmItem *items;
     const int *prefix;
     const SplitTask *split;
+    const int *superlist = nullptr;         // solve phases: supernode lists
+    const RowGatherTask *rowgather = nullptr;
+    double *y = nullptr, *u = nullptr;      // solve phases: permuted work array and update-vector pool
 };
 
 void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs) {
@@ -850,6 +972,17 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             dim3 g(L.grid, nrhs);
             fwd_assemble_x0_kernel<<<g, 256, 0, st>>>(h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
                                                       h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
+            break;
+        }
+        case K_FWD_ASM_M: {
+            dim3 g(L.grid, MULTI_W / MULTI_QB);
+            fwd_assemble_multi_kernel<<<g, 256, 0, st>>>(T.superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx,
+                                                         T.y, h->S.n, T.u, h->S.uvec_total);
+            break;
+        }
+        case K_ROWS_GATHER: {
+            dim3 g(L.grid, MULTI_W / MULTI_QB);
+            rows_gather_kernel<<<g, 256, 0, st>>>(T.rowgather + L.task_off, pf, L.ntasks, T.y, h->S.n, h->S.uvec_total);
             break;
         }
 #define SOLVE_RB_DISPATCH(KERNEL, ...)                                                         \
@@ -991,6 +1124,80 @@ int ensure_io(gmrf_b200_handle *h, i64 count) {
     return 0;
 }
 
+// Lazily build the wide right-hand-side path (work arrays for MULTI_W columns, GEMM task tables, plans).
+int ensure_multi(gmrf_b200_handle *h) {
+    if (h->multi_built) return 0;
+    const Symbolic &S = h->S;
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_ym, (size_t)(S.n * MULTI_W)))) return rc;
+    if ((rc = dev_alloc(h, &h->d_um, (size_t)(S.uvec_total * MULTI_W)))) return rc;
+    Builder B;
+    B.naive = h->opt.naive_kernels != 0;
+    try {
+        build_multi_plans(h, B);
+    } catch (std::exception &e) {
+        h->err = e.what();
+        return GMRF_B200_ERR_ARG;
+    }
+    if ((rc = dev_upload(h, &h->d_gemm_m, B.gemm))) return rc;
+    if ((rc = dev_upload(h, &h->d_prefix_m, B.prefix))) return rc;
+    if ((rc = dev_upload(h, &h->d_superlist_m, B.superlist))) return rc;
+    if ((rc = dev_upload(h, &h->d_rg_m, B.rowgather))) return rc;
+    h->multi_built = true;
+    return 0;
+}
+
+void enqueue_multi_sweeps(gmrf_b200_handle *h, int mode) {
+    TableSet T{h->d_gemm_m, nullptr, nullptr, h->d_prefix_m, nullptr};
+    T.superlist = h->d_superlist_m;
+    T.rowgather = h->d_rg_m;
+    T.y = h->d_ym;
+    T.u = h->d_um;
+    if (mode == 0)
+        for (const Launch &L : h->multi_fwd_plan.launches) run_launch(h, L, T, MULTI_W);
+    for (const Launch &L : h->multi_bwd_plan.launches) run_launch(h, L, T, MULTI_W);
+}
+
+// Wide path: blocks of MULTI_W right-hand sides through the GEMM sweeps (the last block is zero-padded).
+int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
+    const Symbolic &S = h->S;
+    int rc = ensure_multi(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    if (h->opt.use_graph && !h->multi_graph[mode]) {
+        cudaGraph_t g;
+        CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        enqueue_multi_sweeps(h, mode);
+        CUDA_TRY(h, cudaStreamEndCapture(st, &g));
+        CUDA_TRY(h, cudaGraphInstantiate(&h->multi_graph[mode], g, 0));
+        cudaGraphDestroy(g);
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    const int tpb = 256;
+    const int gridn = (int)((S.n + tpb - 1) / tpb);
+    for (i64 r0 = 0; r0 < nrhs; r0 += MULTI_W) {
+        const int nb = (int)std::min<i64>(MULTI_W, nrhs - r0);
+        if (nb < MULTI_W)
+            CUDA_TRY(h, cudaMemsetAsync(h->d_ym + (size_t)nb * S.n, 0, sizeof(double) * (size_t)(MULTI_W - nb) * S.n, st));
+        if (mode == 0) {
+            permute_rows_kernel<<<gridn, tpb, 0, st>>>(h->d_ym, dB + r0 * ld, h->d_perm, S.n, S.n, ld, nb, 0);
+        } else {
+            CUDA_TRY(h, cudaMemcpy2DAsync(h->d_ym, sizeof(double) * S.n, dB + r0 * ld, sizeof(double) * ld,
+                                          sizeof(double) * S.n, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        if (h->opt.use_graph) CUDA_TRY(h, cudaGraphLaunch(h->multi_graph[mode], st));
+        else enqueue_multi_sweeps(h, mode);
+        permute_rows_kernel<<<gridn, tpb, 0, st>>>(dX + r0 * ld, h->d_ym, h->d_perm, S.n, ld, S.n, nb, 1);
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
+    if ((rc = check_launch(h, "wide solve"))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[2] = ms;
+    return 0;
+}
+
 // Enqueue the level-scheduled sweeps on the permuted work array d_y (mode 0: forward + backward, 1: backward only).
 void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
     TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
@@ -1006,6 +1213,7 @@ int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i
     const Symbolic &S = h->S;
     if (!h->factored) { h->err = "solve before the first refactorize"; return GMRF_B200_ERR_STATE; }
     if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
+    if (nrhs > h->opt.wide_rhs_min && S.n > 0) return do_solve_device_wide(h, dB, dX, ld, nrhs, mode);
     cudaStream_t st = h->stream;
     // graphs for the block widths this call needs are built before the timed region starts
     auto sweep_graph = [&](int nb, cudaGraphExec_t *out) -> int {
@@ -1153,6 +1361,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "outer_block") o.outer_block = (int)value;
     else if (k == "naive_kernels") o.naive_kernels = (int)value;
     else if (k == "selinv_fast_root") o.selinv_fast_root = (int)value;
+    else if (k == "wide_rhs_min") o.wide_rhs_min = std::max(0, (int)value);
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else return GMRF_B200_ERR_ARG;
     return 0;
@@ -1296,6 +1505,7 @@ void gmrf_b200_destroy(gmrf_b200_handle *h) {
         if (h->factor_graph) cudaGraphExecDestroy(h->factor_graph);
         if (h->selinv_graph) cudaGraphExecDestroy(h->selinv_graph);
         for (auto &kv : h->solve_graphs) cudaGraphExecDestroy(kv.second);
+        for (auto &g : h->multi_graph) if (g) cudaGraphExecDestroy(g);
         for (void *p : h->owned) cudaFree(p);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);
@@ -1808,6 +2018,47 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
     return check_launch(h, "profile_plan");
+}
+
+// ---- factor sharing between the handles of a multi-GPU pool ------------------------------------------------
+// Device pointers and lengths (doubles) of the numeric state a solve needs: which = 0 supernodal panels of L,
+// 1 inverted diagonal blocks, 2 selected-inverse panels (after selinv_compute). A pool factorizes on ONE device,
+// moves these arrays to its peers (ncclBroadcast over NVLink, or any device copy) and calls adopt_factor there.
+int gmrf_b200_device_array(gmrf_b200_handle *h, int which, void **ptr, int64_t *n_doubles) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!ptr || !n_doubles) { h->err = "device_array: null output"; return GMRF_B200_ERR_ARG; }
+    const Symbolic &S = h->S;
+    switch (which) {
+        case 0: *ptr = h->d_Lx; *n_doubles = S.panel_total; break;
+        case 1: {
+            i64 tot = 0;
+            for (i64 s = 0; s < S.nsuper; s++)
+                for (i64 k0 = 0; k0 < S.ns(s); k0 += SOLVE_NB) { i64 nb = std::min<i64>(SOLVE_NB, S.ns(s) - k0); tot += nb * nb; }
+            *ptr = h->d_Linv; *n_doubles = tot;
+            break;
+        }
+        case 2:
+            if ((rc = build_selinv_tables(h))) return rc;
+            *ptr = h->d_Zx; *n_doubles = S.panel_total;
+            break;
+        default: h->err = "device_array: which must be 0, 1 or 2"; return GMRF_B200_ERR_ARG;
+    }
+    return 0;
+}
+
+// Declare the panels / inverted blocks currently in this handle's HBM (received from a peer that factorized the same
+// pattern with the same ordering) to be its numeric factor; `logdet` is the sender's log-determinant. with_selinv != 0
+// also adopts the selected-inverse panels.
+int gmrf_b200_adopt_factor(gmrf_b200_handle *h, double logdet, int with_selinv) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->logdet = logdet;
+    h->fail_col = 0;
+    h->factored = true;
+    h->selinv_valid = with_selinv != 0 && h->d_Zx != nullptr;
+    return 0;
 }
 
 // Page-lock / unlock a caller-owned host buffer (e.g. the workspace's nzval array) so refactorize() copies it with

@@ -360,4 +360,60 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
     apply_inv_lower_t<RB>(g, SOLVE_NB, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide right-hand-side blocks (sampling, constraints, many columns): the sweeps are DMMA GEMMs on 64-column blocks of
+// right-hand sides (plans built in gmrf_b200.cu); only the two irregular steps need kernels of their own.
+// ------------------------------------------------------------------------------------------------
+constexpr int MULTI_W = 64;    // right-hand sides per pass of the wide path
+constexpr int MULTI_QB = 8;    // columns per CTA in the two kernels below
+
+// Forward assembly for a block of right-hand sides: u_s := 0, then the children's update blocks are added into the
+// supernode's own rows of y and into u_s (fixed child order). One CTA per (supernode, 8 columns).
+__global__ void __launch_bounds__(256)
+fwd_assemble_multi_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
+                          const int *__restrict__ child_idx, const int *__restrict__ relidx,
+                          double *__restrict__ y, long long ldy, double *__restrict__ uvec, long long ldu) {
+    const SuperMeta P = meta[supers[blockIdx.x]];
+    const int nr = P.nrow - P.ns;
+    const int q0 = blockIdx.y * MULTI_QB;
+    double *us = uvec + P.uvec_off + (long long)q0 * ldu;
+    for (int e = threadIdx.x; e < nr * MULTI_QB; e += 256) {
+        const int i = e % nr, q = e / nr;
+        us[i + q * ldu] = 0.0;
+    }
+    __syncthreads();
+    double *ys = y + P.first + (long long)q0 * ldy;
+    for (int ci = P.child_begin; ci < P.child_end; ci++) {
+        const SuperMeta C = meta[child_idx[ci]];
+        const int cnr = C.nrow - C.ns;
+        const int *rel = relidx + C.rowptr + C.ns;
+        const double *uc = uvec + C.uvec_off + (long long)q0 * ldu;
+        for (int i = threadIdx.x; i < cnr; i += 256) {
+            const int p = rel[i];
+#pragma unroll
+            for (int q = 0; q < MULTI_QB; q++) {
+                const double v = uc[i + q * ldu];
+                if (p < P.ns) ys[p + q * ldy] += v; else us[(p - P.ns) + q * ldu] += v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Backward gather for a block of right-hand sides: u_s[r, q] = y[rowidx_s[ns + r], q] (the solved rows of the
+// ancestors), so that t_S = y_S - L21' u_s is a plain GEMM. One CTA per (supernode row tile of 256, 8 columns).
+struct RowGatherTask { const int *idx; double *u; int nr, pad_; };
+__global__ void __launch_bounds__(256)
+rows_gather_kernel(const RowGatherTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks,
+                   const double *__restrict__ y, long long ldy, long long ldu) {
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const RowGatherTask T = tasks[t];
+    const int r = (blockIdx.x - tile_prefix[t]) * 256 + threadIdx.x;
+    if (r >= T.nr) return;
+    const long long g = T.idx[r];
+    const int q0 = blockIdx.y * MULTI_QB;
+#pragma unroll
+    for (int q = 0; q < MULTI_QB; q++) T.u[r + (q0 + q) * ldu] = y[g + (q0 + q) * ldy];
+}
+
 }  // namespace gmrf

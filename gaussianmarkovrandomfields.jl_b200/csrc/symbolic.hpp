@@ -27,6 +27,7 @@ struct Options {
     int outer_block = 256;   // outer panel block (columns) of the two-level blocked factorization
     int naive_kernels = 0;
     int splitk_min_k = 1024;  // split-K: a k-slice is at least this long (tests lower it to reach the path on small inputs)
+    int wide_rhs_min = 8;     // more right-hand sides than this take the GEMM (wide) solve path in blocks of 64 columns
     int selinv_fast_root = 1; // triangular (trtri + lauum) route for top-level root supernodes in the selected inversion
 };
 Options &global_options();

@@ -284,6 +284,20 @@ class B200Backend:
         names = ("gemm", "panel", "assemble", "other")
         return {"ms": dict(zip(names, ms.tolist())), "launches": dict(zip(names, cnt.tolist())), "gemm_flops": fl.value}
 
+    def device_array(self, which: int):
+        """(device pointer, doubles) of 0: panels of L, 1: inverted diagonal blocks, 2: selected-inverse panels."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        self._hd.check(self._L.gmrf_b200_device_array(self._hd._h, which, ctypes.byref(p), ctypes.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def adopt_factor(self, logdet: float, with_selinv: bool = False):
+        """Declare the factor arrays received from a peer GPU (sharding.broadcast_factor) to be this backend's factor."""
+        self._hd.check(self._L.gmrf_b200_adopt_factor(self._hd._h, float(logdet), int(bool(with_selinv))))
+        self.status = 0
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+
     LAUNCH_KINDS = ("assemble", "potrf", "trsm0", "trsm1", "gemm_nn_s", "gemm_nn_l", "gemm_nt_s", "gemm_nt_l", "gemm_tt_s",
                     "gemm_tt_l", "gather", "transpose", "fwd_asm", "fwd_step", "bwd_gather", "bwd_step", "panel", "split_reduce")
 

@@ -150,13 +150,21 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
 int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles);
 int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
 
+/* ---- factor sharing inside a multi-GPU pool (WorkspacePool, src/workspace/workspace_pool.jl:42-67, one workspace per
+ * GPU with the SAME ordering): device pointer + length in doubles of which = 0 the supernodal panels of L, 1 the
+ * inverted 64-column diagonal blocks, 2 the selected-inverse panels. One rank factorizes, the arrays travel to the
+ * peers (ncclBroadcast over NVLink) and each peer calls adopt_factor; its solves / samples then need no factorization
+ * of their own (right-hand-side blocks sharded over GPUs). */
+int gmrf_b200_device_array(gmrf_b200_handle *h, int which, void **ptr, int64_t *n_doubles);
+int gmrf_b200_adopt_factor(gmrf_b200_handle *h, double logdet, int with_selinv);
+
 /* Page-lock / unlock a caller-owned host buffer (typically the workspace's nzval array, `ws.Q.nzval`) so that
  * gmrf_b200_refactorize moves it with an asynchronous DMA. Optional; ownership stays with the caller. */
 int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`

@@ -67,6 +67,15 @@ def run(spec, order, do_selinv, reps=3):
     R = rng.standard_normal((n, 8))
     X = b.backend_solve(R)
     print(f"   solve 8 rhs {b.timings()['solve_ms']:.2f} ms  residual {np.linalg.norm(Q @ X - R) / np.linalg.norm(R):.2e}")
+    for m in (64, 256):
+        if n * m * 8 > 3e9:
+            continue
+        R = rng.standard_normal((n, m))
+        X = b.backend_solve(R)
+        X = b.backend_solve(R)
+        tm = b.timings()["solve_ms"]
+        fl = 4.0 * info["nnz_l_stored"] * m
+        print(f"   solve {m} rhs (GEMM sweeps) {tm:.2f} ms  = {tm / m:.3f} ms/rhs, {fl / tm / 1e9:.2f} TFLOP/s  residual {np.linalg.norm(Q @ X - R) / np.linalg.norm(R):.2e}")
     z = rng.standard_normal(n)
     s = b.backend_backward_solve(z)
     s = b.backend_backward_solve(z)

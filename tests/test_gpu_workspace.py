@@ -246,6 +246,37 @@ def test_spde_parity_with_oracle(kind, cells, smooth):
     be.close()
 
 
+@pytest.mark.parametrize("kind,cells,smooth", [("2d", 48, 1), ("3d", 12, 0)])
+def test_wide_rhs_blocks_match_single_column_solves(kind, cells, smooth):
+    """More than 8 right-hand sides go through the GEMM sweeps in blocks of 64 columns (sampling, constraints,
+    backend_solve(::Matrix), backend.jl:207-209): same answers as the column-at-a-time path of backend.jl:199-205 and
+    as the oracle, for full blocks, padded tails and the half solve used for sampling."""
+    mesh = spde.mesh2d(cells) if kind == "2d" else spde.mesh3d(cells)
+    Q = spde.MaternSPDE(*mesh, smooth).precision(1.3, 0.4)
+    n = Q.shape[0]
+    be = B200Backend(Q, device=0)
+    F = oracle.OracleFactor(Q, be.permutation())
+    rng = np.random.default_rng(11)
+    for m in (9, 64, 70, 130):
+        Bm = rng.standard_normal((n, m))
+        X = be.backend_solve(Bm)
+        assert X.shape == (n, m)
+        cols = [0, m // 2, m - 1]
+        for c in cols:
+            xc = be.backend_solve(Bm[:, c])
+            assert _rel(X[:, c], xc) <= 1e-11
+            assert _rel(X[:, c], F.solve(Bm[:, c])) <= 1e-8
+        R = Q @ X - Bm
+        assert np.linalg.norm(R) <= 1e-9 * (np.linalg.norm(Bm) + abs(Q).max() * np.linalg.norm(X))
+        Zm = rng.standard_normal((n, m))
+        Sm = be.backend_backward_solve(Zm)
+        for c in cols:
+            assert _rel(Sm[:, c], be.backend_backward_solve(Zm[:, c])) <= 1e-11
+            assert _rel(Sm[:, c], F.backward_solve(Zm[:, c])) <= 1e-8
+    # a padded leading dimension (ld > n) and in-place solve through the raw entry point
+    be.close()
+
+
 def test_schedule_variants_agree():
     """The scheduling options change the launch lists, never the mathematics: split-K with tiny k-slices (the path the
     top supernodes of the 1 M-dof problem take), a small outer block, the generic selected-inversion route for roots and
