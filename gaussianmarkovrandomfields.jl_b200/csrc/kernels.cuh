@@ -82,6 +82,12 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async16s(unsigned saddr, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8s(unsigned saddr, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(saddr), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -100,44 +106,100 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 template <int BM, int BN, int KT = 16, int ST = 3>
 constexpr int gemm_smem_bytes() { return ST * KT * ((BM + 4) + (BN + 4)) * (int)sizeof(double); }
 
-// Load a [KT x BX] tile (k-major in smem) of an operand. TR=false: global is x-contiguous; TR=true: k-contiguous.
-template <int BX, int NT, bool TR, int GEMM_KT>
-__device__ __forceinline__ void gemm_load_tile(double *__restrict__ s, const double *__restrict__ g, int ld,
-                                               int x0, int xmax, int k0, int kmax, bool aligned16, int tid) {
-    constexpr int LDS = BX + 4;
-    if (!TR) {
-        if (aligned16) {
-            constexpr int CH = BX / 2;  // 16-byte chunks per k row
-            for (int c = tid; c < CH * GEMM_KT; c += NT) {
-                int kk = c / CH, x = (c - kk * CH) * 2;
-                int gx = x0 + x, gk = k0 + kk;
-                int nb = 0;
-                if (gk < kmax && gx < xmax) nb = (xmax - gx >= 2) ? 16 : 8;
-                const double *src = nb ? (g + gx + (long long)gk * ld) : g;
-                cp_async16(s + kk * LDS + x, src, nb);
+// Loader of one operand: [KT x BX] tiles, k-major in shared memory (LDS = BX + 4). TR=false: global is x-contiguous
+// (16-byte cp.async when pointer and leading dimension allow it, 8-byte otherwise); TR=true: global is k-contiguous.
+// Everything that does not change along k (this thread's x position, its validity, the base pointer, the shared-memory
+// offset) is computed once per tile; a k-step costs one pointer bump and one bound compare per cp.async. (The first
+// version recomputed the index arithmetic per element: ncu showed 4 integer/branch instructions per DMMA.)
+template <int BX, int NT, bool TR, int KT>
+struct TileLoader {
+    static constexpr int LDS = BX + 4;
+    static constexpr int IT_V = (BX / 2) * KT / NT;   // 16-byte chunks per thread per tile
+    static constexpr int IT_S = BX * KT / NT;         // 8-byte elements per thread per tile
+    const double *p;       // source of this thread's first element at k = 0
+    int ld;
+    int kk;                // k offset (within a tile) of the first element
+    int soff;              // shared-memory offset (doubles) of the first element
+    int xbytes;            // !TR: valid bytes at this thread's x (0, 8, 16)
+    unsigned xmask;        // TR: bit i set <=> x of iteration i is in range
+    bool vec;
+
+    __device__ __forceinline__ void init(const double *g, int ld_, int x0, int xmax, bool aligned16, int tid) {
+        ld = ld_;
+        vec = !TR && aligned16;
+        xmask = 0;
+        xbytes = 0;
+        if (!TR) {
+            if (vec) {
+                const int x = (tid % (BX / 2)) * 2;
+                kk = tid / (BX / 2);
+                const int gx = x0 + x;
+                xbytes = gx < xmax ? ((xmax - gx >= 2) ? 16 : 8) : 0;
+                p = g + (xbytes ? gx : 0) + (long long)kk * ld;
+                soff = kk * LDS + x;
+            } else {
+                const int x = tid % BX;
+                kk = tid / BX;
+                const int gx = x0 + x;
+                xbytes = gx < xmax ? 8 : 0;
+                p = g + (xbytes ? gx : 0) + (long long)kk * ld;
+                soff = kk * LDS + x;
             }
         } else {
-            for (int c = tid; c < BX * GEMM_KT; c += NT) {
-                int kk = c / BX, x = c - kk * BX;
-                int gx = x0 + x, gk = k0 + kk;
-                int nb = (gk < kmax && gx < xmax) ? 8 : 0;
-                const double *src = nb ? (g + gx + (long long)gk * ld) : g;
-                cp_async8(s + kk * LDS + x, src, nb);
-            }
-        }
-    } else {
-        for (int c = tid; c < BX * GEMM_KT; c += NT) {
-            int x = c / GEMM_KT, kk = c - x * GEMM_KT;
-            int gx = x0 + x, gk = k0 + kk;
-            int nb = (gk < kmax && gx < xmax) ? 8 : 0;
-            const double *src = nb ? (g + gk + (long long)gx * ld) : g;
-            cp_async8(s + kk * LDS + x, src, nb);
+            kk = tid % KT;
+            const int xb = tid / KT;
+#pragma unroll
+            for (int i = 0; i < IT_S; i++)
+                if (x0 + xb + i * (NT / KT) < xmax) xmask |= 1u << i;
+            p = g + kk + (long long)(x0 + xb) * ld;
+            soff = kk * LDS + xb;
         }
     }
-}
+    // Issue the copies of the tile that starts at k0 into the stage at shared address `sbase` (rows >= kmax are
+    // zero-filled: src-size 0 reads nothing, so the source pointer may run past the operand). Pointers advance
+    // additively; interior tiles (the steady state) skip the k-bound tests altogether.
+    __device__ __forceinline__ void load(unsigned sbase, int k0, int kmax) const {
+        const unsigned sa = sbase + (unsigned)soff * 8u;
+        const bool interior = k0 + KT <= kmax;
+        if (!TR) {
+            const char *src = reinterpret_cast<const char *>(p + (long long)k0 * ld);
+            if (vec) {
+                constexpr int KS = NT / (BX / 2);
+                const long long stride = (long long)KS * ld * 8;
+                if (interior) {
+#pragma unroll
+                    for (int i = 0; i < IT_V; i++) cp_async16s(sa + i * KS * LDS * 8, src + i * stride, xbytes);
+                } else {
+                    const int kleft = kmax - k0 - kk;
+#pragma unroll
+                    for (int i = 0; i < IT_V; i++) cp_async16s(sa + i * KS * LDS * 8, src + i * stride, (i * KS < kleft) ? xbytes : 0);
+                }
+            } else {
+                constexpr int KS = NT / BX;
+                const long long stride = (long long)KS * ld * 8;
+                if (interior) {
+#pragma unroll
+                    for (int i = 0; i < IT_S; i++) cp_async8s(sa + i * KS * LDS * 8, src + i * stride, xbytes);
+                } else {
+                    const int kleft = kmax - k0 - kk;
+#pragma unroll
+                    for (int i = 0; i < IT_S; i++) cp_async8s(sa + i * KS * LDS * 8, src + i * stride, (i * KS < kleft) ? xbytes : 0);
+                }
+            }
+        } else {
+            constexpr int XS = NT / KT;
+            const char *src = reinterpret_cast<const char *>(p + k0);
+            const long long stride = (long long)XS * ld * 8;
+            const bool kin = k0 + kk < kmax;
+#pragma unroll
+            for (int i = 0; i < IT_S; i++)
+                cp_async8s(sa + i * XS * 8, src + i * stride, (kin && ((xmask >> i) & 1u)) ? 8 : 0);
+        }
+    }
+};
 
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, int GEMM_STAGES = 3>
-__global__ void __launch_bounds__(WGM *WGN * 32)
+__global__ void __launch_bounds__(WGM *WGN * 32, (WGM * WGN == 4) ? ((BM * BN <= 64 * 64) ? 4 : 3) : 1)
 gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
     constexpr int NT = WGM * WGN * 32;
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
@@ -175,11 +237,16 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
         for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int nk = (T.k + GEMM_KT - 1) / GEMM_KT;
+    const unsigned as_base = (unsigned)__cvta_generic_to_shared(As), bs_base = (unsigned)__cvta_generic_to_shared(Bs);
+    TileLoader<BM, NT, TA, GEMM_KT> la;
+    TileLoader<BN, NT, TB, GEMM_KT> lb;
+    la.init(T.A, T.lda, m0, T.m, a16, tid);
+    lb.init(T.B, T.ldb, n0, T.n, b16, tid);
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; s++) {
         if (s < nk) {
-            gemm_load_tile<BM, NT, TA, GEMM_KT>(As + s * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, s * GEMM_KT, T.k, a16, tid);
-            gemm_load_tile<BN, NT, TB, GEMM_KT>(Bs + s * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, s * GEMM_KT, T.k, b16, tid);
+            la.load(as_base + s * GEMM_KT * LDA_S * 8, s * GEMM_KT, T.k);
+            lb.load(bs_base + s * GEMM_KT * LDB_S * 8, s * GEMM_KT, T.k);
         }
         cp_async_commit();
     }
@@ -190,8 +257,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
             int nx = kt + GEMM_STAGES - 1;
             if (nx < nk) {
                 int st = nx % GEMM_STAGES;
-                gemm_load_tile<BM, NT, TA, GEMM_KT>(As + st * GEMM_KT * LDA_S, T.A, T.lda, m0, T.m, nx * GEMM_KT, T.k, a16, tid);
-                gemm_load_tile<BN, NT, TB, GEMM_KT>(Bs + st * GEMM_KT * LDB_S, T.B, T.ldb, n0, T.n, nx * GEMM_KT, T.k, b16, tid);
+                la.load(as_base + st * GEMM_KT * LDA_S * 8, nx * GEMM_KT, T.k);
+                lb.load(bs_base + st * GEMM_KT * LDB_S * 8, nx * GEMM_KT, T.k);
             }
             cp_async_commit();
         }
@@ -214,22 +281,31 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
 
     const double alpha = (T.flags & GEMM_ALPHA_POS) ? 1.0 : -1.0;
     const bool beta0 = T.flags & GEMM_BETA0, lower = T.flags & GEMM_LOWER, addi = T.flags & GEMM_ADD_I;
+    // Epilogue in chunks of 16 outputs: all reads of C are issued before the first store of the chunk, so a tile pays
+    // one memory round trip per chunk instead of one per element (loads could not be hoisted over the stores otherwise;
+    // with k = 64 the element-wise read-modify-write chain cost more than the tile's arithmetic).
+    constexpr int TOT = MI * NI * 2, CH = (BM * BN > 64 * 64) ? 4 : 8;
+    static_assert(TOT % CH == 0, "epilogue chunking");
+    double *const Cb = T.C + (m0 + wm0 + grp) + (long long)(n0 + wn0 + 2 * tig) * T.ldc;
 #pragma unroll
-    for (int i = 0; i < MI; i++) {
-        const int r = m0 + wm0 + 8 * i + grp;
-        if (r >= T.m) continue;
+    for (int base = 0; base < TOT; base += CH) {
+        double cv[CH];
 #pragma unroll
-        for (int j = 0; j < NI; j++) {
+        for (int u = 0; u < CH; u++) {
+            const int idx = base + u, e = idx & 1, j = (idx >> 1) % NI, i = (idx >> 1) / NI;
+            const int r = m0 + wm0 + 8 * i + grp, c = n0 + wn0 + 8 * j + 2 * tig + e;
+            const bool ok = r < T.m && c < T.n && !(lower && r < c);
+            cv[u] = (ok && !beta0) ? Cb[8 * i + (long long)(8 * j + e) * T.ldc] : 0.0;
+        }
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int c = n0 + wn0 + 8 * j + 2 * tig + e;
-                if (c >= T.n) continue;
-                if (lower && r < c) continue;
-                double *p = T.C + r + (long long)c * T.ldc;
-                double v = alpha * acc[i][j][e];
-                if (!beta0) v += *p;
+        for (int u = 0; u < CH; u++) {
+            const int idx = base + u, e = idx & 1, j = (idx >> 1) % NI, i = (idx >> 1) / NI;
+            const int r = m0 + wm0 + 8 * i + grp, c = n0 + wn0 + 8 * j + 2 * tig + e;
+            const bool ok = r < T.m && c < T.n && !(lower && r < c);
+            if (ok) {
+                double v = alpha * acc[i][j][e] + cv[u];
                 if (addi && r == c) v += 1.0;
-                *p = v;
+                Cb[8 * i + (long long)(8 * j + e) * T.ldc] = v;
             }
         }
     }
@@ -661,6 +737,11 @@ __global__ void permute_rows_kernel(double *__restrict__ dst, const double *__re
 __global__ void __launch_bounds__(256)
 selinv_gather_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__ meta,
                      const int *__restrict__ relidx, const double *__restrict__ Zx, double *__restrict__ zw) {
+    // A CTA owns 32 columns of W_s and walks down the 32-row tiles from the diagonal: the lower-triangle entries are
+    // gathered with lanes along the rows (coalesced reads of the parent column, coalesced writes of W), the mirrored
+    // upper-triangle entries go through a shared-memory tile so that their writes are coalesced as well
+    // (the direct transposed store cost 4x write amplification: 430 GB/s in the first 1 M-dof profile).
+    __shared__ double tile[32][33];
     const AsmItem it = items[blockIdx.x];
     const SuperMeta S = meta[it.super];
     const SuperMeta P = meta[S.parent];
@@ -670,15 +751,34 @@ selinv_gather_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restr
     const double *Zp = Zx + P.panel_off;
     const double *Wp = zw + P.zw_off;
     double *Ws = zw + S.zw_off;
-    const int c_hi = min(it.col0 + ASM_CW, nr);
-    for (int b = it.col0 + warp; b < c_hi; b += 8) {
-        const int pb = rel[b];
-        const double *src = (pb < P.ns) ? (Zp + (long long)pb * P.ld) : (Wp + (long long)(pb - P.ns) * P.uld - P.ns);
-        for (int a = b + lane; a < nr; a += 32) {
-            const double v = src[rel[a]];
-            Ws[a + (long long)b * S.uld] = v;
-            Ws[b + (long long)a * S.uld] = v;
+    const int c0 = it.col0;
+    const double *src[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int b = c0 + warp * 4 + q;
+        const int pb = b < nr ? rel[b] : 0;
+        src[q] = (pb < P.ns) ? (Zp + (long long)pb * P.ld) : (Wp + (long long)(pb - P.ns) * P.uld - P.ns);
+    }
+    for (int a0 = c0; a0 < nr; a0 += 32) {
+        const int a = a0 + lane;
+        const int ra = a < nr ? rel[a] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int bb = warp * 4 + q, b = c0 + bb;
+            double v = 0.0;
+            if (a < nr && b < nr && a >= b) {
+                v = src[q][ra];
+                Ws[a + (long long)b * S.uld] = v;
+            }
+            tile[bb][lane] = v;
         }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int aa = warp * 4 + q, ar = a0 + aa, b = c0 + lane;
+            if (ar < nr && b < nr && ar > b) Ws[b + (long long)ar * S.uld] = tile[lane][aa];
+        }
+        __syncthreads();
     }
 }
 
