@@ -55,6 +55,24 @@ def _peak():
         return FP64_PEAK_TFLOPS
 
 
+def hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def gemm_traffic():
+    """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def theta_for(step: int, rank: int):
     """Hyperparameter point (tau, range) of the sweep evaluated at (step, rank): a 16x16 log grid."""
     i = (step * 7 + rank * 3) % 16
@@ -275,12 +293,42 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             selinv_ms = float(t.item())
 
+    # ---- triangular solves (mean / Newton step / sampling): 1 right-hand side and one 64-column block ---------------
+    solve = None
+    if args.solve_reps > 0:
+        n = info["n"]
+        rng = np.random.default_rng(7)
+        be.refactorize_device(nz_dev[0].data_ptr(), nnz)
+        b1 = torch.from_numpy(rng.standard_normal(n)).cuda()
+        x1 = torch.empty_like(b1)
+        t1, tl = [], []
+        for r in range(args.solve_reps + 1):
+            be.solve_device(b1.data_ptr(), x1.data_ptr(), n, 1)
+            t1.append(be.timings()["solve_ms"])
+            be.solve_device(b1.data_ptr(), x1.data_ptr(), n, 1, half=True)
+            tl.append(be.timings()["solve_ms"])
+        B64 = torch.from_numpy(rng.standard_normal((64, n))).cuda()      # 64 columns, column-major n x 64
+        X64 = torch.empty_like(B64)
+        t64 = []
+        for r in range(2):
+            be.solve_device(B64.data_ptr(), X64.data_ptr(), n, 64)
+            t64.append(be.timings()["solve_ms"])
+        bytes_l = 8.0 * info["nnz_l_stored"]
+        hbm = hbm_peak()
+        solve = {"solve_1rhs_ms": min(t1[1:]), "solve_1rhs_GBs": 2 * bytes_l / min(t1[1:]) / 1e6,
+                 "solve_1rhs_frac_of_hbm": 2 * bytes_l / min(t1[1:]) / 1e6 / hbm,
+                 "lt_solve_1rhs_ms": min(tl[1:]), "lt_solve_1rhs_GBs": bytes_l / min(tl[1:]) / 1e6,
+                 "solve_64rhs_ms": min(t64), "solve_64rhs_tflops": 4.0 * info["nnz_l_stored"] * 64 / min(t64) / 1e9,
+                 "hbm_peak_GBs": hbm, "bytes": "2 x 8 x nnz(L stored) per forward+backward sweep (the factor panels, streamed once per direction)"}
+        del B64, X64
+
     # ---- roofline of the dominant kernel (live CUDA events around every launch of one more refactorization) ------
     prof = be.profile_refactorize()
     gemm_ms, gemm_launches, gemm_flops = prof["ms"]["gemm"], prof["launches"]["gemm"], prof["gemm_flops"]
     peak = _peak()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
+    traffic = gemm_traffic()
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -308,6 +356,7 @@ def run_gpu(args):
             "fp64_tflops": flops / (ms_per_step * 1e-3) / 1e12,
             "selinv_ms": selinv_ms,
             "selinv_fp64_tflops_equiv": (2.0 * flops / (selinv_ms * 1e-3) / 1e12) if selinv_ms else None,
+            "solves": solve,
             "wall_ms_per_step": wall_ms / args.steps,
             "logdet": logdets[-1], "factor_status": status,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nnz * 8), "d2h_bytes_per_step": 12,
@@ -315,7 +364,8 @@ def run_gpu(args):
             "gpu_launches": int(args.steps * info["graph_nodes"]),
             "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 via mma.sync.m8n8k4.f64)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": FP64_PEAK_SOURCE,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_capture": traffic,
+                         "peak_source": FP64_PEAK_SOURCE,
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": gemm_ms / sum(prof["ms"].values()) if sum(prof["ms"].values()) > 0 else None,
                          "other_kernels_ms": {k: v for k, v in prof["ms"].items() if k != "gemm"}},
@@ -336,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=100, help="cells per axis of the 3D mesh (100 -> 1,030,301 dofs)")
     ap.add_argument("--selinv-reps", type=int, default=1)
+    ap.add_argument("--solve-reps", type=int, default=2)
     ap.add_argument("--cpu-sample-cells", type=int, default=56)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
