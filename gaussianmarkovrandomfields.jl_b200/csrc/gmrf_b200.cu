@@ -880,7 +880,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
 // ------------------------------------------------------------------------------------------------
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
 void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
-    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN>(), st>>>(tasks, prefix, ntasks);
+    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks);
 }
 
 // Opt in to > 48 KB dynamic shared memory for every GEMM instantiation (per device; must run outside stream capture).
@@ -888,8 +888,8 @@ template <int BM, int BN, int WGM, int WGN>
 cudaError_t configure_gemm_tile() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
-    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
-    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, 16, 3, false, true>()))) return e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, 16, 3, true, true>()))) return e;
     return cudaSuccess;
 }
 cudaError_t configure_kernels() {

@@ -103,8 +103,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // CTA tile BM x BN, warp grid WGM x WGN, K tile 16, 3-stage cp.async pipeline.
 // smem tiles are stored k-major: As[stage][kk][m] (+4 padding -> conflict-free 8-byte fragment loads).
 // ------------------------------------------------------------------------------------------------
-template <int BM, int BN, int KT = 16, int ST = 3>
-constexpr int gemm_smem_bytes() { return ST * KT * ((BM + 4) + (BN + 4)) * (int)sizeof(double); }
+// Shared-memory tile of one operand: k-major [KT][BX + 4] for an operand that is x-contiguous in global memory,
+// x-major [BX][KT + 4] for a k-contiguous one (so that its cp.async stores run along the contiguous direction);
+// both paddings make the 8-byte DMMA fragment loads bank-conflict free.
+template <int BX, int KT, bool TR>
+__host__ __device__ constexpr int gemm_tile_doubles() { return TR ? BX * (KT + 4) : KT * (BX + 4); }
+template <int BM, int BN, int KT = 16, int ST = 3, bool TA = false, bool TB = false>
+constexpr int gemm_smem_bytes() { return ST * (gemm_tile_doubles<BM, KT, TA>() + gemm_tile_doubles<BN, KT, TB>()) * (int)sizeof(double); }
 
 // Loader of one operand: [KT x BX] tiles, k-major in shared memory (LDS = BX + 4). TR=false: global is x-contiguous
 // (16-byte cp.async when pointer and leading dimension allow it, 8-byte otherwise); TR=true: global is k-contiguous.
@@ -113,8 +118,9 @@ constexpr int gemm_smem_bytes() { return ST * KT * ((BM + 4) + (BN + 4)) * (int)
 // version recomputed the index arithmetic per element: ncu showed 4 integer/branch instructions per DMMA.)
 template <int BX, int NT, bool TR, int KT>
 struct TileLoader {
-    static constexpr int LDS = BX + 4;
-    static constexpr int IT_V = (BX / 2) * KT / NT;   // 16-byte chunks per thread per tile
+    static constexpr int LDS = BX + 4;                // !TR: k-major rows
+    static constexpr int LDK = KT + 4;                // TR: x-major rows
+    static constexpr int IT_V = (BX / 2) * KT / NT;   // 16-byte chunks per thread per tile (same count for both layouts)
     static constexpr int IT_S = BX * KT / NT;         // 8-byte elements per thread per tile
     const double *p;       // source of this thread's first element at k = 0
     int ld;
@@ -126,7 +132,7 @@ struct TileLoader {
 
     __device__ __forceinline__ void init(const double *g, int ld_, int x0, int xmax, bool aligned16, int tid) {
         ld = ld_;
-        vec = !TR && aligned16;
+        vec = aligned16;
         xmask = 0;
         xbytes = 0;
         if (!TR) {
@@ -146,13 +152,15 @@ struct TileLoader {
                 soff = kk * LDS + x;
             }
         } else {
-            kk = tid % KT;
-            const int xb = tid / KT;
-#pragma unroll
-            for (int i = 0; i < IT_S; i++)
-                if (x0 + xb + i * (NT / KT) < xmax) xmask |= 1u << i;
+            // chunks run along k: a row of the tile is KT contiguous doubles in global AND in shared memory
+            const int per_row = vec ? KT / 2 : KT;         // chunks per x row
+            const int xb = tid / per_row;
+            kk = (tid % per_row) * (vec ? 2 : 1);
+            const int its = vec ? IT_V : IT_S, xs = NT / per_row;
+            for (int i = 0; i < its; i++)
+                if (x0 + xb + i * xs < xmax) xmask |= 1u << i;
             p = g + kk + (long long)(x0 + xb) * ld;
-            soff = kk * LDS + xb;
+            soff = xb * LDK + kk;
         }
     }
     // Issue the copies of the tile that starts at k0 into the stage at shared address `sbase` (rows >= kmax are
@@ -187,13 +195,23 @@ struct TileLoader {
                 }
             }
         } else {
-            constexpr int XS = NT / KT;
             const char *src = reinterpret_cast<const char *>(p + k0);
-            const long long stride = (long long)XS * ld * 8;
-            const bool kin = k0 + kk < kmax;
+            const int kleft = kmax - k0 - kk;               // valid elements from this thread's k position on
+            if (vec) {
+                constexpr int XS = NT / (KT / 2);
+                const long long stride = (long long)XS * ld * 8;
+                const int kb = kleft >= 2 ? 16 : (kleft == 1 ? 8 : 0);
 #pragma unroll
-            for (int i = 0; i < IT_S; i++)
-                cp_async8s(sa + i * XS * 8, src + i * stride, (kin && ((xmask >> i) & 1u)) ? 8 : 0);
+                for (int i = 0; i < IT_V; i++)
+                    cp_async16s(sa + i * XS * LDK * 8, src + i * stride, ((xmask >> i) & 1u) ? kb : 0);
+            } else {
+                constexpr int XS = NT / KT;
+                const long long stride = (long long)XS * ld * 8;
+                const int kb = kleft >= 1 ? 8 : 0;
+#pragma unroll
+                for (int i = 0; i < IT_S; i++)
+                    cp_async8s(sa + i * XS * LDK * 8, src + i * stride, ((xmask >> i) & 1u) ? kb : 0);
+            }
         }
     }
 };
@@ -202,12 +220,13 @@ template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, 
 __global__ void __launch_bounds__(WGM *WGN * 32, (WGM * WGN == 4) ? ((BM * BN <= 64 * 64) ? 4 : 3) : 1)
 gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
     constexpr int NT = WGM * WGN * 32;
-    constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+    constexpr int LDA_S = BM + 4, LDB_S = BN + 4, LDK = GEMM_KT + 4;
+    constexpr int A_TILE = gemm_tile_doubles<BM, GEMM_KT, TA>(), B_TILE = gemm_tile_doubles<BN, GEMM_KT, TB>();
     constexpr int WM = BM / WGM, WN = BN / WGN;
     constexpr int MI = WM / 8, NI = WN / 8;
     extern __shared__ __align__(16) double gemm_smem[];
     double *As = gemm_smem;
-    double *Bs = gemm_smem + GEMM_STAGES * GEMM_KT * LDA_S;
+    double *Bs = gemm_smem + GEMM_STAGES * A_TILE;
 
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const GemmTask T = tasks[t];
@@ -227,8 +246,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp % WGM) * WM, wn0 = (warp / WGM) * WN;
     const int grp = lane >> 2, tig = lane & 3;
-    const bool a16 = !TA && ((((uintptr_t)T.A) & 15) == 0) && ((T.lda & 1) == 0);
-    const bool b16 = !TB && ((((uintptr_t)T.B) & 15) == 0) && ((T.ldb & 1) == 0);
+    const bool a16 = ((((uintptr_t)T.A) & 15) == 0) && ((T.lda & 1) == 0);
+    const bool b16 = ((((uintptr_t)T.B) & 15) == 0) && ((T.ldb & 1) == 0);
 
     double acc[MI][NI][2];
 #pragma unroll
@@ -245,8 +264,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; s++) {
         if (s < nk) {
-            la.load(as_base + s * GEMM_KT * LDA_S * 8, s * GEMM_KT, T.k);
-            lb.load(bs_base + s * GEMM_KT * LDB_S * 8, s * GEMM_KT, T.k);
+            la.load(as_base + s * A_TILE * 8, s * GEMM_KT, T.k);
+            lb.load(bs_base + s * B_TILE * 8, s * GEMM_KT, T.k);
         }
         cp_async_commit();
     }
@@ -257,20 +276,22 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
             int nx = kt + GEMM_STAGES - 1;
             if (nx < nk) {
                 int st = nx % GEMM_STAGES;
-                la.load(as_base + st * GEMM_KT * LDA_S * 8, nx * GEMM_KT, T.k);
-                lb.load(bs_base + st * GEMM_KT * LDB_S * 8, nx * GEMM_KT, T.k);
+                la.load(as_base + st * A_TILE * 8, nx * GEMM_KT, T.k);
+                lb.load(bs_base + st * B_TILE * 8, nx * GEMM_KT, T.k);
             }
             cp_async_commit();
         }
-        const double *as = As + (kt % GEMM_STAGES) * GEMM_KT * LDA_S;
-        const double *bs = Bs + (kt % GEMM_STAGES) * GEMM_KT * LDB_S;
+        const double *as = As + (kt % GEMM_STAGES) * A_TILE;
+        const double *bs = Bs + (kt % GEMM_STAGES) * B_TILE;
 #pragma unroll
         for (int ks = 0; ks < GEMM_KT / 4; ks++) {
             double a[MI], b[NI];
 #pragma unroll
-            for (int i = 0; i < MI; i++) a[i] = as[(ks * 4 + tig) * LDA_S + wm0 + 8 * i + grp];
+            for (int i = 0; i < MI; i++)
+                a[i] = TA ? as[(wm0 + 8 * i + grp) * LDK + ks * 4 + tig] : as[(ks * 4 + tig) * LDA_S + wm0 + 8 * i + grp];
 #pragma unroll
-            for (int j = 0; j < NI; j++) b[j] = bs[(ks * 4 + tig) * LDB_S + wn0 + 8 * j + grp];
+            for (int j = 0; j < NI; j++)
+                b[j] = TB ? bs[(wn0 + 8 * j + grp) * LDK + ks * 4 + tig] : bs[(ks * 4 + tig) * LDB_S + wn0 + 8 * j + grp];
 #pragma unroll
             for (int i = 0; i < MI; i++)
 #pragma unroll
