@@ -28,7 +28,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_POTRF_UNUSED, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE
 };
 
 struct Launch {
@@ -82,6 +82,8 @@ struct gmrf_b200_handle {
     FwdStepTask *d_fwd = nullptr;
     BwdGatherTask *d_bwdg = nullptr;
     BwdStepTask *d_bwds = nullptr;
+    BwdReduceTask *d_bwdr = nullptr;
+    double *d_bwdpart = nullptr;       // partial sums of the row-chunked L21' x_R products (backward sweep)
     double *d_Linv = nullptr;          // inverted 64-column diagonal blocks: written by the factorization (TRSM by
                                        // GEMM), reused by the solve phase
     long long *d_invbase = nullptr;    // per supernode: offset of its first inverted block in d_Linv
@@ -163,6 +165,7 @@ struct Builder {
     std::vector<FwdStepTask> fwd;
     std::vector<BwdGatherTask> bwdg;
     std::vector<BwdStepTask> bwds;
+    std::vector<BwdReduceTask> bwdr;
     std::vector<TransTask> trans;
     std::vector<SplitTask> split;
     std::vector<RowGatherTask> rowgather;
@@ -467,7 +470,10 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     std::vector<int> lst;
     std::vector<FwdStepTask> ft;
     std::vector<BwdGatherTask> gt;
+    std::vector<BwdReduceTask> rt;
     std::vector<BwdStepTask> bt;
+    i64 part_off = 0;
+    const i64 RCH = std::max(32, h->opt.bwd_row_chunk);
     const i64 BB = (i64)SOLVE_NB * SOLVE_NB;
     auto inv_ptr = [&](i64 s, i64 j) { return (const double *)(h->d_Linv + h->inv_base[s] + j * BB); };
     // forward: L y = b
@@ -515,11 +521,29 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
             t.ld = (int)ld; t.ns = (int)ns; t.nr = (int)nr; t.nb_last = (int)(ns - (nblk - 1) * SOLVE_NB);
             t.tile0 = nr > 0 ? 0 : (int)(nblk - 1);
             t.pad_ = 0;
-            gt.push_back(t);
+            t.part = nullptr;
+            if (nr > RCH) {
+                // tall L21: row chunks write partial sums, a second pass folds them (fixed order) and finishes t_S
+                const i64 nch = cdiv(nr, RCH);
+                double *part = h->d_bwdpart + part_off;
+                part_off += nch * BWD_PART_Q * ns;
+                for (i64 k = 0; k < nch; k++) {
+                    BwdGatherTask c = t;
+                    const i64 r0 = k * RCH;
+                    c.L21 = t.L21 + r0; c.idx = t.idx + r0;
+                    c.nr = (int)std::min<i64>(RCH, nr - r0);
+                    c.part = part + k * BWD_PART_Q * ns;
+                    gt.push_back(c);
+                }
+                rt.push_back(BwdReduceTask{part, t.inv_last, t.y, (int)ns, (int)nch, t.nb_last, 0});
+            } else {
+                gt.push_back(t);
+            }
         }
         B.add_tiled(h->bwd_plan, gt, B.bwdg, K_BWD_GATHER, [](const BwdGatherTask &t) {
             return (i64)(cdiv(t.ns, SOLVE_NB) - t.tile0);
         });
+        B.add_tiled(h->bwd_plan, rt, B.bwdr, K_BWD_REDUCE, [](const BwdReduceTask &t) { return (i64)cdiv(t.ns, SOLVE_NB); });
         for (i64 tt = 0; tt + 1 < maxsteps; tt++) {
             for (const i64 *sp = sb; sp < se; sp++) {
                 i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
@@ -998,6 +1022,9 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
         case K_BWD_GATHER:
             SOLVE_RB_DISPATCH(bwd_gather_kernel, h->d_bwdg + L.task_off, pf, L.ntasks, nrhs, h->d_y, (long long)h->S.n);
             break;
+        case K_BWD_REDUCE:
+            SOLVE_RB_DISPATCH(bwd_reduce_kernel, h->d_bwdr + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
+            break;
         case K_BWD_STEP:
             SOLVE_RB_DISPATCH(bwd_step_kernel, h->d_bwds + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
             break;
@@ -1362,6 +1389,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "naive_kernels") o.naive_kernels = (int)value;
     else if (k == "selinv_fast_root") o.selinv_fast_root = (int)value;
     else if (k == "wide_rhs_min") o.wide_rhs_min = std::max(0, (int)value);
+    else if (k == "bwd_row_chunk") o.bwd_row_chunk = std::max(32, (int)value);
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else return GMRF_B200_ERR_ARG;
     return 0;
@@ -1465,6 +1493,11 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
             }
         }
         TRY_RC(dev_alloc(H, &H->d_Linv, (size_t)inv_total));
+        i64 part_total = 0;   // partial sums of the row-chunked backward products
+        for (i64 s = 0; s < S.nsuper; s++)
+            if (S.nr(s) > std::max(32, H->opt.bwd_row_chunk))
+                part_total += cdiv(S.nr(s), std::max(32, H->opt.bwd_row_chunk)) * (i64)BWD_PART_Q * S.ns(s);
+        TRY_RC(dev_alloc(H, &H->d_bwdpart, (size_t)part_total));
         TRY_RC(dev_upload(H, &H->d_invbase, H->inv_base));
     }
     H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
@@ -1488,6 +1521,7 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         TRY_RC(dev_upload(H, &H->d_fwd, B.fwd));
         TRY_RC(dev_upload(H, &H->d_bwdg, B.bwdg));
         TRY_RC(dev_upload(H, &H->d_bwds, B.bwds));
+        TRY_RC(dev_upload(H, &H->d_bwdr, B.bwdr));
         TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
         TRY_RC(dev_upload(H, &H->d_split, B.split));

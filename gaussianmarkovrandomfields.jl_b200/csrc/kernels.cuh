@@ -689,12 +689,24 @@ assemble_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__
         for (int jc = a + warp; jc < b; jc += 8) {
             const int pc = rel[jc];
             const double *src = Uc + (long long)jc * C.uld;
-            if (pc < P.ns) {
-                double *dst = Lp + (long long)pc * P.ld;
-                for (int ic = jc + lane; ic < cnr; ic += 32) dst[rel[ic]] += src[ic];
-            } else {
-                double *dst = Up + (long long)(pc - P.ns) * P.uld - P.ns;
-                for (int ic = jc + lane; ic < cnr; ic += 32) dst[rel[ic]] += src[ic];
+            // rel is strictly increasing, so the 4 read-modify-writes of a batch touch distinct entries: all loads of a
+            // batch are issued before its first store (the plain `dst[rel[i]] += src[i]` loop serialised on possible
+            // aliasing: ncu showed one memory round trip per element, long-scoreboard stalls 67 per issue)
+            double *dst = (pc < P.ns) ? (Lp + (long long)pc * P.ld) : (Up + (long long)(pc - P.ns) * P.uld - P.ns);
+            for (int ic = jc + lane; ic < cnr; ic += 128) {
+                int ri[4];
+                double sv[4], dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = ic + 32 * u;
+                    ri[u] = i < cnr ? rel[i] : -1;
+                    sv[u] = i < cnr ? src[i] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) dv[u] = ri[u] >= 0 ? dst[ri[u]] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (ri[u] >= 0) dst[ri[u]] = dv[u] + sv[u];
             }
         }
         __syncthreads();

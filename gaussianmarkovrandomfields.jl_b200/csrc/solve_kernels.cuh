@@ -37,6 +37,18 @@ struct BwdGatherTask {    // t_S = y_S - L21' x_R for one supernode, then x of t
     double *y;            // own columns of the supernode (ns entries), stride ldy
     int ld, ns, nr, nb_last;
     int tile0, pad_;      // first 64-column tile this task launches (nr == 0: only the last one)
+    double *part;         // nullptr: the task covers all nr rows and finishes t_S itself. Otherwise the task is ONE ROW
+                          // CHUNK of a tall L21 (L21 / idx / nr describe the chunk) and only stores its partial sums
+                          // part[c + q*ns]; bwd_reduce_kernel folds the chunks in fixed order afterwards.
+};
+
+constexpr int BWD_PART_Q = 8;         // right-hand-side planes per chunk in the partial buffer
+
+struct BwdReduceTask {    // t_S = y_S - sum_chunks part, then the last block solve (one CTA per 64 own columns)
+    const double *part;   // chunk k, plane q at part + (k * BWD_PART_Q + q) * ns
+    const double *inv_last;
+    double *y;
+    int ns, nchunks, nb_last, pad_;
 };
 
 struct BwdStepTask {      // block row K_j = [k0, k1) of L11, x_j final in `x`
@@ -276,17 +288,37 @@ bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict
 #pragma unroll
         for (int q = 0; q < RB; q++) acc[i][q] = 0.0;
     if (c0 < T.ns) {
-#pragma unroll 2
-        for (int r = lane; r < T.nr; r += 32) {
-            const long long gr = T.idx[r];
-            double xv[RB];
+        // Rows are walked in blocks of 32*HB; inside a block the warp visits its 8 columns four at a time, so every
+        // column visit reads 256*HB contiguous bytes with 4*HB independent loads per lane in flight (ncu on the first
+        // version: 256-byte visits of 8 interleaved column streams per warp held DRAM at 45 % of the copy rate).
+        constexpr int HB = (RB >= 4) ? 2 : 4;
+        for (int r0 = 0; r0 < T.nr; r0 += 32 * HB) {
+            double xv[HB][RB];
+            bool ok[HB];
 #pragma unroll
-            for (int q = 0; q < RB; q++) xv[q] = (q < nrhs) ? xg[gr + q * ldy] : 0.0;
+            for (int h = 0; h < HB; h++) {
+                const int r = r0 + lane + 32 * h;
+                ok[h] = r < T.nr;
+                const long long gr = ok[h] ? T.idx[r] : 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const double lv = (c0 + i < T.ns) ? T.L21[r + (long long)(c0 + i) * T.ld] : 0.0;
+                for (int q = 0; q < RB; q++) xv[h][q] = (ok[h] && q < nrhs) ? xg[gr + q * ldy] : 0.0;
+            }
 #pragma unroll
-                for (int q = 0; q < RB; q++) acc[i][q] += lv * xv[q];
+            for (int half = 0; half < 2; half++) {
+                double lv[4][HB];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = c0 + 4 * half + i;
+                    const double *col = T.L21 + (long long)c * T.ld + r0 + lane;
+#pragma unroll
+                    for (int h = 0; h < HB; h++) lv[i][h] = (ok[h] && c < T.ns) ? col[32 * h] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int h = 0; h < HB; h++)
+#pragma unroll
+                        for (int q = 0; q < RB; q++) acc[4 * half + i][q] += lv[i][h] * xv[h][q];
             }
         }
     }
@@ -299,9 +331,38 @@ bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict
         const int cl = warp * 8 + warp_reduce8_index(lane);      // column within the tile
         const int c = tile * SOLVE_NB + cl;
         if ((lane & 3) == 0 && c < T.ns && q < nrhs) {
+            if (T.part) { T.part[c + (long long)q * T.ns] = s; continue; }
             const double v = T.y[c + q * ldy] - s;
             if (tail) st[cl][q] = v; else T.y[c + q * ldy] = v;
         }
+    }
+    if (!tail || T.part) return;
+    __syncthreads();
+    apply_inv_lower_t<RB>(g, T.nb_last, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
+}
+
+// Second pass for the supernodes whose L21 was processed in row chunks: fold the partial sums in chunk order.
+template <int RB>
+__global__ void __launch_bounds__(256)
+bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
+                  long long ldy) {
+    __shared__ double st[SOLVE_NB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const BwdReduceTask T = tasks[t];
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (T.ns + SOLVE_NB - 1) / SOLVE_NB;
+    const bool tail = (tile == nblk - 1);
+    double g[16];
+    if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int cl = e % SOLVE_NB, q = e / SOLVE_NB;
+        const int c = tile * SOLVE_NB + cl;
+        if (c >= T.ns || q >= nrhs) continue;
+        double s = 0.0;
+        for (int k = 0; k < T.nchunks; k++) s += T.part[((long long)k * BWD_PART_Q + q) * T.ns + c];
+        const double v = T.y[c + q * ldy] - s;
+        if (tail) st[cl][q] = v; else T.y[c + q * ldy] = v;
     }
     if (!tail) return;
     __syncthreads();

@@ -140,6 +140,11 @@ if __name__ == "__main__":
         gemm_variants()
     if "--gemm" in sys.argv:
         gemm_bench()
+    for a in sys.argv[1:]:
+        if a.startswith("--opt="):                      # library tunables, e.g. --opt=bwd_row_chunk=1024
+            k, v = a[6:].split("=")
+            _lib.set_option(k, float(v))
+            print(f"option {k} = {v}")
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     order = "nd"
     for a in sys.argv[1:]:

@@ -292,8 +292,10 @@ def test_schedule_variants_agree():
     ref = (base.compute_logdet(), base.backend_solve(b), base.get_selinv_diag())
     base.close()
     assert np.max(np.abs(ref[2] - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
-    variants = [{"splitk_min_k": 32}, {"splitk_min_k": 16, "outer_block": 128}, {"selinv_fast_root": 0}, {"use_graph": 0}]
-    defaults = {"splitk_min_k": 1024, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1}
+    variants = [{"splitk_min_k": 32}, {"splitk_min_k": 16, "outer_block": 128}, {"selinv_fast_root": 0}, {"use_graph": 0},
+                {"bwd_row_chunk": 64}, {"wide_rhs_min": 1}]
+    defaults = {"splitk_min_k": 1024, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1, "bwd_row_chunk": 2048,
+                "wide_rhs_min": 8}
     try:
         for v in variants:
             for k, val in {**defaults, **v}.items():
