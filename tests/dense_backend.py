@@ -1,0 +1,47 @@
+"""Dense numpy stand-in for a WorkspaceBackend (test infrastructure only): lets the host logic above the backend --
+GMRFWorkspace state machine, WorkspaceGMRF, the workspace Newton loop -- run on CPU in the `-m "not gpu"` suite, and
+serves as the independent arm of the GPU parity tests, the way the reference's tests compare the workspace path with
+the plain `GMRF` path (test/workspace/test_workspace_gaussian_approximation.jl:8-32)."""
+import numpy as np
+import scipy.sparse as sp
+
+
+class DenseBackend:
+    def __init__(self, Q, **_):
+        self.n = Q.shape[0]
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        self.refactorizations = 0
+        self.refactorize(Q)
+
+    def refactorize(self, Q):
+        A = Q.toarray() if sp.issparse(Q) else np.asarray(Q)
+        self.Qd = 0.5 * (A + A.T) if not np.allclose(A, A.T) else A
+        self.L = np.linalg.cholesky(self.Qd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        self.refactorizations += 1
+
+    def backend_solve(self, rhs):
+        rhs = np.asarray(rhs, dtype=np.float64)
+        y = np.linalg.solve(self.L, rhs)
+        return np.linalg.solve(self.L.T, y)
+
+    def backend_backward_solve(self, x):
+        return np.linalg.solve(self.L.T, np.asarray(x, dtype=np.float64))
+
+    def compute_logdet(self):
+        return 2.0 * float(np.sum(np.log(np.diag(self.L))))
+
+    def compute_selinv(self):
+        pass
+
+    def get_selinv_diag(self):
+        if self.selinv_diag_cache is None:
+            self.selinv_diag_cache = np.diag(np.linalg.inv(self.Qd)).copy()
+        return self.selinv_diag_cache
+
+    def get_selinv(self):
+        if self.selinv_cache is None:
+            self.selinv_cache = sp.csc_matrix(np.linalg.inv(self.Qd))
+        return self.selinv_cache
