@@ -99,6 +99,8 @@ struct gmrf_b200_handle {
     cudaGraphExec_t multi_graph[2] = {nullptr, nullptr};
     TransTask *d_trans = nullptr;
     SplitTask *d_split = nullptr, *d_split_z = nullptr;
+    double *d_basis = nullptr;         // optional value basis (nbasis x nnz) for device-side assembly of nzval
+    int nbasis = 0;
     double *d_splitk = nullptr;        // scratch for split-K partial products
     i64 splitk_cap = 0;                // doubles
     // selinv task tables are built lazily (they need d_Zx / d_zw)
@@ -1579,6 +1581,40 @@ int gmrf_b200_refactorize(gmrf_b200_handle *h, const double *nzval, int64_t nnz)
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
     h->t_ms[0] = ms;
     return rc;
+}
+
+// ---- device-side value assembly (hyperparameter loops) ------------------------------------------------------
+// replaces the host-side re-assembly + upload of nzval per theta: `(model)(ws; theta...)` ->
+// _pad_to_workspace_pattern (src/workspace/latent_model_integration.jl:151-250) + _copy_sparse_values! (backend.jl:165-176).
+// set_value_basis uploads `nbasis` value arrays laid out on the workspace pattern ONCE; refactorize_combination forms
+// nzval = sum_j coeff[j] * basis_j in HBM and factorizes, so a theta evaluation moves `nbasis` doubles over PCIe.
+int gmrf_b200_set_value_basis(gmrf_b200_handle *h, const double *basis, int nbasis) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!basis || nbasis < 1 || nbasis > MAX_VALUE_BASIS) { h->err = "set_value_basis: need 1 <= nbasis <= 8 value arrays"; return GMRF_B200_ERR_ARG; }
+    const size_t cnt = (size_t)nbasis * (size_t)h->S.nnzA;
+    if (h->d_basis && h->nbasis != nbasis) { cudaFree(h->d_basis); h->owned.erase(std::find(h->owned.begin(), h->owned.end(), (void *)h->d_basis)); h->d_basis = nullptr; }
+    if (!h->d_basis && (rc = dev_alloc(h, &h->d_basis, cnt))) return rc;
+    h->nbasis = nbasis;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_basis, basis, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, int nbasis) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->d_basis || nbasis != h->nbasis || !coeff) { h->err = "refactorize_combination: call set_value_basis first (same nbasis)"; return GMRF_B200_ERR_STATE; }
+    BasisCoeff c;
+    for (int j = 0; j < MAX_VALUE_BASIS; j++) c.c[j] = j < nbasis ? coeff[j] : 0.0;
+    const i64 nnz = h->S.nnzA;
+    if (nnz > 0) {
+        const int grid = (int)std::min<i64>((nnz + 255) / 256, 148 * 32);
+        combine_basis_kernel<<<grid, 256, 0, h->stream>>>(h->d_nz, h->d_basis, c, nbasis, nnz);
+        if ((rc = check_launch(h, "value assembly"))) return rc;
+    }
+    h->t_ms[0] = 0;
+    return do_factor(h);
 }
 
 int gmrf_b200_logdet(gmrf_b200_handle *h, double *out) {

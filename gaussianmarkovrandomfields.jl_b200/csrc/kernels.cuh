@@ -641,6 +641,22 @@ __global__ void scatter_q_kernel(double *__restrict__ Lx, const double *__restri
     for (; k < cnt; k += stride) Lx[dst[k]] = nz[src[k]];
 }
 
+// nzval[k] = sum_j coeff[j] * basis[j * nnz + k]: fixed-pattern value assembly for hyperparameter loops (the Matern
+// precision is a polynomial in kappa^2 on a fixed pattern: matern_spde.jl:332-356, fem_utils.jl:313-335). HBM-bound:
+// (nbasis + 1) * 8 * nnz bytes; the coefficients travel as kernel arguments.
+constexpr int MAX_VALUE_BASIS = 8;
+struct BasisCoeff { double c[MAX_VALUE_BASIS]; };
+__global__ void __launch_bounds__(256)
+combine_basis_kernel(double *__restrict__ nz, const double *__restrict__ basis, BasisCoeff coeff, int nbasis, long long nnz) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; k < nnz; k += stride) {
+        double v = 0.0;
+        for (int j = 0; j < nbasis; j++) v += coeff.c[j] * basis[(long long)j * nnz + k];
+        nz[k] = v;
+    }
+}
+
 __global__ void fill_zero_kernel(double *__restrict__ p, long long cnt) {
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;

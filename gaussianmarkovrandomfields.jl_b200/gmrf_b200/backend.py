@@ -268,6 +268,23 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
 
+    def set_value_basis(self, basis: np.ndarray):
+        """Upload value arrays (nbasis x nnz, on this backend's pattern) for device-side assembly of nzval."""
+        basis = np.ascontiguousarray(basis, dtype=np.float64)
+        if basis.ndim != 2:
+            raise ValueError("basis must be (nbasis, nnz)")
+        if basis.shape[1] != self._rowval.size:
+            raise ValueError(f"basis rows hold {basis.shape[1]} values but the pattern has {self._rowval.size} nonzeros")
+        self._hd.check(self._L.gmrf_b200_set_value_basis(self._hd._h, ptr(basis), basis.shape[0]))
+
+    def refactorize_combination(self, coeff):
+        """refactorize with nzval = coeff @ basis formed in HBM (no upload of nzval)."""
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        rc = self._L.gmrf_b200_refactorize_combination(self._hd._h, ptr(coeff), coeff.size)
+        self.status = self._hd.check(rc, allow_positive=not self.check_pd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+
     def selinv_compute(self):
         self._hd.check(self._L.gmrf_b200_selinv_compute(self._hd._h))
 

@@ -182,10 +182,12 @@ class MaternSPDE:
     """MaternModel precision on a fixed mesh: `values(tau, range)` returns nzval on a pattern
     that does not depend on the hyperparameters (ext/.../matern_model.jl:109-121)."""
 
-    def __init__(self, coords, cells, smoothness: int):
+    def __init__(self, coords, cells, smoothness: int, diffusion: float = 1.0):
         self.d = coords.shape[1]
         self.n = coords.shape[0]
         self.c, self.g = p1_mass_stiffness(coords, cells)
+        if diffusion != 1.0:                      # diffusion_factor H = diffusion * I (fem_utils.jl:86-110)
+            self.g = sp.csc_matrix(self.g * diffusion)
         self.nu = smoothness + 1.0 if self.d % 2 == 0 else smoothness + 0.5
         alpha = self.nu + self.d / 2.0
         assert abs(alpha - round(alpha)) < 1e-12
@@ -194,9 +196,10 @@ class MaternSPDE:
         self.colptr = self.pattern.indptr.astype(np.int64)
         self.rowval = self.pattern.indices.astype(np.int64)
 
-    def precision(self, tau: float = 1.0, range_: float = 0.3) -> sp.csc_matrix:
+    def precision(self, tau: float = 1.0, range_: float = 0.3, kappa: float | None = None) -> sp.csc_matrix:
         nu, d = self.nu, self.d
-        kappa = math.sqrt(8.0 * nu) / range_
+        if kappa is None:
+            kappa = math.sqrt(8.0 * nu) / range_
         ratio = math.gamma(nu) / (math.gamma(nu + d / 2.0) * (4.0 * math.pi) ** (d / 2.0) * kappa ** (2.0 * nu))
         k = sp.csc_matrix(kappa ** 2 * sp.diags(self.c) + self.g)
         cinv = sp.diags(1.0 / self.c)
@@ -216,6 +219,104 @@ class MaternSPDE:
 
     def values(self, tau: float = 1.0, range_: float = 0.3) -> np.ndarray:
         return self.precision(tau, range_).data
+
+    # -- O(nnz) re-evaluation for hyperparameter loops -----------------------------------------------------------
+    # K C^-1 K ... K (alpha factors) with K = kappa^2 C + G expands binomially:
+    #     Q(tau, kappa) = tau * ratio(kappa) * sum_j binom(alpha, j) kappa^(2 (alpha - j)) B_j,   B_0 = C, B_j = G (C^-1 G)^(j-1)
+    # so the nzval of any (tau, range) is a linear combination of alpha + 1 fixed arrays laid out on the structural
+    # pattern -- the fixed-pattern value assembly of matern_spde.jl:332-356 / fem_utils.jl:313-335 without sparse
+    # products, cheap enough to run on the device right before a refactorization.
+    def basis(self) -> np.ndarray:
+        if getattr(self, "_basis", None) is None:
+            cinv = sp.diags(1.0 / self.c)
+            mats = [sp.csc_matrix(sp.diags(self.c)), sp.csc_matrix(self.g)]
+            for _ in range(2, self.alpha + 1):
+                mats.append(sp.csc_matrix(mats[-1] @ cinv @ self.g))
+            self._basis = np.stack([_scatter_into_pattern(self.pattern, m) for m in mats[: self.alpha + 1]])
+        return self._basis
+
+    def coefficients(self, tau: float = 1.0, range_: float = 0.3) -> np.ndarray:
+        nu, d, a = self.nu, self.d, self.alpha
+        kappa = math.sqrt(8.0 * nu) / range_
+        ratio = math.gamma(nu) / (math.gamma(nu + d / 2.0) * (4.0 * math.pi) ** (d / 2.0) * kappa ** (2.0 * nu))
+        return np.array([tau * ratio * math.comb(a, j) * kappa ** (2 * (a - j)) for j in range(a + 1)])
+
+    def values_from_basis(self, tau: float = 1.0, range_: float = 0.3) -> np.ndarray:
+        return self.coefficients(tau, range_) @ self.basis()
+
+
+def p1_advection(coords: np.ndarray, cells: np.ndarray, gamma) -> sp.csc_matrix:
+    """P1 advection matrix for a constant velocity gamma: Be[i, j] = |T| / (d + 1) * gamma . grad(phi_j)
+    (assemble_advection_matrix, fem_utils.jl:132-169)."""
+    nv, d = coords.shape
+    x = coords[cells]
+    edges = x[:, 1:, :] - x[:, :1, :]
+    vol = np.abs(np.linalg.det(edges)) / math.factorial(d)
+    inv = np.linalg.inv(edges)
+    grads = np.empty((cells.shape[0], d + 1, d))
+    grads[:, 1:, :] = np.transpose(inv, (0, 2, 1))
+    grads[:, 0, :] = -grads[:, 1:, :].sum(axis=1)
+    gdot = grads @ np.asarray(gamma, dtype=np.float64)              # (ne, d+1): gamma . grad(phi_j)
+    be = (vol / (d + 1))[:, None, None] * np.broadcast_to(gdot[:, None, :], (cells.shape[0], d + 1, d + 1))
+    rows = np.repeat(cells, d + 1, axis=1).ravel()
+    cols = np.tile(cells, (1, d + 1)).ravel()
+    b = sp.coo_matrix((be.ravel(), (rows, cols)), shape=(nv, nv)).tocsc()
+    b.sum_duplicates()
+    b.sort_indices()
+    return b
+
+
+class AdvectionDiffusionSSM:
+    """Space-time precision of the implicit-Euler advection-diffusion SPDE (BASELINE config 5), time-major ordering
+    (block t = all spatial dofs at time t):
+        ext/.../advection_diffusion.jl:103-205   K = kappa^2 M + G (alpha = 1), P = K + B, G_dt = M + dt/c P,
+                                                 noise tau/sqrt(c), Q_s / Q_0 = Matern smoothness 1 / 2 with the same H
+        implicit_euler_ssm.jl:62-88              Sigma^-1 = M^-1 beta^-1 Q_s beta^-1 M^-1, beta^-1 = (1/sqrt(dt)) / noise
+        linear_ssm.jl:63-116                     F^-1 = G' Sigma^-1 G, A'F^-1A = M' Sigma^-1 M, F^-1A = G' Sigma^-1 M;
+                                                 diagonal blocks [Q_0 + A'F^-1A ; (F^-1 + A'F^-1A) x (Nt-2) ; F^-1],
+                                                 lower off-diagonal blocks -F^-1A
+        src/linear_maps/symmetric_block_tridiagonal.jl:77-106  assembled as Symmetric(., :L)
+    `posterior(obs_idx, noise_precision)` adds A' Q_eps A for point observations of the first time slice
+    (src/arithmetic/condition/linear.jl:53-61)."""
+
+    def __init__(self, coords, cells, nt: int, dt: float = 0.01, kappa: float = 3.0, gamma=(0.3, 0.0), diffusion: float = 0.1,
+                 tau: float = 0.1, c: float = 1.0):
+        self.ns, self.nt = coords.shape[0], int(nt)
+        m, g = p1_mass_stiffness(coords, cells)
+        g = sp.csc_matrix(g * diffusion)
+        b = p1_advection(coords, cells, gamma)
+        M = sp.diags(m)
+        P = sp.csc_matrix(kappa ** 2 * M + g + b)
+        G = sp.csc_matrix(M + (dt / c) * P)
+        q_s = MaternSPDE(coords, cells, 1, diffusion).precision(1.0, kappa=kappa)
+        q_0 = MaternSPDE(coords, cells, 2, diffusion).precision(1.0, kappa=kappa)
+        beta_inv = math.sqrt(c) / (tau * math.sqrt(dt))
+        Minv = sp.diags(1.0 / m)
+        sigma_inv = sp.csc_matrix(beta_inv ** 2 * (Minv @ q_s @ Minv))
+        Gt_S = sp.csc_matrix(G.T @ sigma_inv)
+        F_inv = sp.csc_matrix(Gt_S @ G)
+        AtFA = sp.csc_matrix(M @ sigma_inv @ M)
+        FA = sp.csc_matrix(Gt_S @ M)
+        first = sp.csc_matrix(q_0 + AtFA)
+        mid = sp.csc_matrix(F_inv + AtFA)
+        blocks = [[None] * self.nt for _ in range(self.nt)]
+        for t in range(self.nt):
+            blocks[t][t] = first if t == 0 else (mid if t < self.nt - 1 else F_inv)
+            if t + 1 < self.nt:
+                blocks[t + 1][t] = -FA
+                blocks[t][t + 1] = -FA.T
+        Q = sp.csc_matrix(sp.bmat(blocks, format="csc"))
+        Q = sp.csc_matrix((Q + Q.T) * 0.5)              # Symmetric(., :L): exact symmetry of the assembled values
+        Q.sort_indices()
+        self.Q = Q
+        self.n = Q.shape[0]
+
+    def posterior(self, obs_idx, noise_precision: float) -> sp.csc_matrix:
+        d = np.zeros(self.n)
+        np.add.at(d, np.asarray(obs_idx, dtype=np.int64), noise_precision)
+        Qp = sp.csc_matrix(self.Q + sp.diags(d))
+        Qp.sort_indices()
+        return Qp
 
 
 # --------------------------------------------------------------------------- orderings

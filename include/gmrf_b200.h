@@ -71,6 +71,14 @@ const char *gmrf_b200_last_error(const gmrf_b200_handle *h);   /* h may be NULL:
 int gmrf_b200_refactorize(gmrf_b200_handle *h, const double *nzval, int64_t nnz);
 int gmrf_b200_refactorize_device(gmrf_b200_handle *h, const double *d_nzval, int64_t nnz);
 
+/* Device-side value assembly for hyperparameter loops. replaces the per-theta host re-assembly + upload of nzval:
+ * `(model)(ws; theta...)` -> _pad_to_workspace_pattern (src/workspace/latent_model_integration.jl:151-250) followed by
+ * _copy_sparse_values! (backend.jl:165-176). set_value_basis uploads nbasis (<= 8) value arrays laid out on the pattern
+ * given to create (row-major nbasis x nnz) once; refactorize_combination forms nzval = sum_j coeff[j] * basis_j in HBM
+ * and factorizes (same return convention as refactorize). */
+int gmrf_b200_set_value_basis(gmrf_b200_handle *h, const double *basis, int nbasis);
+int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, int nbasis);
+
 /* replaces  compute_logdet(b) = logdet(factor)   backend.jl:211-213 */
 int gmrf_b200_logdet(gmrf_b200_handle *h, double *out);
 

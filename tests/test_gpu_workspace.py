@@ -277,6 +277,56 @@ def test_wide_rhs_blocks_match_single_column_solves(kind, cells, smooth):
     be.close()
 
 
+def test_device_side_value_assembly_for_theta_loops():
+    """nzval(tau, range) of a Matern model is a linear combination of alpha + 1 fixed value arrays on the structural
+    pattern: uploading them once lets a hyperparameter evaluation refactorize without moving nzval over PCIe."""
+    model = spde.MaternSPDE(*spde.mesh2d(24), 1)
+    Q0 = model.precision(1.0, 0.5)
+    be = B200Backend(Q0, device=0)
+    be.set_value_basis(model.basis())
+    b = np.random.default_rng(0).standard_normal(model.n)
+    for tau, rng_ in ((0.3, 0.25), (2.0, 0.7), (1.0, 0.5)):
+        Q = model.precision(tau, rng_)
+        be.refactorize(Q)
+        ld, x = be.compute_logdet(), be.backend_solve(b)
+        be.refactorize_combination(model.coefficients(tau, rng_))
+        assert abs(be.compute_logdet() - ld) <= 1e-12 * abs(ld)
+        assert _rel(be.backend_solve(b), x) <= 1e-9            # cond(Q) ~ 1e8 amplifies the 1-ulp value differences
+        D = Q.toarray()
+        assert abs(be.compute_logdet() - np.linalg.slogdet(D)[1]) <= 1e-10 * abs(ld)
+    with pytest.raises(ValueError):
+        be.set_value_basis(np.ones((2, 5)))
+    be.close()
+
+
+def test_spatiotemporal_advection_diffusion_posterior():
+    """BASELINE config 5 in miniature: block-tridiagonal space-time precision of the implicit-Euler advection-diffusion
+    SPDE (time-major), conditioned on point observations of the first slice; posterior marginal variances by selected
+    inversion and a block of posterior samples through the blocked half solve."""
+    coords, cells = spde.mesh2d(12)
+    model = spde.AdvectionDiffusionSSM(coords, cells, nt=8)
+    rng = np.random.default_rng(3)
+    obs = rng.choice(model.ns, 40, replace=False)                    # observed vertices of time slice 1
+    Q = model.posterior(obs, 1.0 / 0.05 ** 2)
+    n = Q.shape[0]
+    be = B200Backend(Q, device=0)
+    F = oracle.OracleFactor(Q, be.permutation())
+    assert np.array_equal(be.colcounts(), F.colcount)
+    assert abs(be.compute_logdet() - F.logdet()) <= 1e-10 * abs(F.logdet())
+    var = be.get_selinv_diag()
+    assert np.max(np.abs(var - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
+    assert np.all(var[obs] < 1.05 * 0.05 ** 2)                       # observed sites are pinned by the data
+    Z = np.asfortranarray(rng.standard_normal((1024, n)).T)          # column i = i-th randn! draw
+    X = be.backend_backward_solve(Z)                                 # 1024 samples: 16 blocks of 64 columns
+    for c in (0, 63, 64, 1023):
+        assert _rel(X[:, c], F.backward_solve(Z[:, c])) <= 1e-8
+    emp = X.var(axis=1)
+    assert np.median(np.abs(emp - var) / var) < 0.06                 # samples matched in distribution
+    h = rng.standard_normal(n)
+    assert _rel(be.backend_solve(h), F.solve(h)) <= 1e-8             # posterior mean solve
+    be.close()
+
+
 def test_schedule_variants_agree():
     """The scheduling options change the launch lists, never the mathematics: split-K with tiny k-slices (the path the
     top supernodes of the 1 M-dof problem take), a small outer block, the generic selected-inversion route for roots and
