@@ -1,0 +1,91 @@
+"""Host-side mirror of boundary B: the plain `GMRF` object and `linear_condition`, which in
+the reference reach the factorization through a `LinearSolve.LinearCache` instead of a workspace
+(src/gmrf.jl:159-223 constructors, :267 logdetcov, :271-296 _rand!, :318-332 var; src/solvers/{selinv,backward_solve,
+logdet}.jl dispatch tables; src/arithmetic/condition/linear.jl:46-64). As there, every construction analyses and
+factorizes anew (no symbolic reuse guarantee) -- the workspace path is the one for loops. In the Julia integration this is
+`julia/B200LinearSolve.jl` (a LinearSolve algorithm in the manner of ext/GaussianMarkovRandomFieldsPardiso.jl)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+from .backend import B200Backend, _csc
+
+__all__ = ["GMRF", "linear_condition"]
+
+
+class GMRF:
+    """GMRF(mean, Q) or GMRF(information=h, Q): N(Q^-1 h, Q^-1) backed by one B200 factorization of Q."""
+
+    def __init__(self, mean=None, Q=None, information=None, ordering=None, device: int = 0, backend_type=B200Backend):
+        Q = _csc(Q).astype(np.float64)
+        n = Q.shape[0]
+        if Q.shape[0] != Q.shape[1]:
+            raise ValueError("size mismatch")
+        self.precision = Q
+        kw = {"device": device, "ordering": ordering} if backend_type is B200Backend else {}
+        self.linsolve_cache = backend_type(Q, **kw)                     # symbolic analysis + numeric factorization
+        if information is not None:                                     # gmrf.jl:195-223: mean = Q \ h
+            information = np.asarray(information, dtype=np.float64)
+            if information.size != n:
+                raise ValueError("size mismatch")
+            self.information = information.copy()
+            self.mean_ = np.asarray(self.linsolve_cache.backend_solve(self.information))
+        else:
+            mean = np.asarray(mean, dtype=np.float64)
+            if mean.size != n:
+                raise ValueError("size mismatch")
+            self.mean_ = mean.copy()
+            self.information = None
+
+    def __len__(self):
+        return self.precision.shape[0]
+
+    def mean(self):
+        return self.mean_
+
+    def precision_matrix(self):
+        return self.precision
+
+    def information_vector(self):
+        return self.information if self.information is not None else self.precision @ self.mean_
+
+    def logdetcov(self):                                                # _logdet_cov_impl, solvers/logdet.jl:27-31
+        return -self.linsolve_cache.compute_logdet()
+
+    def var(self):                                                      # _selinv_diag_impl, solvers/selinv.jl:70-73
+        return np.array(self.linsolve_cache.get_selinv_diag())
+
+    def std(self):
+        return np.sqrt(self.var())
+
+    def rand(self, rng: np.random.Generator, m: int | None = None):    # _backward_solve_impl, solvers/backward_solve.jl:50-53
+        n = len(self)
+        if m is None:
+            return self.linsolve_cache.backend_backward_solve(rng.standard_normal(n)) + self.mean_
+        Z = np.asfortranarray(rng.standard_normal((m, n)).T)
+        return self.linsolve_cache.backend_backward_solve(Z) + self.mean_[:, None]
+
+    def logpdf(self, z):
+        r = np.asarray(z, dtype=np.float64) - self.mean_
+        return float(-0.5 * (r @ (self.precision @ r)) - 0.5 * self.logdetcov() - 0.5 * len(self) * math.log(2.0 * math.pi))
+
+
+def linear_condition(gmrf: GMRF, A, Q_eps, y, b=None, obs_precision_contrib=None, **gmrf_kwargs) -> GMRF:
+    """Posterior of x | y for y = A x + b + eps, eps ~ N(0, Q_eps^-1) by information-vector arithmetic
+    (condition/linear.jl:46-64): Q_post = Q + A' Q_eps A, h_post = h + A' Q_eps (y - b); the posterior mean is one solve."""
+    Q_prior = gmrf.precision_matrix()
+    n = Q_prior.shape[0]
+    A = sp.csr_matrix(A, dtype=np.float64)
+    m = A.shape[0]
+    Q_eps = sp.identity(m, format="csr") * float(Q_eps) if np.isscalar(Q_eps) else sp.csr_matrix(Q_eps, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    b = np.zeros(m) if b is None else np.asarray(b, dtype=np.float64)
+    if obs_precision_contrib is None:
+        obs_precision_contrib = A.T @ Q_eps @ A
+    Q_post = sp.csc_matrix(Q_prior + obs_precision_contrib)
+    Q_post.sort_indices()
+    h_post = gmrf.information_vector() + A.T @ (Q_eps @ (y - b))
+    return GMRF(information=h_post, Q=Q_post, **gmrf_kwargs)

@@ -165,4 +165,31 @@ end
 checkout(p::B200WorkspacePool) = take!(p.channel)
 checkin(p::B200WorkspacePool, ws) = put!(p.channel, ws)
 
+# ---- hyperparameter loops without re-uploading nzval --------------------------------------------------------------
+# A model whose precision is a fixed linear combination of value arrays on the workspace pattern (the Matern SPDE:
+# K C^-1 K ... expands binomially in kappa^2; fem_utils.jl:313-335 lays every term out on the structural pattern)
+# uploads the arrays once and afterwards refactorizes from `length(coeff)` doubles.
+function set_value_basis!(b::B200Backend, basis::Matrix{Float64})          # nnz x nbasis, column j = j-th value array
+    size(basis, 1) == b.nnz || throw(ArgumentError("basis columns must hold nnz(Q) values"))
+    _check(b, ccall((:gmrf_b200_set_value_basis, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), b.handle, basis, size(basis, 2)))
+end
+function refactorize_combination!(b::B200Backend, coeff::Vector{Float64})
+    _check(b, ccall((:gmrf_b200_refactorize_combination, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), b.handle, coeff, length(coeff)))
+    b.selinv_cache = nothing; b.selinv_diag_cache = nothing
+    return nothing
+end
+
+# ---- one factorization, right-hand-side blocks on every GPU (SURVEY.md 8e, config 5) -------------------------------
+# `device_array` exposes the numeric factor in HBM (which = 0 panels of L, 1 inverted diagonal blocks, 2 Z panels) so the
+# pool can move it between its handles (NCCL.jl `Broadcast!` on `unsafe_wrap(CuArray, ...)`, or a peer copy);
+# the receiver then declares it its own with `adopt_factor!` and serves `backend_solve` / `backend_backward_solve`
+# for its block of columns without factorizing.
+function device_array(b::B200Backend, which::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL); n = Ref{Int64}(0)
+    _check(b, ccall((:gmrf_b200_device_array, libgmrf), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}, Ref{Int64}), b.handle, which, p, n))
+    return p[], n[]
+end
+adopt_factor!(b::B200Backend, logdet::Float64; with_selinv::Bool = false) =
+    _check(b, ccall((:gmrf_b200_adopt_factor, libgmrf), Cint, (Ptr{Cvoid}, Cdouble, Cint), b.handle, logdet, with_selinv))
+
 end # module
