@@ -32,6 +32,11 @@ for phase in phases:
     print("   slowest launches (index kind grid ms):")
     for i in sorted(range(len(rows)), key=lambda i: -rows[i][2])[:top]:
         print(f"     {i:6d} {rows[i][0]:12s} {rows[i][1]:8d} {rows[i][2]:9.4f}")
+    if "dump" in opt:
+        a, b_ = (int(v) for v in opt["dump"].split(":"))
+        print(f"   launches {a}..{b_} (index kind grid ms):")
+        for i in range(a, min(b_, len(rows))):
+            print(f"     {i:6d} {rows[i][0]:12s} {rows[i][1]:8d} {rows[i][2]:9.4f}")
     # cumulative time by position (coarse timeline in 20 buckets)
     nb = 20
     step = max(1, len(rows) // nb)
