@@ -27,13 +27,13 @@ namespace {
 thread_local std::string g_create_error;
 
 enum LaunchKind : int {
-    K_ASSEMBLE, K_POTRF_UNUSED, K_TRSM0, K_TRSM1, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
+    K_ASSEMBLE, K_UNUSED1, K_UNUSED2, K_UNUSED3, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
     K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE
 };
 
 struct Launch {
     int kind;
-    int aux;            // TRSM: NBT bucket
+    int aux;            // panel step: NBT bucket
     i64 task_off;       // first task in the kind's task array
     int ntasks;
     i64 prefix_off;     // offset into the tile-prefix array (ntasks+1 entries) or -1
@@ -77,7 +77,6 @@ struct gmrf_b200_handle {
     SuperMeta *d_meta = nullptr;
     GemmTask *d_gemm = nullptr;
     PanelTask *d_panel = nullptr;
-    TrsmTask *d_trsm = nullptr;
     AsmItem *d_items = nullptr;
     FwdStepTask *d_fwd = nullptr;
     BwdGatherTask *d_bwdg = nullptr;
@@ -105,7 +104,6 @@ struct gmrf_b200_handle {
     i64 splitk_cap = 0;                // doubles
     // selinv task tables are built lazily (they need d_Zx / d_zw)
     GemmTask *d_gemm_z = nullptr;
-    TrsmTask *d_trsm_z = nullptr;
     AsmItem *d_items_z = nullptr;
     int *d_prefix_z = nullptr;
     // selinv CSC materialisation (lazy)
@@ -162,7 +160,6 @@ inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 struct Builder {
     std::vector<GemmTask> gemm;
     std::vector<PanelTask> panel;
-    std::vector<TrsmTask> trsm;
     std::vector<AsmItem> items;
     std::vector<FwdStepTask> fwd;
     std::vector<BwdGatherTask> bwdg;
@@ -270,27 +267,6 @@ struct Builder {
             plan.launches.push_back(L);
         }
     }
-    void add_trsm(Plan &plan, std::vector<TrsmTask> &tasks, int var) {
-        if (tasks.empty()) return;
-        Launch L;
-        L.kind = var ? K_TRSM1 : K_TRSM0;
-        int mx = 0;
-        for (auto &t : tasks) mx = std::max(mx, t.nb);
-        L.aux = mx <= 8 ? 8 : mx <= 16 ? 16 : mx <= 32 ? 32 : 64;
-        L.task_off = (i64)trsm.size();
-        L.ntasks = (int)tasks.size();
-        L.prefix_off = (i64)prefix.size();
-        i64 tot = 0;
-        for (auto &t : tasks) {
-            prefix.push_back((int)tot);
-            tot += cdiv(t.m, TRSM_ROWS);
-            trsm.push_back(t);
-        }
-        prefix.push_back((int)tot);
-        L.grid = (int)tot;
-        plan.launches.push_back(L);
-        tasks.clear();
-    }
     void add_panel(Plan &plan, std::vector<PanelTask> &tasks) {
         if (tasks.empty()) return;
         Launch L;
@@ -380,7 +356,8 @@ constexpr int NB = POTRF_NB;
 
 // Panel factorization of a supernode (nrow x ns, column-major, in place), two-level blocking:
 //   outer blocks of OB columns: left-looking update with ALL previous columns in one large-k DMMA GEMM,
-//   inner blocks of NB=64 columns: fused potrf+trsm step, then a k=64 trailing update confined to the outer block.
+//   inner blocks of NB=64 columns: single-CTA potrf + inverse, TRSM as a GEMM with the inverted block, then a k=64
+//   trailing update confined to the outer block.
 // All supernodes of a level advance in lockstep, so one launch serves every front of the level.
 void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
     const Symbolic &S = h->S;
@@ -932,16 +909,6 @@ void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefi
     else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
 }
 
-template <int VAR>
-void launch_trsm(int nbt, const TrsmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
-    switch (nbt) {
-        case 8: trsm_strip_kernel<VAR, 8><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
-        case 16: trsm_strip_kernel<VAR, 16><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
-        case 32: trsm_strip_kernel<VAR, 32><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
-        default: trsm_strip_kernel<VAR, 64><<<grid, TRSM_ROWS, 0, st>>>(tasks, prefix, ntasks); break;
-    }
-}
-
 template <int BM, int BN, int WGM, int WGN, int KT, int ST>
 void launch_gemm_exp(const GemmTask *tasks, const int *prefix, int grid) {
     auto kern = gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, KT, ST>;
@@ -951,7 +918,6 @@ void launch_gemm_exp(const GemmTask *tasks, const int *prefix, int grid) {
 
 struct TableSet {
     const GemmTask *gemm;
-    const TrsmTask *trsm;
     const AsmItem *items;
     const int *prefix;
     const SplitTask *split;
@@ -977,8 +943,6 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
                 default: potrf_inv64_kernel<<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
             }
             break;
-        case K_TRSM0: launch_trsm<0>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
-        case K_TRSM1: launch_trsm<1>(L.aux, T.trsm + L.task_off, pf, L.ntasks, L.grid, st); break;
         case K_GEMM_NN_S: case K_GEMM_NN_L:
             launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
         case K_GEMM_NT_S: case K_GEMM_NT_L:
@@ -1055,14 +1019,14 @@ void enqueue_factor(gmrf_b200_handle *h) {
         int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
         scatter_q_kernel<<<grid, 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
     }
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
+    TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) run_launch(h, L, T, 0);
     logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
     logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
 }
 
 void enqueue_selinv(gmrf_b200_handle *h) {
-    TableSet T{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
+    TableSet T{h->d_gemm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
     for (const Launch &L : h->selinv_plan.launches) run_launch(h, L, T, 0);
 }
 
@@ -1127,7 +1091,6 @@ int build_selinv_tables(gmrf_b200_handle *h) {
         return GMRF_B200_ERR_ARG;
     }
     if ((rc = dev_upload(h, &h->d_gemm_z, B.gemm))) return rc;
-    if ((rc = dev_upload(h, &h->d_trsm_z, B.trsm))) return rc;
     if ((rc = dev_upload(h, &h->d_items_z, B.items))) return rc;
     if ((rc = dev_upload(h, &h->d_prefix_z, B.prefix))) return rc;
     if ((rc = dev_upload(h, &h->d_trans, B.trans))) return rc;
@@ -1177,7 +1140,7 @@ int ensure_multi(gmrf_b200_handle *h) {
 }
 
 void enqueue_multi_sweeps(gmrf_b200_handle *h, int mode) {
-    TableSet T{h->d_gemm_m, nullptr, nullptr, h->d_prefix_m, nullptr};
+    TableSet T{h->d_gemm_m, nullptr, h->d_prefix_m, nullptr};
     T.superlist = h->d_superlist_m;
     T.rowgather = h->d_rg_m;
     T.y = h->d_ym;
@@ -1229,7 +1192,7 @@ int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 
 
 // Enqueue the level-scheduled sweeps on the permuted work array d_y (mode 0: forward + backward, 1: backward only).
 void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
+    TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     if (mode == 0)
         for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
     for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
@@ -1518,7 +1481,6 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         H->gemm_flops_factor = B.gemm_flops;
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
         TRY_RC(dev_upload(H, &H->d_panel, B.panel));
-        TRY_RC(dev_upload(H, &H->d_trsm, B.trsm));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
         TRY_RC(dev_upload(H, &H->d_fwd, B.fwd));
         TRY_RC(dev_upload(H, &H->d_bwdg, B.bwdg));
@@ -1901,31 +1863,6 @@ int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info) {
     return gmrf_b200_test_potrf_inv(device, n, A, lda, nullptr, info);
 }
 
-int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb) {
-    // n <= 64; variant selected by the sign of m: m > 0 -> X L^T = B, m < 0 -> X L = B
-    if (cudaSetDevice(device) != cudaSuccess) return test_fail("no device");
-    int var = m < 0 ? 1 : 0;
-    if (m < 0) m = -m;
-    if (n > POTRF_NB) return GMRF_B200_ERR_ARG;
-    double *dL, *dB; TrsmTask *dT; int *dP;
-    if (cudaMalloc(&dL, (size_t)ldl * n * 8) || cudaMalloc(&dB, (size_t)ldb * n * 8) || cudaMalloc(&dT, sizeof(TrsmTask)) || cudaMalloc(&dP, 8))
-        return test_fail("alloc");
-    cudaMemcpy(dL, L, (size_t)ldl * n * 8, cudaMemcpyHostToDevice);
-    cudaMemcpy(dB, B, (size_t)ldb * n * 8, cudaMemcpyHostToDevice);
-    TrsmTask T{dL, dB, ldl, ldb, m, n};
-    int tiles = cdiv(m, TRSM_ROWS);
-    int pf[2] = {0, tiles};
-    cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
-    cudaMemcpy(dP, pf, 8, cudaMemcpyHostToDevice);
-    int nbt = n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 64;
-    if (var == 0) launch_trsm<0>(nbt, dT, dP, 1, tiles, 0); else launch_trsm<1>(nbt, dT, dP, 1, tiles, 0);
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaMemcpy(B, dB, (size_t)ldb * n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(dL); cudaFree(dB); cudaFree(dT); cudaFree(dP);
-    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
-    return 0;
-}
-
 // Device-timed GEMM micro-benchmark of the library's own kernel (tests/ and profiling only): operands are
 // allocated and filled on the device; returns the best-of-reps time in ms (CUDA events on the default stream).
 int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, int n, int k, int reps, double *ms_out) {
@@ -1987,7 +1924,7 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
 }
 
 // Live per-kernel-family profile of ONE refactorization (graphs off, a CUDA event pair around every launch on the
-// handle's stream). kinds: 0 gemm (DMMA), 1 fused panel (potrf+trsm), 2 assemble (extend-add), 3 scatter/memset/logdet.
+// handle's stream). kinds: 0 gemm (DMMA, incl. TRSM-by-inverse), 1 panel (potrf + inverse), 2 assemble (extend-add), 3 scatter/memset/logdet.
 // ms[k] = summed device time, count[k] = launches, flops[0] = algorithmic GEMM flops issued (lower-only tasks count half).
 int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *count, double *flops) {
     int rc = ensure_device(h);
@@ -2010,7 +1947,7 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
     i64 cnt = (i64)S.q_src.size();
     if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
+    TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) {
         int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0 : L.kind == K_PANEL ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
         mark(kind);
@@ -2042,7 +1979,7 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     if (rc) return rc;
     if (!h->factored) { h->err = "profile_plan needs a previous refactorize"; return GMRF_B200_ERR_STATE; }
     const Plan *plan = nullptr;
-    TableSet T{h->d_gemm, h->d_trsm, h->d_items, h->d_prefix, h->d_split};
+    TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     cudaStream_t st = h->stream;
     if (phase == 0) {
         plan = &h->factor_plan;
@@ -2054,7 +1991,7 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     } else if (phase == 1) {
         if ((rc = build_selinv_tables(h))) return rc;
         plan = &h->selinv_plan;
-        T = TableSet{h->d_gemm_z, h->d_trsm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
+        T = TableSet{h->d_gemm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
     } else if (phase == 2 || phase == 3) {
         plan = phase == 2 ? &h->fwd_plan : &h->bwd_plan;
         if (nrhs < 1 || nrhs > h->rhs_block) { h->err = "profile_plan: 1 <= nrhs <= 8"; return GMRF_B200_ERR_ARG; }

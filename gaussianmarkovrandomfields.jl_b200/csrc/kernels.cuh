@@ -35,12 +35,6 @@ struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
     int pad_;
 };
 
-struct TrsmTask {        // B[m x nb] := B * L^-T (variant 0) or B * L^-1 (variant 1), L lower nb x nb
-    const double *L;
-    double *B;
-    int ldl, ldb, m, nb;
-};
-
 struct PanelTask {       // diagonal block step: D := chol(D) (nb x nb, in place, lower) and inv := D^-1
     double *D;           // diagonal block, leading dimension ld
     double *inv;         // nb x nb, leading dimension nb, zeros above the diagonal (reused by the solve phase)
@@ -356,60 +350,6 @@ __global__ void gemm_naive_kernel(const GemmTask *__restrict__ tasks, const int 
 }
 
 constexpr int POTRF_NB = 64;
-
-// ------------------------------------------------------------------------------------------------
-// Right-side triangular solve on row strips: one thread owns one row of B (kept in registers), L staged in smem.
-//   VAR 0: X L^T = B  (x_j = (b_j - sum_{k<j} x_k L_jk) / L_jj, j ascending)      -- factorization panels
-//   VAR 1: X L   = B  (x_j = (b_j - sum_{i>j} x_i L_ij) / L_jj, j descending)     -- selected inversion
-// ------------------------------------------------------------------------------------------------
-constexpr int TRSM_ROWS = 64;   // rows per CTA (= threads per CTA)
-
-template <int VAR, int NBT>
-__global__ void __launch_bounds__(TRSM_ROWS)
-trsm_strip_kernel(const TrsmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
-    __shared__ double sL[NBT][NBT + 1];   // sL[i][j] = L_ij, identity-padded beyond nb
-    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const TrsmTask T = tasks[t];
-    const int strip = blockIdx.x - tile_prefix[t];
-    const int nb = T.nb, tid = threadIdx.x;
-    if (tid < NBT) {   // one row of L per thread: NBT independent loads in flight (static unroll), identity padding
-#pragma unroll
-        for (int k = 0; k < NBT; k++) {
-            double v = (k == tid) ? 1.0 : 0.0;
-            if (tid < nb && k < nb && k <= tid) v = T.L[tid + (long long)k * T.ldl];
-            sL[tid][k] = v;
-        }
-    }
-    __syncthreads();
-    const int row = strip * TRSM_ROWS + tid;
-    if (row >= T.m) return;
-    double x[NBT];
-    double *bp = T.B + row;
-#pragma unroll
-    for (int j = 0; j < NBT; j++) x[j] = (j < nb) ? bp[(long long)j * T.ldb] : 0.0;
-    if (VAR == 0) {
-#pragma unroll
-        for (int j = 0; j < NBT; j++) {
-            double s0 = x[j], s1 = 0.0;
-#pragma unroll
-            for (int k = 0; k + 1 < j; k += 2) { s0 -= x[k] * sL[j][k]; s1 -= x[k + 1] * sL[j][k + 1]; }
-            if (j & 1) s0 -= x[j - 1] * sL[j][j - 1];
-            x[j] = (s0 + s1) / sL[j][j];
-        }
-    } else {
-#pragma unroll
-        for (int j = NBT - 1; j >= 0; j--) {
-            double s0 = x[j], s1 = 0.0;
-#pragma unroll
-            for (int i = j + 1; i + 1 < NBT; i += 2) { s0 -= x[i] * sL[i][j]; s1 -= x[i + 1] * sL[i + 1][j]; }
-            if ((NBT - 1 - j) & 1) s0 -= x[NBT - 1] * sL[NBT - 1][j];
-            x[j] = (s0 + s1) / sL[j][j];
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NBT; j++)
-        if (j < nb) bp[(long long)j * T.ldb] = x[j];
-}
 
 // ------------------------------------------------------------------------------------------------
 // Diagonal-block step of the panel factorization (latency-critical: one launch per 64 columns of a chain):

@@ -28,7 +28,7 @@ EXPORTS = [
     "gmrf_b200_info", "gmrf_b200_get_perm", "gmrf_b200_get_colcounts", "gmrf_b200_get_etree",
     "gmrf_b200_get_supernodes", "gmrf_b200_get_rows", "gmrf_b200_get_scatter", "gmrf_b200_last_timings",
     "gmrf_b200_get_factor_panels", "gmrf_b200_get_selinv_panels", "gmrf_b200_set_option",
-    "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_potrf_inv", "gmrf_b200_test_trsm", "gmrf_b200_bench_gemm", "gmrf_b200_profile_refactorize", "gmrf_b200_profile_plan", "gmrf_b200_device_array", "gmrf_b200_set_value_basis", "gmrf_b200_refactorize_combination", "gmrf_b200_adopt_factor", "gmrf_b200_host_register", "gmrf_b200_host_unregister",
+    "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_potrf_inv", "gmrf_b200_bench_gemm", "gmrf_b200_profile_refactorize", "gmrf_b200_profile_plan", "gmrf_b200_device_array", "gmrf_b200_set_value_basis", "gmrf_b200_refactorize_combination", "gmrf_b200_adopt_factor", "gmrf_b200_host_register", "gmrf_b200_host_unregister",
 ]
 
 _lib = None
@@ -103,8 +103,6 @@ def lib():
     L.gmrf_b200_test_potrf.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.gmrf_b200_test_potrf_inv.restype = ctypes.c_int
     L.gmrf_b200_test_potrf_inv.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(ctypes.c_int)]
-    L.gmrf_b200_test_trsm.restype = ctypes.c_int
-    L.gmrf_b200_test_trsm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, ctypes.c_int]
     L.gmrf_b200_bench_gemm.restype = ctypes.c_int
     L.gmrf_b200_bench_gemm.argtypes = [ctypes.c_int] * 8 + [c_f64p]
     L.gmrf_b200_profile_refactorize.restype = ctypes.c_int

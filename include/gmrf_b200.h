@@ -146,8 +146,8 @@ int gmrf_b200_get_scatter(const gmrf_b200_handle *h, int64_t *n_entries, int64_t
  * [0] h2d of nzval, [1] numeric factorization + logdet, [2] solve, [3] selinv, [4] host analysis. */
 int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n);
 /* Live per-kernel-family profile of one refactorization with the values of the previous refactorize (graphs off,
- * CUDA event pairs around every launch on the handle's stream): ms[4]/count[4] for {0: DMMA GEMM, 1: fused panel
- * potrf+trsm, 2: extend-add assembly, 3: memset+scatter+logdet}; *gemm_flops = algorithmic flops of the GEMM tasks. */
+ * CUDA event pairs around every launch on the handle's stream): ms[4]/count[4] for {0: DMMA GEMM (incl. TRSM by
+ * inverted block), 1: panel potrf + inverse, 2: extend-add assembly, 3: memset+scatter+logdet}; *gemm_flops = algorithmic flops of the GEMM tasks. */
 int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *count, double *gemm_flops);
 /* Per-launch device times of one phase (diagnostics; graphs off, event pair around every launch): phase 0 = numeric
  * factorization, 1 = selected inversion, 2 = forward sweep, 3 = backward sweep with `nrhs` (<= 8) columns. Up to `cap`
@@ -178,14 +178,12 @@ int gmrf_b200_set_option(const char *key, double value);
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`
  * and back. gemm: C[m x n] = (beta ? C : 0) + alpha * Aop * Bop^T, where transa/transb = 0 means the operand is
  * stored m x k (resp. n x k), 1 means k x m (resp. k x n); `flags` bits: 1 lower-only, 2 alpha=+1 (default -1),
- * 4 add identity, 8 naive debug kernel, 16 large (128x128) tile. trsm: m > 0 solves X L^T = B, m < 0 solves
- * X L = B (|m| rows), L lower n x n, n <= 64. */
+ * 4 add identity, 8 naive debug kernel, 16 large (128x128) tile. */
 int gmrf_b200_test_gemm(int device, int transa, int transb, int flags, int m, int n, int k,
                         const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
 int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info);
 /* same kernel, also returning inv(L) (n x n, leading dimension n, zeros above the diagonal) */
 int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv, int *info);
-int gmrf_b200_test_trsm(int device, int m, int n, const double *L, int ldl, double *B, int ldb);
 /* Device-timed micro-benchmark of the library's own FP64 GEMM kernel (zero-filled device operands, best of
  * `reps`, CUDA events): used to compare against the measured cuBLAS DGEMM peak in profiles/. */
 int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, int n, int k, int reps, double *ms_out);

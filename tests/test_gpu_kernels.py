@@ -73,26 +73,16 @@ def test_potrf_diag(n):
     # the same kernel also returns inv(L) (dense n x n, zeros above the diagonal): used for TRSM-by-GEMM and the solves
     assert np.array_equal(np.triu(inv, 1), np.zeros((n, n)))
     assert np.abs(inv @ want - np.eye(n)).max() <= 1e-13 * n * np.linalg.cond(want)
+    # the product's TRSM: rows below the block are solved as a GEMM with the inverted block, X = B * inv(L)^T
+    m = 37
+    Bm = np.asfortranarray(rng.standard_normal((m, n)))
+    X = np.zeros((m, n), order="F")
+    invc = np.asfortranarray(inv)
+    assert L.gmrf_b200_test_gemm(0, 0, 0, 2, m, n, n, ptr(Bm), m, ptr(invc), n, 0.0, ptr(X), m) == 0
+    assert np.abs(X @ want.T - Bm).max() <= 1e-12 * n * np.linalg.cond(want) * np.abs(Bm).max()
     # not positive definite: the failing column (1-based) is reported
     if n >= 3:
         A2 = A.copy(); A2[2, 2] = -1.0
         Ab = np.zeros((lda, n), order="F"); Ab[:n] = A2
         assert L.gmrf_b200_test_potrf(0, n, ptr(Ab), lda, ctypes.byref(info)) == 0
         assert info.value == 3
-
-
-@pytest.mark.parametrize("n", [1, 5, 8, 16, 24, 32, 50, 64])
-@pytest.mark.parametrize("m", [1, 63, 64, 65, 300])
-@pytest.mark.parametrize("var", [0, 1])
-def test_trsm_strip(n, m, var):
-    L = _lib.lib()
-    rng = np.random.default_rng(n * 1000 + m)
-    Lm = np.tril(rng.standard_normal((n, n))) + n * np.eye(n)
-    B = rng.standard_normal((m, n))
-    ldl, ldb = n + 1, m + 2
-    Lb = np.zeros((ldl, n), order="F"); Lb[:n] = Lm + np.triu(rng.standard_normal((n, n)), 1)   # junk above the diagonal
-    Bb = np.zeros((ldb, n), order="F"); Bb[:m] = B
-    assert L.gmrf_b200_test_trsm(0, -m if var else m, n, ptr(Lb), ldl, ptr(Bb), ldb) == 0
-    want = np.linalg.solve(Lm, B.T).T if var == 0 else np.linalg.solve(Lm.T, B.T).T
-    # var 0: X L^T = B -> X = B L^-T ; var 1: X L = B -> X = B L^-1
-    assert np.abs(Bb[:m] - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
