@@ -88,14 +88,18 @@ struct gmrf_b200_handle {
     long long *d_invbase = nullptr;    // per supernode: offset of its first inverted block in d_Linv
     std::vector<long long> inv_base;   // host copy
     std::map<int, cudaGraphExec_t> solve_graphs;   // key = nrhs * 2 + mode
-    // wide right-hand-side path (blocks of MULTI_W columns, DMMA GEMM sweeps), built lazily
-    bool multi_built = false;
+    // wide right-hand-side path (blocks of 64 / 128 / 256 columns, DMMA GEMM sweeps), one plan per width, built lazily;
+    // the work arrays are shared (sized for the widest block built so far)
+    struct Multi {
+        bool built = false;
+        GemmTask *d_gemm = nullptr;
+        RowGatherTask *d_rg = nullptr;
+        int *d_prefix = nullptr, *d_superlist = nullptr;
+        Plan fwd_plan, bwd_plan;
+        cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    } multi[MULTI_NW];
     double *d_ym = nullptr, *d_um = nullptr;
-    GemmTask *d_gemm_m = nullptr;
-    RowGatherTask *d_rg_m = nullptr;
-    int *d_prefix_m = nullptr, *d_superlist_m = nullptr;
-    Plan multi_fwd_plan, multi_bwd_plan;
-    cudaGraphExec_t multi_graph[2] = {nullptr, nullptr};
+    int multi_wcap = 0;                // columns the shared work arrays hold
     TransTask *d_trans = nullptr;
     SplitTask *d_split = nullptr, *d_split_z = nullptr;
     double *d_basis = nullptr;         // optional value basis (nbasis x nnz) for device-side assembly of nzval
@@ -543,16 +547,15 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     }
 }
 
-// Wide right-hand-side sweeps (blocks of MULTI_W = 64 columns): every step is a DMMA GEMM on the 64-column block.
+// Wide right-hand-side sweeps (blocks of W = 64, 128 or 256 columns): every step is a DMMA GEMM on the block.
 // Two-level blocking like the factorization: inside an outer block of OB columns the 64-column diagonal blocks are
 // applied through their inverses (one 64 x 64-tile GEMM each, in place) with small k = 64 updates confined to the outer
 // block; the rows below / columns left of the outer block get ONE k = OB update (forward: right-looking over rows,
 // backward: right-looking over columns, exactly the dependency structure of the few-RHS kernels).
-void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
+void build_multi_plans(gmrf_b200_handle *h, Builder &B, int W, Plan &fwd_plan, Plan &bwd_plan) {
     const Symbolic &S = h->S;
     const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
     const i64 BBLK = (i64)NB * NB;
-    const int W = MULTI_W;
     const int ldy = (int)S.n, ldu = (int)S.uvec_total;
     std::vector<int> lst;
     std::vector<GemmTask> st, gt;
@@ -573,7 +576,7 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
             if (S.nr(s) > 0 || S.child_ptr[s + 1] > S.child_ptr[s]) lst.push_back((int)s);
             maxouter = std::max<i64>(maxouter, cdiv(S.ns(s), OB));
         }
-        B.add_superlist(h->multi_fwd_plan, lst, K_FWD_ASM_M);
+        B.add_superlist(fwd_plan, lst, K_FWD_ASM_M);
         for (i64 J = 0; J < maxouter; J++) {
             for (i64 jj = 0; jj < OB / NB; jj++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
@@ -588,8 +591,8 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
                     // y[k1:J1] -= L[k1:J1, K] x_K
                     if (J1 > k1) gt.push_back(task(P + k0 * ld + k1, (int)ld, ys + k0, ldy, ys + k1, ldy, J1 - k1, W, nb, 0));
                 }
-                B.add_gemm(h->multi_fwd_plan, st, 1, true, 0.5);
-                B.add_gemm(h->multi_fwd_plan, gt, 1);
+                B.add_gemm(fwd_plan, st, 1, true, 0.5);
+                B.add_gemm(fwd_plan, gt, 1);
             }
             for (const i64 *sp = sb; sp < se; sp++) {
                 i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
@@ -601,7 +604,7 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
                 if (ns > J1) gt.push_back(task(P + J0 * ld + J1, (int)ld, ys + J0, ldy, ys + J1, ldy, ns - J1, W, J1 - J0, 0));
                 if (nr > 0) gt.push_back(task(P + J0 * ld + ns, (int)ld, ys + J0, ldy, h->d_um + S.uvec_off[s], ldu, nr, W, J1 - J0, 0));
             }
-            B.add_gemm(h->multi_fwd_plan, gt, 1);
+            B.add_gemm(fwd_plan, gt, 1);
         }
     }
     // ---- backward: L^T x = y ---------------------------------------------------------------------------------
@@ -616,8 +619,8 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
             // y_S -= L21^T u_s
             gt.push_back(task(h->d_Lx + S.panel_off[s] + ns, (int)ld, h->d_um + S.uvec_off[s], ldu, h->d_ym + S.sfirst[s], ldy, ns, W, nr, 0));
         }
-        B.add_tiled(h->multi_bwd_plan, rg, B.rowgather, K_ROWS_GATHER, [](const RowGatherTask &t) { return (i64)cdiv(t.nr, 256); });
-        B.add_gemm(h->multi_bwd_plan, gt, 2);
+        B.add_tiled(bwd_plan, rg, B.rowgather, K_ROWS_GATHER, [](const RowGatherTask &t) { return (i64)cdiv(t.nr, 256); });
+        B.add_gemm(bwd_plan, gt, 2);
         for (i64 tJ = 0; tJ < maxouter; tJ++) {
             for (i64 tj = 0; tj < OB / NB; tj++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
@@ -635,8 +638,8 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
                     // t[J0:k0] -= L[K, J0:k0]^T x_K
                     if (k0 > J0) gt.push_back(task(P + J0 * ld + k0, (int)ld, ys + k0, ldy, ys + J0, ldy, k0 - J0, W, nb, 0));
                 }
-                B.add_gemm(h->multi_bwd_plan, st, 2, true, 0.5);
-                B.add_gemm(h->multi_bwd_plan, gt, 2);
+                B.add_gemm(bwd_plan, st, 2, true, 0.5);
+                B.add_gemm(bwd_plan, gt, 2);
             }
             for (const i64 *sp = sb; sp < se; sp++) {
                 i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
@@ -648,7 +651,7 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B) {
                 // t[0:J0] -= L[J, 0:J0]^T x_J
                 gt.push_back(task(P + J0, (int)ld, ys + J0, ldy, ys, ldy, J0, W, J1 - J0, 0));
             }
-            B.add_gemm(h->multi_bwd_plan, gt, 2);
+            B.add_gemm(bwd_plan, gt, 2);
         }
     }
 }
@@ -965,13 +968,13 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         }
         case K_FWD_ASM_M: {
-            dim3 g(L.grid, MULTI_W / MULTI_QB);
+            dim3 g(L.grid, nrhs / MULTI_QB);
             fwd_assemble_multi_kernel<<<g, 256, 0, st>>>(T.superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx,
                                                          T.y, h->S.n, T.u, h->S.uvec_total);
             break;
         }
         case K_ROWS_GATHER: {
-            dim3 g(L.grid, MULTI_W / MULTI_QB);
+            dim3 g(L.grid, nrhs / MULTI_QB);
             rows_gather_kernel<<<g, 256, 0, st>>>(T.rowgather + L.task_off, pf, L.ntasks, T.y, h->S.n, h->S.uvec_total);
             break;
         }
@@ -1116,70 +1119,103 @@ int ensure_io(gmrf_b200_handle *h, i64 count) {
     return 0;
 }
 
-// Lazily build the wide right-hand-side path (work arrays for MULTI_W columns, GEMM task tables, plans).
-int ensure_multi(gmrf_b200_handle *h) {
-    if (h->multi_built) return 0;
+// Lazily build the wide right-hand-side path for block width 64 << wi (GEMM task tables, plans) and make sure the
+// shared work arrays hold that many columns.
+int ensure_multi(gmrf_b200_handle *h, int wi) {
     const Symbolic &S = h->S;
+    const int W = 64 << wi;
     int rc;
-    if ((rc = dev_alloc(h, &h->d_ym, (size_t)(S.n * MULTI_W)))) return rc;
-    if ((rc = dev_alloc(h, &h->d_um, (size_t)(S.uvec_total * MULTI_W)))) return rc;
+    if (h->multi_wcap < W) {
+        // grow-only; plans of narrower widths keep pointing into the old arrays, so every built plan is dropped and
+        // rebuilt on demand against the new buffers (happens at most twice per handle)
+        for (auto &m : h->multi) {
+            for (auto &g : m.graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+            m.built = false;
+            m.fwd_plan.launches.clear();
+            m.bwd_plan.launches.clear();
+        }
+        if ((rc = dev_alloc(h, &h->d_ym, (size_t)(S.n * W)))) return rc;
+        if ((rc = dev_alloc(h, &h->d_um, (size_t)(S.uvec_total * W)))) return rc;
+        h->multi_wcap = W;
+    }
+    gmrf_b200_handle::Multi &M = h->multi[wi];
+    if (M.built) return 0;
     Builder B;
     B.naive = h->opt.naive_kernels != 0;
     try {
-        build_multi_plans(h, B);
+        build_multi_plans(h, B, W, M.fwd_plan, M.bwd_plan);
     } catch (std::exception &e) {
         h->err = e.what();
         return GMRF_B200_ERR_ARG;
     }
-    if ((rc = dev_upload(h, &h->d_gemm_m, B.gemm))) return rc;
-    if ((rc = dev_upload(h, &h->d_prefix_m, B.prefix))) return rc;
-    if ((rc = dev_upload(h, &h->d_superlist_m, B.superlist))) return rc;
-    if ((rc = dev_upload(h, &h->d_rg_m, B.rowgather))) return rc;
-    h->multi_built = true;
+    if ((rc = dev_upload(h, &M.d_gemm, B.gemm))) return rc;
+    if ((rc = dev_upload(h, &M.d_prefix, B.prefix))) return rc;
+    if ((rc = dev_upload(h, &M.d_superlist, B.superlist))) return rc;
+    if ((rc = dev_upload(h, &M.d_rg, B.rowgather))) return rc;
+    M.built = true;
     return 0;
 }
 
-void enqueue_multi_sweeps(gmrf_b200_handle *h, int mode) {
-    TableSet T{h->d_gemm_m, nullptr, h->d_prefix_m, nullptr};
-    T.superlist = h->d_superlist_m;
-    T.rowgather = h->d_rg_m;
+void enqueue_multi_sweeps(gmrf_b200_handle *h, int wi, int mode) {
+    gmrf_b200_handle::Multi &M = h->multi[wi];
+    TableSet T{M.d_gemm, nullptr, M.d_prefix, nullptr};
+    T.superlist = M.d_superlist;
+    T.rowgather = M.d_rg;
     T.y = h->d_ym;
     T.u = h->d_um;
+    const int W = 64 << wi;
     if (mode == 0)
-        for (const Launch &L : h->multi_fwd_plan.launches) run_launch(h, L, T, MULTI_W);
-    for (const Launch &L : h->multi_bwd_plan.launches) run_launch(h, L, T, MULTI_W);
+        for (const Launch &L : M.fwd_plan.launches) run_launch(h, L, T, W);
+    for (const Launch &L : M.bwd_plan.launches) run_launch(h, L, T, W);
 }
 
-// Wide path: blocks of MULTI_W right-hand sides through the GEMM sweeps (the last block is zero-padded).
+// Wide path: the right-hand sides go through the GEMM sweeps in blocks of 256, then 128, then 64 columns (the last
+// block is zero-padded up to its width); wider blocks stream the factor fewer times per column.
 int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
     const Symbolic &S = h->S;
-    int rc = ensure_multi(h);
-    if (rc) return rc;
+    int rc;
     cudaStream_t st = h->stream;
-    if (h->opt.use_graph && !h->multi_graph[mode]) {
+    // widths needed by this call; the widest first so the work arrays are sized once
+    bool need[MULTI_NW] = {false, false, false};
+    for (i64 left = nrhs; left > 0;) {
+        int wi = left > 128 ? 2 : left > 64 ? 1 : 0;
+        need[wi] = true;
+        left -= 64 << wi;
+    }
+    for (int wi = MULTI_NW - 1; wi >= 0; wi--) {
+        if (!need[wi]) continue;
+        if ((rc = ensure_multi(h, wi))) return rc;
+    }
+    for (int wi = 0; wi < MULTI_NW; wi++) {
+        if (!need[wi] || !h->opt.use_graph || h->multi[wi].graph[mode]) continue;
+        if ((rc = ensure_multi(h, wi))) return rc;            // (re)build if a wider block dropped it
         cudaGraph_t g;
         CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        enqueue_multi_sweeps(h, mode);
+        enqueue_multi_sweeps(h, wi, mode);
         CUDA_TRY(h, cudaStreamEndCapture(st, &g));
-        CUDA_TRY(h, cudaGraphInstantiate(&h->multi_graph[mode], g, 0));
+        CUDA_TRY(h, cudaGraphInstantiate(&h->multi[wi].graph[mode], g, 0));
         cudaGraphDestroy(g);
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
     const int tpb = 256;
     const int gridn = (int)((S.n + tpb - 1) / tpb);
-    for (i64 r0 = 0; r0 < nrhs; r0 += MULTI_W) {
-        const int nb = (int)std::min<i64>(MULTI_W, nrhs - r0);
-        if (nb < MULTI_W)
-            CUDA_TRY(h, cudaMemsetAsync(h->d_ym + (size_t)nb * S.n, 0, sizeof(double) * (size_t)(MULTI_W - nb) * S.n, st));
+    for (i64 r0 = 0; r0 < nrhs;) {
+        const i64 left = nrhs - r0;
+        const int wi = left > 128 ? 2 : left > 64 ? 1 : 0;
+        const int W = 64 << wi;
+        const int nb = (int)std::min<i64>(W, left);
+        if (nb < W)
+            CUDA_TRY(h, cudaMemsetAsync(h->d_ym + (size_t)nb * S.n, 0, sizeof(double) * (size_t)(W - nb) * S.n, st));
         if (mode == 0) {
             permute_rows_kernel<<<gridn, tpb, 0, st>>>(h->d_ym, dB + r0 * ld, h->d_perm, S.n, S.n, ld, nb, 0);
         } else {
             CUDA_TRY(h, cudaMemcpy2DAsync(h->d_ym, sizeof(double) * S.n, dB + r0 * ld, sizeof(double) * ld,
                                           sizeof(double) * S.n, nb, cudaMemcpyDeviceToDevice, st));
         }
-        if (h->opt.use_graph) CUDA_TRY(h, cudaGraphLaunch(h->multi_graph[mode], st));
-        else enqueue_multi_sweeps(h, mode);
+        if (h->opt.use_graph) CUDA_TRY(h, cudaGraphLaunch(h->multi[wi].graph[mode], st));
+        else enqueue_multi_sweeps(h, wi, mode);
         permute_rows_kernel<<<gridn, tpb, 0, st>>>(dX + r0 * ld, h->d_ym, h->d_perm, S.n, ld, S.n, nb, 1);
+        r0 += nb;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
     if ((rc = check_launch(h, "wide solve"))) return rc;
@@ -1503,7 +1539,8 @@ void gmrf_b200_destroy(gmrf_b200_handle *h) {
         if (h->factor_graph) cudaGraphExecDestroy(h->factor_graph);
         if (h->selinv_graph) cudaGraphExecDestroy(h->selinv_graph);
         for (auto &kv : h->solve_graphs) cudaGraphExecDestroy(kv.second);
-        for (auto &g : h->multi_graph) if (g) cudaGraphExecDestroy(g);
+        for (auto &m : h->multi)
+            for (auto &g : m.graph) if (g) cudaGraphExecDestroy(g);
         for (void *p : h->owned) cudaFree(p);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);

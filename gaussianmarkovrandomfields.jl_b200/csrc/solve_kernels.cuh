@@ -425,7 +425,8 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
 // Wide right-hand-side blocks (sampling, constraints, many columns): the sweeps are DMMA GEMMs on 64-column blocks of
 // right-hand sides (plans built in gmrf_b200.cu); only the two irregular steps need kernels of their own.
 // ------------------------------------------------------------------------------------------------
-constexpr int MULTI_W = 64;    // right-hand sides per pass of the wide path
+constexpr int MULTI_NW = 3;    // block widths of the wide path: 64, 128, 256 right-hand sides per pass
+constexpr int MULTI_WMAX = 256;
 constexpr int MULTI_QB = 8;    // columns per CTA in the two kernels below
 
 // Forward assembly for a block of right-hand sides: u_s := 0, then the children's update blocks are added into the
