@@ -121,6 +121,7 @@ struct gmrf_b200_handle {
     int rhs_block = 8;
 
     std::vector<void *> owned;   // every cudaMalloc for destroy
+    std::map<void *, size_t> owned_bytes;
 };
 
 namespace {
@@ -144,6 +145,7 @@ int dev_alloc(gmrf_b200_handle *h, T **p, size_t count) {
         return GMRF_B200_ERR_ALLOC;
     }
     h->owned.push_back(*p);
+    h->owned_bytes[(void *)*p] = count * sizeof(T);
     h->device_bytes += count * sizeof(T);
     return 0;
 }
@@ -154,6 +156,18 @@ int dev_upload(gmrf_b200_handle *h, T **p, const std::vector<T> &v) {
     if (rc) return rc;
     if (!v.empty()) CUDA_TRY(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
+}
+
+// Release one allocation made through dev_alloc (grow-only buffers that are being replaced).
+template <class T>
+void dev_free(gmrf_b200_handle *h, T *&p) {
+    if (!p) return;
+    auto it = std::find(h->owned.begin(), h->owned.end(), (void *)p);
+    if (it != h->owned.end()) h->owned.erase(it);
+    auto ib = h->owned_bytes.find((void *)p);
+    if (ib != h->owned_bytes.end()) { h->device_bytes -= ib->second; h->owned_bytes.erase(ib); }
+    cudaFree(p);
+    p = nullptr;
 }
 
 inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
@@ -1109,12 +1123,11 @@ int build_selinv_tables(gmrf_b200_handle *h) {
 int ensure_io(gmrf_b200_handle *h, i64 count) {
     if (h->io_cap >= count) return 0;
     // grow-only staging buffer for host<->device transfers of right-hand sides / results
-    double *p = nullptr;
-    cudaError_t e = cudaMalloc((void **)&p, sizeof(double) * (size_t)count);
-    if (e != cudaSuccess) { h->err = "cudaMalloc failed for the I/O staging buffer"; return GMRF_B200_ERR_ALLOC; }
-    h->owned.push_back(p);
-    h->device_bytes += sizeof(double) * (size_t)count;
-    h->d_io = p;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    dev_free(h, h->d_io);
+    h->io_cap = 0;
+    int rc = dev_alloc(h, &h->d_io, (size_t)count);
+    if (rc) return rc;
     h->io_cap = count;
     return 0;
 }
@@ -1128,12 +1141,16 @@ int ensure_multi(gmrf_b200_handle *h, int wi) {
     if (h->multi_wcap < W) {
         // grow-only; plans of narrower widths keep pointing into the old arrays, so every built plan is dropped and
         // rebuilt on demand against the new buffers (happens at most twice per handle)
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         for (auto &m : h->multi) {
             for (auto &g : m.graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
             m.built = false;
             m.fwd_plan.launches.clear();
             m.bwd_plan.launches.clear();
+            dev_free(h, m.d_gemm); dev_free(h, m.d_rg); dev_free(h, m.d_prefix); dev_free(h, m.d_superlist);
         }
+        dev_free(h, h->d_ym);
+        dev_free(h, h->d_um);
         if ((rc = dev_alloc(h, &h->d_ym, (size_t)(S.n * W)))) return rc;
         if ((rc = dev_alloc(h, &h->d_um, (size_t)(S.uvec_total * W)))) return rc;
         h->multi_wcap = W;
@@ -1592,7 +1609,7 @@ int gmrf_b200_set_value_basis(gmrf_b200_handle *h, const double *basis, int nbas
     if (rc) return rc;
     if (!basis || nbasis < 1 || nbasis > MAX_VALUE_BASIS) { h->err = "set_value_basis: need 1 <= nbasis <= 8 value arrays"; return GMRF_B200_ERR_ARG; }
     const size_t cnt = (size_t)nbasis * (size_t)h->S.nnzA;
-    if (h->d_basis && h->nbasis != nbasis) { cudaFree(h->d_basis); h->owned.erase(std::find(h->owned.begin(), h->owned.end(), (void *)h->d_basis)); h->d_basis = nullptr; }
+    if (h->d_basis && h->nbasis != nbasis) dev_free(h, h->d_basis);
     if (!h->d_basis && (rc = dev_alloc(h, &h->d_basis, cnt))) return rc;
     h->nbasis = nbasis;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_basis, basis, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));

@@ -425,6 +425,7 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
     __shared__ __align__(16) double sA[N * LDS_];     // sA[i * LDS_ + j]
     __shared__ double sdiag[16];                      // published 4 x 4 diagonal tile (lower) ...
     __shared__ double srinv[4];                       // ... and the reciprocals of its diagonal
+    __shared__ double srinv_all[N];                   // 1 / L_ii of every row, reused by the inversion
     __shared__ __align__(16) double spanel2[2][N][4];  // published column panel (rows 0..63 of the current 4 columns),
                                                        // double-buffered: step P+1 publishes while step P is still read
     const PanelTask T = tasks[blockIdx.x];
@@ -454,6 +455,7 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
                 const double r = rsqrt(d);
                 a[c][c] = d * r;
                 srinv[c] = r;
+                srinv_all[4 * P + c] = r;
 #pragma unroll
                 for (int r2 = c + 1; r2 < 4; r2++) a[r2][c] *= r;
 #pragma unroll
@@ -514,9 +516,10 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
         const int i = e % nb, j = e / nb;
         if (i >= j) T.D[i + (long long)j * T.ld] = sA[i * LDS_ + j];
     }
+    double v[N];
     if (tid < N) {
-        // column c = tid of L^-1 by forward substitution; rows of L are read as 16-byte pairs (broadcast)
-        double v[N];
+        // column c = tid of L^-1 by forward substitution; rows of L are read as 16-byte pairs (broadcast), the
+        // divisions are multiplications with the reciprocal pivots kept from the factorization
 #pragma unroll
         for (int i = 0; i < N; i++) {
             double s0 = (i == tid) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -529,13 +532,18 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
             }
 #pragma unroll
             for (int k = (i / 4) * 4; k < i; k++) s0 -= sA[i * LDS_ + k] * v[k];
-            v[i] = (i >= tid) ? ((s0 + s1) + (s2 + s3)) / sA[i * LDS_ + i] : 0.0;
+            v[i] = (i >= tid) ? ((s0 + s1) + (s2 + s3)) * srinv_all[i] : 0.0;
         }
-        if (tid < nb) {
+    }
+    __syncthreads();                                   // everybody is done with the factor in shared memory
+    if (tid < N) {
 #pragma unroll
-            for (int i = 0; i < N; i++)
-                if (i < nb) T.inv[i + (long long)tid * nb] = v[i];
-        }
+        for (int i = 0; i < N; i++) sA[i * LDS_ + tid] = v[i];   // inverse, element (i, c)
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * nb; e += 256) {         // coalesced store: inv[i + c*nb]
+        const int i = e % nb, c = e / nb;
+        T.inv[e] = sA[i * LDS_ + c];
     }
 }
 
