@@ -189,6 +189,7 @@ struct Builder {
     double *splitk_base = nullptr;     // device scratch for split-K partial products
     i64 splitk_cap = 0;
     int splitk_min_k = 1024;
+    int large_tile_mask = 1;           // bit v set: operand-layout variant v (0 NN, 1 NT, 2 TT) may use the 128 x 64 tile
     std::vector<int> superlist;
     std::vector<int> prefix;
     bool naive = false;
@@ -242,7 +243,7 @@ struct Builder {
             gemm_flops += flop_weight * 2.0 * t.m * (double)t.n * t.k * ((t.flags & GEMM_LOWER) ? 0.5 * (1.0 + 1.0 / std::max(1, t.m)) * ((double)t.n <= t.m ? (2.0 - (double)t.n / t.m) : 1.0) : 1.0);
             // measured on B200 (profiles/r01_gemm_variants.log): the 64x64 tile (4 CTAs/SM) wins everywhere except very
             // large square-ish products, where the 128x64 tile (warp tile 64x32) is ~4% faster
-            bool big = !naive && !force_small && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024;
+            bool big = !naive && !force_small && (i64)t.m * t.n >= 4096LL * 4096LL && t.n >= 1024 && ((large_tile_mask >> variant) & 1);
             (big ? large : small).push_back(t);
         }
         for (int pass = 0; pass < 2; pass++) {
@@ -1100,7 +1101,7 @@ int build_selinv_tables(gmrf_b200_handle *h) {
     CUDA_TRY(h, cudaMemset(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total));
     Builder B;
     B.naive = h->opt.naive_kernels != 0;
-    B.splitk_base = h->d_splitk; B.splitk_cap = h->splitk_cap; B.splitk_min_k = h->opt.splitk_min_k;
+    B.splitk_base = h->d_splitk; B.splitk_cap = h->splitk_cap; B.splitk_min_k = h->opt.splitk_min_k; B.large_tile_mask = h->opt.large_tile_mask;
     try {
         build_selinv_plan(h, B);
     } catch (std::exception &e) {
@@ -1408,6 +1409,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "selinv_fast_root") o.selinv_fast_root = (int)value;
     else if (k == "wide_rhs_min") o.wide_rhs_min = std::max(0, (int)value);
     else if (k == "bwd_row_chunk") o.bwd_row_chunk = std::max(32, (int)value);
+    else if (k == "large_tile_mask") o.large_tile_mask = (int)value & 7;
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else return GMRF_B200_ERR_ARG;
     return 0;
@@ -1523,7 +1525,7 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
     {
         Builder B;
         B.naive = H->opt.naive_kernels != 0;
-        B.splitk_base = H->d_splitk; B.splitk_cap = H->splitk_cap; B.splitk_min_k = H->opt.splitk_min_k;
+        B.splitk_base = H->d_splitk; B.splitk_cap = H->splitk_cap; B.splitk_min_k = H->opt.splitk_min_k; B.large_tile_mask = H->opt.large_tile_mask;
         try {
             build_factor_plan(H, B);
             build_solve_plans(H, B);
