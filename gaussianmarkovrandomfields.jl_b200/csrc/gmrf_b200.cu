@@ -117,7 +117,15 @@ struct gmrf_b200_handle {
     bool z_pattern_built = false;
 
     Plan factor_plan, selinv_plan, fwd_plan, bwd_plan;
-    cudaGraphExec_t factor_graph = nullptr, selinv_graph = nullptr;
+    std::map<int, cudaGraphExec_t> factor_graphs;   // key = number of lanes advanced by the graph
+    cudaGraphExec_t selinv_graph = nullptr;
+    // lanes: independent value sets on the same pattern factorized by the same launches (blockIdx.y); every numeric
+    // array of the factorization lives in one arena per lane, lane b starts arena_bytes * b after lane 0
+    int lanes = 1;
+    long long arena_bytes = 0;
+    double *d_arena = nullptr;
+    std::vector<double> lane_logdet;
+    std::vector<int> lane_fail;
     int rhs_block = 8;
 
     std::vector<void *> owned;   // every cudaMalloc for destroy
@@ -900,8 +908,8 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
 // Launch dispatch
 // ------------------------------------------------------------------------------------------------
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
-void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
-    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks);
+void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st, int lanes, long long bstride) {
+    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks, bstride);
 }
 
 // Opt in to > 48 KB dynamic shared memory for every GEMM instantiation (per device; must run outside stream capture).
@@ -921,17 +929,18 @@ cudaError_t configure_kernels() {
 }
 
 template <bool TA, bool TB>
-void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st) {
-    if (naive) gemm_naive_kernel<TA, TB><<<grid, 256, 0, st>>>(tasks, prefix, ntasks);
-    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
-    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st);
+void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st,
+                 int lanes = 1, long long bstride = 0) {
+    if (naive) gemm_naive_kernel<TA, TB><<<dim3(grid, lanes), 256, 0, st>>>(tasks, prefix, ntasks, bstride);
+    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
+    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
 }
 
 template <int BM, int BN, int WGM, int WGN, int KT, int ST>
 void launch_gemm_exp(const GemmTask *tasks, const int *prefix, int grid) {
     auto kern = gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, KT, ST>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, KT, ST>());
-    kern<<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, KT, ST>()>>>(tasks, prefix, 1);
+    kern<<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, KT, ST>()>>>(tasks, prefix, 1, 0LL);
 }
 
 struct TableSet {
@@ -942,33 +951,35 @@ struct TableSet {
     const int *superlist = nullptr;         // solve phases: supernode lists
     const RowGatherTask *rowgather = nullptr;
     double *y = nullptr, *u = nullptr;      // solve phases: permuted work array and update-vector pool
+    int lanes = 1;                          // factorization: lanes advanced per launch (grid.y)
 };
 
 void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs) {
     cudaStream_t st = h->stream;
     const bool naive = h->opt.naive_kernels != 0;
     const int *pf = L.prefix_off >= 0 ? T.prefix + L.prefix_off : nullptr;
+    const long long bstride = T.lanes > 1 ? h->arena_bytes : 0;
     if (L.grid <= 0) return;
     switch (L.kind) {
         case K_ASSEMBLE:
-            assemble_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd);
+            assemble_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd, bstride);
             break;
         case K_PANEL:
             switch (L.aux) {
-                case 8: potrf_inv_kernel<8><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
-                case 16: potrf_inv_kernel<16><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
-                case 32: potrf_inv_kernel<32><<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
-                default: potrf_inv64_kernel<<<L.grid, 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail); break;
+                case 8: potrf_inv_kernel<8><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
+                case 16: potrf_inv_kernel<16><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
+                case 32: potrf_inv_kernel<32><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
+                default: potrf_inv64_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
             }
             break;
         case K_GEMM_NN_S: case K_GEMM_NN_L:
-            launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+            launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
         case K_GEMM_NT_S: case K_GEMM_NT_L:
-            launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+            launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
         case K_GEMM_TT_S: case K_GEMM_TT_L:
-            launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st); break;
+            launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
         case K_SPLIT_REDUCE:
-            splitk_reduce_kernel<<<L.grid, 256, 0, st>>>(T.split + L.task_off, pf, L.ntasks);
+            splitk_reduce_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.split + L.task_off, pf, L.ntasks, bstride);
             break;
         case K_GATHER:
             selinv_gather_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_relidx, h->d_Zx, h->d_zw);
@@ -1025,22 +1036,25 @@ int check_launch(gmrf_b200_handle *h, const char *what) {
     return 0;
 }
 
-void enqueue_factor(gmrf_b200_handle *h) {
+void enqueue_factor(gmrf_b200_handle *h, int lanes = 1) {
     const Symbolic &S = h->S;
     cudaStream_t st = h->stream;
-    cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)S.panel_total, st);
-    const int int_max = INT_MAX;
-    (void)int_max;
-    cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);   // 0x7f7f7f7f: "no failure" sentinel
+    const long long bstride = lanes > 1 ? h->arena_bytes : 0;
+    for (int b = 0; b < lanes; b++) {
+        char *base = reinterpret_cast<char *>(h->d_Lx) + (long long)b * h->arena_bytes;
+        cudaMemsetAsync(base, 0, sizeof(double) * (size_t)S.panel_total, st);
+        cudaMemsetAsync(reinterpret_cast<char *>(h->d_fail) + (long long)b * h->arena_bytes, 0x7f, sizeof(int), st);   // "no failure" sentinel
+    }
     i64 cnt = (i64)S.q_src.size();
     if (cnt > 0) {
         int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
-        scatter_q_kernel<<<grid, 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+        scatter_q_kernel<<<dim3(grid, lanes), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, bstride);
     }
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
+    T.lanes = lanes;
     for (const Launch &L : h->factor_plan.launches) run_launch(h, L, T, 0);
-    logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
-    logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+    logdet_partial_kernel<<<dim3(LOGDET_BLOCKS, lanes), 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial, bstride);
+    logdet_final_kernel<<<dim3(1, lanes), 256, 0, st>>>(h->d_partial, h->d_scalars, bstride);
 }
 
 void enqueue_selinv(gmrf_b200_handle *h) {
@@ -1058,35 +1072,43 @@ int ensure_device(gmrf_b200_handle *h) {
     return 0;
 }
 
-int do_factor(gmrf_b200_handle *h) {
+int do_factor(gmrf_b200_handle *h, int lanes = 1) {
     cudaStream_t st = h->stream;
     CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
     if (h->opt.use_graph) {
-        if (!h->factor_graph) {
+        auto it = h->factor_graphs.find(lanes);
+        if (it == h->factor_graphs.end()) {
             cudaGraph_t g;
+            cudaGraphExec_t ge;
             CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            enqueue_factor(h);
+            enqueue_factor(h, lanes);
             CUDA_TRY(h, cudaStreamEndCapture(st, &g));
-            CUDA_TRY(h, cudaGraphInstantiate(&h->factor_graph, g, 0));
+            CUDA_TRY(h, cudaGraphInstantiate(&ge, g, 0));
             cudaGraphDestroy(g);
+            it = h->factor_graphs.emplace(lanes, ge).first;
         }
-        CUDA_TRY(h, cudaGraphLaunch(h->factor_graph, st));
+        CUDA_TRY(h, cudaGraphLaunch(it->second, st));
     } else {
-        enqueue_factor(h);
+        enqueue_factor(h, lanes);
         int rc = check_launch(h, "factorization");
         if (rc) return rc;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
-    double host_logdet = 0;
-    int host_fail = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&host_logdet, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(&host_fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    h->lane_logdet.assign(lanes, 0.0);
+    h->lane_fail.assign(lanes, 0);
+    for (int b = 0; b < lanes; b++) {      // (a strided 2-D copy would exceed the pitch limit for multi-GB arenas)
+        const char *sc = reinterpret_cast<const char *>(h->d_scalars) + (long long)b * h->arena_bytes;
+        const char *fl = reinterpret_cast<const char *>(h->d_fail) + (long long)b * h->arena_bytes;
+        CUDA_TRY(h, cudaMemcpyAsync(&h->lane_logdet[b], sc, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaMemcpyAsync(&h->lane_fail[b], fl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     h->t_ms[1] = ms;
-    h->logdet = host_logdet;
-    h->fail_col = (host_fail == 0x7f7f7f7f) ? 0 : host_fail;
+    for (auto &f : h->lane_fail) f = (f == 0x7f7f7f7f) ? 0 : f;
+    h->logdet = h->lane_logdet[0];
+    h->fail_col = h->lane_fail[0];
     h->factored = true;
     h->selinv_valid = false;
     return h->fail_col > 0 ? h->fail_col : 0;
@@ -1410,6 +1432,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "wide_rhs_min") o.wide_rhs_min = std::max(0, (int)value);
     else if (k == "bwd_row_chunk") o.bwd_row_chunk = std::max(32, (int)value);
     else if (k == "large_tile_mask") o.large_tile_mask = (int)value & 7;
+    else if (k == "lanes") o.lanes = std::max(1, std::min(64, (int)value));
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else return GMRF_B200_ERR_ARG;
     return 0;
@@ -1469,16 +1492,40 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
     const Symbolic &S = H->S;
     int rc;
 #define TRY_RC(x) do { rc = (x); if (rc) return fail(rc); } while (0)
-    TRY_RC(dev_alloc(H, &H->d_Lx, (size_t)S.panel_total));
-    // one pool serves the update matrices of the factorization and, afterwards, the gathered Z[R,R] blocks of the
-    // selected inversion (the two phases never overlap)
-    TRY_RC(dev_alloc(H, &H->d_upd, (size_t)std::max(S.upd_total, S.zw_total)));
-    TRY_RC(dev_alloc(H, &H->d_nz, (size_t)S.nnzA));
+    // ---- numeric arena: every array a factorization writes, once per lane -------------------------------------
+    i64 inv_total = 0;   // doubles in the inverted diagonal blocks (nb x nb each, 64-column blocks)
+    H->inv_base.assign(S.nsuper, 0);
+    for (i64 s = 0; s < S.nsuper; s++) {
+        H->inv_base[s] = inv_total;
+        for (i64 k0 = 0; k0 < S.ns(s); k0 += SOLVE_NB) {
+            i64 nb = std::min<i64>(SOLVE_NB, S.ns(s) - k0);
+            inv_total += nb * nb;
+        }
+    }
+    H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
+    {
+        auto al = [](i64 x) { return (std::max<i64>(x, 1) + 31) & ~31LL; };   // 256-byte granules
+        // one pool serves the update matrices of the factorization and, afterwards, the gathered Z[R,R] blocks of the
+        // selected inversion (the two phases never overlap)
+        const i64 n_lx = al(S.panel_total), n_upd = al(std::max(S.upd_total, S.zw_total)), n_nz = al(S.nnzA),
+                  n_inv = al(inv_total), n_split = al(H->splitk_cap), n_part = al(LOGDET_BLOCKS), n_sc = al(8), n_fail = al(2);
+        const i64 arena = n_lx + n_upd + n_nz + n_inv + n_split + n_part + n_sc + n_fail;
+        H->lanes = std::max(1, H->opt.lanes);
+        H->arena_bytes = arena * (long long)sizeof(double);
+        TRY_RC(dev_alloc(H, &H->d_arena, (size_t)arena * (size_t)H->lanes));
+        double *p = H->d_arena;
+        H->d_Lx = p; p += n_lx;
+        H->d_upd = p; p += n_upd;
+        H->d_nz = p; p += n_nz;
+        H->d_Linv = p; p += n_inv;
+        H->d_splitk = p; p += n_split;
+        H->d_partial = p; p += n_part;
+        H->d_scalars = p; p += n_sc;
+        H->d_fail = reinterpret_cast<int *>(p);
+    }
+    TRY_RC(dev_upload(H, &H->d_invbase, H->inv_base));
     TRY_RC(dev_alloc(H, &H->d_y, (size_t)(S.n * H->rhs_block)));
     TRY_RC(dev_alloc(H, &H->d_uvec, (size_t)(S.uvec_total * H->rhs_block)));
-    TRY_RC(dev_alloc(H, &H->d_partial, (size_t)LOGDET_BLOCKS));
-    TRY_RC(dev_alloc(H, &H->d_scalars, (size_t)8));
-    TRY_RC(dev_alloc(H, &H->d_fail, (size_t)2));
     {
         std::vector<long long> a(S.q_src.begin(), S.q_src.end()), b(S.q_dst.begin(), S.q_dst.end()),
             c(S.diag_pos.begin(), S.diag_pos.end()), d(S.perm.begin(), S.perm.end());
@@ -1503,25 +1550,12 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         TRY_RC(dev_upload(H, &H->d_meta, meta));
     }
     {
-        i64 inv_total = 0;   // doubles in the inverted diagonal blocks (nb x nb each, 64-column blocks)
-        H->inv_base.assign(S.nsuper, 0);
-        for (i64 s = 0; s < S.nsuper; s++) {
-            H->inv_base[s] = inv_total;
-            for (i64 k0 = 0; k0 < S.ns(s); k0 += SOLVE_NB) {
-                i64 nb = std::min<i64>(SOLVE_NB, S.ns(s) - k0);
-                inv_total += nb * nb;
-            }
-        }
-        TRY_RC(dev_alloc(H, &H->d_Linv, (size_t)inv_total));
         i64 part_total = 0;   // partial sums of the row-chunked backward products
         for (i64 s = 0; s < S.nsuper; s++)
             if (S.nr(s) > std::max(32, H->opt.bwd_row_chunk))
                 part_total += cdiv(S.nr(s), std::max(32, H->opt.bwd_row_chunk)) * (i64)BWD_PART_Q * S.ns(s);
         TRY_RC(dev_alloc(H, &H->d_bwdpart, (size_t)part_total));
-        TRY_RC(dev_upload(H, &H->d_invbase, H->inv_base));
     }
-    H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
-    TRY_RC(dev_alloc(H, &H->d_splitk, (size_t)H->splitk_cap));
     {
         Builder B;
         B.naive = H->opt.naive_kernels != 0;
@@ -1555,7 +1589,7 @@ void gmrf_b200_destroy(gmrf_b200_handle *h) {
     if (h->device >= 0) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
-        if (h->factor_graph) cudaGraphExecDestroy(h->factor_graph);
+        for (auto &kv : h->factor_graphs) cudaGraphExecDestroy(kv.second);
         if (h->selinv_graph) cudaGraphExecDestroy(h->selinv_graph);
         for (auto &kv : h->solve_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &m : h->multi)
@@ -1633,6 +1667,70 @@ int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, 
     }
     h->t_ms[0] = 0;
     return do_factor(h);
+}
+
+// ---- lanes: several value sets factorized side by side ------------------------------------------------------
+// The workload of a hyperparameter sweep (`WorkspacePool` + `(model)(ws; theta...)`, workspace_pool.jl:42-119): many
+// independent numeric factorizations of ONE pattern whose only outputs are log-determinants. A handle created with the
+// option "lanes" = B holds B copies of its numeric arrays and advances all of them with the same launches, which is
+// what fills the GPU on problems (2D meshes) too small to do so alone. Lane 0 is the handle's ordinary factor: solves
+// and selected inversion after a lane call see lane 0.
+static int check_lanes(gmrf_b200_handle *h, int lanes, const void *a, const void *b) {
+    if (lanes < 1 || lanes > h->lanes) {
+        h->err = "lanes = " + std::to_string(lanes) + " but the handle was created with capacity " + std::to_string(h->lanes) +
+                 " (set_option(\"lanes\", B) before create)";
+        return GMRF_B200_ERR_ARG;
+    }
+    if (!a || !b) { h->err = "null buffer"; return GMRF_B200_ERR_ARG; }
+    return 0;
+}
+static void lanes_out(gmrf_b200_handle *h, int lanes, double *logdet, int *status) {
+    for (int b = 0; b < lanes; b++) {
+        logdet[b] = h->lane_logdet[b];
+        if (status) status[b] = h->lane_fail[b];
+    }
+}
+
+int gmrf_b200_lane_capacity(const gmrf_b200_handle *h) { return h ? h->lanes : 0; }
+
+int gmrf_b200_refactorize_lanes(gmrf_b200_handle *h, const double *nzval, int64_t nnz, int lanes, double *logdet, int *status) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if ((rc = check_lanes(h, lanes, nzval, logdet))) return rc;
+    if (nnz != h->S.nnzA) { h->err = "nzval length does not match the pattern"; return GMRF_B200_ERR_ARG; }
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+    for (int b = 0; b < lanes && nnz > 0; b++)
+        CUDA_TRY(h, cudaMemcpyAsync(reinterpret_cast<char *>(h->d_nz) + (long long)b * h->arena_bytes, nzval + (size_t)b * (size_t)nnz,
+                                    sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    rc = do_factor(h, lanes);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[0] = ms;
+    if (rc < 0) return rc;
+    lanes_out(h, lanes, logdet, status);
+    return 0;
+}
+
+int gmrf_b200_refactorize_combination_lanes(gmrf_b200_handle *h, const double *coeff, int nbasis, int lanes, double *logdet, int *status) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if ((rc = check_lanes(h, lanes, coeff, logdet))) return rc;
+    if (!h->d_basis || nbasis != h->nbasis) { h->err = "refactorize_combination_lanes: call set_value_basis first (same nbasis)"; return GMRF_B200_ERR_STATE; }
+    const i64 nnz = h->S.nnzA;
+    for (int b = 0; b < lanes && nnz > 0; b++) {
+        BasisCoeff c;
+        for (int j = 0; j < MAX_VALUE_BASIS; j++) c.c[j] = j < nbasis ? coeff[(size_t)b * nbasis + j] : 0.0;
+        double *nz = reinterpret_cast<double *>(reinterpret_cast<char *>(h->d_nz) + (long long)b * h->arena_bytes);
+        const int grid = (int)std::min<i64>((nnz + 255) / 256, 148 * 32);
+        combine_basis_kernel<<<grid, 256, 0, h->stream>>>(nz, h->d_basis, c, nbasis, nnz);
+    }
+    if ((rc = check_launch(h, "value assembly"))) return rc;
+    h->t_ms[0] = 0;
+    rc = do_factor(h, lanes);
+    if (rc < 0) return rc;
+    lanes_out(h, lanes, logdet, status);
+    return 0;
 }
 
 int gmrf_b200_logdet(gmrf_b200_handle *h, double *out) {
@@ -1901,10 +1999,10 @@ int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv,
     PanelTask T{dA, dI, lda, n, 0, 0};
     cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
     cudaMemset(dF, 0x7f, 4);
-    if (n <= 8) potrf_inv_kernel<8><<<1, 256>>>(dT, dF);
-    else if (n <= 16) potrf_inv_kernel<16><<<1, 256>>>(dT, dF);
-    else if (n <= 32) potrf_inv_kernel<32><<<1, 256>>>(dT, dF);
-    else potrf_inv64_kernel<<<1, 256>>>(dT, dF);
+    if (n <= 8) potrf_inv_kernel<8><<<1, 256>>>(dT, dF, 0LL);
+    else if (n <= 16) potrf_inv_kernel<16><<<1, 256>>>(dT, dF, 0LL);
+    else if (n <= 32) potrf_inv_kernel<32><<<1, 256>>>(dT, dF, 0LL);
+    else potrf_inv64_kernel<<<1, 256>>>(dT, dF, 0LL);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(A, dA, (size_t)lda * n * 8, cudaMemcpyDeviceToHost);
     if (inv) cudaMemcpy(inv, dI, (size_t)n * n * 8, cudaMemcpyDeviceToHost);
@@ -2002,7 +2100,7 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)S.panel_total, st);
     cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
     i64 cnt = (i64)S.q_src.size();
-    if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+    if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, 0LL);
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) {
         int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0 : L.kind == K_PANEL ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
@@ -2010,8 +2108,8 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
         run_launch(h, L, T, 0);
     }
     mark(3);
-    logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial);
-    logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+    logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial, 0LL);
+    logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars, 0LL);
     mark(-1);
     CUDA_TRY(h, cudaStreamSynchronize(st));
     for (size_t i = 0; i + 1 < evs.size(); i++) {
@@ -2042,7 +2140,7 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
         cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)h->S.panel_total, st);
         cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
         i64 cnt = (i64)h->S.q_src.size();
-        if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt);
+        if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, 0LL);
         h->selinv_valid = false;
     } else if (phase == 1) {
         if ((rc = build_selinv_tables(h))) return rc;
@@ -2076,8 +2174,8 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     for (auto e : evs) cudaEventDestroy(e);
     if (count) *count = (int64_t)nl;
     if (phase == 0) {
-        logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, h->S.n, h->d_partial);
-        logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars);
+        logdet_partial_kernel<<<LOGDET_BLOCKS, 256, 0, st>>>(h->d_Lx, h->d_diagpos, h->S.n, h->d_partial, 0LL);
+        logdet_final_kernel<<<1, 256, 0, st>>>(h->d_partial, h->d_scalars, 0LL);
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
     return check_launch(h, "profile_plan");

@@ -11,6 +11,7 @@
 // reductions use a fixed tree, so reruns are bit-identical.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace gmrf {
@@ -59,6 +60,15 @@ struct SuperMeta {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Batched factorization: a handle may hold several numeric "lanes" (independent value sets on the same pattern, e.g.
+// the points of a hyperparameter sweep). All numeric arrays of a lane live in one arena; lane b sits `bstride` bytes
+// after lane 0, the task tables point into lane 0, and blockIdx.y selects the lane. One launch then advances every
+// lane by the same step, which is what fills the GPU on small (2D) problems where a single factorization cannot.
+template <class T>
+__device__ __forceinline__ T *lane_ptr(T *p, long long bstride) {
+    return reinterpret_cast<T *>(reinterpret_cast<char *>(const_cast<typename std::remove_const<T>::type *>(p)) + (long long)blockIdx.y * bstride);
+}
+
 __device__ __forceinline__ int find_task(const int *__restrict__ prefix, int ntasks, int bid) {
     int lo = 0, hi = ntasks;  // prefix has ntasks+1 entries; find t with prefix[t] <= bid < prefix[t+1]
     while (hi - lo > 1) {
@@ -212,7 +222,7 @@ struct TileLoader {
 
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, int GEMM_STAGES = 3>
 __global__ void __launch_bounds__(WGM *WGN * 32, (WGM * WGN == 4) ? ((BM * BN <= 64 * 64) ? 4 : 3) : 1)
-gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride) {
     constexpr int NT = WGM * WGN * 32;
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4, LDK = GEMM_KT + 4;
     constexpr int A_TILE = gemm_tile_doubles<BM, GEMM_KT, TA>(), B_TILE = gemm_tile_doubles<BN, GEMM_KT, TB>();
@@ -223,7 +233,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     double *Bs = gemm_smem + GEMM_STAGES * A_TILE;
 
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const GemmTask T = tasks[t];
+    GemmTask T = tasks[t];
+    T.A = lane_ptr(T.A, bstride); T.B = lane_ptr(T.B, bstride); T.C = lane_ptr(T.C, bstride);
     const int local = blockIdx.x - tile_prefix[t];
     const int mt = (T.m + BM - 1) / BM, nt = (T.n + BN - 1) / BN;
     // L2-friendly rasterisation: consecutive CTAs sweep bands of GEMM_BAND row tiles column by column, so one wave of
@@ -328,9 +339,10 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
 
 // Debug kernel with the same contract (one thread per output element); selected with the "naive_kernels" option.
 template <bool TA, bool TB>
-__global__ void gemm_naive_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+__global__ void gemm_naive_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride) {
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const GemmTask T = tasks[t];
+    GemmTask T = tasks[t];
+    T.A = lane_ptr(T.A, bstride); T.B = lane_ptr(T.B, bstride); T.C = lane_ptr(T.C, bstride);
     const int local = blockIdx.x - tile_prefix[t];
     const int mt = (T.m + 15) / 16;
     const int r = (local % mt) * 16 + (threadIdx.x & 15), c = (local / mt) * 16 + (threadIdx.x >> 4);
@@ -362,9 +374,10 @@ constexpr int POTRF_NB = 64;
 // ------------------------------------------------------------------------------------------------
 template <int NBT>
 __global__ void __launch_bounds__(256)
-potrf_inv_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col) {
+potrf_inv_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col, long long bstride) {
     __shared__ double sA[NBT][NBT + 1];   // identity-padded beyond nb
-    const PanelTask T = tasks[blockIdx.x];
+    PanelTask T = tasks[blockIdx.x];
+    T.D = lane_ptr(T.D, bstride); T.inv = lane_ptr(T.inv, bstride); fail_col = lane_ptr(fail_col, bstride);
     const int nb = T.nb, tid = threadIdx.x;
     for (int e = tid; e < NBT * NBT; e += 256) {
         const int i = e % NBT, j = e / NBT;
@@ -420,7 +433,7 @@ potrf_inv_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col
 //   (c) everybody to the right applies the rank-4 update to its own tile from the published panel.
 // Then the factor sits in shared memory and the first 64 threads invert it column by column as above.
 __global__ void __launch_bounds__(256)
-potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col) {
+potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col, long long bstride) {
     constexpr int N = 64, LDS_ = 66;                  // even leading dimension: 16-byte aligned row pairs
     __shared__ __align__(16) double sA[N * LDS_];     // sA[i * LDS_ + j]
     __shared__ double sdiag[16];                      // published 4 x 4 diagonal tile (lower) ...
@@ -428,7 +441,8 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
     __shared__ double srinv_all[N];                   // 1 / L_ii of every row, reused by the inversion
     __shared__ __align__(16) double spanel2[2][N][4];  // published column panel (rows 0..63 of the current 4 columns),
                                                        // double-buffered: step P+1 publishes while step P is still read
-    const PanelTask T = tasks[blockIdx.x];
+    PanelTask T = tasks[blockIdx.x];
+    T.D = lane_ptr(T.D, bstride); T.inv = lane_ptr(T.inv, bstride); fail_col = lane_ptr(fail_col, bstride);
     const int nb = T.nb, tid = threadIdx.x;
     for (int e = tid; e < N * N; e += 256) {
         const int i = e % N, j = e / N;
@@ -560,9 +574,10 @@ struct SplitTask {
 };
 
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const SplitTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks) {
+splitk_reduce_kernel(const SplitTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride) {
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
-    const SplitTask T = tasks[t];
+    SplitTask T = tasks[t];
+    T.C = lane_ptr(T.C, bstride); T.part = lane_ptr(T.part, bstride);
     const int local = blockIdx.x - tile_prefix[t];
     const int mt = (T.m + 255) / 256;                 // a CTA owns 256 rows x 4 columns
     const int r = (local % mt) * 256 + threadIdx.x;
@@ -583,7 +598,9 @@ splitk_reduce_kernel(const SplitTask *__restrict__ tasks, const int *__restrict_
 // Q.nzval -> panels (after the panel array has been zeroed): Lx[dst[k]] = nzval[src[k]]
 // ------------------------------------------------------------------------------------------------
 __global__ void scatter_q_kernel(double *__restrict__ Lx, const double *__restrict__ nz,
-                                 const long long *__restrict__ src, const long long *__restrict__ dst, long long cnt) {
+                                 const long long *__restrict__ src, const long long *__restrict__ dst, long long cnt,
+                                 long long bstride) {
+    Lx = lane_ptr(Lx, bstride); nz = lane_ptr(nz, bstride);
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; k < cnt; k += stride) Lx[dst[k]] = nz[src[k]];
@@ -621,7 +638,8 @@ constexpr int ASM_CW = 32;
 __global__ void __launch_bounds__(256)
 assemble_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__ meta,
                 const int *__restrict__ child_idx, const int *__restrict__ relidx,
-                double *__restrict__ Lx, double *__restrict__ upd) {
+                double *__restrict__ Lx, double *__restrict__ upd, long long bstride) {
+    Lx = lane_ptr(Lx, bstride); upd = lane_ptr(upd, bstride);
     const AsmItem it = items[blockIdx.x];
     const SuperMeta P = meta[it.super];
     const int c_lo = it.col0, c_hi = min(it.col0 + ASM_CW, P.nrow);
@@ -695,7 +713,8 @@ __device__ __forceinline__ double block_sum_256(double v, double *sh) {
 
 __global__ void __launch_bounds__(256)
 logdet_partial_kernel(const double *__restrict__ Lx, const long long *__restrict__ diag_pos, long long n,
-                      double *__restrict__ partial) {
+                      double *__restrict__ partial, long long bstride) {
+    Lx = lane_ptr(Lx, bstride); partial = lane_ptr(partial, bstride);
     __shared__ double sh[256];
     double acc = 0.0;
     // fixed assignment of indices to (block, thread) and fixed sequential order per thread
@@ -704,7 +723,8 @@ logdet_partial_kernel(const double *__restrict__ Lx, const long long *__restrict
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(256) logdet_final_kernel(const double *__restrict__ partial, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) logdet_final_kernel(const double *__restrict__ partial, double *__restrict__ out, long long bstride) {
+    partial = lane_ptr(partial, bstride); out = lane_ptr(out, bstride);
     __shared__ double sh[256];
     double s = block_sum_256(threadIdx.x < LOGDET_BLOCKS ? partial[threadIdx.x] : 0.0, sh);
     if (threadIdx.x == 0) out[0] = 2.0 * s;

@@ -30,6 +30,7 @@ struct Options {
     int wide_rhs_min = 8;     // more right-hand sides than this take the GEMM (wide) solve path in blocks of 64 columns
     int bwd_row_chunk = 2048; // backward sweep: rows of L21 per partial task (taller panels are reduced in a second pass)
     int large_tile_mask = 1;  // GEMM operand-layout variants (bit 0 NN, 1 NT, 2 TT) allowed to use the 128 x 64 tile (measured: only NN gains)
+    int lanes = 1;            // value sets a handle can factorize side by side (batched hyperparameter evaluations)
     int selinv_fast_root = 1; // triangular (trtri + lauum) route for top-level root supernodes in the selected inversion
 };
 Options &global_options();

@@ -285,6 +285,36 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
 
+    def lane_capacity(self) -> int:
+        return int(self._L.gmrf_b200_lane_capacity(self._hd._h))
+
+    def refactorize_lanes(self, nzvals):
+        """Factorize several value sets of this pattern side by side; returns (logdets, statuses). Lane 0 stays the
+        backend's factor. Capacity = _lib.set_option("lanes", B) before the backend was created."""
+        nz = np.ascontiguousarray(nzvals, dtype=np.float64)
+        if nz.ndim != 2 or nz.shape[1] != self._rowval.size:
+            raise ValueError("nzvals must be (lanes, nnz) on this backend's pattern")
+        ld = np.empty(nz.shape[0])
+        st = np.zeros(nz.shape[0], dtype=np.int32)
+        self._hd.check(self._L.gmrf_b200_refactorize_lanes(self._hd._h, ptr(nz), nz.shape[1], nz.shape[0], ptr(ld), ptr(st)))
+        self.status = int(st[0])
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        return ld, st
+
+    def refactorize_combination_lanes(self, coeffs):
+        """Same with nzval = coeffs[b] @ basis formed in HBM for every lane (set_value_basis first)."""
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if c.ndim != 2:
+            raise ValueError("coeffs must be (lanes, nbasis)")
+        ld = np.empty(c.shape[0])
+        st = np.zeros(c.shape[0], dtype=np.int32)
+        self._hd.check(self._L.gmrf_b200_refactorize_combination_lanes(self._hd._h, ptr(c), c.shape[1], c.shape[0], ptr(ld), ptr(st)))
+        self.status = int(st[0])
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+        return ld, st
+
     def selinv_compute(self):
         self._hd.check(self._L.gmrf_b200_selinv_compute(self._hd._h))
 

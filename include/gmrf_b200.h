@@ -79,6 +79,17 @@ int gmrf_b200_refactorize_device(gmrf_b200_handle *h, const double *d_nzval, int
 int gmrf_b200_set_value_basis(gmrf_b200_handle *h, const double *basis, int nbasis);
 int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, int nbasis);
 
+/* Lanes: B independent value sets of the SAME pattern factorized side by side by the same launches -- the workload of a
+ * hyperparameter sweep over a `WorkspacePool` (src/workspace/workspace_pool.jl:42-119, `(model)(ws; theta...)`
+ * src/workspace/latent_model_integration.jl:151-185) whose outputs are log-determinants. Capacity is the process-wide
+ * option "lanes" at create time (memory: B copies of the numeric arrays). nzval holds `lanes` arrays of nnz values back
+ * to back (coeff: lanes x nbasis); logdet[lanes] and status[lanes] (0 ok / k>0 first non-positive pivot; may be NULL) are
+ * filled. Lane 0 remains the handle's ordinary factor for solves and selected inversion. */
+int gmrf_b200_lane_capacity(const gmrf_b200_handle *h);
+int gmrf_b200_refactorize_lanes(gmrf_b200_handle *h, const double *nzval, int64_t nnz, int lanes, double *logdet, int *status);
+int gmrf_b200_refactorize_combination_lanes(gmrf_b200_handle *h, const double *coeff, int nbasis, int lanes, double *logdet,
+                                            int *status);
+
 /* replaces  compute_logdet(b) = logdet(factor)   backend.jl:211-213 */
 int gmrf_b200_logdet(gmrf_b200_handle *h, double *out);
 
@@ -172,7 +183,7 @@ int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`

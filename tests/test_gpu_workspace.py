@@ -299,6 +299,47 @@ def test_device_side_value_assembly_for_theta_loops():
     be.close()
 
 
+def test_lanes_factorize_a_sweep_side_by_side():
+    """A hyperparameter sweep is many numeric factorizations of one pattern whose outputs are log-determinants: a
+    handle with `lanes` = B advances B value sets with the same launches. Every lane must reproduce, bit for bit, the
+    log-determinant of the one-at-a-time path; lane 0 stays the backend's factor; a non-SPD lane is reported alone."""
+    model = spde.MaternSPDE(*spde.mesh2d(32), 1)
+    thetas = [(0.2, 0.15), (1.0, 0.3), (3.0, 0.6), (0.7, 0.9), (5.0, 0.2)]
+    Q0 = model.precision(*thetas[0])
+    single = B200Backend(Q0, device=0)
+    want = []
+    for th in thetas:
+        single.refactorize(model.precision(*th))
+        want.append(single.compute_logdet())
+    _lib.set_option("lanes", 6)
+    try:
+        be = B200Backend(Q0, ordering=single.permutation(), device=0)
+    finally:
+        _lib.set_option("lanes", 1)
+    assert be.lane_capacity() == 6 and single.lane_capacity() == 1
+    nz = np.stack([model.values(*th) for th in thetas])
+    ld, st = be.refactorize_lanes(nz)
+    assert np.array_equal(ld, np.array(want)) and not st.any()              # deterministic: identical bits per lane
+    be.set_value_basis(model.basis())
+    ld2, st2 = be.refactorize_combination_lanes(np.stack([model.coefficients(*th) for th in thetas]))
+    assert np.allclose(ld2, want, rtol=1e-12) and not st2.any()
+    b = np.random.default_rng(0).standard_normal(model.n)
+    x = be.backend_solve(b)                                                 # lane 0 is the ordinary factor
+    Q = model.precision(*thetas[0])
+    assert np.linalg.norm(Q @ x - b) <= 1e-9 * (np.linalg.norm(b) + abs(Q).max() * np.linalg.norm(x))
+    assert abs(be.compute_logdet() - want[0]) <= 1e-12 * abs(want[0])
+    bad = nz.copy()
+    bad[2] = -bad[2]                                                        # lane 2 is not positive definite
+    ld3, st3 = be.refactorize_lanes(bad)
+    assert st3[2] > 0 and not st3[[0, 1, 3, 4]].any()
+    assert np.array_equal(ld3[[0, 1, 3, 4]], np.array(want)[[0, 1, 3, 4]])
+    with pytest.raises(ValueError):
+        be.refactorize_lanes(np.ones((7, nz.shape[1])))                     # more lanes than the handle holds
+    with pytest.raises(ValueError):
+        single.refactorize_lanes(nz[:2])
+    be.close(); single.close()
+
+
 def test_spatiotemporal_advection_diffusion_posterior():
     """BASELINE config 5 in miniature: block-tridiagonal space-time precision of the implicit-Euler advection-diffusion
     SPDE (time-major), conditioned on point observations of the first slice; posterior marginal variances by selected
