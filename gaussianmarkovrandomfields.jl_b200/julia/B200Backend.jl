@@ -179,6 +179,25 @@ function refactorize_combination!(b::B200Backend, coeff::Vector{Float64})
     return nothing
 end
 
+# Lanes: B value sets of the same pattern per launch (handle created after `set_option("lanes", B)`); returns the B
+# log-determinants and status words. Lane 0 stays the backend's factor.
+set_option(key::AbstractString, value::Real) = ccall((:gmrf_b200_set_option, libgmrf), Cint, (Cstring, Cdouble), key, value)
+function refactorize_lanes!(b::B200Backend, nzvals::Matrix{Float64})       # nnz x B
+    size(nzvals, 1) == b.nnz || throw(ArgumentError("each column must hold nnz(Q) values"))
+    B = size(nzvals, 2); ld = Vector{Float64}(undef, B); st = zeros(Cint, B)
+    _check(b, ccall((:gmrf_b200_refactorize_lanes, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Cint}),
+                    b.handle, nzvals, b.nnz, B, ld, st))
+    b.selinv_cache = nothing; b.selinv_diag_cache = nothing
+    return ld, st
+end
+function refactorize_combination_lanes!(b::B200Backend, coeff::Matrix{Float64})   # nbasis x B
+    B = size(coeff, 2); ld = Vector{Float64}(undef, B); st = zeros(Cint, B)
+    _check(b, ccall((:gmrf_b200_refactorize_combination_lanes, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Cint}),
+                    b.handle, coeff, size(coeff, 1), B, ld, st))
+    b.selinv_cache = nothing; b.selinv_diag_cache = nothing
+    return ld, st
+end
+
 # ---- one factorization, right-hand-side blocks on every GPU (SURVEY.md 8e, config 5) -------------------------------
 # `device_array` exposes the numeric factor in HBM (which = 0 panels of L, 1 inverted diagonal blocks, 2 Z panels) so the
 # pool can move it between its handles (NCCL.jl `Broadcast!` on `unsafe_wrap(CuArray, ...)`, or a peer copy);
