@@ -68,6 +68,15 @@ template <class T>
 __device__ __forceinline__ T *lane_ptr(T *p, long long bstride) {
     return reinterpret_cast<T *>(reinterpret_cast<char *>(const_cast<typename std::remove_const<T>::type *>(p)) + (long long)blockIdx.y * bstride);
 }
+// Same, but opaque to the optimiser: for kernels whose inner loops select between lane-offset base pointers. Without
+// it the offset was rematerialised (special-register read, 64-bit multiply, a branch) inside the extend-add loops,
+// which then ran 91 ms instead of 55 ms per 1 M-dof refactorization. (The GEMM kernel is faster with the plain form.)
+template <class T>
+__device__ __forceinline__ T *lane_ptr_pinned(T *p, long long bstride) {
+    char *q = reinterpret_cast<char *>(const_cast<typename std::remove_const<T>::type *>(p)) + (long long)blockIdx.y * bstride;
+    asm volatile("" : "+l"(q));
+    return reinterpret_cast<T *>(q);
+}
 
 __device__ __forceinline__ int find_task(const int *__restrict__ prefix, int ntasks, int bid) {
     int lo = 0, hi = ntasks;  // prefix has ntasks+1 entries; find t with prefix[t] <= bid < prefix[t+1]
@@ -638,8 +647,9 @@ constexpr int ASM_CW = 32;
 __global__ void __launch_bounds__(256)
 assemble_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__ meta,
                 const int *__restrict__ child_idx, const int *__restrict__ relidx,
-                double *__restrict__ Lx, double *__restrict__ upd, long long bstride) {
-    Lx = lane_ptr(Lx, bstride); upd = lane_ptr(upd, bstride);
+                double *__restrict__ Lx0, double *__restrict__ upd0, long long bstride) {
+    double *__restrict__ Lx = lane_ptr_pinned(Lx0, bstride);
+    double *__restrict__ upd = lane_ptr_pinned(upd0, bstride);
     const AsmItem it = items[blockIdx.x];
     const SuperMeta P = meta[it.super];
     const int c_lo = it.col0, c_hi = min(it.col0 + ASM_CW, P.nrow);
