@@ -1,0 +1,98 @@
+"""The synthetic inputs restate the reference's matrix recipes; these CPU tests pin the restatement
+to the recipes' defining identities so that the parity and bench workloads are what they claim to be."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+from gmrf_b200 import spde  # noqa: E402
+
+
+@pytest.mark.parametrize("kind,cells", [("2d", 6), ("3d", 4)])
+def test_p1_mass_stiffness_identities(kind, cells):
+    coords, el = spde.mesh2d(cells) if kind == "2d" else spde.mesh3d(cells)
+    c, g = spde.p1_mass_stiffness(coords, el)
+    d = coords.shape[1]
+    assert abs(c.sum() - 2.0 ** d) < 1e-12                      # lumped mass sums to the volume of [-1, 1]^d (fem_utils.jl:6-8)
+    assert np.all(c > 0)
+    assert abs(g - g.T).max() < 1e-13                           # stiffness is symmetric ...
+    assert np.abs(g @ np.ones(g.shape[0])).max() < 1e-12        # ... and annihilates constants (fem_utils.jl:86-110)
+    x = coords[:, 0]
+    assert abs(x @ (g @ x) - 2.0 ** d) < 1e-10                  # int |grad x|^2 = volume: P1 reproduces linear fields exactly
+    b = spde.p1_advection(coords, el, np.eye(d)[0])
+    assert np.abs(b @ np.ones(b.shape[0])).max() < 1e-12        # advection of a constant field vanishes (fem_utils.jl:132-169)
+    assert abs((b @ x).sum() - 2.0 ** d) < 1e-10                # sum_i int phi_i d/dx(x) = volume
+
+
+@pytest.mark.parametrize("kind,cells,smooth", [("2d", 8, 1), ("2d", 6, 0), ("3d", 4, 0), ("3d", 3, 1), ("2d", 5, 2)])
+def test_matern_precision_recipe_pattern_and_basis(kind, cells, smooth):
+    coords, el = spde.mesh2d(cells) if kind == "2d" else spde.mesh3d(cells)
+    m = spde.MaternSPDE(coords, el, smooth)
+    d = coords.shape[1]
+    nu = smooth + 1.0 if d % 2 == 0 else smooth + 0.5           # matern_spde.jl:419-422
+    assert m.nu == nu and m.alpha == int(round(nu + d / 2))
+    tau, rng_ = 0.7, 0.45
+    kappa = math.sqrt(8 * nu) / rng_                            # :415-417
+    ratio = math.gamma(nu) / (math.gamma(nu + d / 2) * (4 * math.pi) ** (d / 2) * kappa ** (2 * nu))   # :349-353
+    K = (kappa ** 2 * sp.diags(m.c) + m.g).toarray()
+    Ci = np.diag(1.0 / m.c)
+    Qd = K.copy()
+    for _ in range(m.alpha - 1):
+        Qd = Qd @ Ci @ K                                        # K (C^-1 K)^(alpha-1)  :197-230
+    Qd = tau * ratio * Qd
+    Q = m.precision(tau, rng_)
+    assert np.allclose(Q.toarray(), Qd, rtol=1e-11, atol=1e-13 * np.abs(Qd).max())
+    # structural pattern = (I u pattern(G))^alpha, independent of the hyperparameters (:248-265), explicit zeros kept
+    S = (sp.csc_matrix((np.ones(m.g.nnz), m.g.indices, m.g.indptr), shape=m.g.shape) + sp.identity(m.n)).toarray() > 0
+    P = np.linalg.matrix_power(S.astype(float), m.alpha) > 0
+    assert np.array_equal(Q.toarray() != 0, (Q.toarray() != 0) & P)
+    assert Q.nnz == int(P.sum())
+    Q2 = m.precision(3.0, 0.2)
+    assert np.array_equal(Q.indptr, Q2.indptr) and np.array_equal(Q.indices, Q2.indices)
+    assert np.linalg.eigvalsh(Qd).min() > 0
+    # O(nnz) re-evaluation through the value basis (device-side assembly uses exactly these arrays)
+    assert np.allclose(m.values_from_basis(tau, rng_), Q.data, rtol=1e-12, atol=1e-14 * np.abs(Q.data).max())
+    assert m.basis().shape == (m.alpha + 1, Q.nnz)
+
+
+def test_advection_diffusion_block_structure():
+    coords, el = spde.mesh2d(6)
+    ns, nt = coords.shape[0], 5
+    model = spde.AdvectionDiffusionSSM(coords, el, nt=nt, dt=0.02, kappa=2.5, gamma=(0.3, -0.1), diffusion=0.1, tau=0.2)
+    Q = model.Q
+    assert Q.shape == (ns * nt, ns * nt) and abs(Q - Q.T).max() == 0.0
+    D = Q.toarray()
+    blk = lambda i, j: D[i * ns:(i + 1) * ns, j * ns:(j + 1) * ns]
+    for i in range(nt):
+        for j in range(nt):
+            if abs(i - j) > 1:
+                assert not blk(i, j).any()                      # block tridiagonal, time-major (linear_ssm.jl:93-100)
+    assert np.allclose(blk(1, 1), blk(2, 2)) and np.allclose(blk(2, 1), blk(3, 2))     # interior blocks repeat
+    assert not np.allclose(blk(0, 0), blk(1, 1)) and not np.allclose(blk(nt - 1, nt - 1), blk(1, 1))
+    # last diagonal block is F^-1 alone: interior = F^-1 + A'F^-1A
+    AtFA = blk(1, 1) - blk(nt - 1, nt - 1)
+    assert np.linalg.eigvalsh(0.5 * (AtFA + AtFA.T)).min() > 0
+    assert np.linalg.eigvalsh(D).min() > 0                      # a proper joint precision
+    # conditioning on point observations of the first slice adds to its diagonal only (condition/linear.jl:53-61)
+    Qp = model.posterior([0, 3, 7], 25.0)
+    diff = (Qp - Q).toarray()
+    assert np.count_nonzero(diff) == 3 and np.allclose(diff[[0, 3, 7], [0, 3, 7]], 25.0)
+    # the joint precision reproduces the state-space recursion: x_{t+1} | x_t has precision F^-1 and mean G^-1 M x_t,
+    # i.e. the off-diagonal block is -F^-1 A with A = G^-1 M  ->  -blk(t+1, t) F_inv^-1 ... check via blk(nt-1, nt-1) = F^-1
+    F_inv = blk(nt - 1, nt - 1)
+    A = -np.linalg.solve(F_inv, blk(nt - 1, nt - 2))
+    assert np.allclose(A.T @ F_inv @ A, AtFA, rtol=1e-8, atol=1e-8 * np.abs(AtFA).max())
+
+
+def test_geometric_nd_is_a_permutation():
+    for dims, width in (((9, 9), 3), ((6, 7, 5), 2), ((33, 20), 1)):
+        p = spde.geometric_nd_perm(dims, leaf=8, width=width)
+        assert np.array_equal(np.sort(p), np.arange(int(np.prod(dims))))
