@@ -84,3 +84,34 @@ def test_cpu_supernodal_baseline_matches_oracle(cells):
     assert cpu.status == 0
     assert abs(cpu.logdet - F.logdet()) <= 1e-11 * abs(F.logdet())
     h.close()
+
+
+@pytest.mark.parametrize("kind,cells,smooth", [("2d", 24, 1), ("3d", 8, 0), ("st", 8, 0)])
+def test_oracle_against_superlu_on_spde_inputs(kind, cells, smooth):
+    """Independent cross-check at sizes where dense LinearAlgebra is no longer the natural arm: SciPy's SuperLU
+    (`splu`, a different code base and a different factorization, LU with its own ordering) on the SPDE inputs the GPU
+    parity tests use. Same tolerances as against the golden vectors."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import splu
+    if kind == "st":
+        Q = spde.AdvectionDiffusionSSM(*spde.mesh2d(cells), nt=5).posterior(np.arange(0, 40, 3), 400.0)
+    else:
+        mesh = spde.mesh2d(cells) if kind == "2d" else spde.mesh3d(cells)
+        Q = spde.MaternSPDE(*mesh, smooth).precision(0.7, 0.45)
+    n = Q.shape[0]
+    h = _Handle(n, Q.indptr, Q.indices, None, _lib.ORDER_ND, device=-1)
+    F = oracle.OracleFactor(Q, h.perm())
+    h.close()
+    lu = splu(sp.csc_matrix(Q), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    ld_lu = float(np.sum(np.log(np.abs(lu.U.diagonal()))) + np.sum(np.log(np.abs(lu.L.diagonal()))))
+    assert abs(F.logdet() - ld_lu) <= 1e-10 * abs(ld_lu)
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal(n)
+    x, x_lu = F.solve(b), lu.solve(b)
+    # both are backward stable; they agree to cond(Q) * eps
+    assert np.linalg.norm(Q @ x - b) <= 1e-10 * (np.linalg.norm(b) + abs(Q).max() * np.linalg.norm(x))
+    assert np.linalg.norm(x - x_lu) <= 1e-7 * np.linalg.norm(x_lu)
+    idx = rng.choice(n, 5, replace=False)
+    E = np.zeros((n, 5)); E[idx, np.arange(5)] = 1.0
+    var_lu = lu.solve(E)[idx, np.arange(5)]
+    assert np.max(np.abs(F.selinv_diag()[idx] - var_lu) / var_lu) <= 1e-8
