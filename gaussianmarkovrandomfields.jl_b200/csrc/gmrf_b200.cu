@@ -102,6 +102,10 @@ struct gmrf_b200_handle {
     int multi_wcap = 0;                // columns the shared work arrays hold
     TransTask *d_trans = nullptr;
     SplitTask *d_split = nullptr, *d_split_z = nullptr;
+    double *d_base = nullptr;          // optional resident copy of a prior's nzval (Newton loops: Q_prior - H on the device)
+    double *d_hdiag = nullptr;
+    long long *d_diagnz = nullptr;     // nzval position of every diagonal entry of the input pattern (-1: not stored)
+    std::vector<long long> diag_nzpos;
     double *d_basis = nullptr;         // optional value basis (nbasis x nnz) for device-side assembly of nzval
     int nbasis = 0;
     double *d_splitk = nullptr;        // scratch for split-K partial products
@@ -1464,6 +1468,12 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
             pm.assign(perm, perm + n);
             for (auto &v : pm) v -= index_base;
         }
+        h->diag_nzpos.assign((size_t)n, -1);
+        for (i64 j = 0; j < n; j++) {
+            const i64 *b = rv.data() + cp[j], *e = rv.data() + cp[j + 1];
+            const i64 *it = std::lower_bound(b, e, j);
+            if (it != e && *it == j) h->diag_nzpos[(size_t)j] = (long long)(it - rv.data());
+        }
         analyze(h->S, n, cp.data(), rv.data(), perm ? pm.data() : nullptr, ordering, h->opt);
     } catch (std::exception &e) {
         g_create_error = e.what();
@@ -1683,6 +1693,45 @@ int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, 
     }
     h->t_ms[0] = 0;
     return do_factor(h);
+}
+
+// ---- Newton loops: Q_k = Q_prior - Diagonal(h_k) formed in HBM -------------------------------------------------
+// replaces, for diagonal observation Hessians, the per-iterate host rebuild + upload of nzval in
+// _update_hessian! (src/workspace/gaussian_approximation.jl:96-129) followed by refactorize! (backend.jl:178-189):
+// the prior's values are uploaded once, an iterate moves n doubles.
+int gmrf_b200_set_base_values(gmrf_b200_handle *h, const double *nzval, int64_t nnz) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (nnz != h->S.nnzA || (!nzval && nnz > 0)) { h->err = "set_base_values: nzval must hold nnz(Q) values"; return GMRF_B200_ERR_ARG; }
+    if (!h->d_base) {
+        if ((rc = dev_alloc(h, &h->d_base, (size_t)nnz))) return rc;
+        if ((rc = dev_alloc(h, &h->d_hdiag, (size_t)h->S.n))) return rc;
+        if ((rc = dev_upload(h, &h->d_diagnz, h->diag_nzpos))) return rc;
+    }
+    if (nnz > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_base, nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gmrf_b200_refactorize_base_minus_diag(gmrf_b200_handle *h, const double *diag, int64_t n) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->d_base) { h->err = "refactorize_base_minus_diag: call set_base_values first"; return GMRF_B200_ERR_STATE; }
+    if (n != h->S.n || (!diag && n > 0)) { h->err = "refactorize_base_minus_diag: diag must hold n values"; return GMRF_B200_ERR_ARG; }
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    if (n > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_hdiag, diag, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_nz, h->d_base, sizeof(double) * (size_t)h->S.nnzA, cudaMemcpyDeviceToDevice, st));
+        minus_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d_nz, h->d_diagnz, h->d_hdiag, n);
+        if ((rc = check_launch(h, "diagonal update"))) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
+    rc = do_factor(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[0] = ms;
+    return rc;
 }
 
 // ---- lanes: several value sets factorized side by side ------------------------------------------------------

@@ -631,6 +631,16 @@ combine_basis_kernel(double *__restrict__ nz, const double *__restrict__ basis, 
     }
 }
 
+// nz[diagpos[i]] = base[diagpos[i]] - diag[i]: the Newton iterate Q_prior - H(x_k) for a diagonal observation Hessian
+// (_subtract_diagonal_hessian!, src/workspace/gaussian_approximation.jl:63-72) formed on values resident in HBM.
+__global__ void __launch_bounds__(256)
+minus_diag_kernel(double *__restrict__ nz, const long long *__restrict__ diagpos, const double *__restrict__ diag, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long p = diagpos[i];
+    if (p >= 0) nz[p] -= diag[i];
+}
+
 __global__ void fill_zero_kernel(double *__restrict__ p, long long cnt) {
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;

@@ -285,6 +285,21 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
 
+    def set_base_values(self, nzval):
+        """Keep a prior's nzval resident in HBM (Newton loops with a diagonal observation Hessian)."""
+        nz = np.ascontiguousarray(nzval, dtype=np.float64)
+        if nz.size != self._rowval.size:
+            raise ValueError(f"nzval holds {nz.size} values but the pattern has {self._rowval.size} nonzeros")
+        self._hd.check(self._L.gmrf_b200_set_base_values(self._hd._h, ptr(nz), nz.size))
+
+    def refactorize_minus_diag(self, hdiag):
+        """refactorize Q_prior - Diagonal(hdiag) from the resident prior values: an iterate moves n doubles."""
+        d = np.ascontiguousarray(hdiag, dtype=np.float64)
+        rc = self._L.gmrf_b200_refactorize_base_minus_diag(self._hd._h, ptr(d), d.size)
+        self.status = self._hd.check(rc, allow_positive=not self.check_pd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+
     def lane_capacity(self) -> int:
         return int(self._L.gmrf_b200_lane_capacity(self._hd._h))
 

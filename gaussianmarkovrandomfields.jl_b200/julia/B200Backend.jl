@@ -179,6 +179,15 @@ function refactorize_combination!(b::B200Backend, coeff::Vector{Float64})
     return nothing
 end
 
+# Newton loop, diagonal observation Hessian: the iterate Q_prior - H is formed in HBM from the resident prior values.
+set_base_values!(b::B200Backend, nzval::Vector{Float64}) =
+    _check(b, ccall((:gmrf_b200_set_base_values, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), b.handle, nzval, length(nzval)))
+function refactorize_minus_diag!(b::B200Backend, hdiag::Vector{Float64})
+    _check(b, ccall((:gmrf_b200_refactorize_base_minus_diag, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), b.handle, hdiag, length(hdiag)))
+    b.selinv_cache = nothing; b.selinv_diag_cache = nothing
+    return nothing
+end
+
 # Lanes: B value sets of the same pattern per launch (handle created after `set_option("lanes", B)`); returns the B
 # log-determinants and status words. Lane 0 stays the backend's factor.
 set_option(key::AbstractString, value::Real) = ccall((:gmrf_b200_set_option, libgmrf), Cint, (Cstring, Cdouble), key, value)

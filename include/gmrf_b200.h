@@ -79,6 +79,12 @@ int gmrf_b200_refactorize_device(gmrf_b200_handle *h, const double *d_nzval, int
 int gmrf_b200_set_value_basis(gmrf_b200_handle *h, const double *basis, int nbasis);
 int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, int nbasis);
 
+/* Newton loops with a diagonal observation Hessian: set_base_values keeps the prior's nzval in HBM; every iterate then
+ * refactorizes Q_prior - Diagonal(diag) from n doubles. replaces the host rebuild + upload in _update_hessian!
+ * (src/workspace/gaussian_approximation.jl:96-129, _subtract_diagonal_hessian! :63-72) + refactorize! (backend.jl:178-189). */
+int gmrf_b200_set_base_values(gmrf_b200_handle *h, const double *nzval, int64_t nnz);
+int gmrf_b200_refactorize_base_minus_diag(gmrf_b200_handle *h, const double *diag, int64_t n);
+
 /* Lanes: B independent value sets of the SAME pattern factorized side by side by the same launches -- the workload of a
  * hyperparameter sweep over a `WorkspacePool` (src/workspace/workspace_pool.jl:42-119, `(model)(ws; theta...)`
  * src/workspace/latent_model_integration.jl:151-185) whose outputs are log-determinants. Capacity is the process-wide

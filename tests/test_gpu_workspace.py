@@ -299,6 +299,31 @@ def test_device_side_value_assembly_for_theta_loops():
     be.close()
 
 
+def test_newton_iterate_formed_on_the_device():
+    """Q_k = Q_prior - Diagonal(h_k) with the prior's values resident in HBM must equal the host-assembled iterate
+    (_update_hessian!, workspace/gaussian_approximation.jl:96-129) bit for bit: the same subtraction on the same entries."""
+    model = spde.MaternSPDE(*spde.mesh2d(20), 1)
+    Q = model.precision(1.0, 0.5)
+    n = Q.shape[0]
+    be = B200Backend(Q, device=0)
+    be.set_base_values(Q.data)
+    from gmrf_b200.workspace_gmrf import _diagonal_indices
+    diag_idx = _diagonal_indices(Q)
+    rng = np.random.default_rng(4)
+    b = rng.standard_normal(n)
+    for _ in range(3):
+        h = -np.exp(rng.standard_normal(n))                       # Poisson: loghessian = -exp(eta) <= 0
+        Qk = Q.copy()
+        Qk.data[diag_idx] -= h                                    # host path: same pattern, explicit zeros kept
+        be.refactorize(Qk)
+        ld, x = be.compute_logdet(), be.backend_solve(b)
+        be.refactorize_minus_diag(h)
+        assert be.compute_logdet() == ld and np.array_equal(be.backend_solve(b), x)
+    with pytest.raises(ValueError):
+        be.refactorize_minus_diag(np.ones(n + 1))
+    be.close()
+
+
 def test_lanes_factorize_a_sweep_side_by_side():
     """A hyperparameter sweep is many numeric factorizations of one pattern whose outputs are log-determinants: a
     handle with `lanes` = B advances B value sets with the same launches. Every lane must reproduce, bit for bit, the
