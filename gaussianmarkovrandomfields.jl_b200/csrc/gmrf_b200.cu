@@ -1215,10 +1215,15 @@ void enqueue_multi_sweeps(gmrf_b200_handle *h, int wi, int mode) {
 
 // Wide path: the right-hand sides go through the GEMM sweeps in blocks of 256, then 128, then 64 columns (the last
 // block is zero-padded up to its width); wider blocks stream the factor fewer times per column.
-int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
+int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode);
+
+int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs_all, int mode) {
     const Symbolic &S = h->S;
     int rc;
     cudaStream_t st = h->stream;
+    // a short tail (<= 8 columns beyond whole 64-column blocks) is cheaper through the few-RHS kernels than as a padded block
+    const i64 tail = (nrhs_all > 64 && nrhs_all % 64 != 0 && nrhs_all % 64 <= h->opt.wide_rhs_min) ? nrhs_all % 64 : 0;
+    const i64 nrhs = nrhs_all - tail;
     // widths needed by this call; the widest first so the work arrays are sized once
     bool need[MULTI_NW] = {false, false, false};
     for (i64 left = nrhs; left > 0;) {
@@ -1266,6 +1271,10 @@ int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 
     CUDA_TRY(h, cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    if (tail > 0) {
+        if ((rc = do_solve_device(h, dB + nrhs * ld, dX + nrhs * ld, ld, tail, mode))) return rc;
+        ms += (float)h->t_ms[2];
+    }
     h->t_ms[2] = ms;
     return 0;
 }
@@ -1344,19 +1353,24 @@ int do_solve_host(gmrf_b200_handle *h, const double *B, double *X, i64 ld, i64 n
     if (!B || !X) { h->err = "null buffer"; return GMRF_B200_ERR_ARG; }
     if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
     if (nrhs == 0 || S.n == 0) return 0;
-    // stage in chunks so the device footprint stays bounded for very wide right-hand sides
-    const i64 chunk = std::max<i64>(h->rhs_block, std::min<i64>(nrhs, (i64)(256LL << 20) / std::max<i64>(S.n, 1)));
+    // stage in chunks so the device footprint stays bounded for very wide right-hand sides; chunks are whole multiples
+    // of the wide path's block widths so that no chunk ends in a mostly padded block
+    i64 chunk = std::max<i64>(h->rhs_block, std::min<i64>(nrhs, (i64)(256LL << 20) / std::max<i64>(S.n, 1)));
+    if (chunk < nrhs) chunk = chunk >= MULTI_WMAX ? chunk / MULTI_WMAX * MULTI_WMAX : chunk >= 64 ? chunk / 64 * 64 : chunk;
     if ((rc = ensure_io(h, S.n * std::min(chunk, nrhs)))) return rc;
+    double solve_ms = 0;
     for (i64 r0 = 0; r0 < nrhs; r0 += chunk) {
         i64 nb = std::min(chunk, nrhs - r0);
         CUDA_TRY(h, cudaMemcpy2DAsync(h->d_io, sizeof(double) * S.n, B + r0 * ld, sizeof(double) * ld, sizeof(double) * S.n,
                                       nb, cudaMemcpyHostToDevice, h->stream));
         rc = do_solve_device(h, h->d_io, h->d_io, S.n, nb, mode);
         if (rc) return rc;
+        solve_ms += h->t_ms[2];
         CUDA_TRY(h, cudaMemcpy2DAsync(X + r0 * ld, sizeof(double) * ld, h->d_io, sizeof(double) * S.n, sizeof(double) * S.n,
                                       nb, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
+    h->t_ms[2] = solve_ms;      // device time of the sweeps of all chunks (copies excluded)
     return 0;
 }
 
