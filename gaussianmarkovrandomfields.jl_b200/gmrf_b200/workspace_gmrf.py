@@ -306,10 +306,13 @@ def _frozen_finish(prior, obs_lik, solve_step, x, newton_dec_tol):
 def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int = 50, mean_change_tol: float = 1e-4,
                            newton_dec_tol: float = 1e-5, adaptive_stepsize: bool = True, max_linesearch_iter: int = 10,
                            step_recovery: str = "retry_full", predictive_convergence: bool = True, verbose: bool = False,
-                           stats: dict | None = None) -> WorkspaceGMRF:
+                           stats: dict | None = None, device_iterates: bool = False) -> WorkspaceGMRF:
     """Workspace-aware Gaussian approximation by Fisher scoring (workspace/gaussian_approximation.jl:191-313). Every
     iterate rebuilds the nzval of `Q_prior - H(x_k)` on the fixed pattern, refactorizes numerically and solves once.
-    `stats` (optional dict) receives the iteration / refactorization / solve counts."""
+    `stats` (optional dict) receives the iteration / refactorization / solve counts. `device_iterates=True` keeps the
+    prior's values resident on the device and forms every iterate there (`set_base_values` /
+    `refactorize_minus_diag`), so an iterate uploads n doubles instead of nnz(Q) -- what a method of `_update_hessian!`
+    specialised on the B200 backend does in the Julia integration; the iterates are bit-identical."""
     if step_recovery not in ("retry_full", "sqrt"):
         raise ValueError(f"step_recovery must be :retry_full or :sqrt, got :{step_recovery}")
     retry_full = step_recovery == "retry_full"
@@ -320,6 +323,9 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
     diag_idx = _diagonal_indices(ws.Q)
     alpha, dec_prev = 1.0, 0.0
     counts = {"iterations": 0, "refactorizations": 0, "solves": 0}
+    on_device = device_iterates and hasattr(ws.backend, "refactorize_minus_diag")
+    if on_device:
+        ws.backend.set_base_values(prior.precision.data)
 
     def solve(g):
         counts["solves"] += 1
@@ -341,7 +347,11 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
         H_k = obs_lik.loghessian(x_k)
         g_l = obs_lik.loggrad(x_k)
         _update_hessian(ws, H_k, Q_p.data, diag_idx)
-        ws.ensure_numeric()
+        if on_device:
+            ws.backend.refactorize_minus_diag(H_k)          # same values as ws.Q, formed in HBM
+            ws.numeric_valid, ws.selinv_valid, ws.logdet_valid = True, False, False
+        else:
+            ws.ensure_numeric()
         counts["refactorizations"] += 1
         neg_score = (Q_p @ x_k - h) - g_l
         step = solve(neg_score)

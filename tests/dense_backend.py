@@ -12,6 +12,8 @@ class DenseBackend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
         self.refactorizations = 0
+        Qc = sp.csc_matrix(Q)
+        self._indices, self._indptr = Qc.indices.copy(), Qc.indptr.copy()
         self.refactorize(Q)
 
     def refactorize(self, Q):
@@ -21,6 +23,14 @@ class DenseBackend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
         self.refactorizations += 1
+
+    # device-side Newton iterates (B200Backend.set_base_values / refactorize_minus_diag), dense stand-in
+    def set_base_values(self, nzval):
+        self._base = np.array(nzval, dtype=np.float64)
+
+    def refactorize_minus_diag(self, hdiag):
+        Q = sp.csc_matrix((self._base.copy(), self._indices, self._indptr), shape=(self.n, self.n))
+        self.refactorize(Q - sp.diags(np.asarray(hdiag, dtype=np.float64)))
 
     def backend_solve(self, rhs):
         rhs = np.asarray(rhs, dtype=np.float64)

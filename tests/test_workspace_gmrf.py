@@ -153,6 +153,20 @@ def test_poisson_ga_matches_dense_arm(kw):
 
 
 @pytest.mark.parametrize("kw", BACKENDS)
+def test_device_side_iterates_follow_the_host_path(kw):
+    n = 60
+    Q = tridiag(n, 2.01, -1.0)
+    lik = PoissonLikelihood(np.round(np.exp(2.0 * np.sin(np.linspace(0.0, 4.0 * np.pi, n)))))
+    host, dev = {}, {}
+    a = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik, stats=host)
+    b = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik, stats=dev, device_iterates=True)
+    assert host == dev
+    assert np.allclose(a.mean(), b.mean(), rtol=1e-13, atol=1e-15)
+    assert np.array_equal(a.precision.data, b.precision.data)
+    assert np.allclose(b.var(), np.diag(np.linalg.inv(b.precision.toarray())), rtol=1e-8)
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
 def test_repeated_ga_reuses_the_workspace(kw):
     n = 10
     Q = tridiag(n, 2.0, -0.8)
