@@ -51,6 +51,16 @@ class DenseBackend:
             self.selinv_diag_cache = np.diag(np.linalg.inv(self.Qd)).copy()
         return self.selinv_diag_cache
 
+    def selinv_extract_at(self, B):
+        B = sp.csc_matrix(B)
+        S = np.linalg.inv(self.Qd)
+        cols = np.repeat(np.arange(B.shape[1]), np.diff(B.indptr))
+        return sp.csc_matrix((S[B.indices, cols], B.indices.copy(), B.indptr.copy()), shape=B.shape)
+
+    def selinv_dot(self, B):
+        B = sp.csc_matrix(B)
+        return float(np.dot(self.selinv_extract_at(B).data, B.data))
+
     def get_selinv(self):
         if self.selinv_cache is None:
             self.selinv_cache = sp.csc_matrix(np.linalg.inv(self.Qd))

@@ -126,6 +126,32 @@ def test_batched_rand_is_the_sequential_stream(kw):
     assert np.allclose(X.mean(axis=1), d.mean(), atol=0.03)
 
 
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_linear_predictor_variances_read_sigma_locally(kw):
+    """diag(A Sigma A') through selinv_extract_at on the pattern of A'A (linear_predictor_marginals.jl:137-165), with and
+    without constraints, against the dense product."""
+    from gmrf_b200.linear_predictor import linear_predictor_variances
+    n = 40
+    rng = np.random.default_rng(8)
+    Q = (tridiag(n, 2.4, -1.0) + sp.diags(rng.uniform(0, 0.4, n))).tocsc()
+    rows = np.repeat(np.arange(15), 2)
+    cols = np.stack([rng.integers(0, n - 1, 15), np.zeros(15, dtype=int)], axis=1)
+    cols[:, 1] = cols[:, 0] + 1                                   # each observation touches two NEIGHBOURING sites
+    A = sp.csr_matrix((rng.standard_normal(30), (rows, cols.ravel())), shape=(15, n))
+    Sigma = np.linalg.inv(Q.toarray())
+    ga = WorkspaceGMRF(np.zeros(n), Q, **kw())
+    v = linear_predictor_variances(ga, A)
+    assert np.allclose(v, np.einsum("ij,jk,ik->i", A.toarray(), Sigma, A.toarray()), rtol=1e-8)
+    C = np.ones((1, n))
+    gc = WorkspaceGMRF(np.zeros(n), Q, ga.workspace, C, [0.0])
+    K = Sigma @ C.T @ np.linalg.inv(C @ Sigma @ C.T)
+    Sigma_c = Sigma - K @ C @ Sigma
+    vc = linear_predictor_variances(gc, A)
+    assert np.allclose(vc, np.einsum("ij,jk,ik->i", A.toarray(), Sigma_c, A.toarray()), rtol=1e-7, atol=1e-12)
+    with pytest.raises(ValueError):
+        linear_predictor_variances(ga, sp.csr_matrix((3, n + 1)))
+
+
 # ------------------------------------------------------------------------------------------------ Newton loop
 @pytest.mark.parametrize("kw", BACKENDS)
 def test_poisson_ga_matches_dense_arm(kw):
