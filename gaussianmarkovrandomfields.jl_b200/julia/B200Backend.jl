@@ -91,6 +91,14 @@ function backend_backward_solve(b::B200Backend, x::AbstractVector)   # factor.UP
     return X
 end
 
+# blocked half solve: column i of Z is the i-th randn! draw, so a matrix `_rand!` keeps the reference's random stream
+function backend_backward_solve(b::B200Backend, Z::Matrix{Float64})
+    X = similar(Z)
+    _check(b, ccall((:gmrf_b200_solve_Lt, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64),
+        b.handle, Z, X, b.n, size(Z, 2)))
+    return X
+end
+
 function compute_logdet(b::B200Backend)
     out = Ref{Float64}(0.0)
     _check(b, ccall((:gmrf_b200_logdet, libgmrf), Cint, (Ptr{Cvoid}, Ref{Float64}), b.handle, out))
