@@ -41,93 +41,181 @@ void order_metis_nd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Minimum-degree ordering on the quotient graph (elements + variables, external degree updated
-// exactly for the neighbours of each pivot, element absorption, no supervariables). Quality is that
-// of classic MMD without multiple elimination; used when the caller asks for an AMD-family ordering.
+// Approximate minimum degree on the quotient graph (Amestoy, Davis & Duff 1996, restated from the paper): elements
+// replace eliminated pivots, the external degree of a variable is bounded by
+//     d_i <= min( n_left - nv_i,  d_i(old) + |L_p \ i|,  |A_i \ i| + |L_p \ i| + sum_{e in E_i \ p} |L_e \ L_p| ),
+// the set differences |L_e \ L_p| come from one counting pass over the new element, elements contained in L_p are
+// absorbed (aggressive absorption), variables whose quotient-graph adjacency coincides are merged into supervariables
+// (found by hashing) and variables adjacent to nothing but the new element are eliminated with it (mass elimination).
 void order_amd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm) {
     perm.clear();
     perm.reserve(n);
-    // adjacency of variables: variable neighbours and element neighbours
-    std::vector<std::vector<i64>> vadj(n), eadj(n), elem(n);  // elem[e] = variables of element e
-    for (i64 v = 0; v < n; v++) vadj[v].assign(adj.begin() + xadj[v], adj.begin() + xadj[v + 1]);
-    std::vector<char> eliminated(n, 0), absorbed(n, 0);
-    std::vector<i64> degree(n), mark(n, -1);
-    // bucket lists by degree
-    std::vector<i64> head(n + 1, -1), next(n, -1), prev(n, -1);
-    auto bucket_insert = [&](i64 v) {
-        i64 d = degree[v];
-        prev[v] = -1;
-        next[v] = head[d];
+    if (n == 0) return;
+    typedef int32_t I;
+    std::vector<std::vector<I>> A(n), E(n), Le(n);      // variable lists, element lists, element patterns
+    for (i64 v = 0; v < n; v++) {
+        A[v].reserve(xadj[v + 1] - xadj[v]);
+        for (i64 p = xadj[v]; p < xadj[v + 1]; p++)
+            if (adj[p] != v) A[v].push_back((I)adj[p]);
+    }
+    enum : char { VAR = 0, ELEM = 1, DEAD = 2, MERGED = 3 };
+    std::vector<char> state(n, VAR);
+    std::vector<i64> nv(n, 1), degree(n), elem_deg(n, 0), w(n, 0), inLp(n, -1), hashv(n, 0);
+    std::vector<I> head(n + 1, -1), next(n, -1), prev(n, -1), hhead(n, -1), hnext(n, -1);
+    std::vector<std::vector<I>> members(n);              // variables merged into / eliminated with a principal variable
+    auto list_insert = [&](I v) {
+        i64 d = std::min<i64>(degree[v], n);
+        prev[v] = -1; next[v] = head[d];
         if (head[d] != -1) prev[head[d]] = v;
         head[d] = v;
     };
-    auto bucket_remove = [&](i64 v) {
-        i64 d = degree[v];
+    auto list_remove = [&](I v) {
+        i64 d = std::min<i64>(degree[v], n);
         if (prev[v] != -1) next[prev[v]] = next[v]; else head[d] = next[v];
         if (next[v] != -1) prev[next[v]] = prev[v];
     };
-    for (i64 v = 0; v < n; v++) {
-        degree[v] = (i64)vadj[v].size();
-        bucket_insert(v);
-    }
-    i64 mindeg = 0, stamp = 0, tstamp = 0;
-    std::vector<i64> reach, tag(n, -1);
-    for (i64 step = 0; step < n; step++) {
-        while (mindeg < n && head[mindeg] == -1) mindeg++;
-        i64 p = head[mindeg];
-        bucket_remove(p);
-        eliminated[p] = 1;
-        perm.push_back(p);
-        // reach(p) = variable neighbours + variables of adjacent elements
-        reach.clear();
-        stamp++;
-        mark[p] = stamp;
-        for (i64 u : vadj[p])
-            if (!eliminated[u] && mark[u] != stamp) { mark[u] = stamp; reach.push_back(u); }
-        for (i64 e : eadj[p]) {
-            if (absorbed[e]) continue;
-            for (i64 u : elem[e])
-                if (!eliminated[u] && mark[u] != stamp) { mark[u] = stamp; reach.push_back(u); }
-            absorbed[e] = 1;
-            std::vector<i64>().swap(elem[e]);
+    for (i64 v = 0; v < n; v++) { degree[v] = (i64)A[v].size(); list_insert((I)v); }
+    i64 mindeg = 0, wflg = 1, nleft = n, pstamp = 0;
+    std::vector<I> Lp, order_heads;
+    order_heads.reserve(n);
+    auto emit = [&](I root) {                            // root followed by everything merged into it (iteratively)
+        std::vector<I> stack{root};
+        while (!stack.empty()) {
+            I v = stack.back(); stack.pop_back();
+            perm.push_back(v);
+            for (I m : members[v]) stack.push_back(m);
         }
-        elem[p] = reach;  // new element p
-        std::vector<i64>().swap(vadj[p]);
-        std::vector<i64>().swap(eadj[p]);
-        // update the neighbours
-        for (i64 u : reach) {
-            // prune: drop eliminated / reach variables from vadj[u] (they are covered by element p),
-            // drop absorbed elements, add p
-            auto &va = vadj[u];
-            size_t w = 0;
-            for (size_t t = 0; t < va.size(); t++) {
-                i64 x = va[t];
-                if (!eliminated[x] && mark[x] != stamp) va[w++] = x;
+    };
+    while (nleft > 0) {
+        while (mindeg <= n && head[mindeg] == -1) mindeg++;
+        const I p = head[mindeg];
+        list_remove(p);
+        // ---- 1. new element p: L_p = (A_p  U  union of L_e, e in E_p) \ {p}, principal live variables only -------
+        pstamp++;
+        Lp.clear();
+        i64 degp = 0;
+        inLp[p] = pstamp;
+        for (I u : A[p])
+            if (state[u] == VAR && nv[u] > 0 && inLp[u] != pstamp) { inLp[u] = pstamp; Lp.push_back(u); degp += nv[u]; }
+        for (I e : E[p]) {
+            if (state[e] != ELEM) continue;
+            for (I u : Le[e])
+                if (state[u] == VAR && nv[u] > 0 && inLp[u] != pstamp) { inLp[u] = pstamp; Lp.push_back(u); degp += nv[u]; }
+            state[e] = DEAD;                              // absorbed into p
+            std::vector<I>().swap(Le[e]);
+        }
+        std::vector<I>().swap(A[p]);
+        std::vector<I>().swap(E[p]);
+        state[p] = ELEM;
+        const i64 nvp = nv[p];
+        nleft -= nvp;
+        // ---- 2. |L_e \ L_p| for every element adjacent to a variable of L_p ----------------------------------------
+        if (wflg + n + 2 < wflg) { std::fill(w.begin(), w.end(), 0); wflg = 1; }
+        for (I i : Lp)
+            for (I e : E[i]) {
+                if (state[e] != ELEM) continue;
+                if (w[e] >= wflg) w[e] -= nv[i];
+                else w[e] = elem_deg[e] + wflg - nv[i];
             }
-            va.resize(w);
-            auto &ea = eadj[u];
-            w = 0;
-            for (size_t t = 0; t < ea.size(); t++)
-                if (!absorbed[ea[t]]) ea[w++] = ea[t];
-            ea.resize(w);
-            ea.push_back(p);
+        // ---- 3. update the variables of L_p -----------------------------------------------------------------------
+        std::vector<I> touched_hash;
+        for (I i : Lp) {
+            list_remove(i);
+            i64 deg = 0;
+            u_int64_t hsh = 0;
+            auto &Ei = E[i];
+            size_t k = 0;
+            for (size_t t = 0; t < Ei.size(); t++) {
+                I e = Ei[t];
+                if (state[e] != ELEM) continue;
+                const i64 dext = w[e] - wflg;
+                if (dext > 0) { deg += dext; Ei[k++] = e; hsh += (u_int64_t)e; }
+                else { state[e] = DEAD; std::vector<I>().swap(Le[e]); }   // aggressive absorption: L_e inside L_p
+            }
+            Ei.resize(k);
+            auto &Ai = A[i];
+            k = 0;
+            for (size_t t = 0; t < Ai.size(); t++) {
+                I j = Ai[t];
+                if (state[j] != VAR || nv[j] <= 0 || inLp[j] == pstamp) continue;   // covered by element p or gone
+                deg += nv[j];
+                Ai[k++] = j;
+                hsh += (u_int64_t)j;
+            }
+            Ai.resize(k);
+            if (Ei.empty() && Ai.empty()) {
+                // mass elimination: i is adjacent to nothing but p -> eliminated together with p
+                degp -= nv[i];
+                nleft -= nv[i];
+                members[p].push_back(i);
+                nv[i] = 0;
+                state[i] = MERGED;
+                continue;
+            }
+            Ei.push_back(p);
+            hsh += (u_int64_t)p;
+            degree[i] = std::min<i64>(degree[i], deg);   // first two terms of the bound; |L_p \ i| added below
+            hashv[i] = (i64)(hsh % (u_int64_t)n);
+            I hb = (I)hashv[i];
+            if (hhead[hb] == -1) touched_hash.push_back(hb);
+            hnext[i] = hhead[hb];
+            hhead[hb] = i;
         }
-        for (i64 u : reach) {
-            // exact external degree = |vadj[u] U (union of elem[e], e in eadj[u])| - {u}
-            tstamp++;
-            tag[u] = tstamp;
-            i64 d = 0;
-            for (i64 x : vadj[u])
-                if (tag[x] != tstamp) { tag[x] = tstamp; d++; }
-            for (i64 e : eadj[u])
-                for (i64 x : elem[e])
-                    if (!eliminated[x] && tag[x] != tstamp) { tag[x] = tstamp; d++; }
-            bucket_remove(u);
-            degree[u] = d;
-            bucket_insert(u);
-            if (d < mindeg) mindeg = d;
+        // ---- 4. supervariables: identical quotient-graph adjacency --------------------------------------------------
+        wflg += n + 1;                                    // step-2 counters live in [wflg, wflg + n]: step past them
+        for (I hb : touched_hash) {
+            for (I i = hhead[hb]; i != -1; i = hnext[i]) {
+                if (nv[i] <= 0) continue;
+                // tag the adjacency of i
+                wflg++;
+                for (I e : E[i]) w[e] = wflg;
+                for (I j : A[i]) w[j] = wflg;
+                I prevj = i;
+                for (I j = hnext[i]; j != -1; j = hnext[j]) {
+                    if (nv[j] <= 0 || E[j].size() != E[i].size() || A[j].size() != A[i].size()) { prevj = j; continue; }
+                    bool same = true;
+                    for (I e : E[j]) if (w[e] != wflg) { same = false; break; }
+                    if (same) for (I x : A[j]) if (w[x] != wflg) { same = false; break; }
+                    if (same) {
+                        nv[i] += nv[j];
+                        nv[j] = 0;
+                        state[j] = MERGED;
+                        members[i].push_back(j);
+                        std::vector<I>().swap(A[j]);
+                        std::vector<I>().swap(E[j]);
+                        hnext[prevj] = hnext[j];           // unlink j from the bucket
+                    } else {
+                        prevj = j;
+                    }
+                }
+            }
+            hhead[hb] = -1;
         }
+        wflg += n + 1;                                    // invalidate every w[] stamp of this round
+        // ---- 5. final element list, degrees back into the lists ---------------------------------------------------
+        size_t k = 0;
+        for (I i : Lp) {
+            if (nv[i] <= 0) continue;
+            Lp[k++] = i;
+        }
+        Lp.resize(k);
+        i64 lp_weight = 0;
+        for (I i : Lp) lp_weight += nv[i];
+        for (I i : Lp) {
+            i64 d = degree[i] + lp_weight - nv[i];
+            d = std::min<i64>(d, nleft - nv[i]);
+            degree[i] = std::max<i64>(d, 0);
+            list_insert(i);
+            if (degree[i] < mindeg) mindeg = degree[i];
+        }
+        elem_deg[p] = lp_weight;
+        Le[p] = Lp;
+        if (Lp.empty()) state[p] = DEAD;
+        order_heads.push_back(p);
+        (void)degp;
     }
+    for (I p : order_heads) emit(p);
+    if ((i64)perm.size() != n) throw std::runtime_error("order_amd: internal error (incomplete permutation)");
 }
 
 // ------------------------------------------------------------------------------------------------
