@@ -108,6 +108,8 @@ struct gmrf_b200_handle {
     std::vector<long long> diag_nzpos;
     double *d_basis = nullptr;         // optional value basis (nbasis x nnz) for device-side assembly of nzval
     int nbasis = 0;
+    double *d_dot = nullptr;           // selinv_dot: DOT_BLOCKS partial sums per value set, then the results
+    double *d_qzw = nullptr;           // basis traces: weight per scatter-map entry (1 diagonal, 2 off-diagonal)
     double *d_splitk = nullptr;        // scratch for split-K partial products
     i64 splitk_cap = 0;                // doubles
     // selinv task tables are built lazily (they need d_Zx / d_zw)
@@ -1914,18 +1916,20 @@ int gmrf_b200_selinv_values(gmrf_b200_handle *h, double *nzval) {
     return gather_to_host(h, h->d_zpos, h->z_colptr[h->S.n], nzval);
 }
 
-int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
-                             int index_base, double *out) {
-    int rc = gmrf_b200_selinv_compute(h);
-    if (rc) return rc;
+// Position of Sigma_ij in the Z panels for every entry of a caller pattern (n x n CSC); -1 outside the factor's pattern.
+static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
+                             int index_base, std::vector<long long> &pos) {
     const Symbolic &S = h->S;
-    if (ncol != S.n || !colptr || !out) { h->err = "selinv_extract: pattern must be n x n"; return GMRF_B200_ERR_ARG; }
-    i64 cnt = colptr[ncol] - index_base;
-    std::vector<long long> pos((size_t)std::max<i64>(cnt, 0));
+    if (ncol != S.n || !colptr || (!rowval && colptr[ncol] - index_base > 0)) {
+        h->err = std::string(who) + ": pattern must be n x n";
+        return GMRF_B200_ERR_ARG;
+    }
+    const i64 cnt = colptr[ncol] - index_base;
+    pos.assign((size_t)std::max<i64>(cnt, 0), -1LL);
     for (i64 j = 0; j < ncol; j++)
         for (i64 p = colptr[j] - index_base; p < colptr[j + 1] - index_base; p++) {
             i64 i = rowval[p] - index_base;
-            if (i < 0 || i >= S.n) { h->err = "selinv_extract: row index out of range"; return GMRF_B200_ERR_ARG; }
+            if (i < 0 || i >= S.n) { h->err = std::string(who) + ": row index out of range"; return GMRF_B200_ERR_ARG; }
             i64 a = S.iperm[i], b = S.iperm[j];
             i64 col = std::min(a, b), row = std::max(a, b);
             i64 s = S.col2super[col];
@@ -1933,6 +1937,17 @@ int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *c
             const i32 *it = std::lower_bound(rb, re, (i32)row);
             pos[p] = (it != re && *it == (i32)row) ? (long long)(S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb)) : -1LL;
         }
+    return 0;
+}
+
+int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
+                             int index_base, double *out) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (!out) { h->err = "selinv_extract: null out"; return GMRF_B200_ERR_ARG; }
+    std::vector<long long> pos;
+    if ((rc = pattern_positions(h, "selinv_extract", ncol, colptr, rowval, index_base, pos))) return rc;
+    const i64 cnt = (i64)pos.size();
     if (cnt <= 0) return 0;
     long long *d_pos = nullptr;
     CUDA_TRY(h, cudaMalloc((void **)&d_pos, sizeof(long long) * (size_t)cnt));
@@ -1941,6 +1956,72 @@ int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *c
     else { h->err = "H2D copy failed"; rc = GMRF_B200_ERR_CUDA; }
     cudaFree(d_pos);
     return rc;
+}
+
+// ---- traces against the selected inverse, contracted on the device ---------------------------------------------
+static int ensure_dot(gmrf_b200_handle *h) {
+    if (h->d_dot) return 0;
+    return dev_alloc(h, &h->d_dot, (size_t)MAX_VALUE_BASIS * (DOT_BLOCKS + 1));
+}
+
+// partial sums + fixed-shape final reduction for `nsets` value sets, results to the host
+static int run_dot(gmrf_b200_handle *h, const long long *d_pos, const long long *d_idx, const double *d_w, const double *d_val,
+                   long long vstride, i64 cnt, int nsets, double *out) {
+    int rc;
+    double *d_res = h->d_dot + (size_t)MAX_VALUE_BASIS * DOT_BLOCKS;
+    gather_dot_partial_kernel<<<dim3(DOT_BLOCKS, nsets), 256, 0, h->stream>>>(h->d_Zx, d_pos, d_idx, d_w, d_val, vstride, cnt, h->d_dot);
+    gather_dot_final_kernel<<<dim3(1, nsets), 256, 0, h->stream>>>(h->d_dot, d_res);
+    if ((rc = check_launch(h, "selinv_dot"))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_res, sizeof(double) * (size_t)nsets, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval, int index_base,
+                         const double *values, double *out) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (!out) { h->err = "selinv_dot: null out"; return GMRF_B200_ERR_ARG; }
+    std::vector<long long> pos;
+    if ((rc = pattern_positions(h, "selinv_dot", ncol, colptr, rowval, index_base, pos))) return rc;
+    const i64 cnt = (i64)pos.size();
+    *out = 0.0;
+    if (cnt <= 0) return 0;
+    if (!values) { h->err = "selinv_dot: null values"; return GMRF_B200_ERR_ARG; }
+    if ((rc = ensure_dot(h))) return rc;
+    if ((rc = ensure_io(h, cnt))) return rc;
+    long long *d_pos = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&d_pos, sizeof(long long) * (size_t)cnt));
+    cudaError_t e = cudaMemcpyAsync(d_pos, pos.data(), sizeof(long long) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_io, values, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = run_dot(h, d_pos, nullptr, nullptr, h->d_io, 0, cnt, 1, out);
+    else { h->err = "H2D copy failed"; rc = GMRF_B200_ERR_CUDA; }
+    if (rc) cudaStreamSynchronize(h->stream);   // pos / values are pageable host memory: nothing may still be in flight
+    cudaFree(d_pos);
+    return rc;
+}
+
+int gmrf_b200_selinv_dot_basis(gmrf_b200_handle *h, double *out, int nbasis) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (!h->d_basis || nbasis != h->nbasis || !out) { h->err = "selinv_dot_basis: call set_value_basis first (same nbasis)"; return GMRF_B200_ERR_STATE; }
+    const Symbolic &S = h->S;
+    const i64 cnt = (i64)S.q_src.size();
+    for (int j = 0; j < nbasis; j++) out[j] = 0.0;
+    if (cnt == 0) return 0;
+    if ((rc = ensure_dot(h))) return rc;
+    if (!h->d_qzw) {
+        // the factor and Z share one panel layout, so the Q -> panel scatter map doubles as the gather map; it lists
+        // the stored upper triangle once per unordered pair: off-diagonal entries count twice in the trace
+        std::vector<double> w((size_t)cnt, 2.0);
+        std::vector<long long> dn;
+        for (long long p : h->diag_nzpos) if (p >= 0) dn.push_back(p);
+        std::sort(dn.begin(), dn.end());
+        for (i64 k = 0; k < cnt; k++)
+            if (std::binary_search(dn.begin(), dn.end(), (long long)S.q_src[(size_t)k])) w[(size_t)k] = 1.0;
+        if ((rc = dev_upload(h, &h->d_qzw, w))) return rc;
+    }
+    return run_dot(h, h->d_qdst, h->d_qsrc, h->d_qzw, h->d_basis, (long long)S.nnzA, cnt, nbasis, out);
 }
 
 // ---- introspection -------------------------------------------------------------------------------

@@ -863,4 +863,39 @@ __global__ void gather_values_kernel(double *__restrict__ out, const double *__r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tr(Q^-1 B) = sum_k w_k * Z[pos_k] * B[idx_k]  with the contraction on the device (selinv_dot, backend.jl:265-267):
+// the gathered values never leave HBM, 8 bytes per value set travel back. Fixed assignment of entries to
+// (block, thread), fixed order per thread, fixed-shape tree per block and over the blocks => bit-reproducible.
+// blockIdx.y selects the value set (stride `vstride` doubles); idx == nullptr: B[k]; w == nullptr: weight 1.
+// HBM-bound: 8 (pos) + 8 (Z, scattered sector reads) + 8 (B) [+ 8 idx + 8 w] bytes per entry.
+// ------------------------------------------------------------------------------------------------
+constexpr int DOT_BLOCKS = 256;
+
+__global__ void __launch_bounds__(256)
+gather_dot_partial_kernel(const double *__restrict__ Zx, const long long *__restrict__ pos,
+                          const long long *__restrict__ idx, const double *__restrict__ w,
+                          const double *__restrict__ val, long long vstride, long long cnt,
+                          double *__restrict__ partial) {
+    __shared__ double sh[256];
+    val += (long long)blockIdx.y * vstride;
+    double acc = 0.0;
+    for (long long k = blockIdx.x * 256LL + threadIdx.x; k < cnt; k += 256LL * DOT_BLOCKS) {
+        const long long p = pos[k];
+        if (p < 0) continue;                       // outside the factor's pattern: Sigma is not available there, counts 0
+        const double b = val[idx ? idx[k] : k];
+        const double z = Zx[p];
+        acc += (w ? w[k] : 1.0) * (z * b);
+    }
+    const double s = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * DOT_BLOCKS + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) gather_dot_final_kernel(const double *__restrict__ partial, double *__restrict__ out) {
+    __shared__ double sh[256];
+    const double s = block_sum_256(threadIdx.x < DOT_BLOCKS ? partial[(long long)blockIdx.y * DOT_BLOCKS + threadIdx.x] : 0.0, sh);
+    if (threadIdx.x == 0) out[blockIdx.y] = s;
+}
+
 }  // namespace gmrf

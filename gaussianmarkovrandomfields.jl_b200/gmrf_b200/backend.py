@@ -156,6 +156,7 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
         self._selinv_pattern = None
+        self._nbasis = 0
         self._pinned = []
         self.status = 0
         if factorize and device >= 0:
@@ -240,10 +241,28 @@ class B200Backend:
         return sp.csc_matrix((out, B.indices.copy(), B.indptr.copy()), shape=B.shape)
 
     def selinv_dot(self, B) -> float:
-        """tr(Q^-1 B) for B on a subset of the factor's pattern (backend.jl:265-267): the values are read on
-        the device at B's pattern, the O(nnz(B)) dot is host work."""
+        """tr(Q^-1 B) (backend.jl:265-267): Sigma is gathered at B's pattern and contracted on the device
+        (gmrf_b200_selinv_dot, fixed-shape reduction); positions outside the factor's pattern count 0."""
         B = _csc(B)
-        return float(np.dot(self.selinv_extract_at(B).data, B.data))
+        if B.shape != (self.n, self.n):
+            raise ValueError("pattern matrix has the wrong shape")
+        cp = B.indptr.astype(np.int64)
+        rv = B.indices.astype(np.int64)
+        vals = np.ascontiguousarray(B.data, dtype=np.float64)
+        out = ctypes.c_double()
+        self._hd.check(self._L.gmrf_b200_selinv_dot(self._hd._h, self.n, ptr(cp), ptr(rv), 0, ptr(vals), ctypes.byref(out)))
+        return float(out.value)
+
+    def selinv_dot_basis(self) -> np.ndarray:
+        """tr(Q^-1 B_j) for every array of the resident value basis: d logdet Q / d c_j for Q = sum_j c_j B_j
+        (the contraction the logdetcov / logpdf pullbacks of src/workspace/autodiff.jl:8-91 need for
+        fixed-pattern hyperparameter models), computed without any pattern or value upload."""
+        nb = self._nbasis
+        if not nb:
+            raise RuntimeError("selinv_dot_basis: call set_value_basis first")
+        out = np.empty(nb, dtype=np.float64)
+        self._hd.check(self._L.gmrf_b200_selinv_dot_basis(self._hd._h, ptr(out), nb))
+        return out
 
     # -- extras --------------------------------------------------------------------------------------
     def info(self) -> dict:
@@ -276,6 +295,7 @@ class B200Backend:
         if basis.shape[1] != self._rowval.size:
             raise ValueError(f"basis rows hold {basis.shape[1]} values but the pattern has {self._rowval.size} nonzeros")
         self._hd.check(self._L.gmrf_b200_set_value_basis(self._hd._h, ptr(basis), basis.shape[0]))
+        self._nbasis = basis.shape[0]
 
     def refactorize_combination(self, coeff):
         """refactorize with nzval = coeff @ basis formed in HBM (no upload of nzval)."""

@@ -146,9 +146,17 @@ function selinv_extract_at(b::B200Backend, B::SparseMatrixCSC)
     return SparseMatrixCSC(size(B)..., copy(SparseArrays.getcolptr(B)), copy(rowvals(B)), out)
 end
 
-# tr(Q^-1 B): values are read on the device at B's pattern, the O(nnz(B)) dot stays generic so that
-# ForwardDiff.Dual-valued B keeps working (ext/forwarddiff/logdetcov.jl:23)
+# tr(Q^-1 B). Float64 B: gathered and contracted on the device, one double comes back. Any other element type
+# (ForwardDiff.Dual-valued B, ext/forwarddiff/logdetcov.jl:23): values are read on the device at B's pattern and the
+# O(nnz(B)) dot stays generic.
 selinv_dot(b::B200Backend, B::SparseMatrixCSC) = dot(nonzeros(selinv_extract_at(b, B)), nonzeros(B))
+function selinv_dot(b::B200Backend, B::SparseMatrixCSC{Float64})
+    out = Ref{Float64}(0.0)
+    cp = Vector{Int64}(SparseArrays.getcolptr(B)); rv = Vector{Int64}(rowvals(B))
+    _check(b, ccall((:gmrf_b200_selinv_dot, libgmrf), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Float64}, Ref{Float64}), b.handle, b.n, cp, rv, 1, nonzeros(B), out))
+    return out[]
+end
 
 # GMRFWorkspace(Q, B200Backend; ...) -- copy of cliquetrees_backend.jl:132-150
 function GMRFWorkspace(Q::SparseMatrixCSC{T}, ::Type{B200Backend}; kw...) where {T}
@@ -185,6 +193,14 @@ function refactorize_combination!(b::B200Backend, coeff::Vector{Float64})
     _check(b, ccall((:gmrf_b200_refactorize_combination, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), b.handle, coeff, length(coeff)))
     b.selinv_cache = nothing; b.selinv_diag_cache = nothing
     return nothing
+end
+
+# tr(Q^-1 B_j) for every array of the resident value basis = d logdet Q / d c_j: what the logdetcov / logpdf pullbacks
+# (src/workspace/autodiff.jl:8-91) contract Q-bar with when Q(theta) = sum_j c_j(theta) B_j; nbasis doubles come back.
+function selinv_dot_basis(b::B200Backend, nbasis::Integer)
+    out = Vector{Float64}(undef, nbasis)
+    _check(b, ccall((:gmrf_b200_selinv_dot_basis, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), b.handle, out, nbasis))
+    return out
 end
 
 # Newton loop, diagonal observation Hessian: the iterate Q_prior - H is formed in HBM from the resident prior values.

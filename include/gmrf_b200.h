@@ -128,6 +128,18 @@ int gmrf_b200_selinv_values(gmrf_b200_handle *h, double *nzval);
  * nnz entries), 0.0 where the position is outside the factor's pattern. */
 int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr,
                              const int64_t *rowval, int index_base, double *out);
+/* replaces  selinv_dot(b, B) = dot(Z, B) = tr(Q^-1 B)   backend.jl:265-267 (generic fallback :30), for
+ * Float64-valued B (n x n CSC, both triangles as stored): Sigma is gathered at B's pattern and contracted
+ * on the device (fixed-shape reduction, bit-reproducible); positions outside the factor's pattern count 0.
+ * Dual-valued B (ext/forwarddiff/logdetcov.jl:23) keeps using selinv_extract + a host dot. */
+int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
+                         int index_base, const double *values, double *out);
+/* out[j] = tr(Q^-1 B_j) for the resident value basis (set_value_basis): with Q(theta) = sum_j c_j(theta) B_j
+ * this is d logdet Q / d c_j, the contraction the logdetcov / logpdf pullbacks (src/workspace/autodiff.jl:8-91,
+ * compute_precision_gradient src/autodiff/precision_gradient.jl:137-146) apply to Q-bar = c * selinv(ws)
+ * when Q is a fixed-pattern combination. The B_j are read as symmetric matrices through their stored upper
+ * triangle, like the factorization reads Q. Nothing but nbasis doubles crosses PCIe. */
+int gmrf_b200_selinv_dot_basis(gmrf_b200_handle *h, double *out, int nbasis);
 
 /* ---- introspection (symbolic facts; all host-side, valid on analysis-only handles) -----------*/
 enum {

@@ -32,6 +32,20 @@ class DenseBackend:
         Q = sp.csc_matrix((self._base.copy(), self._indices, self._indptr), shape=(self.n, self.n))
         self.refactorize(Q - sp.diags(np.asarray(hdiag, dtype=np.float64)))
 
+    # device-side value assembly and basis traces (B200Backend.set_value_basis / refactorize_combination /
+    # selinv_dot_basis), dense stand-in
+    def set_value_basis(self, basis):
+        self._basis = np.array(basis, dtype=np.float64)
+
+    def refactorize_combination(self, coeff):
+        vals = np.asarray(coeff, dtype=np.float64) @ self._basis
+        self.refactorize(sp.csc_matrix((vals, self._indices, self._indptr), shape=(self.n, self.n)))
+
+    def selinv_dot_basis(self):
+        S = np.linalg.inv(self.Qd)
+        cols = np.repeat(np.arange(self.n), np.diff(self._indptr))
+        return self._basis @ S[self._indices, cols]
+
     def backend_solve(self, rhs):
         rhs = np.asarray(rhs, dtype=np.float64)
         y = np.linalg.solve(self.L, rhs)
