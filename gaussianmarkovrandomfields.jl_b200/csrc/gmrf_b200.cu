@@ -121,6 +121,10 @@ struct gmrf_b200_handle {
     long long *d_zpos = nullptr, *d_zdiagpos = nullptr;
     double *d_zout = nullptr;
     bool z_pattern_built = false;
+    // factor export P'L as CSC (lazy; CholeskySqrt-style consumers)
+    std::vector<i64> l_colptr, l_rowval;
+    long long *d_lpos = nullptr;
+    bool l_pattern_built = false;
 
     Plan factor_plan, selinv_plan, fwd_plan, bwd_plan;
     std::map<int, cudaGraphExec_t> factor_graphs;   // key = number of lanes advanced by the graph
@@ -1429,6 +1433,36 @@ void build_z_pattern(gmrf_b200_handle *h) {
     h->z_pattern_built = true;
 }
 
+void build_l_pattern(gmrf_b200_handle *h) {
+    // P'L as CSC: column k = k-th pivot (elimination order), row indices in the original numbering, sorted;
+    // pos = position of the entry in the factor panels (stored pattern: relaxed supernodes carry explicit zeros)
+    if (h->l_pattern_built) return;
+    const Symbolic &S = h->S;
+    const i64 n = S.n;
+    h->l_colptr.assign((size_t)n + 1, 0);
+    for (i64 s = 0; s < S.nsuper; s++)
+        for (i64 lc = 0; lc < S.ns(s); lc++) h->l_colptr[(size_t)(S.sfirst[s] + lc) + 1] = S.nrow(s) - lc;
+    for (i64 j = 0; j < n; j++) h->l_colptr[(size_t)j + 1] += h->l_colptr[(size_t)j];
+    const i64 nnz = h->l_colptr[(size_t)n];
+    std::vector<i64> rowv((size_t)nnz);
+    std::vector<long long> pos((size_t)nnz);
+    std::vector<std::pair<i64, long long>> tmp;
+    for (i64 s = 0; s < S.nsuper; s++) {
+        const i64 ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+        const i32 *rows = S.rowidx.data() + S.rowptr[s];
+        for (i64 lc = 0; lc < ns; lc++) {
+            tmp.resize((size_t)(nrow - lc));
+            for (i64 i = lc; i < nrow; i++) tmp[(size_t)(i - lc)] = {S.perm[rows[i]], (long long)(S.panel_off[s] + lc * ld + i)};
+            std::sort(tmp.begin(), tmp.end());
+            i64 w = h->l_colptr[(size_t)(S.sfirst[s] + lc)];
+            for (auto &t : tmp) { rowv[(size_t)w] = t.first; pos[(size_t)w++] = t.second; }
+        }
+    }
+    h->l_rowval.swap(rowv);
+    if (h->device >= 0) dev_upload(h, &h->d_lpos, pos);
+    h->l_pattern_built = true;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1871,12 +1905,12 @@ int gmrf_b200_selinv_compute(gmrf_b200_handle *h) {
     return 0;
 }
 
-static int gather_to_host(gmrf_b200_handle *h, const long long *d_pos, i64 cnt, double *out) {
+static int gather_to_host(gmrf_b200_handle *h, const long long *d_pos, i64 cnt, double *out, const double *d_src = nullptr) {
     int rc;
     if ((rc = ensure_io(h, std::max<i64>(cnt, 1)))) return rc;
     if (cnt == 0) return 0;
     int grid = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
-    gather_values_kernel<<<grid, 256, 0, h->stream>>>(h->d_io, h->d_Zx, d_pos, cnt);
+    gather_values_kernel<<<grid, 256, 0, h->stream>>>(h->d_io, d_src ? d_src : h->d_Zx, d_pos, cnt);
     if ((rc = check_launch(h, "gather"))) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(out, h->d_io, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1914,6 +1948,34 @@ int gmrf_b200_selinv_values(gmrf_b200_handle *h, double *nzval) {
     build_z_pattern(h);
     if (!h->d_zpos) { h->err = "selinv pattern upload failed"; return GMRF_B200_ERR_ALLOC; }
     return gather_to_host(h, h->d_zpos, h->z_colptr[h->S.n], nzval);
+}
+
+// ---- factor export: the square root P'L of Q as a sparse matrix -----------------------------------------------------
+int gmrf_b200_factor_nnz(gmrf_b200_handle *h, int64_t *nnz) {
+    if (!h || !nnz) return GMRF_B200_ERR_ARG;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    build_l_pattern(h);
+    *nnz = h->l_colptr[(size_t)h->S.n];
+    return 0;
+}
+
+int gmrf_b200_factor_pattern(gmrf_b200_handle *h, int64_t *colptr, int64_t *rowval, int index_base) {
+    if (!h || !colptr || !rowval) return GMRF_B200_ERR_ARG;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    build_l_pattern(h);
+    for (i64 j = 0; j <= h->S.n; j++) colptr[j] = h->l_colptr[(size_t)j] + index_base;
+    for (size_t k = 0; k < h->l_rowval.size(); k++) rowval[k] = h->l_rowval[k] + index_base;
+    return 0;
+}
+
+int gmrf_b200_factor_values(gmrf_b200_handle *h, double *nzval) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored) { h->err = "factor_values before the first refactorize"; return GMRF_B200_ERR_STATE; }
+    if (!nzval) { h->err = "null out"; return GMRF_B200_ERR_ARG; }
+    build_l_pattern(h);
+    if (!h->d_lpos) { h->err = "factor pattern upload failed"; return GMRF_B200_ERR_ALLOC; }
+    return gather_to_host(h, h->d_lpos, h->l_colptr[(size_t)h->S.n], nzval, h->d_Lx);
 }
 
 // Position of Sigma_ij in the Z panels for every entry of a caller pattern (n x n CSC); -1 outside the factor's pattern.

@@ -116,6 +116,15 @@ class _Handle:
         self.check(self._L.gmrf_b200_get_perm(self._h, ptr(p), 0))
         return p
 
+    def factor_pattern(self):
+        """(colptr, rowval) of the square root P'L as CSC, 0-based (symbolic: valid on analysis-only handles)."""
+        nnz = ctypes.c_int64()
+        self.check(self._L.gmrf_b200_factor_nnz(self._h, ctypes.byref(nnz)))
+        cp = np.empty(self.n + 1, dtype=np.int64)
+        rv = np.empty(nnz.value, dtype=np.int64)
+        self.check(self._L.gmrf_b200_factor_pattern(self._h, ptr(cp), ptr(rv), 0))
+        return cp, rv
+
     def close(self):
         if self._h is not None and self._h.value:
             self._L.gmrf_b200_destroy(self._h)
@@ -156,6 +165,7 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
         self._selinv_pattern = None
+        self._factor_pattern = None
         self._nbasis = 0
         self._pinned = []
         self.status = 0
@@ -263,6 +273,17 @@ class B200Backend:
         out = np.empty(nb, dtype=np.float64)
         self._hd.check(self._L.gmrf_b200_selinv_dot_basis(self._hd._h, ptr(out), nb))
         return out
+
+    def cholesky_sqrt(self):
+        """The square root R = P'L of Q as a CSC matrix (R R' = Q): `sparse_cho_sqrt(cho)` =
+        `sparse(cho.L)[invperm(cho.p), :]`, src/linear_maps/cholesky_sqrt.jl:6-21 (the matrix behind `CholeskySqrt`).
+        The pattern is fetched once per backend, the values are gathered out of the factor panels on the device."""
+        if self._factor_pattern is None:
+            self._factor_pattern = self._hd.factor_pattern()
+        cp, rv = self._factor_pattern
+        vals = np.empty(rv.size, dtype=np.float64)
+        self._hd.check(self._L.gmrf_b200_factor_values(self._hd._h, ptr(vals)))
+        return sp.csc_matrix((vals, rv, cp), shape=(self.n, self.n))
 
     # -- extras --------------------------------------------------------------------------------------
     def info(self) -> dict:

@@ -11,7 +11,8 @@ using GaussianMarkovRandomFields
 using LinearAlgebra, SparseArrays
 import GaussianMarkovRandomFields: WorkspaceBackend, GMRFWorkspace, refactorize!, backend_solve, compute_logdet,
     compute_selinv!, get_selinv, get_selinv_diag, backend_backward_solve, selinv_dot, selinv_extract_at,
-    ordering_permutation, AbstractLatentWorkspacePool, checkout, checkin
+    ordering_permutation, AbstractLatentWorkspacePool, checkout, checkin, CholeskySqrt
+using LinearMaps: LinearMap
 
 const libgmrf = get(ENV, "GMRF_B200_LIB", "libgmrf_b200.so")
 
@@ -28,6 +29,7 @@ mutable struct B200Backend <: WorkspaceBackend
     selinv_cache::Union{Nothing, SparseMatrixCSC{Float64, Int}}
     selinv_diag_cache::Union{Nothing, Vector{Float64}}
     selinv_pattern::Union{Nothing, Tuple{Vector{Int}, Vector{Int}}}
+    factor_pattern::Union{Nothing, Tuple{Vector{Int}, Vector{Int}}}
 end
 
 _errmsg(h) = unsafe_string(ccall((:gmrf_b200_last_error, libgmrf), Cstring, (Ptr{Cvoid},), h))
@@ -55,7 +57,7 @@ function B200Backend(Q::SparseMatrixCSC{Float64, Int}; ordering = nothing, devic
         (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Cint),
         href, n, SparseArrays.getcolptr(Q), rowvals(Q), 1, isempty(permvec) ? C_NULL : pointer(permvec), 1, device)
     rc == 0 || throw(ArgumentError(unsafe_string(ccall((:gmrf_b200_last_error, libgmrf), Cstring, (Ptr{Cvoid},), C_NULL))))
-    b = B200Backend(href[], n, nnz(Q), device, check, nothing, nothing, nothing)
+    b = B200Backend(href[], n, nnz(Q), device, check, nothing, nothing, nothing, nothing)
     finalizer(x -> ccall((:gmrf_b200_destroy, libgmrf), Cvoid, (Ptr{Cvoid},), x.handle), b)
     refactorize!(b, Symmetric(Q))
     return b
@@ -157,6 +159,23 @@ function selinv_dot(b::B200Backend, B::SparseMatrixCSC{Float64})
         (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Float64}, Ref{Float64}), b.handle, b.n, cp, rv, 1, nonzeros(B), out))
     return out[]
 end
+
+# The square root P'L of Q as a sparse matrix (sparse_cho_sqrt, src/linear_maps/cholesky_sqrt.jl:6-21): what
+# `CholeskySqrt(cho)` wraps for a CHOLMOD factor. Pattern once per backend, values gathered on the device.
+function cholesky_sqrt(b::B200Backend)
+    if b.factor_pattern === nothing
+        nz = Ref{Int64}(0)
+        _check(b, ccall((:gmrf_b200_factor_nnz, libgmrf), Cint, (Ptr{Cvoid}, Ref{Int64}), b.handle, nz))
+        cp = Vector{Int64}(undef, b.n + 1); rv = Vector{Int64}(undef, nz[])
+        _check(b, ccall((:gmrf_b200_factor_pattern, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint), b.handle, cp, rv, 1))
+        b.factor_pattern = (cp, rv)
+    end
+    cp, rv = b.factor_pattern
+    vals = Vector{Float64}(undef, length(rv))
+    _check(b, ccall((:gmrf_b200_factor_values, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.handle, vals))
+    return SparseMatrixCSC(b.n, b.n, copy(cp), copy(rv), vals)
+end
+CholeskySqrt(b::B200Backend) = LinearMap(cholesky_sqrt(b))
 
 # GMRFWorkspace(Q, B200Backend; ...) -- copy of cliquetrees_backend.jl:132-150
 function GMRFWorkspace(Q::SparseMatrixCSC{T}, ::Type{B200Backend}; kw...) where {T}

@@ -141,6 +141,17 @@ int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colpt
  * triangle, like the factorization reads Q. Nothing but nbasis doubles crosses PCIe. */
 int gmrf_b200_selinv_dot_basis(gmrf_b200_handle *h, double *out, int nbasis);
 
+/* ---- factor export ------------------------------------------------------------------------------
+ * replaces  sparse_cho_sqrt(cho) = sparse(cho.L)[invperm(cho.p), :]   src/linear_maps/cholesky_sqrt.jl:6-21
+ * (CholeskySqrt, used by cholesky_factorized_map.jl:40): the square root R = P'L of Q as CSC, n x n,
+ * column k = k-th pivot of the elimination order, row indices in the ORIGINAL numbering, sorted, so
+ * that R R' = Q. The pattern is the stored (relaxed-supernode) one: a superset of the exact pattern
+ * of L whose extra entries are explicit zeros; it depends on the symbolic analysis only (fetch once,
+ * valid on analysis-only handles), values after each refactorize. */
+int gmrf_b200_factor_nnz(gmrf_b200_handle *h, int64_t *nnz);
+int gmrf_b200_factor_pattern(gmrf_b200_handle *h, int64_t *colptr, int64_t *rowval, int index_base);
+int gmrf_b200_factor_values(gmrf_b200_handle *h, double *nzval);
+
 /* ---- introspection (symbolic facts; all host-side, valid on analysis-only handles) -----------*/
 enum {
     GMRF_B200_INFO_N = 0,

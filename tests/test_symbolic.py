@@ -142,3 +142,39 @@ def test_amd_on_graphs_with_indistinguishable_and_isolated_nodes():
     F = oracle.OracleFactor(Q, T.perm)
     assert T.info["nnz_l"] == F.nnzL == 21 + 3 + 17   # no fill: clique 6*7/2, 3 singletons, star hub last (9 + 8)
     h.close()
+
+
+@pytest.mark.parametrize("name", ["grid_border", "rand400", "matern2d_16", "matern3d_6", "diag", "one"])
+def test_factor_export_pattern_is_the_square_root_layout(name):
+    """`gmrf_b200_factor_pattern` (P'L as CSC, sparse_cho_sqrt of src/linear_maps/cholesky_sqrt.jl:6-21) on an
+    analysis-only handle: sorted original row indices per pivot column, a superset of the exact pattern of L, and --
+    filled from host-replayed panels through the panel layout -- a matrix R with R R' = Q."""
+    Q = sp.csc_matrix(CASES[name]())
+    n = Q.shape[0]
+    h = _handle(Q)
+    T = replay.Tables(h)
+    cp, rv = h.factor_pattern()
+    assert cp[0] == 0 and cp[-1] == rv.size and T.info["nnz_l"] <= rv.size <= T.info["nnz_l_stored"]
+    Lx = replay.factor(T, Q.data)
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[T.perm] = np.arange(n)
+    vals = np.empty(rv.size)
+    for s in range(T.nsuper):
+        rows = T.rows(s)
+        for lc in range(T.ns(s)):
+            k = int(T.super_ptr[s]) + lc
+            r = rv[cp[k]:cp[k + 1]]
+            assert np.all(np.diff(r) > 0)                                  # sorted, no duplicates
+            t = np.searchsorted(rows, iperm[r])
+            assert np.array_equal(rows[t], iperm[r]) and np.all(t >= lc)   # inside the supernode's trapezoid
+            assert r.size == T.nrow(s) - lc and T.perm[k] in r
+            vals[cp[k]:cp[k + 1]] = Lx[int(T.panel_off[s]) + lc * int(T.panel_ld[s]) + t]
+    R = sp.csc_matrix((vals, rv, cp), shape=(n, n))
+    assert abs(R @ R.T - Q).max() <= 1e-12 * abs(Q).max()
+    F = oracle.OracleFactor(Q, T.perm)                                     # exact pattern of L is contained in it
+    Lo = sp.csc_matrix((F.Lx, F.Li, F.Lp), shape=(n, n))
+    Ro = sp.csc_matrix(Lo[iperm, :])                                       # sparse(L)[invperm(p), :]
+    pat = sp.csc_matrix((np.ones(rv.size), rv, cp), shape=(n, n))
+    assert (Ro != 0).multiply(pat).nnz == (Ro != 0).nnz
+    assert abs(R - Ro).max() <= 1e-10 * abs(Ro).max()
+    h.close()

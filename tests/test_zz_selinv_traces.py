@@ -250,3 +250,36 @@ def test_basis_trace_gather_map_on_replayed_panels():
     scale = np.abs(basis) @ np.abs(Sigma[Q.indices, cols])
     assert np.all(np.abs(got - want) <= 1e-9 * scale)
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------- factor export, GPU only
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["matern2d", "matern3d", "tridiag"])
+def test_cholesky_sqrt_export(case):
+    """R = P'L gathered out of the factor panels on the device: R R' = Q, equal to the oracle's
+    `sparse(L)[invperm(p), :]` under the same ordering (sparse_cho_sqrt, src/linear_maps/cholesky_sqrt.jl:6-21), and
+    refreshed by a refactorization with the pattern object reused."""
+    import oracle
+    from gmrf_b200.backend import B200Backend
+    Q = {"matern2d": lambda: spde.MaternSPDE(*spde.mesh2d(30), 1).precision(1.0, 0.5),
+         "matern3d": lambda: spde.MaternSPDE(*spde.mesh3d(8), 0).precision(1.0, 0.5),
+         "tridiag": lambda: spde.tridiag_fixture(10)}[case]()
+    Q = sp.csc_matrix(Q)
+    n = Q.shape[0]
+    be = B200Backend(Q, device=0)
+    R = be.cholesky_sqrt()
+    assert abs(R @ R.T - Q).max() <= 1e-12 * abs(Q).max()
+    p = be.permutation()
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[p] = np.arange(n)
+    F = oracle.OracleFactor(Q, p)
+    Ro = sp.csc_matrix(sp.csc_matrix((F.Lx, F.Li, F.Lp), shape=(n, n))[iperm, :])
+    assert abs(R - Ro).max() <= 1e-9 * abs(Ro).max()
+    assert abs(2.0 * np.sum(np.log(R[p, np.arange(n)])) - be.compute_logdet()) <= 1e-10 * abs(be.compute_logdet())
+    z = np.random.default_rng(0).standard_normal(n)
+    assert np.linalg.norm(R.T @ be.backend_backward_solve(z) - z) <= 1e-9 * np.linalg.norm(z)   # L' P x = z
+    be.refactorize(2.0 * Q)
+    R2 = be.cholesky_sqrt()
+    assert R2.indices is R.indices or np.array_equal(R2.indices, R.indices)
+    assert abs(R2 - np.sqrt(2.0) * R).max() <= 1e-12 * abs(R).max()
+    be.close()
