@@ -1986,19 +1986,25 @@ static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol,
         h->err = std::string(who) + ": pattern must be n x n";
         return GMRF_B200_ERR_ARG;
     }
+    for (i64 j = 0; j < ncol; j++)
+        if (colptr[j + 1] < colptr[j] || colptr[j] < index_base) { h->err = std::string(who) + ": colptr must be non-decreasing from index_base"; return GMRF_B200_ERR_ARG; }
     const i64 cnt = colptr[ncol] - index_base;
     pos.assign((size_t)std::max<i64>(cnt, 0), -1LL);
-    for (i64 j = 0; j < ncol; j++)
-        for (i64 p = colptr[j] - index_base; p < colptr[j + 1] - index_base; p++) {
-            i64 i = rowval[p] - index_base;
-            if (i < 0 || i >= S.n) { h->err = std::string(who) + ": row index out of range"; return GMRF_B200_ERR_ARG; }
-            i64 a = S.iperm[i], b = S.iperm[j];
-            i64 col = std::min(a, b), row = std::max(a, b);
-            i64 s = S.col2super[col];
-            const i32 *rb = S.rowidx.data() + S.rowptr[s], *re = S.rowidx.data() + S.rowptr[s + 1];
-            const i32 *it = std::lower_bound(rb, re, (i32)row);
-            pos[p] = (it != re && *it == (i32)row) ? (long long)(S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb)) : -1LL;
-        }
+    if (cnt > 0 && gmrf::pattern_positions(S, colptr, rowval, index_base, pos.data()) >= 0) {
+        h->err = std::string(who) + ": row index out of range";
+        return GMRF_B200_ERR_ARG;
+    }
+    return 0;
+}
+
+// introspection twin of the lookup above (host-side, valid on analysis-only handles): the panel offsets themselves
+int gmrf_b200_pattern_positions(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval, int index_base,
+                                int64_t *pos) {
+    if (!h || !pos) return GMRF_B200_ERR_ARG;
+    std::vector<long long> p;
+    int rc = pattern_positions(h, "pattern_positions", ncol, colptr, rowval, index_base, p);
+    if (rc) return rc;
+    std::copy(p.begin(), p.end(), pos);
     return 0;
 }
 

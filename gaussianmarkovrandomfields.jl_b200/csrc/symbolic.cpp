@@ -732,4 +732,33 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
     S.analysis_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
 
+// ------------------------------------------------------------------------------------------------
+// caller pattern -> panel offsets (selinv_extract / selinv_dot): one binary search in the owning supernode's row list
+// per entry, ~40 ns each single-threaded (cache-missing), so the columns are spread over the host cores
+// ------------------------------------------------------------------------------------------------
+i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i64 index_base, long long *pos) {
+    const i64 n = S.n;
+    i64 bad = -1;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (i64 j = 0; j < n; j++) {
+        const i64 b = S.iperm[j];
+        for (i64 p = colptr[j] - index_base; p < colptr[j + 1] - index_base; p++) {
+            const i64 i = rowval[p] - index_base;
+            if (i < 0 || i >= n) {
+                pos[p] = -1;
+#pragma omp critical(gmrf_pattern_positions_bad)
+                if (bad < 0 || p < bad) bad = p;
+                continue;
+            }
+            const i64 a = S.iperm[i];
+            const i64 col = std::min(a, b), row = std::max(a, b);
+            const i64 s = S.col2super[col];
+            const i32 *rb = S.rowidx.data() + S.rowptr[s], *re = S.rowidx.data() + S.rowptr[s + 1];
+            const i32 *it = std::lower_bound(rb, re, (i32)row);
+            pos[p] = (it != re && *it == (i32)row) ? (long long)(S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb)) : -1LL;
+        }
+    }
+    return bad;
+}
+
 }  // namespace gmrf

@@ -89,6 +89,11 @@ struct Symbolic {
 void analyze(Symbolic &S, i64 n, const i64 *colptr, const i64 *rowval, const i64 *user_perm, int ordering,
              const Options &opt);
 
+// Offset in the panel array of entry (i, j) = (j, i) of a symmetric matrix living on the factor's stored pattern, for
+// every entry of an n x n CSC pattern (pos[p] = -1 outside the pattern). Columns are independent: OpenMP over columns.
+// Returns -1, or the index p of the first entry whose row index is out of range.
+i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i64 index_base, long long *pos);
+
 // orderings (0-based adjacency without self loops: xadj[n+1], adj[])
 void order_metis_nd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);
 void order_amd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);

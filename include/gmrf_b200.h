@@ -182,6 +182,10 @@ int gmrf_b200_get_supernodes(const gmrf_b200_handle *h, int64_t *super_ptr, int6
                              int64_t *upd_off, int64_t *upd_ld);
 int gmrf_b200_get_rows(const gmrf_b200_handle *h, int64_t *row_idx, int64_t *rel_idx);  /* row_ptr[nsuper] entries each */
 int gmrf_b200_get_scatter(const gmrf_b200_handle *h, int64_t *n_entries, int64_t *src, int64_t *dst);
+/* panel offset of every entry of a caller pattern (n x n CSC; -1 outside the factor's stored pattern): the host-side
+ * lookup behind selinv_extract / selinv_dot, exposed for tests of the index arithmetic without a device */
+int gmrf_b200_pattern_positions(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
+                                int index_base, int64_t *pos);
 /* Wall-clock of the last call's phases in milliseconds (CUDA events on the handle's stream):
  * [0] h2d of nzval, [1] numeric factorization + logdet, [2] solve, [3] selinv, [4] host analysis. */
 int gmrf_b200_last_timings(const gmrf_b200_handle *h, double *ms, int n);

@@ -178,3 +178,63 @@ def test_factor_export_pattern_is_the_square_root_layout(name):
     assert (Ro != 0).multiply(pat).nnz == (Ro != 0).nnz
     assert abs(R - Ro).max() <= 1e-10 * abs(Ro).max()
     h.close()
+
+
+def _positions(h, B, base=0):
+    B = sp.csc_matrix(B)
+    B.sort_indices()
+    cp = (B.indptr.astype(np.int64) + base)
+    rv = (B.indices.astype(np.int64) + base)
+    pos = np.empty(rv.size, dtype=np.int64)
+    rc = h._L.gmrf_b200_pattern_positions(h._h, B.shape[1], _lib.ptr(cp), _lib.ptr(rv), base, _lib.ptr(pos))
+    return rc, pos
+
+
+def test_pattern_positions_lookup():
+    """The host lookup behind selinv_extract / selinv_dot (OpenMP over columns): panel offsets of a caller pattern,
+    against offsets derived independently from the exported tables; -1 outside the stored pattern; both index bases;
+    symmetric in (i, j); usage errors."""
+    Q = sp.csc_matrix(CASES["matern3d_6"]())
+    n = Q.shape[0]
+    h = _handle(Q)
+    T = replay.Tables(h)
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[T.perm] = np.arange(n)
+    col2super = np.repeat(np.arange(T.nsuper), np.diff(T.super_ptr))
+    rng = np.random.default_rng(0)
+    B = sp.csc_matrix(Q + sp.random(n, n, density=0.02, random_state=rng, format="csc"))
+    B.sort_indices()
+    rc, pos = _positions(h, B)
+    assert rc == 0
+    C = B.tocoo()
+    order = np.lexsort((C.row, C.col))                                  # CSC order
+    rows, cols = C.row[order], C.col[order]
+    want = np.empty(rows.size, dtype=np.int64)
+    for k, (i, j) in enumerate(zip(rows, cols)):
+        a, b = iperm[i], iperm[j]
+        c, r = min(a, b), max(a, b)
+        s = col2super[c]
+        rs = T.rows(s)
+        t = np.searchsorted(rs, r)
+        want[k] = (T.panel_off[s] + (c - T.super_ptr[s]) * T.panel_ld[s] + t) if t < rs.size and rs[t] == r else -1
+    assert np.array_equal(pos, want)
+    assert (pos < 0).any() and (pos >= 0).any()
+    rc1, pos1 = _positions(h, B, base=1)
+    assert rc1 == 0 and np.array_equal(pos1, pos)
+    rcT, posT = _positions(h, B.T)                                     # Sigma is symmetric: (j, i) reads the same entry
+    CT = sp.csc_matrix(B.T).tocoo()
+    oT = np.lexsort((CT.row, CT.col))
+    lut = dict(zip(zip(rows.tolist(), cols.tolist()), pos.tolist()))
+    assert rcT == 0 and all(lut[(j, i)] == p for i, j, p in zip(CT.row[oT].tolist(), CT.col[oT].tolist(), posT.tolist()))
+    # entries of Q itself are the scatter map (upper triangle)
+    rcq, posq = _positions(h, Q)
+    assert rcq == 0 and np.array_equal(posq[T.q_src], T.q_dst)
+    # errors: wrong size, row index out of range
+    assert _positions(h, sp.identity(n + 1, format="csc"))[0] == -1
+    bad = sp.csc_matrix(Q)
+    cp, rv = bad.indptr.astype(np.int64), bad.indices.astype(np.int64).copy()
+    rv[5] = n + 3
+    out = np.empty(rv.size, dtype=np.int64)
+    assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv), 0, _lib.ptr(out)) == -1
+    assert b"row index out of range" in h._L.gmrf_b200_last_error(h._h)
+    h.close()
