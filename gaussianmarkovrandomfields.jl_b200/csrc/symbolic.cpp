@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -381,6 +382,15 @@ inline i64 round_up(i64 x, i64 m) { return (x + m - 1) / m * m; }
 void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_perm, int ordering,
              const Options &opt) {
     auto t0 = std::chrono::steady_clock::now();
+    // GMRF_B200_TRACE_ANALYSIS=1: per-phase wall clock of the analysis on stderr (diagnostics)
+    const bool trace = std::getenv("GMRF_B200_TRACE_ANALYSIS") != nullptr;
+    auto tphase = t0;
+    auto phase = [&](const char *name) {
+        if (!trace) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[gmrf_b200 analysis] %-28s %9.1f ms\n", name, std::chrono::duration<double, std::milli>(t - tphase).count());
+        tphase = t;
+    };
     if (n < 0) throw std::runtime_error("n must be non-negative");
     if (n > 2000000000LL) throw std::runtime_error("n exceeds 32-bit row index range");
     S = Symbolic();
@@ -435,34 +445,55 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
         else throw std::runtime_error("unknown ordering");
     }
 
+    phase("ordering");
     // ---- 2. etree, postorder (children by ascending column count), exact column counts ------------
     std::vector<i64> iperm0(n);
     for (i64 k = 0; k < n; k++) iperm0[perm0[k]] = k;
     UpperCSC C;
     build_permuted_upper(n, Ap, Ai, iperm0, C);
+    phase("  permuted upper triangle");
     std::vector<i64> parent0, post, cc0;
     etree(n, C, parent0);
-    // first postorder -> relabel -> counts; then second postorder with the heaviest child last
-    auto relabel = [&](const std::vector<i64> &po) {
+    phase("  etree");
+    // first postorder -> relabel -> counts; then second postorder with the heaviest child last. A postorder is an
+    // equivalent reordering: an upper-triangular entry (a, b), a < b, has b an ancestor of a, so it stays upper
+    // triangular under the relabelling, the tree is the relabelled tree and every node keeps its column count --
+    // nothing is recomputed from A, the permuted matrix / parent / counts are relabelled in place.
+    std::vector<i64> ipo(n), tmp(n);
+    auto relabel = [&](const std::vector<i64> &po, std::vector<i64> *cc) {
         // po[k] = old label of new label k
-        std::vector<i64> newperm(n);
-        for (i64 k = 0; k < n; k++) newperm[k] = perm0[po[k]];
-        perm0.swap(newperm);
+        for (i64 k = 0; k < n; k++) ipo[po[k]] = k;
+        for (i64 k = 0; k < n; k++) tmp[k] = perm0[po[k]];
+        perm0.swap(tmp);
         for (i64 k = 0; k < n; k++) iperm0[perm0[k]] = k;
-        build_permuted_upper(n, Ap, Ai, iperm0, C);
-        etree(n, C, parent0);
+        for (i64 k = 0; k < n; k++) tmp[k] = parent0[po[k]] == -1 ? -1 : ipo[parent0[po[k]]];
+        parent0.swap(tmp);
+        if (cc) {
+            for (i64 k = 0; k < n; k++) tmp[k] = (*cc)[po[k]];
+            cc->swap(tmp);
+        }
+        UpperCSC D;
+        D.ptr.assign(n + 1, 0);
+        for (i64 k = 0; k < n; k++) D.ptr[k + 1] = D.ptr[k] + (C.ptr[po[k] + 1] - C.ptr[po[k]]);
+        D.idx.resize(C.idx.size());
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < n; k++) {
+            i64 w = D.ptr[k];
+            for (i64 p = C.ptr[po[k]]; p < C.ptr[po[k] + 1]; p++) D.idx[w++] = ipo[C.idx[p]];
+        }
+        C.ptr.swap(D.ptr);
+        C.idx.swap(D.idx);
     };
     postorder(n, parent0, nullptr, post);
-    relabel(post);
+    relabel(post, nullptr);
+    phase("  postorder + relabel");
     column_counts(n, C, parent0, cc0);
+    phase("  column counts");
     postorder(n, parent0, &cc0, post);
     {
         bool ident = true;
         for (i64 k = 0; k < n; k++) if (post[k] != k) { ident = false; break; }
-        if (!ident) {
-            relabel(post);
-            column_counts(n, C, parent0, cc0);
-        }
+        if (!ident) relabel(post, &cc0);
     }
     S.perm = perm0;
     S.iperm = iperm0;
@@ -476,6 +507,7 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
         S.flops += (double)cc0[j] * (double)cc0[j];
     }
 
+    phase("etree/postorder/colcounts");
     // ---- 3. supernodes: maximal chains, then relaxed amalgamation ------------------------------------
     struct Grp { i64 first, ns, nrow; double exact; i64 last_orig; };
     std::vector<i64> fund_first;  // first column of each fundamental supernode
@@ -554,6 +586,7 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
             if (S.sparent[s] != -1) S.child_idx[w[S.sparent[s]]++] = s;
     }
 
+    phase("supernodes");
     // ---- 4. row structures ----------------------------------------------------------------------------
     // lower-triangular column lists of the permuted matrix
     std::vector<i64> lptr(n + 1, 0), lidx;
@@ -601,6 +634,7 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
             // children's row lists are no longer needed once the parent is built; free eagerly
         }
     }
+    phase("row structures");
     // relative indices
     S.relidx.assign(S.rowidx.size(), -1);
     for (i64 s = 0; s < S.nsuper; s++) {
@@ -618,6 +652,7 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
         }
     }
 
+    phase("relative indices");
     // ---- 5. panel layout -----------------------------------------------------------------------------
     S.panel_off.assign(S.nsuper + 1, 0);
     S.panel_ld.resize(S.nsuper);
@@ -656,6 +691,7 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
         for (i64 s = 0; s < S.nsuper; s++) S.level_idx[w[S.level[s]]++] = s;
     }
 
+    phase("layout/levels");
     // ---- 7. pools -------------------------------------------------------------------------------------
     S.upd_off.assign(S.nsuper, 0);
     S.upd_ld.assign(S.nsuper, 0);
@@ -703,31 +739,43 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
         S.zw_total = pz.top;
     }
 
+    phase("pools");
     // ---- 8. scatter map Q.nzval -> panels ------------------------------------------------------------
     {
-        i64 cnt = 0;
-        for (i64 j = 0; j < n; j++)
+        // upper-triangle entries in storage order; columns are independent (one binary search per entry): OpenMP
+        std::vector<i64> start(n + 1, 0);
+        for (i64 j = 0; j < n; j++) {
+            i64 c = 0;
             for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
-                if (Ai[p] <= j) cnt++;
+                if (Ai[p] <= j) c++;
+            start[j + 1] = start[j] + c;
+        }
+        const i64 cnt = start[n];
         S.q_src.resize(cnt);
         S.q_dst.resize(cnt);
-        i64 k = 0;
-        for (i64 j = 0; j < n; j++)
+        i64 bad = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : bad)
+        for (i64 j = 0; j < n; j++) {
+            i64 k = start[j];
+            const i64 b = S.iperm[j];
             for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
                 i64 i = Ai[p];
                 if (i > j) continue;
-                i64 a = S.iperm[i], b = S.iperm[j];
+                i64 a = S.iperm[i];
                 i64 col = std::min(a, b), row = std::max(a, b);
                 i64 s = S.col2super[col];
                 const i32 *rb = S.rowidx.data() + S.rowptr[s];
                 const i32 *re = S.rowidx.data() + S.rowptr[s + 1];
                 const i32 *it = std::lower_bound(rb, re, (i32)row);
-                if (it == re || *it != (i32)row) throw std::runtime_error("internal: Q entry outside factor pattern");
+                if (it == re || *it != (i32)row) { bad++; it = rb; }
                 S.q_src[k] = p;
                 S.q_dst[k] = S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb);
                 k++;
             }
+        }
+        if (bad) throw std::runtime_error("internal: Q entry outside factor pattern");
     }
+    phase("scatter map");
     auto t1 = std::chrono::steady_clock::now();
     S.analysis_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
