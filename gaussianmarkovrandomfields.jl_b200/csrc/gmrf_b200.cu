@@ -121,6 +121,13 @@ struct gmrf_b200_handle {
     long long *d_zpos = nullptr, *d_zdiagpos = nullptr;
     double *d_zout = nullptr;
     bool z_pattern_built = false;
+    // last caller pattern looked up by selinv_extract / selinv_dot (host-side, content-compared): a repeated pattern
+    // (gradient loops, linear-predictor marginals) skips the lookup
+    std::vector<i64> pp_colptr, pp_rowval;
+    std::vector<long long> pp_pos;
+    int pp_base = 0;
+    bool pp_valid = false;
+    i64 pp_hits = 0;
     // factor export P'L as CSC (lazy; CholeskySqrt-style consumers)
     std::vector<i64> l_colptr, l_rowval;
     long long *d_lpos = nullptr;
@@ -1979,20 +1986,35 @@ int gmrf_b200_factor_values(gmrf_b200_handle *h, double *nzval) {
 }
 
 // Position of Sigma_ij in the Z panels for every entry of a caller pattern (n x n CSC); -1 outside the factor's pattern.
+// The result lives in the handle (h->pp_pos) together with a copy of the pattern it belongs to.
 static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol, const int64_t *colptr, const int64_t *rowval,
-                             int index_base, std::vector<long long> &pos) {
+                             int index_base, const std::vector<long long> **out) {
     const Symbolic &S = h->S;
+    *out = &h->pp_pos;
     if (ncol != S.n || !colptr || (!rowval && colptr[ncol] - index_base > 0)) {
         h->err = std::string(who) + ": pattern must be n x n";
         return GMRF_B200_ERR_ARG;
     }
+    const i64 cnt = colptr[ncol] - index_base;
+    if (h->pp_valid && h->pp_base == index_base && (i64)h->pp_rowval.size() == cnt && (i64)h->pp_colptr.size() == ncol + 1 &&
+        std::memcmp(h->pp_colptr.data(), colptr, sizeof(i64) * (size_t)(ncol + 1)) == 0 &&
+        (cnt <= 0 || std::memcmp(h->pp_rowval.data(), rowval, sizeof(i64) * (size_t)cnt) == 0)) {
+        h->pp_hits++;
+        return 0;
+    }
+    h->pp_valid = false;
     for (i64 j = 0; j < ncol; j++)
         if (colptr[j + 1] < colptr[j] || colptr[j] < index_base) { h->err = std::string(who) + ": colptr must be non-decreasing from index_base"; return GMRF_B200_ERR_ARG; }
-    const i64 cnt = colptr[ncol] - index_base;
-    pos.assign((size_t)std::max<i64>(cnt, 0), -1LL);
-    if (cnt > 0 && gmrf::pattern_positions(S, colptr, rowval, index_base, pos.data()) >= 0) {
+    h->pp_pos.assign((size_t)std::max<i64>(cnt, 0), -1LL);
+    if (cnt > 0 && gmrf::pattern_positions(S, colptr, rowval, index_base, h->pp_pos.data()) >= 0) {
         h->err = std::string(who) + ": row index out of range";
         return GMRF_B200_ERR_ARG;
+    }
+    if (cnt <= (i64)1 << 27) {       // remember the pattern (16 bytes per entry) unless it is huge
+        h->pp_colptr.assign(colptr, colptr + ncol + 1);
+        h->pp_rowval.assign(rowval, rowval + std::max<i64>(cnt, 0));
+        h->pp_base = index_base;
+        h->pp_valid = true;
     }
     return 0;
 }
@@ -2001,10 +2023,10 @@ static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol,
 int gmrf_b200_pattern_positions(gmrf_b200_handle *h, int64_t ncol, const int64_t *colptr, const int64_t *rowval, int index_base,
                                 int64_t *pos) {
     if (!h || !pos) return GMRF_B200_ERR_ARG;
-    std::vector<long long> p;
-    int rc = pattern_positions(h, "pattern_positions", ncol, colptr, rowval, index_base, p);
+    const std::vector<long long> *p;
+    int rc = pattern_positions(h, "pattern_positions", ncol, colptr, rowval, index_base, &p);
     if (rc) return rc;
-    std::copy(p.begin(), p.end(), pos);
+    std::copy(p->begin(), p->end(), pos);
     return 0;
 }
 
@@ -2013,8 +2035,9 @@ int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *c
     int rc = gmrf_b200_selinv_compute(h);
     if (rc) return rc;
     if (!out) { h->err = "selinv_extract: null out"; return GMRF_B200_ERR_ARG; }
-    std::vector<long long> pos;
-    if ((rc = pattern_positions(h, "selinv_extract", ncol, colptr, rowval, index_base, pos))) return rc;
+    const std::vector<long long> *ppos;
+    if ((rc = pattern_positions(h, "selinv_extract", ncol, colptr, rowval, index_base, &ppos))) return rc;
+    const std::vector<long long> &pos = *ppos;
     const i64 cnt = (i64)pos.size();
     if (cnt <= 0) return 0;
     long long *d_pos = nullptr;
@@ -2050,8 +2073,9 @@ int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colpt
     int rc = gmrf_b200_selinv_compute(h);
     if (rc) return rc;
     if (!out) { h->err = "selinv_dot: null out"; return GMRF_B200_ERR_ARG; }
-    std::vector<long long> pos;
-    if ((rc = pattern_positions(h, "selinv_dot", ncol, colptr, rowval, index_base, pos))) return rc;
+    const std::vector<long long> *ppos;
+    if ((rc = pattern_positions(h, "selinv_dot", ncol, colptr, rowval, index_base, &ppos))) return rc;
+    const std::vector<long long> &pos = *ppos;
     const i64 cnt = (i64)pos.size();
     *out = 0.0;
     if (cnt <= 0) return 0;
@@ -2111,6 +2135,7 @@ int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info) {
     v[GMRF_B200_INFO_DEVICE_BYTES] = (int64_t)h->device_bytes;
     v[GMRF_B200_INFO_GRAPH_NODES] = (int64_t)h->factor_plan.launches.size() + 5;
     v[GMRF_B200_INFO_SELINV_NODES] = (int64_t)h->selinv_plan.launches.size();
+    v[GMRF_B200_INFO_PATTERN_CACHE_HITS] = (int64_t)h->pp_hits;
     for (int i = 0; i < n_info && i < GMRF_B200_INFO_COUNT; i++) info[i] = v[i];
     return 0;
 }

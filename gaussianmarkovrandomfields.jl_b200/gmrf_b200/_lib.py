@@ -16,7 +16,7 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_vp = ctypes.c_void_p
 
 INFO_KEYS = ["n", "nnz_q", "nnz_l", "nnz_l_stored", "nsuper", "nlevels", "max_front", "max_ns", "update_pool",
-             "flops_chol", "flops_chol_stored", "device_bytes", "graph_nodes", "selinv_nodes"]
+             "flops_chol", "flops_chol_stored", "device_bytes", "graph_nodes", "selinv_nodes", "pattern_cache_hits"]
 
 ORDER_NATURAL, ORDER_ND, ORDER_AMD = 0, 1, 2
 

@@ -168,7 +168,8 @@ enum {
     GMRF_B200_INFO_DEVICE_BYTES = 11,
     GMRF_B200_INFO_GRAPH_NODES = 12,   /* kernel launches in one refactorization */
     GMRF_B200_INFO_SELINV_NODES = 13,  /* kernel launches in one selected inversion */
-    GMRF_B200_INFO_COUNT = 14
+    GMRF_B200_INFO_PATTERN_CACHE_HITS = 14, /* selinv_extract / selinv_dot calls that reused the previous pattern's lookup */
+    GMRF_B200_INFO_COUNT = 15
 };
 int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info);
 int gmrf_b200_get_perm(const gmrf_b200_handle *h, int64_t *perm, int index_base);       /* final elimination order */

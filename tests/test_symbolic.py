@@ -238,3 +238,43 @@ def test_pattern_positions_lookup():
     assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv), 0, _lib.ptr(out)) == -1
     assert b"row index out of range" in h._L.gmrf_b200_last_error(h._h)
     h.close()
+
+
+def test_pattern_positions_remembers_the_last_pattern():
+    """A repeated pattern (gradient loops, linear-predictor marginals) skips the lookup: content-compared, one entry,
+    replaced on any difference (pattern, index base); results identical either way."""
+    Q = sp.csc_matrix(CASES["matern2d_16"]())
+    n = Q.shape[0]
+    h = _handle(Q)
+    hits = lambda: h.info()["pattern_cache_hits"]
+    B = sp.csc_matrix(Q + sp.random(n, n, density=0.05, random_state=np.random.default_rng(1), format="csc"))
+    rc, p0 = _positions(h, Q)
+    assert rc == 0 and hits() == 0
+    rc, p1 = _positions(h, Q)
+    assert rc == 0 and hits() == 1 and np.array_equal(p0, p1)
+    rc, pb = _positions(h, B)                               # different pattern: miss, cache replaced
+    assert rc == 0 and hits() == 1
+    rc, pb2 = _positions(h, B)
+    assert rc == 0 and hits() == 2 and np.array_equal(pb, pb2)
+    rc, p2 = _positions(h, Q)                               # back to the first: miss again, same answer
+    assert rc == 0 and hits() == 2 and np.array_equal(p2, p0)
+    rc, p3 = _positions(h, Q, base=1)                       # same pattern, other index base: miss, same answer
+    assert rc == 0 and hits() == 2 and np.array_equal(p3, p0)
+    C = Q.copy()                                            # same sizes, one row index changed
+    C.indices = C.indices.copy()
+    j = int(np.flatnonzero(np.diff(C.indptr) >= 2)[0])
+    C.indices[C.indptr[j]], C.indices[C.indptr[j] + 1] = C.indices[C.indptr[j] + 1], C.indices[C.indptr[j]]
+    cp, rv = C.indptr.astype(np.int64), C.indices.astype(np.int64)
+    out = np.empty(rv.size, dtype=np.int64)
+    assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv), 0, _lib.ptr(out)) == 0
+    assert hits() == 2 and out[cp[j]] == p0[cp[j] + 1] and out[cp[j] + 1] == p0[cp[j]]
+    # a failed lookup must not leave a stale entry behind
+    rv_bad = rv.copy()
+    rv_bad[0] = -7
+    assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv_bad), 0, _lib.ptr(out)) == -1
+    assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv_bad), 0, _lib.ptr(out)) == -1
+    rc, p4 = _positions(h, Q)
+    assert rc == 0 and np.array_equal(p4, p0)
+    empty = sp.csc_matrix((n, n))
+    assert _positions(h, empty)[0] == 0 and _positions(h, empty)[0] == 0
+    h.close()
