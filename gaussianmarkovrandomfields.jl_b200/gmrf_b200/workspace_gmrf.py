@@ -233,14 +233,40 @@ def _merit_atol(scale):
     return 64.0 * np.finfo(np.float64).eps * max(scale, 1.0)       # condition/gaussian_approximation.jl:246
 
 
-def _update_hessian(ws: GMRFWorkspace, H_diag, prior_nzval, diag_idx):
-    """ws.Q := Q_prior - H (diagonal Hessian), invalidate, drop ownership (workspace/gaussian_approximation.jl:96-129)."""
+def _sparse_hessian_map(Q: sp.csc_matrix, H: sp.csc_matrix) -> np.ndarray:
+    """Q.nzval position of every stored entry of H (workspace/gaussian_approximation.jl:31-61); ValueError if H has a
+    nonzero outside Q's pattern."""
+    n = Q.shape[1]
+    qkey = np.repeat(np.arange(n, dtype=np.int64), np.diff(Q.indptr)) * Q.shape[0] + Q.indices
+    hcol = np.repeat(np.arange(n, dtype=np.int64), np.diff(H.indptr))
+    hkey = hcol * Q.shape[0] + H.indices
+    pos = np.searchsorted(qkey, hkey)
+    ok = pos < qkey.size
+    ok[ok] = qkey[pos[ok]] == hkey[ok]
+    if not np.all(ok):
+        k = int(np.flatnonzero(~ok)[0])
+        raise ValueError(f"Hessian has nonzero at ({int(H.indices[k]) + 1}, {int(hcol[k]) + 1}) which is outside the "
+                         "workspace Q sparsity pattern.")
+    return pos
+
+
+def _update_hessian(ws: GMRFWorkspace, H_k, prior_nzval, diag_idx, sparse_hess_map=None):
+    """ws.Q := Q_prior - H, invalidate, drop ownership (workspace/gaussian_approximation.jl:96-129). `H_k` is either the
+    diagonal of a diagonal Hessian (1-D array, the reference's `Diagonal`) or a sparse matrix whose pattern lies inside the
+    workspace's; the index map of the sparse case is built once per Newton loop and returned."""
     if prior_nzval.size != ws.Q.data.size:
         raise ValueError(f"prior precision has {prior_nzval.size} stored entries but the workspace pattern has {ws.Q.data.size}")
     ws.Q.data[:] = prior_nzval
-    ws.Q.data[diag_idx] -= H_diag
+    if isinstance(H_k, np.ndarray) and H_k.ndim == 1:
+        ws.Q.data[diag_idx] -= H_k                                   # _subtract_diagonal_hessian! :63-72
+    else:
+        H_sparse = _csc(H_k)
+        if sparse_hess_map is None:
+            sparse_hess_map = _sparse_hessian_map(ws.Q, H_sparse)
+        np.subtract.at(ws.Q.data, sparse_hess_map, H_sparse.data)    # _subtract_sparse_hessian! :74-83
     ws._invalidate()
     ws.loaded_version = 0
+    return sparse_hess_map
 
 
 def _constrain_step(step, ws, constraints):
@@ -331,9 +357,11 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
         counts["solves"] += 1
         return _constrain_step(ws.workspace_solve(g), ws, constraints)
 
+    hess_map = [None]                                                # sparse Hessians: index map built once (:257)
+
     def build_result(x_final):
         Q_p, _, _ = _prior_local(prior, x_final)
-        _update_hessian(ws, obs_lik.loghessian(x_final), Q_p.data, diag_idx)
+        hess_map[0] = _update_hessian(ws, obs_lik.loghessian(x_final), Q_p.data, diag_idx, hess_map[0])
         Q_post = sp.csc_matrix((ws.Q.data.copy(), ws.Q.indices, ws.Q.indptr), shape=ws.Q.shape)   # _snapshot_Q
         if stats is not None:
             stats.update(counts)
@@ -346,8 +374,8 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
         Q_p, h, energy_k = _prior_local(prior, x_k)
         H_k = obs_lik.loghessian(x_k)
         g_l = obs_lik.loggrad(x_k)
-        _update_hessian(ws, H_k, Q_p.data, diag_idx)
-        if on_device:
+        hess_map[0] = _update_hessian(ws, H_k, Q_p.data, diag_idx, hess_map[0])
+        if on_device and isinstance(H_k, np.ndarray) and H_k.ndim == 1:
             ws.backend.refactorize_minus_diag(H_k)          # same values as ws.Q, formed in HBM
             ws.numeric_valid, ws.selinv_valid, ws.logdet_valid = True, False, False
         else:
