@@ -196,3 +196,57 @@ def test_pool_from_model():                               # test_workspace_pool.
         d = evaluate_with_workspace(model, ws, tau=2.0, rho=0.4)
         assert abs(d.logpdf(z) - _dense_logpdf(model.precision_matrix(2.0, 0.4), np.zeros(16), z)) <= 1e-10 * abs(d.logpdf(z))
     assert pool.checkout() is not None
+
+
+# ---------------------------------------------------------------------------------------------- test_workspace_pool.jl
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_workspace_pool_protocol(kw):
+    import threading
+    from gmrf_b200.workspace import GMRFWorkspace, WorkspacePool
+    n = 30
+    rng = np.random.default_rng(7)
+    A = sp.random(n, n, density=0.1, random_state=rng, format="csc")
+    Q = sp.csc_matrix(A + A.T + 10.0 * sp.identity(n))
+    Q.sort_indices()
+    Qd = Q.toarray()
+    base = kw()
+    pkw = lambda: {**{k: v for k, v in base.items() if k != "device"}, "devices": (base.get("device", 0),)}
+    pool = WorkspacePool(Q, size=2, **pkw())                     # :15-33 checkout / checkin
+    assert len(pool.workspaces) == 2
+    ws1, ws2 = pool.checkout(), pool.checkout()
+    assert isinstance(ws1, GMRFWorkspace) and ws1.dimension() == n and ws1 is not ws2
+    pool.checkin(ws1)
+    pool.checkin(ws2)
+    ws3 = pool.checkout()
+    pool.checkin(ws3)
+    with pool.with_workspace() as ws:                            # :35-45 RAII
+        assert np.isfinite(np.linalg.norm(ws.workspace_solve(rng.standard_normal(n))))
+    one = WorkspacePool(Q, size=1, **pkw())                       # :47-62 returned on exception
+    with pytest.raises(RuntimeError):
+        with one.with_workspace():
+            raise RuntimeError("intentional error")
+    one.checkin(one.checkout())
+    b = rng.standard_normal(n)                                   # :64-86 independent workspaces
+    three = WorkspacePool(Q, size=3, **pkw())
+    for i in (1, 2, 3):
+        ws = three.checkout()
+        ws.update_precision(Q * float(i))
+        x = ws.workspace_solve(b)
+        three.checkin(ws)
+        assert np.allclose(x, np.linalg.solve(Qd * i, b), rtol=1e-10, atol=1e-13)
+    results, errs = [None] * 20, []                             # :88-115 parallel correctness
+
+    def work(i):
+        try:
+            with three.with_workspace() as ws:
+                ws.update_precision(Q * float(i + 1))
+                results[i] = np.linalg.norm(ws.workspace_solve(np.ones(n)))
+        except Exception as e:       # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(20)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for i in range(20):
+        assert abs(results[i] - np.linalg.norm(np.linalg.solve(Qd * (i + 1), np.ones(n)))) <= 1e-10 * results[i]
