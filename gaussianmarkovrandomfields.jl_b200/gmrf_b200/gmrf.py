@@ -13,20 +13,25 @@ import scipy.sparse as sp
 
 from .backend import B200Backend, _csc
 
-__all__ = ["GMRF", "linear_condition"]
+__all__ = ["GMRF", "linear_condition", "gaussian_approximation"]
 
 
 class GMRF:
     """GMRF(mean, Q) or GMRF(information=h, Q): N(Q^-1 h, Q^-1) backed by one B200 factorization of Q."""
 
-    def __init__(self, mean=None, Q=None, information=None, ordering=None, device: int = 0, backend_type=B200Backend):
+    def __init__(self, mean=None, Q=None, information=None, ordering=None, device: int = 0, backend_type=B200Backend,
+                 linsolve_cache=None):
         Q = _csc(Q).astype(np.float64)
         n = Q.shape[0]
         if Q.shape[0] != Q.shape[1]:
             raise ValueError("size mismatch")
         self.precision = Q
-        kw = {"device": device, "ordering": ordering} if backend_type is B200Backend else {}
-        self.linsolve_cache = backend_type(Q, **kw)                     # symbolic analysis + numeric factorization
+        self._backend_type, self._device = backend_type, device
+        if linsolve_cache is not None:                                  # GMRF(x, Q; linsolve_cache = solver), gmrf.jl:159-193:
+            self.linsolve_cache = linsolve_cache                        # the cache already holds the factorization of Q
+        else:
+            kw = {"device": device, "ordering": ordering} if backend_type is B200Backend else {}
+            self.linsolve_cache = backend_type(Q, **kw)                 # symbolic analysis + numeric factorization
         if information is not None:                                     # gmrf.jl:195-223: mean = Q \ h
             information = np.asarray(information, dtype=np.float64)
             if information.size != n:
@@ -89,3 +94,36 @@ def linear_condition(gmrf: GMRF, A, Q_eps, y, b=None, obs_precision_contrib=None
     Q_post.sort_indices()
     h_post = gmrf.information_vector() + A.T @ (Q_eps @ (y - b))
     return GMRF(information=h_post, Q=Q_post, **gmrf_kwargs)
+
+
+def gaussian_approximation(prior: GMRF, obs_lik, **kwargs) -> GMRF:
+    """Gaussian approximation for a plain `GMRF` prior -- the cache-backed Newton loop of
+    src/arithmetic/condition/gaussian_approximation.jl:197-229, :428-498: one solver is set up for the pattern of
+    `Q_prior - H(x0)` (`_ga_init_solver` / `_ga_resolve_cache`, :88-110), every iterate is a values-only refactorization
+    (`_ga_refactor!` -> `_update_linsolve_cache!`, :61-76, :112-116) plus one solve, and the posterior `GMRF` adopts the
+    solver (`_ga_make_posterior`, :126-129). On this backend "one solver per pattern" is exactly a workspace, so the loop is
+    the workspace Newton loop on a workspace built for the joint pattern with the prior's ordering; the iterates and the
+    result are those of `workspace_gmrf.gaussian_approximation`. Keyword arguments as there."""
+    from .latent_model_integration import ones_pattern, copy_values_into
+    from .workspace import GMRFWorkspace
+    from . import workspace_gmrf as wg
+
+    Q_prior = prior.precision_matrix()
+    n = Q_prior.shape[0]
+    x_init = np.asarray(kwargs.get("x0") if kwargs.get("x0") is not None else prior.mean(), dtype=np.float64)
+    H = obs_lik.loghessian(x_init)
+    H_sparse = sp.csc_matrix(sp.diags(H)) if isinstance(H, np.ndarray) and H.ndim == 1 else _csc(H)
+    joint = _csc(ones_pattern(Q_prior) + ones_pattern(H_sparse))       # storage of Q_prior - H
+    copy_values_into(joint, Q_prior)
+    bkw = {"backend_type": prior._backend_type}
+    if prior._backend_type is B200Backend:
+        bkw["device"] = prior._device
+        if joint.nnz == Q_prior.nnz:                                    # same pattern: "deepcopy(cache)" = same ordering
+            bkw["ordering"] = prior.linsolve_cache.permutation()
+    ws = GMRFWorkspace(joint, **bkw)
+    wprior = wg.WorkspaceGMRF(prior.mean(), joint, ws)
+    post = wg.gaussian_approximation(wprior, obs_lik, **kwargs)
+    post.ensure_loaded()
+    ws.ensure_numeric()                                                 # the solver holds the factorization of Q_post
+    return GMRF(mean=post.mean(), Q=post.precision, backend_type=prior._backend_type, device=prior._device,
+                linsolve_cache=ws.backend)

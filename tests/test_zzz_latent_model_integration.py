@@ -250,3 +250,58 @@ def test_workspace_pool_protocol(kw):
     assert not errs
     for i in range(20):
         assert abs(results[i] - np.linalg.norm(np.linalg.solve(Qd * (i + 1), np.ones(n)))) <= 1e-10 * results[i]
+
+
+# ------------------------------------------------------------------- plain GMRF prior: the cache-backed Newton loop (a13)
+def _gmrf_kw(kw):
+    base = kw()
+    return {"backend_type": base["backend_type"]} if base["backend_type"] is DenseBackend else {"device": base["device"]}
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_gaussian_approximation_of_a_plain_gmrf(kw):
+    """test/workspace/test_workspace_gaussian_approximation.jl:8-32 run the other way round: the plain `GMRF` path
+    (condition/gaussian_approximation.jl:197-229) against the workspace path and against a dense Newton iteration."""
+    from gmrf_b200.gmrf import GMRF, gaussian_approximation as ga_gmrf
+    n = 10
+    Q = sp.diags([np.full(n - 1, -0.8), np.full(n, 2.0), np.full(n - 1, -0.8)], [-1, 0, 1]).tocsc()
+    y = np.array([2, 1, 3, 0, 4, 1, 2, 3, 1, 0], dtype=float)
+    lik = PoissonLikelihood(y)
+    prior = GMRF(np.zeros(n), Q, **_gmrf_kw(kw))
+    post = ga_gmrf(prior, lik)
+    assert isinstance(post, GMRF) and post.linsolve_cache is not prior.linsolve_cache
+    ref = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **dense_kw()), lik)
+    assert np.allclose(post.mean(), ref.mean(), rtol=1e-8, atol=1e-10)
+    assert np.allclose(post.precision.toarray(), ref.precision.toarray(), rtol=1e-8)
+    x = np.zeros(n)                                                   # dense Newton to the mode
+    Qd = Q.toarray()
+    for _ in range(50):
+        g = Qd @ x - (y - np.exp(x))
+        x = x - np.linalg.solve(Qd + np.diag(np.exp(x)), g)
+    assert np.allclose(post.mean(), x, atol=1e-4)
+    # the posterior GMRF owns a live factorization of Q_post: var / logdetcov / rand come straight from it
+    Qp = post.precision.toarray()
+    assert np.allclose(post.var(), np.diag(np.linalg.inv(Qp)), rtol=1e-8)
+    assert abs(post.logdetcov() + np.linalg.slogdet(Qp)[1]) <= 1e-10 * abs(post.logdetcov())
+    assert post.rand(np.random.default_rng(0), 4).shape == (n, 4)
+    # the prior is untouched
+    assert np.allclose(prior.var(), np.diag(np.linalg.inv(Qd)), rtol=1e-8)
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_plain_gmrf_with_a_non_diagonal_hessian(kw):
+    """`_ga_resolve_cache` (:98-110): the posterior precision's storage differs from the prior's, the solver is built for
+    the joint pattern. Gaussian likelihood => exact posterior, equal to `linear_condition`."""
+    from gmrf_b200.gmrf import GMRF, gaussian_approximation as ga_gmrf, linear_condition
+    n, m_obs = 9, 7
+    rng = np.random.default_rng(11)
+    A = sp.random(m_obs, n, density=0.5, random_state=rng, format="csr")
+    yv = rng.standard_normal(m_obs)
+    Q = AR1Model(n).precision_matrix(1.5, 0.4)
+    mu = rng.standard_normal(n)
+    prior = GMRF(mu, Q, **_gmrf_kw(kw))
+    post = ga_gmrf(prior, LinearGaussianLikelihood(A, yv, 0.5))
+    exact = linear_condition(prior, A, 4.0, yv, **_gmrf_kw(kw))
+    assert np.allclose(post.mean(), exact.mean(), rtol=1e-8, atol=1e-10)
+    assert np.allclose(post.precision.toarray(), exact.precision.toarray(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(post.var(), exact.var(), rtol=1e-8)
