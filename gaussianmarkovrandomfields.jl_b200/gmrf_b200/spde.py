@@ -320,13 +320,18 @@ class AdvectionDiffusionSSM:
 
 
 # --------------------------------------------------------------------------- orderings
-def geometric_nd_perm(dims, leaf: int = 64, width: int = 1) -> np.ndarray:
+def geometric_nd_perm(dims, leaf: int = 64, width=1) -> np.ndarray:
     """Geometric nested-dissection permutation of a structured vertex grid `dims`
-    (x fastest). `width` = separator thickness (stencil hop count). Returns perm with
+    (x fastest). `width` = separator thickness (stencil hop count), one number or one per axis (anisotropic stencils:
+    a space-time precision couples 5 hops in space but only neighbouring time slices); the cut goes through the axis
+    with the most separator-widths left, so cheap (thin-separator) axes are cut first at equal extent. Returns perm with
     perm[k] = original index of the k-th eliminated vertex (0-based). This is a host-side
     ordering a caller may pass as `ordering=perm` (src/workspace/backend.jl:147-153)."""
     dims = tuple(int(v) for v in dims)
     nd = len(dims)
+    widths = tuple(int(w) for w in (width if np.ndim(width) else (width,) * nd))
+    if len(widths) != nd or min(widths) < 1:
+        raise ValueError("width must be a positive number or one positive number per axis")
     strides = np.cumprod((1,) + dims[:-1])
     out = []
 
@@ -335,7 +340,8 @@ def geometric_nd_perm(dims, leaf: int = 64, width: int = 1) -> np.ndarray:
         npts = int(np.prod(ext))
         if npts == 0:
             return
-        ax = int(np.argmax(ext))
+        ax = int(np.argmax([e / w for e, w in zip(ext, widths)]))
+        width = widths[ax]
         if npts <= leaf or ext[ax] <= 2 * width:
             out.append(_box_indices(lo, hi, strides))
             return

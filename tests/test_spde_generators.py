@@ -96,3 +96,30 @@ def test_geometric_nd_is_a_permutation():
     for dims, width in (((9, 9), 3), ((6, 7, 5), 2), ((33, 20), 1)):
         p = spde.geometric_nd_perm(dims, leaf=8, width=width)
         assert np.array_equal(np.sort(p), np.arange(int(np.prod(dims))))
+
+
+def test_geometric_nd_with_per_axis_separator_widths():
+    """Space-time precision: 5 hops in space, 1 in time. Separators of thickness (5, 5, 1) disconnect the halves (fill on
+    a par with METIS nested dissection); thinner spatial separators do not (fill doubles)."""
+    from gmrf_b200 import _lib
+    from gmrf_b200.backend import _Handle
+    cells, nt = 24, 12
+    model = spde.AdvectionDiffusionSSM(*spde.mesh2d(cells), nt=nt)
+    Q = model.Q
+    n = Q.shape[0]
+    cp, rv = Q.indptr.astype(np.int64), Q.indices.astype(np.int64)
+
+    def nnz_l(perm, code=_lib.ORDER_ND):
+        h = _Handle(n, cp, rv, perm, code, device=-1)
+        v = h.info()["nnz_l"]
+        h.close()
+        return v
+
+    dims = (cells + 1, cells + 1, nt)
+    p = spde.geometric_nd_perm(dims, leaf=64, width=(5, 5, 1))
+    assert np.array_equal(np.sort(p), np.arange(n))
+    good, thin, metis = nnz_l(p), nnz_l(spde.geometric_nd_perm(dims, leaf=64, width=(3, 3, 1))), nnz_l(None)
+    assert good <= 1.15 * metis and thin >= 1.5 * good
+    with pytest.raises(ValueError):
+        spde.geometric_nd_perm(dims, width=(5, 5))
+    assert np.array_equal(spde.geometric_nd_perm((7, 5), leaf=4, width=1), spde.geometric_nd_perm((7, 5), leaf=4, width=(1, 1)))
