@@ -1519,6 +1519,8 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
         if (cp[0] != 0) throw std::runtime_error("colptr[0] must equal index_base");
         i64 nnz = cp[n];
         if (nnz < 0) throw std::runtime_error("negative nnz");
+        for (i64 j = 0; j < n; j++)
+            if (cp[j + 1] < cp[j] || cp[j + 1] > nnz) throw std::runtime_error("colptr must be non-decreasing");
         rv.assign(rowval, rowval + nnz);
         for (auto &v : rv) v -= index_base;
         if (perm) {

@@ -396,11 +396,16 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
     S = Symbolic();
     S.n = n;
     S.nnzA = Ap[n];
-    for (i64 j = 0; j < n; j++) {
+    if (Ap[0] != 0) throw std::runtime_error("colptr[0] must equal index_base");
+    for (i64 j = 0; j < n; j++)
         if (Ap[j + 1] < Ap[j]) throw std::runtime_error("colptr must be non-decreasing");
-        for (i64 p = Ap[j]; p < Ap[j + 1]; p++)
+    // SparseMatrixCSC invariants (the scatter map and the diagonal lookups rely on them): row indices in range and
+    // strictly increasing within a column (sorted, no duplicates)
+    for (i64 j = 0; j < n; j++)
+        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
             if (Ai[p] < 0 || Ai[p] >= n) throw std::runtime_error("row index out of range");
-    }
+            if (p > Ap[j] && Ai[p] <= Ai[p - 1]) throw std::runtime_error("row indices must be strictly increasing within each column (sorted, no duplicates)");
+        }
 
     // ---- 1. ordering ---------------------------------------------------------------------------
     std::vector<i64> perm0(n);

@@ -278,3 +278,21 @@ def test_pattern_positions_remembers_the_last_pattern():
     empty = sp.csc_matrix((n, n))
     assert _positions(h, empty)[0] == 0 and _positions(h, empty)[0] == 0
     h.close()
+
+
+def test_create_rejects_patterns_that_break_the_csc_invariants():
+    """SparseMatrixCSC invariants are checked up front (ArgumentError-like -1 with a message), never read past."""
+    def rc_msg(n, cp, rv, perm=None, ordering=_lib.ORDER_ND):
+        try:
+            _Handle(n, np.asarray(cp, dtype=np.int64), np.asarray(rv, dtype=np.int64), perm, ordering, device=-1).close()
+            return None
+        except ValueError as e:
+            return str(e)
+    assert "strictly increasing" in rc_msg(2, [0, 3, 5], [0, 0, 1, 0, 1])            # duplicate entry
+    assert "strictly increasing" in rc_msg(3, [0, 2, 5, 7], [1, 0, 2, 0, 1, 2, 1])   # unsorted rows
+    assert "non-decreasing" in rc_msg(2, [0, 3, 2], [0, 1, 1])                       # colptr goes backwards
+    assert "row index out of range" in rc_msg(2, [0, 2, 4], [0, 5, 0, 1])
+    assert "not a permutation" in rc_msg(2, [0, 2, 4], [0, 1, 0, 1], perm=np.array([0, 0], dtype=np.int64))
+    assert "unknown ordering" in rc_msg(2, [0, 2, 4], [0, 1, 0, 1], ordering=7)
+    assert rc_msg(0, [0], []) is None                                                # the empty matrix is fine
+    assert rc_msg(2, [0, 1, 2], [0, 1]) is None
