@@ -206,16 +206,15 @@ _FROZEN_FINISH_STEPS = 3          # condition/gaussian_approximation.jl:381
 
 
 def _diagonal_indices(Q: sp.csc_matrix) -> np.ndarray:
-    """nzval positions of the diagonal entries (workspace/gaussian_approximation.jl:9-22)."""
+    """nzval positions of the diagonal entries (workspace/gaussian_approximation.jl:9-22), vectorised."""
     n = Q.shape[0]
-    idx = np.empty(n, dtype=np.int64)
-    for col in range(n):
-        lo, hi = Q.indptr[col], Q.indptr[col + 1]
-        k = lo + np.searchsorted(Q.indices[lo:hi], col)
-        if k >= hi or Q.indices[k] != col:
-            raise ValueError(f"workspace Q has no stored diagonal entry in column {col}")
-        idx[col] = k
-    return idx
+    cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(Q.indptr))
+    idx = np.flatnonzero(Q.indices == cols)
+    if idx.size != n or not np.array_equal(cols[idx], np.arange(n)):
+        present = np.zeros(n, dtype=bool)
+        present[cols[idx]] = True
+        raise ValueError(f"workspace Q has no stored diagonal entry in column {int(np.flatnonzero(~present)[0])}")
+    return idx.astype(np.int64)
 
 
 def _prior_local(prior: WorkspaceGMRF, x):
