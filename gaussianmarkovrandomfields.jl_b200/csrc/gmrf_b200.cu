@@ -9,6 +9,8 @@
 #include "solve_kernels.cuh"
 #include "symbolic.hpp"
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
+
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -150,6 +152,14 @@ struct gmrf_b200_handle {
 };
 
 namespace {
+
+// NVTX range per phase (`ncu --nvtx --nvtx-include "gmrf_b200:factor/"` etc. narrows a capture to one phase)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define CUDA_TRY(h, expr)                                                                         \
     do {                                                                                          \
@@ -1090,6 +1100,7 @@ int ensure_device(gmrf_b200_handle *h) {
 }
 
 int do_factor(gmrf_b200_handle *h, int lanes = 1) {
+    NvtxRange nvtx_("gmrf_b200:factor");
     cudaStream_t st = h->stream;
     CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
     if (h->opt.use_graph) {
@@ -1304,6 +1315,7 @@ void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
 // The sweeps of one block are a static launch list on fixed buffers -> captured once per (block width, mode) into a
 // CUDA graph and replayed (thousands of dependent micro-launches on the chains of the top supernodes).
 int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode) {
+    NvtxRange nvtx_("gmrf_b200:solve");
     const Symbolic &S = h->S;
     if (!h->factored) { h->err = "solve before the first refactorize"; return GMRF_B200_ERR_STATE; }
     if (nrhs < 0 || ld < S.n) { h->err = "solve: need nrhs >= 0 and ld >= n"; return GMRF_B200_ERR_ARG; }
@@ -1533,6 +1545,7 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
             const i64 *it = std::lower_bound(b, e, j);
             if (it != e && *it == j) h->diag_nzpos[(size_t)j] = (long long)(it - rv.data());
         }
+        NvtxRange nvtx_("gmrf_b200:analysis");
         analyze(h->S, n, cp.data(), rv.data(), perm ? pm.data() : nullptr, ordering, h->opt);
     } catch (std::exception &e) {
         g_create_error = e.what();
@@ -1884,6 +1897,7 @@ int gmrf_b200_solve_Lt_device(gmrf_b200_handle *h, const double *dZ, double *dX,
 }
 
 int gmrf_b200_selinv_compute(gmrf_b200_handle *h) {
+    NvtxRange nvtx_("gmrf_b200:selinv");
     int rc = ensure_device(h);
     if (rc) return rc;
     if (!h->factored) { h->err = "selinv before the first refactorize"; return GMRF_B200_ERR_STATE; }
