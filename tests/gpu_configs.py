@@ -23,6 +23,38 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def _peaks():
+    """Roofline denominators: measured HBM copy rate (MEASURED_PEAKS.json, else the round-1 figure) and the measured
+    cuBLAS DGEMM rate (profiles/r01_fp64_probe.json)."""
+    hbm, fp64 = 6541.5, 36.086
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    return hbm, fp64
+
+
+def roofline(info, factor_ms=None, solve_ms=None, half_solve_ms=None, selinv_ms=None, nrhs=1):
+    """Achieved rates against the roofline that bounds each phase: factorization / selected inversion in
+    algorithmic FP64 TFLOP/s (sum cc_j^2, and 2x that), few-RHS solves in GB/s of factor panels streamed."""
+    hbm, fp64 = _peaks()
+    out = {}
+    flops, lbytes = float(info["flops_chol"]), 8.0 * float(info["nnz_l_stored"])
+    if factor_ms:
+        out["factor_tflops"] = round(flops / (factor_ms * 1e-3) / 1e12, 3)
+        out["factor_frac_of_dgemm"] = round(out["factor_tflops"] / fp64, 4)
+    if selinv_ms:
+        out["selinv_tflops_equiv"] = round(2.0 * flops / (selinv_ms * 1e-3) / 1e12, 3)
+        out["selinv_frac_of_dgemm"] = round(out["selinv_tflops_equiv"] / fp64, 4)
+    if solve_ms:
+        out["solve_GBs"] = round(2.0 * lbytes / (solve_ms * 1e-3) / 1e9, 1)
+        out["solve_frac_of_hbm"] = round(out["solve_GBs"] / hbm, 4)
+    if half_solve_ms:
+        out["half_solve_GBs"] = round(lbytes / (half_solve_ms * 1e-3) / 1e9, 1)
+        out["half_solve_frac_of_hbm"] = round(out["half_solve_GBs"] / hbm, 4)
+    return out
+
+
 def config1():
     cells = 64 if small else 224
     coords, tri = spde.mesh2d(cells)
@@ -51,7 +83,8 @@ def config1():
     ref = ws.workspace_solve(E)[idx, np.arange(4)]
     emit(config=1, n=n, nnz_q=int(Q.nnz), setup_s=round(setup, 2), **{k: round(v, 3) for k, v in times.items()},
          logdet=ld, residual=float(np.linalg.norm(Q @ x - b) / np.linalg.norm(b)),
-         std_vs_unit_solves=float(np.max(np.abs(std[idx] ** 2 - ref) / ref)), info=be.info()["graph_nodes"])
+         std_vs_unit_solves=float(np.max(np.abs(std[idx] ** 2 - ref) / ref)), info=be.info()["graph_nodes"],
+         roofline=roofline(be.info(), times["factor_logdet_ms"], times["mean_solve_ms"], times["rand_ms"], times["selinv_ms"]))
 
 
 def config2():
@@ -75,7 +108,8 @@ def config2():
     t1 = time.perf_counter(); sd = post.std(); t_std = time.perf_counter() - t1
     emit(config=2, n=n, nnz_q=int(Q.nnz), setup_s=round(setup, 2), newton_wall_s=round(wall, 3), **stats,
          factor_ms_last=round(be.timings()["factor_ms"], 3), solve_ms_last=round(be.timings()["solve_ms"], 3),
-         grad_inf=float(np.max(np.abs(g))), posterior_std_s=round(t_std, 3), std_range=[float(sd.min()), float(sd.max())])
+         grad_inf=float(np.max(np.abs(g))), posterior_std_s=round(t_std, 3), std_range=[float(sd.min()), float(sd.max())],
+         roofline=roofline(be.info(), be.timings()["factor_ms"], be.timings()["solve_ms"]))
 
 
 def config3():
@@ -128,7 +162,7 @@ def config3():
          evals_per_s=round(len(thetas) / wall, 1), lanes=lanes, lanes_sweep_wall_s=round(wall_l, 3),
          lanes_device_ms_per_eval=round(lane_ms / len(thetas), 3), lanes_evals_per_s=round(len(thetas) / wall_l, 1),
          lanes_vs_single_max_rel=float(np.max(np.abs(out_l - out) / np.abs(out))), logpdf_spotcheck_rel=float(abs(chk - out[len(thetas) // 2]) / abs(chk)),
-         status=be.status)
+         status=be.status, roofline={"single": roofline(be.info(), dev_ms / len(thetas)), "lanes": roofline(be.info(), lane_ms / len(thetas))})
 
 
 def config5():
@@ -154,7 +188,9 @@ def config5():
     emit(config=5, n=n, nnz_q=int(Q.nnz), nnz_l=info["nnz_l"], flops=float(info["flops_chol"]), setup_s=round(setup, 2),
          factor_ms=round(f_ms, 2), selinv_ms=round(s_ms, 2), samples=m, sampling_ms=round(smp_ms, 2),
          ms_per_sample=round(smp_ms / m, 4), var_vs_samples_median_rel=float(np.median(np.abs(emp - var) / var)),
-         observed_var_max=float(var[obs].max()))
+         observed_var_max=float(var[obs].max()),
+         roofline={**roofline(info, f_ms, selinv_ms=s_ms),
+                   "sampling_tflops": round(2.0 * float(info["nnz_l"]) * m / (smp_ms * 1e-3) / 1e12, 3)})
 
 
 for c in which:
