@@ -117,3 +117,58 @@ def test_factor_broadcast_two_gpus():
                         "--master-port", str(_free_port()), script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "broadcast ok" in r.stdout
+
+
+def _grad_worker(rank, world, port, tmp):
+    """A sharded hyperparameter sweep that returns the log-density AND its gradient with respect to the coefficients of the
+    value basis: model(ws; theta...) with the values assembled from the resident basis, then the contracted pullbacks."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dense_backend import DenseBackend
+    from latent_stand_ins import MaternModel
+    from gmrf_b200 import spde
+    from gmrf_b200.autodiff import logpdf_basis_gradient
+    from gmrf_b200.latent_model_integration import evaluate_with_workspace, make_workspace
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = MaternModel(spde.MaternSPDE(*spde.mesh2d(6), 1))
+        ws = make_workspace(model, {"backend_type": DenseBackend}, tau=1.0, range_=0.5)     # this rank's replica
+        z = 0.1 * np.random.default_rng(0).standard_normal(model.n)
+        thetas = [(0.5 + 0.3 * i, 0.4 + 0.05 * i) for i in range(5)]                         # 5 points on 2 ranks (3 + 2)
+
+        def evaluate(th):
+            d = evaluate_with_workspace(model, ws, on_device=True, tau=th[0], range_=th[1])
+            return np.concatenate([[d.logpdf(z)], logpdf_basis_gradient(d, z, model.basis())])
+
+        out = sharding.sharded_map(evaluate, thetas)
+        np.save(os.path.join(tmp, f"grad_rank{rank}.npy"), out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gradient_sweep_world2(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from latent_stand_ins import MaternModel
+    from gmrf_b200 import spde
+    world, port = 2, _free_port()
+    mp.spawn(_grad_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f"grad_rank{r}.npy") for r in range(world))
+    assert np.array_equal(r0, r1)
+    model = MaternModel(spde.MaternSPDE(*spde.mesh2d(6), 1))
+    n = model.n
+    z = 0.1 * np.random.default_rng(0).standard_normal(n)
+    basis = model.basis()
+    assert r0.shape == (5, 1 + basis.shape[0])
+    for i in range(5):
+        tau, rho = 0.5 + 0.3 * i, 0.4 + 0.05 * i
+        Q = model.precision_matrix(tau, rho)
+        Qd = Q.toarray()
+        lp = -0.5 * z @ Qd @ z + 0.5 * np.linalg.slogdet(Qd)[1] - 0.5 * n * np.log(2 * np.pi)
+        assert abs(r0[i, 0] - lp) <= 1e-10 * abs(lp)
+        Sigma = np.linalg.inv(Qd)
+        cols = np.repeat(np.arange(n), np.diff(Q.indptr))
+        want = 0.5 * (basis @ Sigma[Q.indices, cols] - basis @ (z[Q.indices] * z[cols]))
+        assert np.allclose(r0[i, 1:], want, rtol=1e-8, atol=1e-8 * np.max(np.abs(want)))
