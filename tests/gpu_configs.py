@@ -153,6 +153,18 @@ def config3():
         lane_ms += be.timings()["factor_ms"]
         out_l[i0:i0 + lanes] = 0.5 * ld - 0.5 * (c @ zBz) - 0.5 * n * np.log(2 * np.pi)
     wall_l = time.perf_counter() - t1
+    # the same points with gradients: + selected inversion + tr(Q^-1 B_j) against the resident basis (d logpdf / d c_j)
+    ng = min(16, len(thetas))
+    t2 = time.perf_counter()
+    sel_ms = 0.0
+    grads = np.empty((ng, basis.shape[0]))
+    for i, (tau, rng_) in enumerate(thetas[:ng]):
+        c = model.coefficients(tau, rng_)
+        be.refactorize_combination(c)
+        be.selinv_compute(); sel_ms += be.timings()["selinv_ms"]
+        grads[i] = 0.5 * (be.selinv_dot_basis() - zBz)
+    wall_g = time.perf_counter() - t2
+    trace_identity = float(np.max(np.abs(np.array([model.coefficients(*th) @ (2.0 * g + zBz) for th, g in zip(thetas[:ng], grads)]) - n)) / n)
     # spot check one point against the host-assembled matrix
     tau, rng_ = thetas[len(thetas) // 2]
     Q = model.precision(tau, rng_)
@@ -162,7 +174,8 @@ def config3():
          evals_per_s=round(len(thetas) / wall, 1), lanes=lanes, lanes_sweep_wall_s=round(wall_l, 3),
          lanes_device_ms_per_eval=round(lane_ms / len(thetas), 3), lanes_evals_per_s=round(len(thetas) / wall_l, 1),
          lanes_vs_single_max_rel=float(np.max(np.abs(out_l - out) / np.abs(out))), logpdf_spotcheck_rel=float(abs(chk - out[len(thetas) // 2]) / abs(chk)),
-         status=be.status, roofline={"single": roofline(be.info(), dev_ms / len(thetas)), "lanes": roofline(be.info(), lane_ms / len(thetas))})
+         gradient_evals=ng, gradient_wall_ms_per_eval=round(1e3 * wall_g / ng, 3), selinv_ms_per_eval=round(sel_ms / ng, 3),
+         trace_identity_rel=trace_identity, status=be.status, roofline={"single": roofline(be.info(), dev_ms / len(thetas)), "lanes": roofline(be.info(), lane_ms / len(thetas))})
 
 
 def config5():
