@@ -106,3 +106,20 @@ class LinearGaussianLikelihood:
 
     def loghessian(self, x):
         return self._H
+
+
+class BernoulliLikelihood:
+    """y_i ~ Bernoulli(logistic(x_i)) (canonical logit link; ExponentialFamily(Bernoulli) of the reference's tests)."""
+
+    def __init__(self, y):
+        self.y = np.asarray(y, dtype=np.float64)
+
+    def loglik(self, x):
+        return float(np.sum(self.y * x - np.logaddexp(0.0, x)))
+
+    def loggrad(self, x):
+        return self.y - 1.0 / (1.0 + np.exp(-x))
+
+    def loghessian(self, x):
+        p = 1.0 / (1.0 + np.exp(-x))
+        return -p * (1.0 - p)

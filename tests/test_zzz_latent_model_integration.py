@@ -306,3 +306,53 @@ def test_plain_gmrf_with_a_non_diagonal_hessian(kw):
     assert np.allclose(post.mean(), exact.mean(), rtol=1e-8, atol=1e-10)
     assert np.allclose(post.precision.toarray(), exact.precision.toarray(), rtol=1e-12, atol=1e-12)
     assert np.allclose(post.var(), exact.var(), rtol=1e-8)
+
+
+# --------------------------------------------------------- constrained Gaussian approximation (test_workspace_constrained.jl:88-133)
+def _kkt_mode(Q, A, e, grad, hess_diag, x0, iters=100):
+    """Dense equality-constrained Newton: minimise 0.5 x'Qx - loglik(x) subject to A x = e."""
+    x = x0.copy()
+    m = A.shape[0]
+    for _ in range(iters):
+        H = Q - np.diag(hess_diag(x))
+        g = Q @ x - grad(x)
+        K = np.block([[H, A.T], [A, np.zeros((m, m))]])
+        step = np.linalg.solve(K, np.concatenate([-g, e - A @ x]))[: x.size]
+        x = x + step
+        if np.linalg.norm(step) < 1e-13:
+            break
+    return x
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+@pytest.mark.parametrize("family", ["poisson", "bernoulli"])
+def test_constrained_gaussian_approximation(kw, family):
+    """The Newton step is projected onto the constraint's tangent space with one blocked multi-RHS solve
+    (`_workspace_constrain_step`, workspace/gaussian_approximation.jl:137-149); the mode is the KKT point."""
+    from latent_stand_ins import BernoulliLikelihood
+    if family == "poisson":
+        y = np.array([2, 1, 3, 0, 4, 1, 2, 3], dtype=float)
+        lik, max_iter = PoissonLikelihood(y), 50
+    else:
+        y = np.array([1, 0, 1, 0], dtype=float)
+        lik, max_iter = BernoulliLikelihood(y), 20
+    n = y.size
+    Q = sp.identity(n, format="csc")
+    A, e = np.ones((1, n)), np.zeros(1)
+    prior = WorkspaceGMRF(np.zeros(n), Q, A=A, e=e, **kw())
+    post = gaussian_approximation(prior, lik, max_iter=max_iter, mean_change_tol=1e-10, newton_dec_tol=1e-12)
+    assert isinstance(post, WorkspaceGMRF) and post.has_constraints()
+    assert abs(np.sum(post.mean())) <= 1e-6
+    mode = _kkt_mode(Q.toarray(), A, e, lik.loggrad, lik.loghessian, np.zeros(n))
+    assert np.allclose(post.mean(), mode, rtol=1e-6, atol=1e-8)
+    # default tolerances, as in the reference's test: same mode to its rtol
+    post_d = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, A=A, e=e, **kw()), lik, max_iter=max_iter)
+    assert np.allclose(post_d.mean(), mode, rtol=1e-4, atol=1e-5) and abs(np.sum(post_d.mean())) <= 1e-6
+    # two constraints with a non-zero right-hand side
+    if family == "poisson":
+        A2 = np.vstack([np.ones(n), (np.arange(n) % 2 == 0).astype(float)])
+        e2 = np.array([0.5, -0.25])
+        post2 = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, A=A2, e=e2, **kw()), lik, mean_change_tol=1e-10, newton_dec_tol=1e-12)
+        assert np.allclose(A2 @ post2.mean(), e2, atol=1e-8)
+        x0 = np.linalg.lstsq(A2, e2, rcond=None)[0]
+        assert np.allclose(post2.mean(), _kkt_mode(Q.toarray(), A2, e2, lik.loggrad, lik.loghessian, x0), rtol=1e-6, atol=1e-8)
