@@ -27,6 +27,16 @@ def fixtures():
     }
 
 
+def dot_matrix_values(Q):
+    """(Q as sorted CSC, column of every stored entry, values of the deterministic non-symmetric B on Q's pattern) used by
+    the `dot_value` goldens; tests rebuild B from this formula instead of storing it."""
+    Qc = sp.csc_matrix(Q)
+    Qc.sort_indices()
+    cols = np.repeat(np.arange(Qc.shape[1]), np.diff(Qc.indptr))
+    bvals = np.sin(1.0 + 0.37 * np.arange(Qc.nnz)) + 0.25 * np.cos(0.11 * Qc.indices * (cols + 1))
+    return Qc, cols, bvals
+
+
 def main():
     out = {}
     for name, Q in fixtures().items():
@@ -45,6 +55,12 @@ def main():
         out[name + "/inv_rows"] = coo.row[sel]
         out[name + "/inv_cols"] = coo.col[sel]
         out[name + "/inv_vals"] = Dinv[coo.row[sel], coo.col[sel]]
+        # tr(Q^-1 B) for a deterministic (non-symmetric) B on Q's pattern -- selinv_dot, backend.jl:265-267 -- with the sum
+        # of |terms| as the scale of its tolerance; and tr(Q^-1 Q) = n
+        Qc, cols, bvals = dot_matrix_values(Q)
+        terms = Dinv[Qc.indices, cols] * bvals
+        out[name + "/dot_value"] = np.array(terms.sum())
+        out[name + "/dot_scale"] = np.array(np.abs(terms).sum())
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures.npz"), **out)
     print("wrote", len(out), "arrays")
 

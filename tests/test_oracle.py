@@ -38,6 +38,11 @@ def test_oracle_against_golden(name, order):
     S = F.selinv()
     got = np.asarray(S[GOLD[name + "/inv_rows"], GOLD[name + "/inv_cols"]]).ravel()
     assert np.allclose(got, GOLD[name + "/inv_vals"], rtol=1e-6, atol=0)
+    # tr(Q^-1 B) for the golden's deterministic non-symmetric B on Q's pattern (selinv_dot, backend.jl:265-267):
+    # entries of the selected inverse to relative 1e-8 => the trace to 1e-8 * sum |terms|
+    Qc, cols, bvals = make_golden.dot_matrix_values(Q)
+    tr = float(np.dot(np.asarray(S[Qc.indices, cols]).ravel(), bvals))
+    assert abs(tr - GOLD[name + "/dot_value"]) <= 1e-8 * GOLD[name + "/dot_scale"]
 
 
 def test_oracle_sampling_half_solve_covariance():

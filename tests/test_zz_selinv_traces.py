@@ -283,3 +283,26 @@ def test_cholesky_sqrt_export(case):
     assert R2.indices is R.indices or np.array_equal(R2.indices, R.indices)
     assert abs(R2 - np.sqrt(2.0) * R).max() <= 1e-12 * abs(R).max()
     be.close()
+
+
+# ---------------------------------------------------------------------------------------------- golden traces, GPU only
+@pytest.mark.gpu
+@pytest.mark.parametrize("ordering", [None, "amd", "natural"])
+def test_selinv_dot_against_golden_traces(ordering):
+    """tr(Q^-1 B) of the six golden fixtures (dense LAPACK inverse, tests/golden/make_golden.py) through the device-side
+    contraction, under three orderings."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "fixtures.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    for name, Q in mg.fixtures().items():
+        Qc, cols, bvals = mg.dot_matrix_values(Q)
+        B = sp.csc_matrix((bvals, Qc.indices, Qc.indptr), shape=Qc.shape)
+        kw = {} if ordering is None else {"ordering": ordering}
+        ws = GMRFWorkspace(Q, device=0, **kw)
+        got = ws.selinv_dot(B)
+        assert abs(got - float(gold[name + "/dot_value"])) <= 1e-8 * float(gold[name + "/dot_scale"]), name
+        assert abs(ws.selinv_dot(Q) - Q.shape[0]) <= 1e-8 * float(abs(Q).multiply(abs(ws.selinv_extract_at(Q))).sum()), name
