@@ -130,6 +130,7 @@ struct gmrf_b200_handle {
     int pp_base = 0;
     bool pp_valid = false;
     i64 pp_hits = 0;
+    unsigned long long pattern_hash = 0;   // of the (0-based) input pattern: ties an exported analysis to its matrix
     // factor export P'L as CSC (lazy; CholeskySqrt-style consumers)
     std::vector<i64> l_colptr, l_rowval;
     long long *d_lpos = nullptr;
@@ -1513,8 +1514,8 @@ int gmrf_b200_set_option(const char *key, double value) {
 
 const char *gmrf_b200_last_error(const gmrf_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
-                     const int64_t *perm, int ordering, int device) {
+static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
+                       const int64_t *perm, int ordering, int device, const void *analysis, int64_t analysis_bytes) {
     g_create_error.clear();
     if (!out) { g_create_error = "out is null"; return GMRF_B200_ERR_ARG; }
     *out = nullptr;
@@ -1546,7 +1547,9 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
             if (it != e && *it == j) h->diag_nzpos[(size_t)j] = (long long)(it - rv.data());
         }
         NvtxRange nvtx_("gmrf_b200:analysis");
-        analyze(h->S, n, cp.data(), rv.data(), perm ? pm.data() : nullptr, ordering, h->opt);
+        h->pattern_hash = gmrf::pattern_hash(n, cp.data(), rv.data());
+        if (analysis) gmrf::deserialize(h->S, static_cast<const char *>(analysis), (size_t)analysis_bytes, n, nnz, h->pattern_hash);
+        else analyze(h->S, n, cp.data(), rv.data(), perm ? pm.data() : nullptr, ordering, h->opt);
     } catch (std::exception &e) {
         g_create_error = e.what();
         return GMRF_B200_ERR_ARG;
@@ -1680,6 +1683,38 @@ int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, c
 #undef TRY_RC
     *out = h.release();
     return 0;
+}
+
+int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
+                     const int64_t *perm, int ordering, int device) {
+    return create_impl(out, n, colptr, rowval, index_base, perm, ordering, device, nullptr, 0);
+}
+
+// ---- persisting / sharing the symbolic analysis ------------------------------------------------------------------
+int gmrf_b200_create_from_analysis(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
+                                   const void *analysis, int64_t analysis_bytes, int device) {
+    if (!analysis || analysis_bytes <= 0) {
+        g_create_error = "create_from_analysis: empty analysis blob";
+        if (out) *out = nullptr;
+        return GMRF_B200_ERR_ARG;
+    }
+    return create_impl(out, n, colptr, rowval, index_base, nullptr, 0, device, analysis, analysis_bytes);
+}
+
+int gmrf_b200_analysis_export(const gmrf_b200_handle *h, void *buf, int64_t capacity, int64_t *bytes) {
+    if (!h || !bytes) return GMRF_B200_ERR_ARG;
+    std::vector<char> blob;
+    gmrf::serialize(h->S, h->pattern_hash, blob);
+    *bytes = (int64_t)blob.size();
+    if (!buf) return 0;                                   // size query
+    if (capacity < (int64_t)blob.size()) return GMRF_B200_ERR_ARG;
+    std::memcpy(buf, blob.data(), blob.size());
+    return 0;
+}
+
+int gmrf_b200_analysis_equal(const gmrf_b200_handle *a, const gmrf_b200_handle *b) {
+    if (!a || !b) return GMRF_B200_ERR_ARG;
+    return gmrf::equal(a->S, b->S) && a->diag_nzpos == b->diag_nzpos ? 1 : 0;
 }
 
 void gmrf_b200_destroy(gmrf_b200_handle *h) {

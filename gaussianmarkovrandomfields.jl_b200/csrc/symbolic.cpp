@@ -814,4 +814,104 @@ i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i
     return bad;
 }
 
+// ------------------------------------------------------------------------------------------------
+// serialization of the analysis
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// ONE enumeration of the members of Symbolic, shared by serialize / deserialize / equal (keep in step with symbolic.hpp)
+template <class V>
+void visit_members(Symbolic &S, V &v) {
+    v.scalar(S.n); v.scalar(S.nnzA);
+    v.vec(S.perm); v.vec(S.iperm); v.vec(S.parent); v.vec(S.colcount);
+    v.scalar(S.nnzL); v.scalar(S.flops);
+    v.scalar(S.nsuper);
+    v.vec(S.sfirst); v.vec(S.sparent); v.vec(S.col2super); v.vec(S.rowptr); v.vec(S.rowidx); v.vec(S.relidx);
+    v.vec(S.panel_off); v.vec(S.panel_ld);
+    v.scalar(S.panel_total); v.scalar(S.flops_stored);
+    v.vec(S.child_ptr); v.vec(S.child_idx); v.vec(S.level);
+    v.scalar(S.nlevels);
+    v.vec(S.level_ptr); v.vec(S.level_idx);
+    v.vec(S.upd_off); v.vec(S.upd_ld);
+    v.scalar(S.upd_total);
+    v.vec(S.zw_off);
+    v.scalar(S.zw_total);
+    v.vec(S.uvec_off);
+    v.scalar(S.uvec_total);
+    v.vec(S.q_src); v.vec(S.q_dst); v.vec(S.diag_pos);
+    v.scalar(S.max_front); v.scalar(S.max_ns);
+}
+// symbolic.hpp: 13 stored scalars + analysis_ms (not stored) + 24 vectors; a new member changes this size
+static_assert(sizeof(Symbolic) == 13 * 8 + 8 /*analysis_ms*/ + 24 * sizeof(std::vector<i64>), "Symbolic changed: update visit_members");
+
+struct Writer {
+    std::vector<char> &out;
+    template <class T> void raw(const T *p, size_t cnt) { const char *c = reinterpret_cast<const char *>(p); out.insert(out.end(), c, c + cnt * sizeof(T)); }
+    template <class T> void scalar(T &x) { raw(&x, 1); }
+    template <class T> void vec(std::vector<T> &x) { i64 cnt = (i64)x.size(), w = (i64)sizeof(T); raw(&cnt, 1); raw(&w, 1); raw(x.data(), x.size()); }
+};
+struct Reader {
+    const char *p, *end;
+    template <class T> void raw(T *dst, size_t cnt) {
+        if ((size_t)(end - p) < cnt * sizeof(T)) throw std::runtime_error("analysis blob is truncated");
+        std::memcpy(dst, p, cnt * sizeof(T));
+        p += cnt * sizeof(T);
+    }
+    template <class T> void scalar(T &x) { raw(&x, 1); }
+    template <class T> void vec(std::vector<T> &x) {
+        i64 cnt = 0, w = 0;
+        raw(&cnt, 1); raw(&w, 1);
+        if (cnt < 0 || w != (i64)sizeof(T) || (size_t)(end - p) < (size_t)cnt * sizeof(T)) throw std::runtime_error("analysis blob is malformed");
+        x.resize((size_t)cnt);
+        raw(x.data(), (size_t)cnt);
+    }
+};
+constexpr char BLOB_MAGIC[8] = {'G', 'M', 'R', 'F', 'S', 'Y', 'M', '1'};
+
+}  // namespace
+
+unsigned long long pattern_hash(i64 n, const i64 *colptr, const i64 *rowval) {
+    unsigned long long h = 1469598103934665603ULL;          // FNV-1a, one 64-bit word per step
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ULL; h ^= h >> 29; };
+    mix((unsigned long long)n);
+    for (i64 j = 0; j <= n; j++) mix((unsigned long long)colptr[j]);
+    for (i64 p = 0; p < colptr[n]; p++) mix((unsigned long long)rowval[p]);
+    return h;
+}
+
+void serialize(const Symbolic &S, unsigned long long ph, std::vector<char> &out) {
+    out.clear();
+    Writer w{out};
+    w.raw(BLOB_MAGIC, 8);
+    w.scalar(ph);
+    visit_members(const_cast<Symbolic &>(S), w);
+}
+
+void deserialize(Symbolic &S, const char *data, size_t len, i64 n, i64 nnz, unsigned long long pattern_hash_) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (!data || len < 16 || std::memcmp(data, BLOB_MAGIC, 8) != 0) throw std::runtime_error("not an analysis blob of this library version");
+    Reader r{data + 8, data + len};
+    unsigned long long ph = 0;
+    r.scalar(ph);
+    S = Symbolic();
+    visit_members(S, r);
+    if (r.p != r.end) throw std::runtime_error("analysis blob has trailing bytes");
+    if (S.n != n || S.nnzA != nnz) throw std::runtime_error("analysis blob belongs to a different matrix (size / nnz)");
+    if (ph != pattern_hash_) throw std::runtime_error("analysis blob belongs to a different sparsity pattern");
+    // cheap structural sanity of what the device code indexes with
+    if ((i64)S.perm.size() != n || (i64)S.iperm.size() != n || (i64)S.col2super.size() != n || (i64)S.diag_pos.size() != n ||
+        (i64)S.sfirst.size() != S.nsuper + 1 || (i64)S.rowptr.size() != S.nsuper + 1 || (i64)S.panel_off.size() != S.nsuper + 1 ||
+        (i64)S.level_ptr.size() != S.nlevels + 1 || S.rowidx.size() != S.relidx.size() || S.q_src.size() != S.q_dst.size())
+        throw std::runtime_error("analysis blob is inconsistent");
+    S.analysis_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+bool equal(const Symbolic &a, const Symbolic &b) {
+    std::vector<char> x, y;
+    Writer wx{x}, wy{y};
+    visit_members(const_cast<Symbolic &>(a), wx);
+    visit_members(const_cast<Symbolic &>(b), wy);
+    return x == y;
+}
+
 }  // namespace gmrf

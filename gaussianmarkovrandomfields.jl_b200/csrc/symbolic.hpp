@@ -94,6 +94,14 @@ void analyze(Symbolic &S, i64 n, const i64 *colptr, const i64 *rowval, const i64
 // Returns -1, or the index p of the first entry whose row index is out of range.
 i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i64 index_base, long long *pos);
 
+// Persisting the analysis (the only state worth keeping across sessions / sharing between the handles of a pool):
+// a self-describing little-endian byte stream of every member of Symbolic plus a hash of the pattern it belongs to.
+// deserialize throws std::runtime_error on a malformed / truncated stream or a pattern mismatch.
+unsigned long long pattern_hash(i64 n, const i64 *colptr, const i64 *rowval);   // 0-based CSC pattern
+void serialize(const Symbolic &S, unsigned long long pattern_hash, std::vector<char> &out);
+void deserialize(Symbolic &S, const char *data, size_t len, i64 n, i64 nnz, unsigned long long pattern_hash);
+bool equal(const Symbolic &a, const Symbolic &b);   // every member (analysis_ms excepted)
+
 // orderings (0-based adjacency without self loops: xadj[n+1], adj[])
 void order_metis_nd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);
 void order_amd(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, std::vector<i64> &perm);

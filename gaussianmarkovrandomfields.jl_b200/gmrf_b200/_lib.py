@@ -31,6 +31,7 @@ EXPORTS = [
     "gmrf_b200_test_gemm", "gmrf_b200_test_potrf", "gmrf_b200_test_potrf_inv", "gmrf_b200_bench_gemm", "gmrf_b200_profile_refactorize", "gmrf_b200_profile_plan", "gmrf_b200_device_array", "gmrf_b200_set_value_basis", "gmrf_b200_set_base_values", "gmrf_b200_refactorize_base_minus_diag", "gmrf_b200_lane_capacity", "gmrf_b200_refactorize_lanes", "gmrf_b200_refactorize_combination_lanes", "gmrf_b200_refactorize_combination", "gmrf_b200_adopt_factor", "gmrf_b200_host_register", "gmrf_b200_host_unregister",
     "gmrf_b200_selinv_dot", "gmrf_b200_selinv_dot_basis",
     "gmrf_b200_factor_nnz", "gmrf_b200_factor_pattern", "gmrf_b200_factor_values", "gmrf_b200_pattern_positions",
+    "gmrf_b200_create_from_analysis", "gmrf_b200_analysis_export", "gmrf_b200_analysis_equal",
 ]
 
 _lib = None
@@ -77,6 +78,12 @@ def lib():
     L.gmrf_b200_selinv_values.argtypes = [c_vp, c_vp]
     L.gmrf_b200_selinv_extract.restype = ctypes.c_int
     L.gmrf_b200_selinv_extract.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp]
+    L.gmrf_b200_create_from_analysis.restype = ctypes.c_int
+    L.gmrf_b200_create_from_analysis.argtypes = [ctypes.POINTER(c_vp), c_i64, c_vp, c_vp, ctypes.c_int, c_vp, c_i64, ctypes.c_int]
+    L.gmrf_b200_analysis_export.restype = ctypes.c_int
+    L.gmrf_b200_analysis_export.argtypes = [c_vp, c_vp, c_i64, c_i64p]
+    L.gmrf_b200_analysis_equal.restype = ctypes.c_int
+    L.gmrf_b200_analysis_equal.argtypes = [c_vp, c_vp]
     L.gmrf_b200_pattern_positions.restype = ctypes.c_int
     L.gmrf_b200_pattern_positions.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp]
     L.gmrf_b200_factor_nnz.restype = ctypes.c_int

@@ -80,14 +80,18 @@ def ordering_permutation(A, ordering) -> np.ndarray:
 class _Handle:
     """Owns one gmrf_b200_handle*."""
 
-    def __init__(self, n, colptr, rowval, perm, ordering_code, device):
+    def __init__(self, n, colptr, rowval, perm, ordering_code, device, analysis: bytes | None = None):
         L = _lib.lib()
         self._L = L
         self._h = ctypes.c_void_p()
         cp = np.ascontiguousarray(colptr, dtype=np.int64)
         rv = np.ascontiguousarray(rowval, dtype=np.int64)
         pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int64)
-        rc = L.gmrf_b200_create(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(pm), int(ordering_code), int(device))
+        if analysis is not None:       # symbolic analysis read from an exported stream instead of recomputed
+            blob = np.frombuffer(analysis, dtype=np.uint8)
+            rc = L.gmrf_b200_create_from_analysis(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(blob), blob.size, int(device))
+        else:
+            rc = L.gmrf_b200_create(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(pm), int(ordering_code), int(device))
         if rc != 0:
             msg = L.gmrf_b200_last_error(None).decode()
             self._h = None
@@ -115,6 +119,14 @@ class _Handle:
         p = np.empty(self.n, dtype=np.int64)
         self.check(self._L.gmrf_b200_get_perm(self._h, ptr(p), 0))
         return p
+
+    def export_analysis(self) -> bytes:
+        """The symbolic analysis as a byte stream for `_Handle(..., analysis=...)` / `B200Backend(Q, analysis=...)`."""
+        nbytes = ctypes.c_int64()
+        self.check(self._L.gmrf_b200_analysis_export(self._h, None, 0, ctypes.byref(nbytes)))
+        buf = np.empty(nbytes.value, dtype=np.uint8)
+        self.check(self._L.gmrf_b200_analysis_export(self._h, ptr(buf), buf.size, ctypes.byref(nbytes)))
+        return buf.tobytes()
 
     def factor_pattern(self):
         """(colptr, rowval) of the square root P'L as CSC, 0-based (symbolic: valid on analysis-only handles)."""
@@ -145,21 +157,22 @@ class B200Backend:
     (test_gmrf_workspace.jl:214,219): `selinv_cache`, `selinv_diag_cache`.
     """
 
-    def __init__(self, Q, ordering=None, device: int = 0, check: bool = False, factorize: bool = True):
+    def __init__(self, Q, ordering=None, device: int = 0, check: bool = False, factorize: bool = True,
+                 analysis: bytes | None = None):
         Q = _csc(Q)
         if Q.shape[0] != Q.shape[1]:
             raise ValueError("Q must be square")
         self.n = Q.shape[0]
         self.check_pd = check
         perm, code = None, _lib.ORDER_ND
-        if ordering is not None:
+        if ordering is not None and analysis is None:
             if isinstance(ordering, str) and not isinstance(ordering, PinDenseColumns):
                 code = _ORDER_CODES[ordering.lower()]
             else:
                 perm = ordering_permutation(Q, ordering)
         self._colptr = Q.indptr.astype(np.int64)
         self._rowval = Q.indices.astype(np.int64)
-        self._hd = _Handle(self.n, self._colptr, self._rowval, perm, code, device)
+        self._hd = _Handle(self.n, self._colptr, self._rowval, perm, code, device, analysis=analysis)
         self._L = self._hd._L
         self.device = device
         self.selinv_cache = None
@@ -284,6 +297,11 @@ class B200Backend:
         vals = np.empty(rv.size, dtype=np.float64)
         self._hd.check(self._L.gmrf_b200_factor_values(self._hd._h, ptr(vals)))
         return sp.csc_matrix((vals, rv, cp), shape=(self.n, self.n))
+
+    def export_analysis(self) -> bytes:
+        """Byte stream of this backend's symbolic analysis: `B200Backend(Q2, analysis=blob)` on the same pattern skips
+        ordering, elimination tree, supernodes and schedule construction (another session, another GPU of a pool)."""
+        return self._hd.export_analysis()
 
     # -- extras --------------------------------------------------------------------------------------
     def info(self) -> dict:

@@ -49,13 +49,22 @@ Symbolic analysis once (host) + first numeric factorization on `device`. `orderi
 vector, a CliqueTrees elimination algorithm, or `PinDenseColumns(...)` -- resolved on the host by the package's
 own `ordering_permutation` and handed over as a 1-based permutation.
 """
-function B200Backend(Q::SparseMatrixCSC{Float64, Int}; ordering = nothing, device::Integer = 0, check::Bool = false)
+function B200Backend(Q::SparseMatrixCSC{Float64, Int}; ordering = nothing, device::Integer = 0, check::Bool = false,
+        analysis::Union{Nothing, Vector{UInt8}} = nothing)
     n = size(Q, 1)
-    permvec = ordering === nothing ? Int[] : ordering_permutation(Q, ordering)
     href = Ref{Ptr{Cvoid}}(C_NULL)
+    if analysis !== nothing
+        # symbolic analysis read from `export_analysis(other_backend)` (same pattern): a later session on the same mesh,
+        # or the other GPUs of a pool -- ordering, elimination tree, supernodes and schedules are not recomputed
+        rc = GC.@preserve Q analysis ccall((:gmrf_b200_create_from_analysis, libgmrf), Cint,
+            (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{UInt8}, Int64, Cint),
+            href, n, SparseArrays.getcolptr(Q), rowvals(Q), 1, analysis, length(analysis), device)
+    else
+    permvec = ordering === nothing ? Int[] : ordering_permutation(Q, ordering)
     rc = GC.@preserve Q permvec ccall((:gmrf_b200_create, libgmrf), Cint,
         (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Cint),
         href, n, SparseArrays.getcolptr(Q), rowvals(Q), 1, isempty(permvec) ? C_NULL : pointer(permvec), 1, device)
+    end
     rc == 0 || throw(ArgumentError(unsafe_string(ccall((:gmrf_b200_last_error, libgmrf), Cstring, (Ptr{Cvoid},), C_NULL))))
     b = B200Backend(href[], n, nnz(Q), device, check, nothing, nothing, nothing, nothing)
     finalizer(x -> ccall((:gmrf_b200_destroy, libgmrf), Cvoid, (Ptr{Cvoid},), x.handle), b)
@@ -177,6 +186,15 @@ function cholesky_sqrt(b::B200Backend)
 end
 CholeskySqrt(b::B200Backend) = LinearMap(cholesky_sqrt(b))
 
+# The symbolic analysis as bytes (write it next to the mesh; `B200Backend(Q; analysis = bytes)` restores it)
+function export_analysis(b::B200Backend)
+    nb = Ref{Int64}(0)
+    _check(b, ccall((:gmrf_b200_analysis_export, libgmrf), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ref{Int64}), b.handle, C_NULL, 0, nb))
+    buf = Vector{UInt8}(undef, nb[])
+    _check(b, ccall((:gmrf_b200_analysis_export, libgmrf), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ref{Int64}), b.handle, buf, length(buf), nb))
+    return buf
+end
+
 # GMRFWorkspace(Q, B200Backend; ...) -- copy of cliquetrees_backend.jl:132-150
 function GMRFWorkspace(Q::SparseMatrixCSC{T}, ::Type{B200Backend}; kw...) where {T}
     n = size(Q, 1)
@@ -192,8 +210,12 @@ end
 function B200WorkspacePool(Q::SparseMatrixCSC; devices = 0:0, ordering = nothing)
     perm = ordering === nothing ? nothing : ordering_permutation(Q, ordering)
     ch = Channel{Any}(length(devices))
+    blob = nothing                                   # one analysis for the whole pool (workspace_pool.jl:55-58)
     for d in devices
-        put!(ch, GMRFWorkspace(Q, B200Backend; ordering = perm, device = d))
+        ws = blob === nothing ? GMRFWorkspace(Q, B200Backend; ordering = perm, device = d) :
+            GMRFWorkspace(Q, B200Backend; analysis = blob, device = d)
+        blob === nothing && (blob = export_analysis(ws.backend))
+        put!(ch, ws)
     end
     return B200WorkspacePool(ch)
 end

@@ -59,6 +59,18 @@ enum {
  * perm (optional): perm[k] = index (in `index_base`) of the k-th pivot. device < 0 -> analysis only. */
 int gmrf_b200_create(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval,
                      int index_base, const int64_t *perm, int ordering, int device);
+/* Persisting / sharing the symbolic analysis (the reference has no serialization: the symbolic half of its CHOLMOD
+ * factor lives and dies with the backend, backend.jl:32-61; SURVEY.md section 5 names the analysis as the one state worth
+ * keeping). `analysis_export` writes a self-describing byte stream (call with buf = NULL for the size);
+ * `create_from_analysis` is `create` with the ordering / etree / supernodes / schedules read from such a stream instead
+ * of recomputed -- for a second session on the same mesh, or for the other handles of a pool (one analysis, one handle
+ * per GPU: workspace_pool.jl:55-58 "resolve the permutation ONCE"). The stream is tied to the pattern by a hash; a
+ * different pattern, a truncated or foreign stream give -1 with a message. */
+int gmrf_b200_create_from_analysis(gmrf_b200_handle **out, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                                   int index_base, const void *analysis, int64_t analysis_bytes, int device);
+int gmrf_b200_analysis_export(const gmrf_b200_handle *h, void *buf, int64_t capacity, int64_t *bytes);
+/* 1 if the two handles hold identical analyses (every table), 0 if not: test hook for the round trip above */
+int gmrf_b200_analysis_equal(const gmrf_b200_handle *a, const gmrf_b200_handle *b);
 void gmrf_b200_destroy(gmrf_b200_handle *h);
 const char *gmrf_b200_last_error(const gmrf_b200_handle *h);   /* h may be NULL: last create error */
 

@@ -356,3 +356,33 @@ def test_constrained_gaussian_approximation(kw, family):
         assert np.allclose(A2 @ post2.mean(), e2, atol=1e-8)
         x0 = np.linalg.lstsq(A2, e2, rcond=None)[0]
         assert np.allclose(post2.mean(), _kkt_mode(Q.toarray(), A2, e2, lik.loggrad, lik.loghessian, x0), rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------- analysis export / import on the device
+@pytest.mark.gpu
+def test_backend_from_exported_analysis_is_bit_identical():
+    """`B200Backend(Q, analysis=blob)` skips ordering / etree / supernodes / schedules and must be indistinguishable from
+    the backend the blob came from: same permutation, bit-identical log-determinant, solve, half solve and variances."""
+    from gmrf_b200.backend import B200Backend
+    model = spde.MaternSPDE(*spde.mesh3d(8), 0)
+    Q = model.precision(1.0, 0.5)
+    n = Q.shape[0]
+    a = B200Backend(Q, device=0)
+    blob = a.export_analysis()
+    b = B200Backend(Q, device=0, analysis=blob)
+    assert np.array_equal(a.permutation(), b.permutation()) and a.info()["nnz_l"] == b.info()["nnz_l"]
+    rng = np.random.default_rng(0)
+    rhs = rng.standard_normal(n)
+    assert a.compute_logdet() == b.compute_logdet()
+    assert np.array_equal(a.backend_solve(rhs), b.backend_solve(rhs))
+    assert np.array_equal(a.backend_backward_solve(rhs), b.backend_backward_solve(rhs))
+    assert np.array_equal(a.get_selinv_diag(), b.get_selinv_diag())
+    Q2 = model.precision(0.4, 0.9)
+    a.refactorize(Q2)
+    b.refactorize(Q2)
+    assert a.compute_logdet() == b.compute_logdet()
+    assert abs(b.compute_logdet() - np.linalg.slogdet(Q2.toarray())[1]) <= 1e-10 * abs(b.compute_logdet())
+    with pytest.raises(ValueError):
+        B200Backend(spde.MaternSPDE(*spde.mesh3d(7), 0).precision(1.0, 0.5), device=0, analysis=blob)
+    a.close()
+    b.close()
