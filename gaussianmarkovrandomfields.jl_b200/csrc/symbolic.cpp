@@ -1,6 +1,10 @@
 // symbolic.cpp -- see symbolic.hpp. Integer graph work only; no floating-point matrix values are touched.
 #include "symbolic.hpp"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -606,38 +610,72 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
             for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
                 if (C.idx[p] < k) lidx[w[C.idx[p]]++] = k;
     }
+    phase("  lower-triangular column lists");
+    // the sizes are known from the supernode partition (a merged group has exactly cols(child) + rows(parent) rows), so the
+    // structures are written straight into their final place; a child's list is read from there by its parent
     S.rowptr.assign(S.nsuper + 1, 0);
+    for (i64 s = 0; s < S.nsuper; s++) S.rowptr[s + 1] = S.rowptr[s] + stack[s].nrow;
+    S.rowidx.resize(S.rowptr[S.nsuper]);
     {
-        std::vector<i64> mark(n, -1);
-        std::vector<std::vector<i32>> rows(S.nsuper);
-        i64 total = 0;
+        // a supernode needs only its children's finished lists: the supernodes of one assembly-tree level are independent
+        // and are built concurrently, each thread with its own marker array (stamp = supernode index)
+        std::vector<i32> lev(S.nsuper, 0);
+        i32 nlev = 0;
         for (i64 s = 0; s < S.nsuper; s++) {
-            i64 f = S.sfirst[s], l = S.sfirst[s + 1];
-            std::vector<i32> &r = rows[s];
-            for (i64 j = f; j < l; j++) { mark[j] = s; r.push_back((i32)j); }
-            for (i64 j = f; j < l; j++)
-                for (i64 p = lptr[j]; p < lptr[j + 1]; p++) {
-                    i64 i = lidx[p];
-                    if (mark[i] != s) { mark[i] = s; r.push_back((i32)i); }
+            const i64 p = S.sparent[s];
+            if (p != -1) lev[p] = std::max(lev[p], lev[s] + 1);
+            nlev = std::max(nlev, lev[s] + 1);
+        }
+        std::vector<i64> lptr_(nlev + 1, 0), lidx_(S.nsuper);
+        for (i64 s = 0; s < S.nsuper; s++) lptr_[lev[s] + 1]++;
+        for (i32 v = 0; v < nlev; v++) lptr_[v + 1] += lptr_[v];
+        {
+            std::vector<i64> w(lptr_.begin(), lptr_.end() - 1);
+            for (i64 s = 0; s < S.nsuper; s++) lidx_[w[lev[s]]++] = s;
+        }
+        int nthreads = 1;
+#ifdef _OPENMP
+        nthreads = omp_get_max_threads();
+#endif
+        std::vector<std::vector<i64>> marks((size_t)nthreads);
+        int bad = 0;
+        for (i32 v = 0; v < nlev; v++) {
+            const i64 a = lptr_[v], b = lptr_[v + 1];
+#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad) if (b - a >= 64)
+            for (i64 t = a; t < b; t++) {
+                int tid = 0;
+#ifdef _OPENMP
+                tid = omp_get_thread_num();
+#endif
+                std::vector<i64> &mark = marks[(size_t)tid];
+                if (mark.empty()) mark.assign((size_t)n, -1);
+                const i64 s = lidx_[t];
+                const i64 f = S.sfirst[s], l = S.sfirst[s + 1], cap = S.rowptr[s + 1] - S.rowptr[s];
+                i32 *r = S.rowidx.data() + S.rowptr[s];
+                i64 cnt = 0;
+                auto push = [&](i64 i) {
+                    if (mark[i] == s) return;
+                    if (cnt >= cap) { bad |= 1; return; }
+                    mark[i] = s;
+                    r[cnt++] = (i32)i;
+                };
+                for (i64 j = f; j < l; j++) push(j);
+                for (i64 j = f; j < l; j++)
+                    for (i64 p = lptr[j]; p < lptr[j + 1]; p++) push(lidx[p]);
+                for (i64 cp = S.child_ptr[s]; cp < S.child_ptr[s + 1]; cp++) {
+                    const i64 c = S.child_idx[cp];
+                    const i64 cns = S.sfirst[c + 1] - S.sfirst[c];
+                    const i32 *cr = S.rowidx.data() + S.rowptr[c];
+                    const i64 cn = S.rowptr[c + 1] - S.rowptr[c];
+                    for (i64 u = cns; u < cn; u++) push(cr[u]);
                 }
-            for (i64 cp = S.child_ptr[s]; cp < S.child_ptr[s + 1]; cp++) {
-                i64 c = S.child_idx[cp];
-                const std::vector<i32> &cr = rows[c];
-                i64 cns = S.sfirst[c + 1] - S.sfirst[c];
-                for (size_t t = (size_t)cns; t < cr.size(); t++) {
-                    i64 i = cr[t];
-                    if (mark[i] != s) { mark[i] = s; r.push_back((i32)i); }
-                }
+                if (cnt != cap) bad |= 2;
+                std::sort(r + (l - f), r + cnt);
             }
-            std::sort(r.begin() + (l - f), r.end());
-            total += (i64)r.size();
-            S.rowptr[s + 1] = total;
+            if (bad) break;
         }
-        S.rowidx.resize(total);
-        for (i64 s = 0; s < S.nsuper; s++) {
-            std::copy(rows[s].begin(), rows[s].end(), S.rowidx.begin() + S.rowptr[s]);
-            // children's row lists are no longer needed once the parent is built; free eagerly
-        }
+        if (bad & 1) throw std::runtime_error("internal: supernode row structure larger than its column count");
+        if (bad & 2) throw std::runtime_error("internal: supernode row structure smaller than its column count");
     }
     phase("row structures");
     // relative indices
