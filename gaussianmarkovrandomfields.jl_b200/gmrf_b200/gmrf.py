@@ -73,6 +73,13 @@ class GMRF:
         Z = np.asfortranarray(rng.standard_normal((m, n)).T)
         return self.linsolve_cache.backend_backward_solve(Z) + self.mean_[:, None]
 
+    def sqmahal(self, x):                                               # gmrf.jl:94-97
+        d = np.asarray(x, dtype=np.float64) - self.mean_
+        return float(d @ (self.precision @ d))
+
+    def gradlogpdf(self, x):                                            # gmrf.jl:100
+        return -(self.precision @ (np.asarray(x, dtype=np.float64) - self.mean_))
+
     def logpdf(self, z):
         r = np.asarray(z, dtype=np.float64) - self.mean_
         return float(-0.5 * (r @ (self.precision @ r)) - 0.5 * self.logdetcov() - 0.5 * len(self) * math.log(2.0 * math.pi))

@@ -167,6 +167,15 @@ class WorkspaceGMRF:
         return float(val)
 
 
+    # generic AbstractGMRF methods, src/gmrf.jl:94-100 (about the mean `mean(d)` returns: the constrained one, if any)
+    def sqmahal(self, x):
+        d = np.asarray(x, dtype=np.float64) - self.mean()
+        return float(d @ (self.precision @ d))
+
+    def gradlogpdf(self, x):
+        return -(self.precision @ (np.asarray(x, dtype=np.float64) - self.mean()))
+
+
 class PoissonLikelihood:
     """Poisson observations with the canonical log link: y_i ~ Poisson(exp(x[indices[i]])). `loghessian` returns the
     diagonal (length n) of the (diagonal) Hessian, the `Diagonal` of canonical_implementations.jl:265-270."""

@@ -386,3 +386,68 @@ def test_backend_from_exported_analysis_is_bit_identical():
         B200Backend(spde.MaternSPDE(*spde.mesh3d(7), 0).precision(1.0, 0.5), device=0, analysis=blob)
     a.close()
     b.close()
+
+
+# ------------------------------------------------------- remaining testsets of test_workspace_gmrf.jl / test_workspace_gaussian_approximation.jl
+def _tri(n, d, e):
+    return sp.diags([np.full(n - 1, e), np.full(n, d), np.full(n - 1, e)], [-1, 0, 1]).tocsc()
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_sqmahal_gradlogpdf_and_shared_means(kw):           # test_workspace_gmrf.jl:76-88, :147-160
+    from gmrf_b200.workspace import GMRFWorkspace
+    n = 12
+    rng = np.random.default_rng(0)
+    Q = (_tri(n, 2.5, -0.9) + sp.diags(rng.uniform(0, 0.3, n))).tocsc()
+    Qd = Q.toarray()
+    mu = rng.standard_normal(n)
+    wg = WorkspaceGMRF(mu, Q, **kw())
+    x = rng.standard_normal(n)
+    assert abs(wg.sqmahal(x) - (x - mu) @ Qd @ (x - mu)) <= 1e-10 * wg.sqmahal(x) and abs(wg.sqmahal(mu)) <= 1e-12
+    assert np.allclose(wg.gradlogpdf(mu), 0.0, atol=1e-10)
+    assert np.allclose(wg.gradlogpdf(x), -Qd @ (x - mu), rtol=1e-10)
+    ws = GMRFWorkspace(Q, **kw())
+    wa, wb = WorkspaceGMRF(np.zeros(n), Q, ws), WorkspaceGMRF(np.ones(n), Q, ws)
+    z = rng.standard_normal(n)
+    assert np.array_equal(wa.mean(), np.zeros(n)) and np.array_equal(wb.mean(), np.ones(n))
+    for w, m in ((wa, np.zeros(n)), (wb, np.ones(n))):
+        assert abs(w.logpdf(z) - _dense_logpdf(Q, m, z)) <= 1e-10 * abs(w.logpdf(z))
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_prior_and_posterior_stay_coherent_around_a_gaussian_approximation(kw):
+    """test_workspace_gmrf.jl:162-204 and test_workspace_gaussian_approximation.jl:76-122: GA leaves the shared workspace
+    at Q_post; the prior keeps evaluating against Q_prior, GA seeds from its owner's snapshot, the posterior's
+    factorization is deferred to its first consumer, the prior's precision object is untouched."""
+    from gmrf_b200.workspace import GMRFWorkspace
+    y5 = np.array([2, 1, 3, 0, 4], dtype=float)
+    lik5 = PoissonLikelihood(y5)
+    Qp = _tri(5, 2.0, -0.3)
+    z = np.random.default_rng(1).standard_normal(5)
+    z -= z.mean()
+    ws = GMRFWorkspace(Qp.copy(), **kw())
+    prior = WorkspaceGMRF(np.zeros(5), Qp.copy(), ws)
+    lp_ref = _dense_logpdf(Qp, np.zeros(5), z)
+    assert abs(prior.logpdf(z) - lp_ref) <= 1e-10 * abs(lp_ref)
+    gaussian_approximation(prior, lik5)
+    assert abs(prior.logpdf(z) - lp_ref) <= 1e-10 * abs(lp_ref)          # both the quadratic form and the logdet
+    # two priors on one workspace: GA on A after B touched the workspace last
+    Qa, Qb = _tri(5, 2.0, -0.3), _tri(5, 5.0, -0.7)
+    ws2 = GMRFWorkspace(Qa.copy(), **kw())
+    wa, wb = WorkspaceGMRF(np.zeros(5), Qa.copy(), ws2), WorkspaceGMRF(np.zeros(5), Qb.copy(), ws2)
+    wb.logpdf(np.random.default_rng(2).standard_normal(5))
+    post = gaussian_approximation(wa, lik5)
+    ref = gaussian_approximation(WorkspaceGMRF(np.zeros(5), Qa.copy(), **dense_kw()), lik5)
+    assert np.allclose(post.mean(), ref.mean(), rtol=1e-8, atol=1e-12)
+    assert abs(post.logpdf(np.zeros(5)) - ref.logpdf(np.zeros(5))) <= 1e-8 * abs(ref.logpdf(np.zeros(5)))
+    # deferred final factorization and untouched prior
+    n = 10
+    Q10 = _tri(n, 2.0, -0.8)
+    lik10 = PoissonLikelihood(np.array([2, 1, 3, 0, 4, 1, 2, 3, 1, 0], dtype=float))
+    wg = WorkspaceGMRF(np.zeros(n), Q10, **kw())
+    Q_copy = Q10.copy()
+    res = gaussian_approximation(wg, lik10)
+    assert not res.workspace.numeric_valid
+    v = res.var()
+    assert np.all(v > 0) and v.size == n and res.workspace.numeric_valid and np.isfinite(res.logdetcov())
+    assert (wg.precision_matrix() != Q_copy).nnz == 0 and (res.precision_matrix() != Q_copy).nnz > 0
