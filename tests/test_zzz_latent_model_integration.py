@@ -451,3 +451,59 @@ def test_prior_and_posterior_stay_coherent_around_a_gaussian_approximation(kw):
     v = res.var()
     assert np.all(v > 0) and v.size == n and res.workspace.numeric_valid and np.isfinite(res.logdetcov())
     assert (wg.precision_matrix() != Q_copy).nnz == 0 and (res.precision_matrix() != Q_copy).nnz > 0
+
+
+# ---------------------------------------------------------------------------- test/gaussian_approximation/test_predictive_convergence.jl
+def test_predictive_convergence_look_ahead_gate():          # :32-58
+    from gmrf_b200.workspace_gmrf import _predict_converged as pc
+    tol = 1e-8
+    assert pc(1e-6, 1e-2, 1.0, 1.0, tol, 2)                  # quadratic contraction, both steps undamped
+    assert not pc(1e-6, 1e-2, 1.0, 1.0, tol, 1)              # first iteration: nothing to estimate from
+    assert not pc(1e-6, 1e-2, 0.999, 1.0, tol, 2)            # damped step
+    assert not pc(1e-6, 1e-2, 1.0, 0.316, tol, 2)            # previous step damped
+    assert not pc(1e-4, 1e-2, 1.0, 1.0, tol, 2)              # contraction too slow
+    assert not pc(1e-2, 1e-2, 1.0, 1.0, tol, 2)              # no contraction
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_predictive_convergence_reuses_the_factorization(kw):   # :60-125 (workspace path)
+    from gmrf_b200.gmrf import GMRF, gaussian_approximation as ga_gmrf
+    n = 200
+    Q = _tri(n, 2.01, -1.0)
+    y = np.round(np.exp(2.0 * np.sin(np.linspace(0.0, 4.0 * np.pi, n))))
+    lik = PoissonLikelihood(y)
+    warm = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **dense_kw()), lik).mean()
+    Q11 = sp.csc_matrix(1.1 * Q)
+    tolkw = dict(newton_dec_tol=1e-8, mean_change_tol=1e-12)
+    s_on, s_off = {}, {}
+    prior = WorkspaceGMRF(np.zeros(n), Q11, **kw())
+    post_on = gaussian_approximation(prior, lik, x0=warm, stats=s_on, **tolkw)
+    post_off = gaussian_approximation(prior, lik, x0=warm, predictive_convergence=False, stats=s_off, **tolkw)
+    assert s_off["iterations"] > 1 and s_on["iterations"] == s_off["iterations"] - 1     # one loop trip fewer ...
+    assert s_on["refactorizations"] == s_off["refactorizations"] - 1                      # ... i.e. one factorization fewer
+    assert np.allclose(post_on.mean(), post_off.mean(), rtol=1e-6, atol=1e-10)
+    assert np.allclose(post_on.precision.toarray(), post_off.precision.toarray(), rtol=1e-8)
+
+    def returned_decrement(post):                            # g' H^-1 g at the returned mode (:14-18)
+        x = post.mean()
+        g = Q11 @ x - lik.loggrad(x)
+        return float(g @ np.linalg.solve(post.precision.toarray(), g))
+
+    assert returned_decrement(post_on) < 1e-3 * tolkw["newton_dec_tol"]       # the chord steps land far inside
+    assert returned_decrement(post_off) < tolkw["newton_dec_tol"]
+    # same mode as the cache-backed (plain GMRF) path
+    gk = {"backend_type": DenseBackend} if kw is dense_kw else {"device": 0}
+    cache_post = ga_gmrf(GMRF(np.zeros(n), Q11, **gk), lik, x0=warm, **tolkw)
+    assert np.allclose(post_on.mean(), cache_post.mean(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_predictive_convergence_is_inert_while_the_line_search_damps(kw):   # :127-152
+    m = 5
+    weak = sp.csc_matrix(0.01 * sp.identity(m))
+    lik = PoissonLikelihood(np.array([200, 50, 500, 10, 1000], dtype=float))
+    tolkw = dict(newton_dec_tol=1e-8, mean_change_tol=1e-12)
+    for extra in (dict(step_recovery="sqrt"), dict()):
+        on = gaussian_approximation(WorkspaceGMRF(np.zeros(m), weak, **kw()), lik, **extra, **tolkw)
+        off = gaussian_approximation(WorkspaceGMRF(np.zeros(m), weak, **kw()), lik, predictive_convergence=False, **extra, **tolkw)
+        assert np.array_equal(on.mean(), off.mean())
