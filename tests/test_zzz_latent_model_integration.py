@@ -507,3 +507,39 @@ def test_predictive_convergence_is_inert_while_the_line_search_damps(kw):   # :1
         on = gaussian_approximation(WorkspaceGMRF(np.zeros(m), weak, **kw()), lik, **extra, **tolkw)
         off = gaussian_approximation(WorkspaceGMRF(np.zeros(m), weak, **kw()), lik, predictive_convergence=False, **extra, **tolkw)
         assert np.array_equal(on.mean(), off.mean())
+
+
+# ------------------------------------------------------------ remaining behaviours of test_gaussian_approximation.jl on this path
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_newton_loop_edge_behaviours(kw):
+    from gmrf_b200.gmrf import GMRF, gaussian_approximation as ga_gmrf
+    gk = {"backend_type": DenseBackend} if kw is dense_kw else {"device": 0}
+    # non-convergence path, max_iter = 1 (:238-255): still a finite approximation of the right type
+    n = 5
+    far = PoissonLikelihood(np.array([10, 15, 8, 12, 20], dtype=float))
+    res = ga_gmrf(GMRF(np.zeros(n), sp.identity(n, format="csc"), **gk), far, max_iter=1)
+    assert isinstance(res, GMRF) and res.mean().size == n and np.all(np.isfinite(res.mean()))
+    # extreme counts under a weak prior (:323-348, :467-): the line search keeps the iterates finite
+    one = ga_gmrf(GMRF(np.zeros(1), sp.csc_matrix(np.array([[0.01]])), **gk), PoissonLikelihood(np.array([100.0])))
+    assert np.isfinite(one.mean()[0]) and abs(one.mean()[0] - np.log(100.0)) < 1.0 and one.precision[0, 0] > 0
+    y5 = np.array([200, 50, 500, 10, 1000], dtype=float)
+    many = gaussian_approximation(WorkspaceGMRF(np.zeros(5), sp.csc_matrix(0.01 * sp.identity(5)), **kw()), PoissonLikelihood(y5))
+    assert np.all(np.isfinite(many.mean())) and np.all(np.abs(many.mean() - np.log(y5)) < 1.0)
+    # convergence criteria agree (:302-321); Gaussian likelihood through the generic loop
+    yv = np.array([0.1, -0.1, 0.2, -0.2])
+    lik = LinearGaussianLikelihood(sp.identity(4, format="csr"), yv, 0.5)
+    r1 = ga_gmrf(GMRF(np.zeros(4), sp.identity(4, format="csc"), **gk), lik, newton_dec_tol=1e-10)
+    r2 = ga_gmrf(GMRF(np.zeros(4), sp.identity(4, format="csc"), **gk), lik, mean_change_tol=1e-8)
+    assert np.linalg.norm(r1.mean() - r2.mean()) < 1e-6 and np.allclose(r1.mean(), yv * 4.0 / 5.0, rtol=1e-10)
+    # :retry_full is the default (:424-430), and a converged mode is a fixed point of the iteration (:450-465)
+    n = 200
+    Q = _tri(n, 2.01, -1.0)
+    lik200 = PoissonLikelihood(np.round(np.exp(3.0 * np.sin(np.linspace(0.0, 6.0 * np.pi, n)))))
+    tight = dict(newton_dec_tol=1e-12, mean_change_tol=1e-12)
+    a = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik200, max_iter=8, **tight)
+    b = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik200, max_iter=8, step_recovery="retry_full", **tight)
+    assert np.array_equal(a.mean(), b.mean())
+    star = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik200, **tight).mean()
+    warm = gaussian_approximation(WorkspaceGMRF(np.zeros(n), Q, **kw()), lik200, x0=star, **tight).mean()
+    gn = lambda x: np.max(np.abs(Q @ x - lik200.loggrad(x)))
+    assert np.allclose(warm, star, atol=1e-10) and gn(warm) < 1e-12
