@@ -230,25 +230,63 @@ struct UpperCSC {  // upper triangle (row <= col) of the permuted matrix, column
     std::vector<i64> ptr, idx;
 };
 
+// Counting sort of the (destination column, value) pairs that `emit(j, sink)` produces for the source columns
+// j = 0 .. n_src-1, in parallel and in EXACTLY the order of the serial double loop: the source columns are cut into one
+// contiguous chunk per thread, every thread counts its pairs per destination column, the per-thread counts become write
+// offsets (threads in chunk order), and a second enumeration writes the values. Deterministic for any thread count.
+template <class Emit>
+void bucket_by_column(i64 n_src, i64 n_dst, Emit emit, std::vector<i64> &ptr, std::vector<i64> &idx) {
+    int T = 1;
+#ifdef _OPENMP
+    T = std::max(1, omp_get_max_threads());
+#endif
+    if (n_src < 100000 || (double)T * (double)n_dst > 4e8) T = 1;          // small inputs / huge histograms: serial
+    std::vector<std::vector<i64>> hist((size_t)T);
+    ptr.assign((size_t)n_dst + 1, 0);
+#pragma omp parallel num_threads(T)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const i64 a = n_src * t / T, b = n_src * (t + 1) / T;
+        std::vector<i64> &h = hist[(size_t)t];
+        h.assign((size_t)n_dst, 0);
+        for (i64 j = a; j < b; j++) emit(j, [&](i64 dst, i64) { h[(size_t)dst]++; });
+#pragma omp barrier
+#pragma omp for schedule(static)
+        for (i64 d = 0; d < n_dst; d++) {                                    // counts -> offsets within the column
+            i64 run = 0;
+            for (int u = 0; u < T; u++) { const i64 c = hist[(size_t)u][(size_t)d]; hist[(size_t)u][(size_t)d] = run; run += c; }
+            ptr[(size_t)d + 1] = run;
+        }
+#pragma omp single
+        {
+            for (i64 d = 0; d < n_dst; d++) ptr[(size_t)d + 1] += ptr[(size_t)d];
+            idx.resize((size_t)ptr[(size_t)n_dst]);
+        }
+        for (i64 j = a; j < b; j++) emit(j, [&](i64 dst, i64 val) { idx[(size_t)(ptr[(size_t)dst] + h[(size_t)dst]++)] = val; });
+    }
+}
+
 void build_permuted_upper(i64 n, const i64 *Ap, const i64 *Ai, const std::vector<i64> &iperm, UpperCSC &C) {
-    C.ptr.assign(n + 1, 0);
-    for (i64 j = 0; j < n; j++)
+    bucket_by_column(n, n, [&](i64 j, auto sink) {
+        const i64 b = iperm[j];
         for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
-            i64 i = Ai[p];
+            const i64 i = Ai[p];
             if (i > j) continue;
-            i64 a = iperm[i], b = iperm[j];
-            C.ptr[std::max(a, b) + 1]++;
+            const i64 a = iperm[i];
+            sink(std::max(a, b), std::min(a, b));
         }
-    for (i64 j = 0; j < n; j++) C.ptr[j + 1] += C.ptr[j];
-    C.idx.resize(C.ptr[n]);
-    std::vector<i64> w(C.ptr.begin(), C.ptr.end() - 1);
-    for (i64 j = 0; j < n; j++)
-        for (i64 p = Ap[j]; p < Ap[j + 1]; p++) {
-            i64 i = Ai[p];
-            if (i > j) continue;
-            i64 a = iperm[i], b = iperm[j];
-            C.idx[w[std::max(a, b)]++] = std::min(a, b);
-        }
+    }, C.ptr, C.idx);
+}
+
+// lower-triangular column lists of C: for column j the rows i > j with A_ij != 0 (transpose of the strict upper part)
+void lower_lists(i64 n, const UpperCSC &C, std::vector<i64> &lptr, std::vector<i64> &lidx) {
+    bucket_by_column(n, n, [&](i64 k, auto sink) {
+        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
+            if (C.idx[p] < k) sink(C.idx[p], k);
+    }, lptr, lidx);
 }
 
 void etree(i64 n, const UpperCSC &C, std::vector<i64> &parent) {
@@ -297,18 +335,8 @@ void postorder(i64 n, const std::vector<i64> &parent, const std::vector<i64> *ke
 // Gilbert-Ng-Peyton column counts; matrix must already be labelled in postorder (parent[j] > j).
 void column_counts(i64 n, const UpperCSC &C, const std::vector<i64> &parent, std::vector<i64> &cc) {
     // lower-triangular column lists: for column j the rows i > j with A_ij != 0  == transpose of C's strict upper
-    std::vector<i64> lptr(n + 1, 0), lidx;
-    for (i64 k = 0; k < n; k++)
-        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
-            if (C.idx[p] < k) lptr[C.idx[p] + 1]++;
-    for (i64 j = 0; j < n; j++) lptr[j + 1] += lptr[j];
-    lidx.resize(lptr[n]);
-    {
-        std::vector<i64> w(lptr.begin(), lptr.end() - 1);
-        for (i64 k = 0; k < n; k++)
-            for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
-                if (C.idx[p] < k) lidx[w[C.idx[p]]++] = k;
-    }
+    std::vector<i64> lptr, lidx;
+    lower_lists(n, C, lptr, lidx);
     std::vector<i64> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n), delta(n);
     for (i64 k = 0; k < n; k++) {
         i64 j = k;
@@ -598,18 +626,8 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
     phase("supernodes");
     // ---- 4. row structures ----------------------------------------------------------------------------
     // lower-triangular column lists of the permuted matrix
-    std::vector<i64> lptr(n + 1, 0), lidx;
-    for (i64 k = 0; k < n; k++)
-        for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
-            if (C.idx[p] < k) lptr[C.idx[p] + 1]++;
-    for (i64 j = 0; j < n; j++) lptr[j + 1] += lptr[j];
-    lidx.resize(lptr[n]);
-    {
-        std::vector<i64> w(lptr.begin(), lptr.end() - 1);
-        for (i64 k = 0; k < n; k++)
-            for (i64 p = C.ptr[k]; p < C.ptr[k + 1]; p++)
-                if (C.idx[p] < k) lidx[w[C.idx[p]]++] = k;
-    }
+    std::vector<i64> lptr, lidx;
+    lower_lists(n, C, lptr, lidx);
     phase("  lower-triangular column lists");
     // the sizes are known from the supernode partition (a merged group has exactly cols(child) + rows(parent) rows), so the
     // structures are written straight into their final place; a child's list is read from there by its parent
