@@ -245,11 +245,12 @@ void bucket_by_column(i64 n_src, i64 n_dst, Emit emit, std::vector<i64> &ptr, st
     ptr.assign((size_t)n_dst + 1, 0);
 #pragma omp parallel num_threads(T)
     {
-        int t = 0;
+        int t = 0, Tn = 1;                                                   // the team the runtime actually gave us
 #ifdef _OPENMP
         t = omp_get_thread_num();
+        Tn = omp_get_num_threads();
 #endif
-        const i64 a = n_src * t / T, b = n_src * (t + 1) / T;
+        const i64 a = n_src * t / Tn, b = n_src * (t + 1) / Tn;
         std::vector<i64> &h = hist[(size_t)t];
         h.assign((size_t)n_dst, 0);
         for (i64 j = a; j < b; j++) emit(j, [&](i64 dst, i64) { h[(size_t)dst]++; });
@@ -257,7 +258,7 @@ void bucket_by_column(i64 n_src, i64 n_dst, Emit emit, std::vector<i64> &ptr, st
 #pragma omp for schedule(static)
         for (i64 d = 0; d < n_dst; d++) {                                    // counts -> offsets within the column
             i64 run = 0;
-            for (int u = 0; u < T; u++) { const i64 c = hist[(size_t)u][(size_t)d]; hist[(size_t)u][(size_t)d] = run; run += c; }
+            for (int u = 0; u < Tn; u++) { const i64 c = hist[(size_t)u][(size_t)d]; hist[(size_t)u][(size_t)d] = run; run += c; }
             ptr[(size_t)d + 1] = run;
         }
 #pragma omp single
