@@ -405,3 +405,35 @@ def test_schedule_replay_at_10k_dofs_against_superlu():
     ref = lu.solve(E)[idx, np.arange(idx.size)]
     assert np.max(np.abs(d[idx] - ref) / ref) <= 1e-8
     h.close()
+
+
+def test_analysis_tables_do_not_depend_on_the_thread_count():
+    """Above 10^5 columns the analysis runs its counting sorts, row structures, scatter map and position lookups on all
+    cores; every table (and the exported analysis stream) must be identical to the single-threaded result."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    script = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "from gmrf_b200 import _lib, spde\n"
+        "from gmrf_b200.backend import _Handle\n"
+        "Q = spde.MaternSPDE(*spde.mesh2d(330), 1).precision(1.0, 0.3); Q.sort_indices(); n = Q.shape[0]\n"
+        "cp, rv = Q.indptr.astype(np.int64), Q.indices.astype(np.int64)\n"
+        "m = hashlib.sha256()\n"
+        "for o in (_lib.ORDER_AMD, _lib.ORDER_NATURAL):\n"
+        "    h = _Handle(n, cp, rv, None, o, device=-1); m.update(h.export_analysis()); h.close()\n"
+        "h = _Handle(n, cp, rv, spde.geometric_nd_perm((331, 331), leaf=64, width=3), 1, device=-1)\n"
+        "pos = np.empty(rv.size, dtype=np.int64)\n"
+        "assert h._L.gmrf_b200_pattern_positions(h._h, n, _lib.ptr(cp), _lib.ptr(rv), 0, _lib.ptr(pos)) == 0\n"
+        "m.update(h.export_analysis()); m.update(pos.tobytes()); print(n, m.hexdigest())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+         os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gaussianmarkovrandomfields.jl_b200"))
+    outs = []
+    for threads in ("1", "4"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and outs[0].startswith("109561 ")
