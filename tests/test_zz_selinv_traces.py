@@ -306,3 +306,30 @@ def test_selinv_dot_against_golden_traces(ordering):
         got = ws.selinv_dot(B)
         assert abs(got - float(gold[name + "/dot_value"])) <= 1e-8 * float(gold[name + "/dot_scale"]), name
         assert abs(ws.selinv_dot(Q) - Q.shape[0]) <= 1e-8 * float(abs(Q).multiply(abs(ws.selinv_extract_at(Q))).sum()), name
+
+
+# ---------------------------------------------------------------------------------------------- gradient at the closed-form optimum
+@pytest.mark.parametrize("kw", BACKENDS)
+def test_basis_gradient_vanishes_at_the_closed_form_scale_estimate(kw):
+    """For fixed range, Q = tau * Q_1 and the maximum-likelihood scale is tau_hat = n / (z' Q_1 z). The chain rule through
+    the contracted pullback, d logpdf / d log tau = sum_j c_j * d logpdf / d c_j, must vanish there and have the sign of
+    (tau_hat - tau) elsewhere."""
+    model = spde.MaternSPDE(*spde.mesh2d(9), 1)
+    n = model.n
+    rho = 0.5
+    basis = model.basis()
+    Q1 = model.precision(1.0, rho)
+    z = np.linalg.solve(np.linalg.cholesky(Q1.toarray() * 2.5).T, np.random.default_rng(3).standard_normal(n))   # ~ N(0, (2.5 Q_1)^-1)
+    tau_hat = n / float(z @ (Q1 @ z))
+    x = WorkspaceGMRF(np.zeros(n), model.precision(tau_hat, rho), **kw())
+    be = x.workspace.backend
+    be.set_value_basis(basis)
+
+    def dlogpdf_dlogtau(tau):
+        c = model.coefficients(tau, rho)
+        d = WorkspaceGMRF(np.zeros(n), model.precision(tau, rho), x.workspace)
+        return float(c @ logpdf_basis_gradient(d, z, basis))
+
+    assert abs(dlogpdf_dlogtau(tau_hat)) <= 1e-7 * n          # = 0.5 (n - tau z'Q_1 z): terms of size n/2 cancel
+    assert dlogpdf_dlogtau(0.5 * tau_hat) > 0.2 * n and dlogpdf_dlogtau(2.0 * tau_hat) < -0.4 * n
+    assert abs(dlogpdf_dlogtau(0.5 * tau_hat) - 0.25 * n) <= 1e-6 * n and abs(dlogpdf_dlogtau(2.0 * tau_hat) + 0.5 * n) <= 1e-6 * n
