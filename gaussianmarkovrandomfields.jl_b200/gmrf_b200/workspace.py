@@ -139,15 +139,23 @@ def update_precision_values(ws, nz): return ws.update_precision_values(nz)
 class WorkspacePool:
     """Pool of independent workspaces sharing ONE resolved ordering (src/workspace/workspace_pool.jl:42-119):
     `checkout`/`checkin`/`with_workspace`. One workspace per slot; `devices` assigns slots to GPUs round-robin,
-    which is how independent hyperparameter evaluations shard across an 8xB200 box."""
+    which is how independent hyperparameter evaluations shard across an 8xB200 box. `share_analysis=True` analyses the
+    pattern once and creates the other slots from the exported analysis (`gmrf_b200_create_from_analysis`)."""
 
-    def __init__(self, Q, size: int = 1, ordering=None, devices=(0,), **kw):
+    def __init__(self, Q, size: int = 1, ordering=None, devices=(0,), share_analysis: bool = False, **kw):
         Q = _csc(Q)
         perm = ordering_permutation(Q, "nd" if ordering is None else ordering)   # resolved ONCE (workspace_pool.jl:55-58)
         self._q = queue.Queue()
         self.workspaces = []
+        blob = None
         for i in range(size):
-            ws = GMRFWorkspace(Q, ordering=perm, device=devices[i % len(devices)], **kw)
+            if blob is not None:
+                # not only the permutation: the whole symbolic analysis of the first slot is handed to the others
+                ws = GMRFWorkspace(Q, analysis=blob, device=devices[i % len(devices)], **kw)
+            else:
+                ws = GMRFWorkspace(Q, ordering=perm, device=devices[i % len(devices)], **kw)
+                if share_analysis and hasattr(ws.backend, "export_analysis"):
+                    blob = ws.backend.export_analysis()
             self.workspaces.append(ws)
             self._q.put(ws)
 

@@ -437,3 +437,16 @@ def test_analysis_tables_do_not_depend_on_the_thread_count():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1] and outs[0].startswith("109561 ")
+
+
+def test_pool_can_share_one_analysis():
+    """`WorkspacePool(..., share_analysis=True)`: the first slot analyses, the others are created from its exported
+    analysis (analysis-only handles here: device = -1)."""
+    from gmrf_b200.workspace import WorkspacePool
+    Q = sp.csc_matrix(CASES["matern2d_16"]())
+    pool = WorkspacePool(Q, size=3, devices=(-1,), share_analysis=True, factorize=False)
+    hs = [ws.backend._hd for ws in pool.workspaces]
+    assert all(hs[0]._L.gmrf_b200_analysis_equal(hs[0]._h, h._h) == 1 for h in hs[1:])
+    assert all(np.array_equal(ws.backend.permutation(), pool.workspaces[0].backend.permutation()) for ws in pool.workspaces)
+    plain = WorkspacePool(Q, size=2, devices=(-1,), factorize=False)
+    assert hs[0]._L.gmrf_b200_analysis_equal(hs[0]._h, plain.workspaces[1].backend._hd._h) == 1    # same result either way
