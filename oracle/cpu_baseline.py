@@ -91,3 +91,46 @@ class CpuSupernodalCholesky:
         self.status = status
         self.logdet = float(self._L.cpu_logdet(self.diag_pos.size, self.diag_pos, self.Lx))
         return time.perf_counter() - t0
+
+    def selinv(self) -> float:
+        """Supernodal Takahashi selected inversion of the current factor on the host cores (top-down over the levels,
+        OpenMP across the fronts of a level / threaded BLAS inside the big ones). Returns the wall time in seconds; the
+        result stays in `self.Zx` (same panel layout as the factor), `selinv_diag()` reads the marginal variances."""
+        import scipy.linalg.cython_blas as cb
+        from threadpoolctl import threadpool_limits
+        T = self.T
+        L = self._L
+        f = L.cpu_supernodal_selinv_level
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int64, _i64p] + [_i64p] * 7 + [_f64p, _f64p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                          ctypes.c_void_p, ctypes.c_int]
+        L.cpu_supernodal_selinv_cleanup.restype = None
+        L.cpu_supernodal_selinv_cleanup.argtypes = [ctypes.c_int64, ctypes.c_void_p]
+        gemm = _capsule_ptr(cb.__pyx_capi__["dgemm"])
+        trsm = self.ptrs[1]
+        ns = T.nsuper
+        if getattr(self, "Zx", None) is None:
+            self.Zx = np.zeros_like(self.Lx)
+        W = (ctypes.c_void_p * max(ns, 1))()
+        pending = np.ascontiguousarray(np.diff(self.child_ptr), dtype=np.int32)
+        sparent = np.ascontiguousarray(T.sparent, dtype=np.int64)
+        t0 = time.perf_counter()
+        rc = 0
+        try:
+            for sup in reversed(self.levels):
+                parallel = 1 if sup.size >= 2 * self.threads else 0
+                with threadpool_limits(limits=1 if parallel else self.threads, user_api="blas"):
+                    rc = f(sup.size, sup, T.super_ptr, sparent, T.row_ptr, T.rel_idx, T.panel_off, T.panel_ld, self.child_ptr,
+                           self.Lx, self.Zx, ctypes.cast(W, ctypes.c_void_p), pending.ctypes.data_as(ctypes.c_void_p), gemm, trsm,
+                           parallel)
+                if rc:
+                    raise MemoryError("cpu selinv: could not allocate a W block")
+        finally:
+            L.cpu_supernodal_selinv_cleanup(ns, ctypes.cast(W, ctypes.c_void_p))
+        return time.perf_counter() - t0
+
+    def selinv_diag(self) -> np.ndarray:
+        """diag(Q^-1) in the original ordering from the Z panels of the last `selinv()`."""
+        d = np.empty(self.T.n)
+        d[self.T.perm] = self.Zx[self.diag_pos]
+        return d

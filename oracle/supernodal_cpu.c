@@ -8,7 +8,8 @@
  * taken from the OpenBLAS that ships inside SciPy (function pointers are passed in from Python, see
  * oracle/cpu_baseline.py), OpenMP across independent fronts of a level and threaded BLAS inside the big fronts.
  * It is only ever TIMED (bench.py cpu_baseline / --impl reference) and cross-checked against the simplicial oracle
- * in tests/; it is never linked into libgmrf_b200.so.
+ * in tests/; it is never linked into libgmrf_b200.so. The second half of the file is the matching supernodal selected
+ * inversion (the CPU stand-in for SelectedInversion.selinv), so that `selinv ms` has a host-core number beside it too.
  */
 #include <math.h>
 #include <stdint.h>
@@ -120,4 +121,116 @@ int cpu_num_threads(void)
 #else
     return 1;
 #endif
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Supernodal Takahashi selected inversion on the host cores (the CPU stand-in for SelectedInversion.selinv on a
+ * supernodal CHOLMOD factor, /root/reference/src/workspace/backend.jl:226-236), top-down over the assembly tree:
+ *   W  = Z[R,R] gathered from the parent's Z panel and the parent's own W,
+ *   T' = -W L21,  G = I - L21' T',  [H; Z_RS] = [G; T'] L11^-1,  Z_SS = H' L11^-1
+ * (the formulation the device plan uses, validated in tests/replay.py). Same panel layout as the factor; the diagonal
+ * block of a Z panel is stored as a full square. W matrices are heap blocks owned by their supernode and freed when the
+ * last child has gathered from them. Only ever timed / cross-checked; never linked into libgmrf_b200.so.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef void (*dgemm_t)(char *, char *, int *, int *, int *, double *, double *, int *, double *, int *, double *, double *, int *);
+
+typedef struct {
+    const i64 *super_ptr, *super_parent, *row_ptr, *rel_idx, *panel_off, *panel_ld, *child_ptr;
+    const double *Lx;
+    double *Zx;
+    double **W;        /* [nsuper] heap block nr x nr (ld = nr) or NULL */
+    int *pending;      /* [nsuper] children that still have to gather from W[s] */
+    dgemm_t gemm;
+    dtrsm_t trsm;
+    int inner_parallel;   /* fronts are processed one after another: thread the gather of a big W as well */
+} selinv_ctx;
+
+static int selinv_one(const selinv_ctx *c, i64 s)
+{
+    const i64 ns = c->super_ptr[s + 1] - c->super_ptr[s];
+    const i64 nrow = c->row_ptr[s + 1] - c->row_ptr[s];
+    const i64 nr = nrow - ns, ld = c->panel_ld[s];
+    const double *P = c->Lx + c->panel_off[s];
+    double *Z = c->Zx + c->panel_off[s];
+    double one = 1.0, zero = 0.0, mone = -1.0;
+    int ns_ = (int)ns, nr_ = (int)nr, ld_ = (int)ld, nrow_ = (int)nrow;
+    double *Ws = NULL;
+    /* X = [G; T'] lives in the Z panel itself (nrow x ns, ld) */
+    if (nr > 0) {
+        const i64 p = c->super_parent[s];
+        const i64 pns = c->super_ptr[p + 1] - c->super_ptr[p], pld = c->panel_ld[p];
+        const i64 pnr = (c->row_ptr[p + 1] - c->row_ptr[p]) - pns;
+        const double *Zp = c->Zx + c->panel_off[p];
+        const double *Wp = c->W[p];
+        const i64 *rel = c->rel_idx + c->row_ptr[s] + ns;
+        Ws = (double *)malloc(sizeof(double) * (size_t)nr * (size_t)nr);
+        if (!Ws) return -1;
+#pragma omp parallel for schedule(dynamic, 16) if (c->inner_parallel && nr >= 512)
+        for (i64 b = 0; b < nr; b++) {
+            const i64 pb = rel[b];
+            for (i64 a = b; a < nr; a++) {
+                const i64 pa = rel[a];     /* pa >= pb: row lists are sorted */
+                const double v = pb < pns ? Zp[pa + pb * pld] : Wp[(pa - pns) + (pb - pns) * pnr];
+                Ws[a + b * nr] = v;
+                Ws[b + a * nr] = v;
+            }
+        }
+        {   /* this child is done reading the parent's W: the last one to finish frees it */
+            int left;
+#pragma omp atomic capture
+            left = --c->pending[p];
+            if (left == 0 && c->W[p]) { free(c->W[p]); c->W[p] = NULL; }
+        }
+        /* T' = -W L21 -> rows ns.. of the Z panel */
+        c->gemm("N", "N", &nr_, &ns_, &nr_, &mone, Ws, &nr_, (double *)P + ns, &ld_, &zero, Z + ns, &ld_);
+        /* G = I - L21' T' -> rows 0..ns of the Z panel */
+        c->gemm("T", "N", &ns_, &ns_, &nr_, &mone, (double *)P + ns, &ld_, Z + ns, &ld_, &zero, Z, &ld_);
+        for (i64 j = 0; j < ns; j++) Z[j + j * ld] += 1.0;
+    } else {
+        for (i64 j = 0; j < ns; j++) {
+            memset(Z + j * ld, 0, sizeof(double) * (size_t)ns);
+            Z[j + j * ld] = 1.0;
+        }
+    }
+    /* [H; Z_RS] = [G; T'] L11^-1 */
+    c->trsm("R", "L", "N", "N", &nrow_, &ns_, &one, (double *)P, &ld_, Z, &ld_);
+    /* Z_SS = H' L11^-1: transpose H in place (ns x ns block), then the same solve on it */
+    for (i64 j = 0; j < ns; j++)
+        for (i64 i = j + 1; i < ns; i++) {
+            const double t = Z[i + j * ld];
+            Z[i + j * ld] = Z[j + i * ld];
+            Z[j + i * ld] = t;
+        }
+    c->trsm("R", "L", "N", "N", &ns_, &ns_, &one, (double *)P, &ld_, Z, &ld_);
+    c->W[s] = Ws;
+    if (c->pending[s] == 0 && Ws) { free(Ws); c->W[s] = NULL; }     /* a leaf of the assembly tree: nobody gathers from it */
+    return 0;
+}
+
+/* Selected inversion of the supernodes supers[0..count) of one level (call the levels top-down). parallel as above.
+ * W / pending are caller-allocated arrays of nsuper entries (W zero-initialised, pending[s] = number of children of s).
+ * Returns 0, or -1 if a W block could not be allocated. */
+int cpu_supernodal_selinv_level(i64 count, const i64 *supers, const i64 *super_ptr, const i64 *super_parent, const i64 *row_ptr,
+                                const i64 *rel_idx, const i64 *panel_off, const i64 *panel_ld, const i64 *child_ptr,
+                                const double *Lx, double *Zx, void **W, int *pending, void *gemm, void *trsm, int parallel)
+{
+    selinv_ctx c = {super_ptr, super_parent, row_ptr, rel_idx, panel_off, panel_ld, child_ptr, Lx, Zx, (double **)W, pending,
+                    (dgemm_t)gemm, (dtrsm_t)trsm, !parallel};
+    int status = 0;
+#pragma omp parallel for schedule(dynamic, 1) if (parallel)
+    for (i64 t = 0; t < count; t++) {
+        const i64 s = supers[t];
+        if (selinv_one(&c, s)) {
+#pragma omp atomic write
+            status = -1;
+        }
+    }
+    return status;
+}
+
+/* free whatever W blocks are still alive (error paths) */
+void cpu_supernodal_selinv_cleanup(i64 nsuper, void **W)
+{
+    for (i64 s = 0; s < nsuper; s++)
+        if (W[s]) { free(W[s]); W[s] = NULL; }
 }

@@ -88,6 +88,13 @@ def test_cpu_supernodal_baseline_matches_oracle(cells):
     F = oracle.OracleFactor(Q, T.perm)
     assert cpu.status == 0
     assert abs(cpu.logdet - F.logdet()) <= 1e-11 * abs(F.logdet())
+    # supernodal Takahashi recursion of the CPU baseline against the simplicial one of the oracle
+    cpu.selinv()
+    d, d_ref = cpu.selinv_diag(), F.selinv_diag()
+    assert np.max(np.abs(d - d_ref) / d_ref) <= 1e-10
+    cpu.refactorize(2.0 * Q.data)                      # a second round on the same buffers: variances halve
+    cpu.selinv()
+    assert np.max(np.abs(cpu.selinv_diag() - 0.5 * d_ref) / d_ref) <= 1e-10
     h.close()
 
 
