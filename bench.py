@@ -184,6 +184,15 @@ def run_reference(args):
         t += cpu.refactorize(model.values(*theta_for(args.warmup + k, 0)))
     per = t / args.steps
     value = (flops / per) / full
+    # the other half of the metric ("selinv ms") on the host cores: one supernodal Takahashi recursion on the same sample,
+    # scaled by flops like the factorization. Reported alongside; never part of `value`.
+    selinv = None
+    try:
+        ts = cpu.selinv()
+        selinv = {"sample_seconds": round(ts, 3), "selinv_ms_scaled": round(1e3 * ts * full / flops, 1),
+                  "selinv_over_factor": round(ts / per, 2)}
+    except Exception as e:       # the reference line must not depend on it
+        selinv = {"error": str(e)[:200]}
     sample = (f"each step = one numeric Cholesky+logdet of the same recipe at {sample_cells}^3 cells (n={model.n}, {flops:.3g} flop, "
               f"{per:.2f} s/step = {flops / per / 1e9:.0f} GFLOP/s on {cpu.threads} threads), scaled by flops to the {full:.3g}-flop workload")
     line = {
@@ -195,6 +204,7 @@ def run_reference(args):
                                "path cannot run here (no Julia / libcholmod in the image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_selinv": selinv,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
