@@ -193,6 +193,18 @@ def run_reference(args):
                   "selinv_over_factor": round(ts / per, 2)}
     except Exception as e:       # the reference line must not depend on it
         selinv = {"error": str(e)[:200]}
+    # ... and one-right-hand-side solves (bandwidth-bound: scaled by the factor's size, not by flops)
+    solve = None
+    try:
+        rhs = np.random.default_rng(0).standard_normal(model.n)
+        cpu.solve(rhs)
+        t_full = min(cpu.solve(rhs)[1] for _ in range(3))
+        t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(3))
+        lbytes = 8.0 * float(T.info["nnz_l_stored"])
+        solve = {"sample_solve_ms": round(1e3 * t_full, 2), "sample_half_solve_ms": round(1e3 * t_half, 2),
+                 "solve_GBs": round(2.0 * lbytes / t_full / 1e9, 1), "half_solve_GBs": round(lbytes / t_half / 1e9, 1)}
+    except Exception as e:
+        solve = {"error": str(e)[:200]}
     sample = (f"each step = one numeric Cholesky+logdet of the same recipe at {sample_cells}^3 cells (n={model.n}, {flops:.3g} flop, "
               f"{per:.2f} s/step = {flops / per / 1e9:.0f} GFLOP/s on {cpu.threads} threads), scaled by flops to the {full:.3g}-flop workload")
     line = {
@@ -205,6 +217,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_selinv": selinv,
+        "cpu_solve": solve,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)

@@ -129,6 +129,33 @@ class CpuSupernodalCholesky:
             L.cpu_supernodal_selinv_cleanup(ns, ctypes.cast(W, ctypes.c_void_p))
         return time.perf_counter() - t0
 
+    def solve(self, b, half: bool = False):
+        """(x, seconds): Q x = b (or x = P' L^-T b with `half=True`, the sampling half solve) with the current factor, one
+        right-hand side, supernodal forward / backward sweeps level by level on the host cores."""
+        import scipy.linalg.cython_blas as cb
+        from threadpoolctl import threadpool_limits
+        T = self.T
+        f = self._L.cpu_supernodal_solve_level
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int64, _i64p] + [_i64p] * 8 + [_f64p, _f64p, _f64p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        trsv, gemv = _capsule_ptr(cb.__pyx_capi__["dtrsv"]), _capsule_ptr(cb.__pyx_capi__["dgemv"])
+        if getattr(self, "_u", None) is None:
+            self._u = np.zeros(max(int(T.row_ptr[-1]), 1))
+        b = np.asarray(b, dtype=np.float64)
+        y = np.ascontiguousarray(b[T.perm]) if not half else b.copy()      # F.UP \\ x = P' L^-T x: the input is in factor coordinates
+        t0 = time.perf_counter()
+        sweeps = ([(self.levels, 0)] if not half else []) + [(list(reversed(self.levels)), 1)]
+        for levels, backward in sweeps:
+            for sup in levels:
+                parallel = 1 if sup.size >= 2 * self.threads else 0
+                with threadpool_limits(limits=1 if parallel else self.threads, user_api="blas"):
+                    f(sup.size, sup, T.super_ptr, T.row_ptr, T.row_idx, T.rel_idx, T.panel_off, T.panel_ld, self.child_ptr,
+                      self.child_idx, self.Lx, y, self._u, trsv, gemv, backward, parallel)
+        dt = time.perf_counter() - t0
+        x = np.empty_like(y)
+        x[T.perm] = y
+        return x, dt
+
     def selinv_diag(self) -> np.ndarray:
         """diag(Q^-1) in the original ordering from the Z panels of the last `selinv()`."""
         d = np.empty(self.T.n)

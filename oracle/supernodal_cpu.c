@@ -234,3 +234,58 @@ void cpu_supernodal_selinv_cleanup(i64 nsuper, void **W)
     for (i64 s = 0; s < nsuper; s++)
         if (W[s]) { free(W[s]); W[s] = NULL; }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Supernodal triangular solves on the host cores (the CPU stand-in for `F \ rhs` / `F.UP \ x`,
+ * /root/reference/src/workspace/backend.jl:191-193, :281-284), one right-hand side, level by level:
+ *   forward  (levels ascending):  the parent pulls its children's update vectors, x_S = L11^-1 y_S, u = L21 x_S (+ pulled);
+ *   backward (levels descending): x_S = L11^-T (y_S - L21' x_R), x_R read from the ancestors' finished entries.
+ * `y` is the right-hand side in elimination order (overwritten by the solution), `u` a work array indexed like row_idx
+ * (u_s lives at u[row_ptr[s] + ns .. row_ptr[s+1])). No two fronts of a level write the same entry.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef void (*dtrsv_t)(char *, char *, char *, int *, double *, int *, double *, int *);
+typedef void (*dgemv_t)(char *, int *, int *, double *, double *, int *, double *, int *, double *, double *, int *);
+
+int cpu_supernodal_solve_level(i64 count, const i64 *supers, const i64 *super_ptr, const i64 *row_ptr, const i64 *row_idx,
+                               const i64 *rel_idx, const i64 *panel_off, const i64 *panel_ld, const i64 *child_ptr,
+                               const i64 *child_idx, const double *Lx, double *y, double *u, void *trsv_, void *gemv_,
+                               int backward, int parallel)
+{
+    dtrsv_t trsv = (dtrsv_t)trsv_;
+    dgemv_t gemv = (dgemv_t)gemv_;
+#pragma omp parallel for schedule(dynamic, 4) if (parallel)
+    for (i64 t = 0; t < count; t++) {
+        const i64 s = supers[t];
+        const i64 f = super_ptr[s], ns = super_ptr[s + 1] - f;
+        const i64 nrow = row_ptr[s + 1] - row_ptr[s], nr = nrow - ns, ld = panel_ld[s];
+        double *P = (double *)Lx + panel_off[s];
+        double *us = u + row_ptr[s] + ns;
+        int ns_ = (int)ns, nr_ = (int)nr, ld_ = (int)ld, inc = 1;
+        double one = 1.0, zero = 0.0, mone = -1.0;
+        if (!backward) {
+            for (i64 i = 0; i < nr; i++) us[i] = 0.0;
+            for (i64 ci = child_ptr[s]; ci < child_ptr[s + 1]; ci++) {
+                const i64 c = child_idx[ci];
+                const i64 cns = super_ptr[c + 1] - super_ptr[c], cnr = (row_ptr[c + 1] - row_ptr[c]) - cns;
+                const i64 *rel = rel_idx + row_ptr[c] + cns;
+                const double *uc = u + row_ptr[c] + cns;
+                for (i64 k = 0; k < cnr; k++) {
+                    const i64 pos = rel[k];
+                    if (pos < ns) y[f + pos] -= uc[k];
+                    else us[pos - ns] += uc[k];
+                }
+            }
+            trsv("L", "N", "N", &ns_, P, &ld_, y + f, &inc);
+            if (nr > 0) gemv("N", &nr_, &ns_, &one, P + ns, &ld_, y + f, &inc, &one, us, &inc);
+        } else {
+            if (nr > 0) {
+                const i64 *rows = row_idx + row_ptr[s] + ns;
+                for (i64 i = 0; i < nr; i++) us[i] = y[rows[i]];
+                gemv("T", &nr_, &ns_, &mone, P + ns, &ld_, us, &inc, &one, y + f, &inc);
+            }
+            trsv("L", "T", "N", &ns_, P, &ld_, y + f, &inc);
+        }
+        (void)zero;
+    }
+    return 0;
+}

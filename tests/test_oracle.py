@@ -88,6 +88,12 @@ def test_cpu_supernodal_baseline_matches_oracle(cells):
     F = oracle.OracleFactor(Q, T.perm)
     assert cpu.status == 0
     assert abs(cpu.logdet - F.logdet()) <= 1e-11 * abs(F.logdet())
+    # supernodal sweeps of the CPU baseline against the oracle's solves
+    rhs = np.random.default_rng(0).standard_normal(Q.shape[0])
+    x, _ = cpu.solve(rhs)
+    assert np.linalg.norm(x - F.solve(rhs)) <= 1e-10 * np.linalg.norm(x)
+    xh, _ = cpu.solve(rhs, half=True)
+    assert np.linalg.norm(xh - F.backward_solve(rhs)) <= 1e-10 * np.linalg.norm(xh)
     # supernodal Takahashi recursion of the CPU baseline against the simplicial one of the oracle
     cpu.selinv()
     d, d_ref = cpu.selinv_diag(), F.selinv_diag()
