@@ -1,0 +1,44 @@
+"""CPU-baseline timings of the BASELINE.json 2D configs with the supernodal CPU port in oracle/ (the stand-in for the
+reference's CHOLMOD path; not a pytest file, no GPU needed):   python tests/cpu_configs.py [1] [2] [3]
+One JSON line per config: numeric factorization + logdet, one solve, one half solve, selected inversion, on all host
+threads, same inputs and the same (geometric nested dissection) ordering as tests/gpu_configs.py."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200"), os.path.join(ROOT, "tests")]
+from gmrf_b200 import _lib, spde  # noqa: E402
+from gmrf_b200.backend import _Handle  # noqa: E402
+from gmrf_b200.introspect import Tables  # noqa: E402
+from oracle.cpu_baseline import CpuSupernodalCholesky  # noqa: E402
+
+CELLS = {1: 224, 2: 500, 3: 316}
+for c in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3]:
+    cells = CELLS[c]
+    model = spde.MaternSPDE(*spde.mesh2d(cells), 1)
+    Q = model.precision(1.0, 0.3)
+    n = Q.shape[0]
+    t0 = time.perf_counter()
+    h = _Handle(n, Q.indptr.astype(np.int64), Q.indices.astype(np.int64),
+                spde.geometric_nd_perm((cells + 1, cells + 1), leaf=64, width=3), _lib.ORDER_ND, device=-1)
+    T = Tables(h)
+    t_analysis = time.perf_counter() - t0
+    cpu = CpuSupernodalCholesky(T)
+    cpu.refactorize(Q.data)
+    t_factor = min(cpu.refactorize(Q.data) for _ in range(3))
+    rhs = np.random.default_rng(0).standard_normal(n)
+    x, _ = cpu.solve(rhs)
+    t_solve = min(cpu.solve(rhs)[1] for _ in range(3))
+    t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(3))
+    t_selinv = min(cpu.selinv() for _ in range(2))
+    flops = float(T.info["flops_chol"])
+    print(json.dumps({"config": c, "n": n, "threads": cpu.threads, "analysis_s": round(t_analysis, 2),
+                      "factor_logdet_ms": round(1e3 * t_factor, 2), "factor_gflops": round(flops / t_factor / 1e9, 1),
+                      "solve_ms": round(1e3 * t_solve, 2), "half_solve_ms": round(1e3 * t_half, 2),
+                      "selinv_ms": round(1e3 * t_selinv, 1),
+                      "residual": float(np.linalg.norm(Q @ x - rhs) / np.linalg.norm(rhs)), "logdet": cpu.logdet}), flush=True)
+    h.close()
