@@ -42,3 +42,19 @@ for c in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3]:
                       "selinv_ms": round(1e3 * t_selinv, 1),
                       "residual": float(np.linalg.norm(Q @ x - rhs) / np.linalg.norm(rhs)), "logdet": cpu.logdet}), flush=True)
     h.close()
+    if c == 2 and "--newton" in sys.argv:
+        # the config's actual workload: the Poisson Newton loop through the host mirror, CPU port as the backend
+        from cpu_port_backend import CpuPortBackend
+        from gmrf_b200.workspace_gmrf import PoissonLikelihood, WorkspaceGMRF, gaussian_approximation
+        coords = spde.mesh2d(cells)[0]
+        lam = np.exp(0.5 + 0.5 * np.sin(2 * np.pi * coords[:, 0]) * np.cos(2 * np.pi * coords[:, 1]))
+        lik = PoissonLikelihood(np.random.default_rng(1).poisson(lam))
+        prior = WorkspaceGMRF(np.zeros(n), Q, backend_type=CpuPortBackend,
+                              ordering=spde.geometric_nd_perm((cells + 1, cells + 1), leaf=64, width=3))
+        stats = {}
+        t0 = time.perf_counter()
+        post = gaussian_approximation(prior, lik, stats=stats)
+        wall = time.perf_counter() - t0
+        g = Q @ post.mean() - lik.loggrad(post.mean())
+        print(json.dumps({"config": 2, "workload": "Poisson Newton loop", "n": n, "newton_wall_s": round(wall, 2), **stats,
+                          "grad_inf": float(np.max(np.abs(g)))}), flush=True)
