@@ -72,9 +72,16 @@ class CpuSupernodalCholesky:
             T.panel_off[s] + np.arange(T.ns(s)) * (T.panel_ld[s] + 1) for s in range(ns)]).astype(np.int64) if ns else np.zeros(0, np.int64)
         self.ptrs = _blas_ptrs()
 
+    def _blas_threads(self, k: int):
+        """Context limiting the BLAS pool to k threads. The controller is built once: discovering the loaded BLAS libraries
+        costs ~2 ms, which per level of a sweep would be a large share of a CPU solve."""
+        if getattr(self, "_tpc", None) is None:
+            from threadpoolctl import ThreadpoolController
+            self._tpc = ThreadpoolController()
+        return self._tpc.limit(limits=k, user_api="blas")
+
     def refactorize(self, nzval) -> float:
         """Returns the wall time in seconds of scatter + numeric factorization + logdet."""
-        from threadpoolctl import threadpool_limits
         T = self.T
         nz = np.ascontiguousarray(nzval, dtype=np.float64)
         t0 = time.perf_counter()
@@ -82,7 +89,7 @@ class CpuSupernodalCholesky:
         status = 0
         for sup in self.levels:
             parallel = 1 if sup.size >= 2 * self.threads else 0
-            with threadpool_limits(limits=1 if parallel else self.threads, user_api="blas"):
+            with self._blas_threads(1 if parallel else self.threads):
                 r = self._L.cpu_supernodal_factor_level(
                     sup.size, sup, T.super_ptr, T.row_ptr, T.row_idx, T.rel_idx, T.panel_off, T.panel_ld,
                     T.upd_off, T.upd_ld, self.child_ptr, self.child_idx, self.Lx, self.upd, *self.ptrs, parallel)
@@ -97,7 +104,6 @@ class CpuSupernodalCholesky:
         OpenMP across the fronts of a level / threaded BLAS inside the big ones). Returns the wall time in seconds; the
         result stays in `self.Zx` (same panel layout as the factor), `selinv_diag()` reads the marginal variances."""
         import scipy.linalg.cython_blas as cb
-        from threadpoolctl import threadpool_limits
         T = self.T
         L = self._L
         f = L.cpu_supernodal_selinv_level
@@ -119,7 +125,7 @@ class CpuSupernodalCholesky:
         try:
             for sup in reversed(self.levels):
                 parallel = 1 if sup.size >= 2 * self.threads else 0
-                with threadpool_limits(limits=1 if parallel else self.threads, user_api="blas"):
+                with self._blas_threads(1 if parallel else self.threads):
                     rc = f(sup.size, sup, T.super_ptr, sparent, T.row_ptr, T.rel_idx, T.panel_off, T.panel_ld, self.child_ptr,
                            self.Lx, self.Zx, ctypes.cast(W, ctypes.c_void_p), pending.ctypes.data_as(ctypes.c_void_p), gemm, trsm,
                            parallel)
@@ -133,7 +139,6 @@ class CpuSupernodalCholesky:
         """(x, seconds): Q x = b (or x = P' L^-T b with `half=True`, the sampling half solve) with the current factor, one
         right-hand side, supernodal forward / backward sweeps level by level on the host cores."""
         import scipy.linalg.cython_blas as cb
-        from threadpoolctl import threadpool_limits
         T = self.T
         f = self._L.cpu_supernodal_solve_level
         f.restype = ctypes.c_int
@@ -148,7 +153,7 @@ class CpuSupernodalCholesky:
         for levels, backward in sweeps:
             for sup in levels:
                 parallel = 1 if sup.size >= 2 * self.threads else 0
-                with threadpool_limits(limits=1 if parallel else self.threads, user_api="blas"):
+                with self._blas_threads(1 if parallel else self.threads):
                     f(sup.size, sup, T.super_ptr, T.row_ptr, T.row_idx, T.rel_idx, T.panel_off, T.panel_ld, self.child_ptr,
                       self.child_idx, self.Lx, y, self._u, trsv, gemv, backward, parallel)
         dt = time.perf_counter() - t0
