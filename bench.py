@@ -198,8 +198,8 @@ def run_reference(args):
     try:
         rhs = np.random.default_rng(0).standard_normal(model.n)
         cpu.solve(rhs)
-        t_full = min(cpu.solve(rhs)[1] for _ in range(3))
-        t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(3))
+        t_full = min(cpu.solve(rhs)[1] for _ in range(7))
+        t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(7))
         lbytes = 8.0 * float(T.info["nnz_l_stored"])
         solve = {"sample_solve_ms": round(1e3 * t_full, 2), "sample_half_solve_ms": round(1e3 * t_half, 2),
                  "solve_GBs": round(2.0 * lbytes / t_full / 1e9, 1), "half_solve_GBs": round(lbytes / t_half / 1e9, 1)}

@@ -150,10 +150,10 @@ class CpuSupernodalCholesky:
         y = np.ascontiguousarray(b[T.perm]) if not half else b.copy()      # F.UP \\ x = P' L^-T x: the input is in factor coordinates
         t0 = time.perf_counter()
         sweeps = ([(self.levels, 0)] if not half else []) + [(list(reversed(self.levels)), 1)]
-        for levels, backward in sweeps:
-            for sup in levels:
-                parallel = 1 if sup.size >= 2 * self.threads else 0
-                with self._blas_threads(1 if parallel else self.threads):
+        with self._blas_threads(1):        # one thread pool for the whole sweep: OpenMP over fronts, or over the rows of a big one
+            for levels, backward in sweeps:
+                for sup in levels:
+                    parallel = 1 if sup.size >= 2 else 0
                     f(sup.size, sup, T.super_ptr, T.row_ptr, T.row_idx, T.rel_idx, T.panel_off, T.panel_ld, self.child_ptr,
                       self.child_idx, self.Lx, y, self._u, trsv, gemv, backward, parallel)
         dt = time.perf_counter() - t0

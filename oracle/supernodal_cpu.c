@@ -276,12 +276,34 @@ int cpu_supernodal_solve_level(i64 count, const i64 *supers, const i64 *super_pt
                 }
             }
             trsv("L", "N", "N", &ns_, P, &ld_, y + f, &inc);
-            if (nr > 0) gemv("N", &nr_, &ns_, &one, P + ns, &ld_, y + f, &inc, &one, us, &inc);
+            if (nr > 0) {
+                if (parallel || nr < 2048) gemv("N", &nr_, &ns_, &one, P + ns, &ld_, y + f, &inc, &one, us, &inc);
+                else {
+                    /* one big front at a time (top of the tree): its rows are split over the OpenMP threads, so that the whole
+                     * sweep runs on ONE thread pool (BLAS single-threaded throughout; alternating pools costs more than the solve) */
+                    const i64 CH = 1024, nch = (nr + CH - 1) / CH;
+#pragma omp parallel for schedule(static)
+                    for (i64 b = 0; b < nch; b++) {
+                        int m_ = (int)((b + 1) * CH <= nr ? CH : nr - b * CH), one_i = 1;
+                        double o = 1.0;
+                        gemv("N", &m_, &ns_, &o, P + ns + b * CH, &ld_, y + f, &one_i, &o, us + b * CH, &one_i);
+                    }
+                }
+            }
         } else {
             if (nr > 0) {
                 const i64 *rows = row_idx + row_ptr[s] + ns;
                 for (i64 i = 0; i < nr; i++) us[i] = y[rows[i]];
-                gemv("T", &nr_, &ns_, &mone, P + ns, &ld_, us, &inc, &one, y + f, &inc);
+                if (parallel || ns < 256 || nr < 2048) gemv("T", &nr_, &ns_, &mone, P + ns, &ld_, us, &inc, &one, y + f, &inc);
+                else {
+                    const i64 CH = 64, nch = (ns + CH - 1) / CH;                /* columns of L21 split over the threads */
+#pragma omp parallel for schedule(static)
+                    for (i64 b = 0; b < nch; b++) {
+                        int n_ = (int)((b + 1) * CH <= ns ? CH : ns - b * CH), one_i = 1;
+                        double o = 1.0, mo = -1.0;
+                        gemv("T", &nr_, &n_, &mo, P + ns + b * CH * ld, &ld_, us, &one_i, &o, y + f + b * CH, &one_i);
+                    }
+                }
             }
             trsv("L", "T", "N", &ns_, P, &ld_, y + f, &inc);
         }

@@ -32,8 +32,8 @@ for c in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3]:
     t_factor = min(cpu.refactorize(Q.data) for _ in range(3))
     rhs = np.random.default_rng(0).standard_normal(n)
     x, _ = cpu.solve(rhs)
-    t_solve = min(cpu.solve(rhs)[1] for _ in range(3))
-    t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(3))
+    t_solve = min(cpu.solve(rhs)[1] for _ in range(7))
+    t_half = min(cpu.solve(rhs, half=True)[1] for _ in range(7))
     t_selinv = min(cpu.selinv() for _ in range(2))
     flops = float(T.info["flops_chol"])
     print(json.dumps({"config": c, "n": n, "threads": cpu.threads, "analysis_s": round(t_analysis, 2),
