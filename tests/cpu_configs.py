@@ -42,6 +42,18 @@ for c in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3]:
                       "selinv_ms": round(1e3 * t_selinv, 1),
                       "residual": float(np.linalg.norm(Q @ x - rhs) / np.linalg.norm(rhs)), "logdet": cpu.logdet}), flush=True)
     h.close()
+    if "--superlu" in sys.argv:
+        # independent third-party data point: SciPy SuperLU, single thread, LU not Cholesky
+        import scipy.sparse.linalg as spl
+        t0 = time.perf_counter()
+        lu = spl.splu(Q, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0, options=dict(SymmetricMode=True))
+        t_lu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        xs = lu.solve(rhs)
+        t_s = time.perf_counter() - t0
+        print(json.dumps({"config": c, "superlu_factor_ms": round(1e3 * t_lu, 1), "superlu_solve_ms": round(1e3 * t_s, 2),
+                          "superlu_logdet": float(np.sum(np.log(np.abs(lu.U.diagonal())))),
+                          "solution_rel_diff_vs_port": float(np.linalg.norm(xs - x) / np.linalg.norm(x))}), flush=True)
     if c == 2 and "--newton" in sys.argv:
         # the config's actual workload: the Poisson Newton loop through the host mirror, CPU port as the backend
         from cpu_port_backend import CpuPortBackend
