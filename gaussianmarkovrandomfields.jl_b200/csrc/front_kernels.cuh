@@ -1,0 +1,618 @@
+// front_kernels.cuh -- fused kernels for the latency-bound part of the numeric factorization: the many small fronts at
+// the bottom of the assembly tree and the 64-column chains of the separators above them (north star: "register-tiled
+// kernels for the many small ones"). Measured on a B200 before these existed (profiles/r02_plan_2d224_before.log): a
+// 50 k-dof 2D refactorization was 172 dependent launches -- per 64 columns of a chain one single-CTA potrf+inverse
+// (31 us), one TRSM-by-inverse GEMM launch and one k = 64 update launch (12-15 us each at grids of 10-200 CTAs) -- and
+// ran at 4 % of the FP64 roofline.
+//
+//   front_small_kernel   ONE CTA per front, whole panel resident in shared memory: children pulled in (extend-add),
+//                        diagonal blocks factored, rows below solved, update matrix formed and the children's
+//                        remaining contributions added -- one launch per tree level instead of 4-5.
+//   chain_step_kernel    ONE launch per 128 columns of the chains of a level, one CTA per 64-row tile and NO
+//                        communication between CTAs: every CTA factors the 128 x 128 diagonal square REDUNDANTLY in its
+//                        own shared memory (bit-identical everywhere: same code, same inputs) and then solves / updates
+//                        its own rows. The diagonal CTA parks the factored square in a scratch array, because the other
+//                        CTAs of the launch are still reading the unfactored one from the panel.
+//   chain_finalize_kernel  one launch per factorization: copies the parked squares into the panels and inverts every
+//                        64-column diagonal block (the inverses serve the solve and selected-inversion phases; taking
+//                        them off the chain's critical path is half of the gain).
+//
+// Determinism: every entry has one owner thread and a fixed summation order; no floating-point atomics.
+#pragma once
+#include "kernels.cuh"
+
+namespace gmrf {
+
+constexpr int FB = 64;                 // block order
+constexpr int FLD = 66;                // leading dimension of a 64 x 64 tile in shared memory (column-major; even ->
+                                       // 16-byte aligned row pairs, 66 mod 32 banks spreads the columns)
+constexpr int FTILE = FB * FLD;        // doubles per tile
+constexpr int FPLD = 68;               // leading dimension of the published 4-column panel (k-major)
+constexpr int FSCRATCH = 2 * 3 * 4 * FPLD + FB;   // panel-step scratch: double-buffered published panel (diagonal tile + 2 row tiles) + reciprocal pivots
+
+// ------------------------------------------------------------------------------------------------
+// Panel step on 64 columns in shared memory, 256 threads: Cholesky of the diagonal tile sD (column-major
+// sD[j * FLD + i], identity-padded beyond the true order nb) TOGETHER with the solve X L^T = B of up to RT further
+// 64-row tiles of the same columns -- i.e. the factorization of a (1 + RT) * 64 x 64 panel. Everything is held as
+// 4 x 4 register tiles on a 16 x 16 thread grid (thread (ty, tx) owns rows 4ty.., columns 4tx.. of every tile);
+// nb/4 column-panel steps, rolled (the first version solved the rows with a fully unrolled one-thread-per-row
+// substitution: 4000 straight-line instructions per call that two warps execute once -- ncu showed 80 % of its
+// samples stalled on instruction fetch, 20 us per call):
+//   (a) the diagonal thread factors its 4 x 4 tile and publishes it                         [FACTOR only]
+//   (b) the threads of column-panel P solve their tiles against it and publish the (1 + RT) * 64 x 4 panel,
+//   (c) everybody to the right applies the rank-4 update from the published panel (k-major: conflict-free reads).
+// FACTOR = false: sD already holds L (and srinv the reciprocal pivots); only the row tiles are solved.
+// `scratch`: panel_scratch_doubles(RT) doubles (FSCRATCH covers RT <= 2). Non-positive pivots: integer atomicMin of the 1-based column, NaNs propagate.
+// ------------------------------------------------------------------------------------------------
+// Cholesky of the 4 x 4 diagonal tile held by one thread (4 dependent rsqrt chains); publishes the tile (k-major) and
+// the reciprocal pivots.
+__device__ __forceinline__ void factor_diag_tile(double (&a)[4][4], double *__restrict__ pb, double *__restrict__ srinv, int P, int nb,
+                                                 int col0, int *fail_col, bool report) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const double d = a[c][c];
+        if (report && !(d > 0.0) && 4 * P + c < nb) atomicMin(fail_col, col0 + 4 * P + c + 1);
+        const double r = rsqrt(d);
+        a[c][c] = d * r;
+        srinv[4 * P + c] = r;
+#pragma unroll
+        for (int r2 = c + 1; r2 < 4; r2++) a[r2][c] *= r;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 4; c2++)
+#pragma unroll
+            for (int r2 = c2; r2 < 4; r2++) a[r2][c2] -= a[r2][c] * a[c2][c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) pb[c * FPLD + 4 * P + r] = (c <= r) ? a[r][c] : 0.0;
+}
+
+struct RowTile {
+    double *p;      // element (i, j) of the tile at p[j * ld + i]
+    int ld, nr;     // rows >= nr read as zero and are not written back
+};
+__host__ __device__ constexpr int panel_scratch_doubles(int RT) { return 2 * (1 + RT) * 4 * FPLD + FB; }
+
+template <int RT, bool FACTOR>
+__device__ __forceinline__ void panel_solve64(double *__restrict__ sD, double *__restrict__ scratch, const RowTile (&rt)[RT > 0 ? RT : 1],
+                                              int nb, int col0, int *fail_col, bool report) {
+    constexpr int PB = (1 + RT) * 4 * FPLD;          // doubles per published panel (diagonal tile rows first)
+    double *srinv = scratch + 2 * PB;
+    // column tiles are spread over the WARPS (warp w owns tx = 2w, 2w + 1), row tiles over the lanes: at step P only the
+    // warps with a column tile right of P issue anything (with tx on the lanes every warp kept issuing for a shrinking
+    // set of active lanes: ncu counted 2.4x the ideal FP64 issue slots), and all shared-memory reads are 512-byte rows
+    const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+    const bool active = ty >= tx;
+    const int nsteps = (nb + 3) >> 2;                // the identity padding needs no work
+    double a[4][4];
+    double x[RT > 0 ? RT : 1][4][4];
+    if (FACTOR) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) a[r][c] = active ? sD[(4 * tx + c) * FLD + 4 * ty + r] : 0.0;
+        for (int i = 4 * nsteps + tid; i < FB; i += 256) srinv[i] = 1.0;   // (entries below are written by the diagonal threads)
+    }
+#pragma unroll
+    for (int q = 0; q < RT; q++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                x[q][r][c] = (4 * ty + r < rt[q].nr && 4 * tx + c < nb) ? rt[q].p[(4 * tx + c) * rt[q].ld + 4 * ty + r] : 0.0;
+#pragma unroll 1
+    for (int P = 0; P < nsteps; P++) {
+        double *pb = scratch + (P & 1) * PB;
+        if (FACTOR && P == 0) {
+            if (ty == 0 && tx == 0) factor_diag_tile(a, pb, srinv, 0, nb, col0, fail_col, report);
+            __syncthreads();
+        }
+        if (tx == P) {
+            // X * L_PP^T = B on 4 x 4 tiles, column by column
+            double lpp[4][4], ri[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                ri[c] = srinv[4 * P + c];
+#pragma unroll
+                for (int k = 0; k < 4; k++) lpp[c][k] = FACTOR ? pb[k * FPLD + 4 * P + c] : sD[(4 * P + k) * FLD + 4 * P + c];
+            }
+            if (FACTOR && ty > P) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        double s = a[r][c];
+#pragma unroll
+                        for (int k = 0; k < c; k++) s -= a[r][k] * lpp[c][k];
+                        a[r][c] = s * ri[c];
+                    }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pb[c * FPLD + 4 * ty + r] = a[r][c];
+            }
+#pragma unroll
+            for (int q = 0; q < RT; q++) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        double s = x[q][r][c];
+#pragma unroll
+                        for (int k = 0; k < c; k++) s -= x[q][r][k] * lpp[c][k];
+                        x[q][r][c] = s * ri[c];
+                    }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pb[(4 * (q + 1) + c) * FPLD + 4 * ty + r] = x[q][r][c];
+            }
+        }
+        __syncthreads();
+        if (tx > P) {
+            double pc[4][4];          // L[4tx + c][4P + k]
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) pc[c][k] = FACTOR ? pb[k * FPLD + 4 * tx + c] : sD[(4 * P + k) * FLD + 4 * tx + c];
+            if (FACTOR && active) {
+                double pr[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pr[r][k] = pb[k * FPLD + 4 * ty + r];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) a[r][c] -= pr[r][k] * pc[c][k];
+                // look-ahead: the next diagonal tile is final now -- factor it while the other warps are still updating
+                if (ty == P + 1 && tx == P + 1 && P + 1 < nsteps)
+                    factor_diag_tile(a, scratch + ((P + 1) & 1) * PB, srinv, P + 1, nb, col0, fail_col, report);
+            }
+#pragma unroll
+            for (int q = 0; q < RT; q++) {
+                double pr[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pr[r][k] = pb[(4 * (q + 1) + k) * FPLD + 4 * ty + r];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[q][r][c] -= pr[r][k] * pc[c][k];
+            }
+        }
+        if (FACTOR) __syncthreads();      // the next diagonal tile is published
+        // (!FACTOR: the next step publishes into the other panel buffer, one barrier per step is enough)
+    }
+    if (FACTOR && active) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) sD[(4 * tx + c) * FLD + 4 * ty + r] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < RT; q++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (4 * ty + r < rt[q].nr && 4 * tx + c < nb) rt[q].p[(4 * tx + c) * rt[q].ld + 4 * ty + r] = x[q][r][c];
+    __syncthreads();
+}
+
+// C[64 x 64] -= A[64 x 64] B[64 x 64]^T on column-major shared-memory tiles (C(i,j) at sC[j*FLD+i], A(i,k) at sA[k*FLD+i],
+// B(j,k) at sB[k*FLD+j]); 256 threads x 4 x 4 register tiles; lower: only tiles on / below the diagonal.
+__device__ __forceinline__ void rank64_update(double *__restrict__ sC, const double *__restrict__ sA, const double *__restrict__ sB, bool lower) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (lower && ty < tx) return;
+    double c[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) c[i][j] = sC[(4 * tx + j) * FLD + 4 * ty + i];
+#pragma unroll 8
+    for (int k = 0; k < FB; k++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a[i] = sA[k * FLD + 4 * ty + i]; b[i] = sB[k * FLD + 4 * tx + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) c[i][j] -= a[i] * b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) sC[(4 * tx + j) * FLD + 4 * ty + i] = c[i][j];
+}
+
+// global (column-major, leading dimension ld) -> shared tile; entries outside nr x nc read as 0 (tri: only i >= j is
+// read, the diagonal beyond the true order is padded with ones so that the padded tile stays positive definite)
+// Asynchronous (cp.async, 8 bytes per element: the row offsets of a panel tile may be odd) -- a plain load / store
+// loop serialises on in-order issue: the store of one element stalls the load of the next. Call tile_pad_identity
+// after cp_async_wait + barrier for `tri` tiles.
+__device__ __forceinline__ void load_tile(double *__restrict__ s, const double *__restrict__ g, long long ld, int nr, int nc, bool tri) {
+    const int i = threadIdx.x & 63, j0 = threadIdx.x >> 6;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s + j0 * FLD + i);
+    const double *src = g + i + (long long)j0 * ld;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int j = j0 + 4 * q;
+        const bool ok = i < nr && j < nc && (!tri || i >= j);
+        cp_async8s(sa + q * 4 * FLD * 8, ok ? (const void *)(src + (long long)q * 4 * ld) : (const void *)g, ok ? 8 : 0);
+    }
+}
+__device__ __forceinline__ void tile_pad_identity(double *__restrict__ s, int nb) {
+    if (threadIdx.x < FB && threadIdx.x >= nb) s[threadIdx.x * FLD + threadIdx.x] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chain step: columns [k0, k0 + nb0 + nb1) of one supernode panel (nb0 <= 64; nb1 > 0 only if nb0 == 64).
+// CTA 0 of a task is the diagonal CTA, CTA t >= 1 owns rows [k2 + 64 (t - 1), ...) with k2 = k0 + nb0 + nb1.
+// ------------------------------------------------------------------------------------------------
+struct ChainTask {
+    double *P;          // panel base (column-major, leading dimension ld)
+    double *sq;         // parked factored square: 128 x 128 doubles, column-major, leading dimension 128
+    int ld, nrow;
+    int k0, nb0, nb1;
+    int col0;           // global (permuted) column of k0, for pivot reporting
+};
+
+constexpr int CHAIN_SMEM_BYTES = (5 * FTILE + FSCRATCH) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int *__restrict__ fail_col,
+                  long long bstride) {
+    extern __shared__ __align__(16) double fsm[];
+    double *sD0 = fsm, *sH = fsm + FTILE, *sD1 = fsm + 2 * FTILE, *sB0 = fsm + 3 * FTILE, *sB1 = fsm + 4 * FTILE;
+    double *scr = fsm + 5 * FTILE;
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    ChainTask T = tasks[t];
+    T.P = lane_ptr(T.P, bstride); T.sq = lane_ptr(T.sq, bstride); fail_col = lane_ptr(fail_col, bstride);
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x;
+    const long long ld = T.ld;
+    const bool two = T.nb1 > 0, diag = tile == 0;
+    const int k1 = T.k0 + FB, k2 = T.k0 + T.nb0 + T.nb1;
+    const int row0 = k2 + (tile - 1) * FB;
+    const int nrv = diag ? 0 : min(FB, T.nrow - row0);
+    // ---- loads (asynchronous, all in flight together) ----
+    load_tile(sD0, T.P + (long long)T.k0 * ld + T.k0, ld, T.nb0, T.nb0, true);
+    load_tile(sH, T.P + (long long)T.k0 * ld + k1, ld, T.nb1, FB, false);
+    load_tile(sD1, T.P + (long long)k1 * ld + k1, ld, T.nb1, T.nb1, true);
+    load_tile(sB0, T.P + (long long)T.k0 * ld + row0, ld, nrv, T.nb0, false);
+    load_tile(sB1, T.P + (long long)k1 * ld + row0, ld, nrv, T.nb1, false);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    tile_pad_identity(sD0, T.nb0);
+    tile_pad_identity(sD1, T.nb1);
+    __syncthreads();
+    // ---- block 0: [D0; H; B0] is one 192 x 64 panel ----
+    {
+        const RowTile rt[2] = {{sH, FLD, T.nb1}, {sB0, FLD, nrv}};
+        panel_solve64<2, true>(sD0, scr, rt, T.nb0, T.col0, fail_col, diag);
+    }
+    for (int e = tid; e < FB * FB; e += 256) {          // X0 -> HBM (coalesced along the rows)
+        const int i = e & 63, j = e >> 6;
+        if (i < nrv && j < T.nb0) T.P[(long long)(T.k0 + j) * ld + row0 + i] = sB0[j * FLD + i];
+    }
+    if (two) {
+        rank64_update(sD1, sH, sH, true);
+        if (!diag) rank64_update(sB1, sB0, sH, false);
+        __syncthreads();
+        const RowTile rt[1] = {{sB1, FLD, nrv}};
+        panel_solve64<1, true>(sD1, scr, rt, T.nb1, T.col0 + FB, fail_col, diag);
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e & 63, j = e >> 6;
+            if (i < nrv && j < T.nb1) T.P[(long long)(k1 + j) * ld + row0 + i] = sB1[j * FLD + i];
+        }
+    }
+    if (diag) {
+        // park the factored square (the other CTAs of this launch may still be reading the panel's copy)
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e & 63, j = e >> 6;
+            T.sq[j * 128 + i] = sD0[j * FLD + i];
+            if (two) {
+                T.sq[j * 128 + 64 + i] = sH[j * FLD + i];
+                T.sq[(64 + j) * 128 + 64 + i] = sD1[j * FLD + i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalize: park -> panel copy of the factored diagonal squares and inversion of every 64-column diagonal block that
+// a fused kernel produced (inv = L_kk^-1, nb x nb, leading dimension nb, zeros above the diagonal).
+// ------------------------------------------------------------------------------------------------
+struct FinalizeTask {
+    const double *sq;   // parked square (leading dimension 128) or nullptr: the factor already sits in the panel
+    double *P;          // panel + k0 * ld + k0 (the diagonal square's corner)
+    double *inv0, *inv1;
+    int ld, nb0, nb1, pad_;
+};
+
+constexpr int FINALIZE_SMEM_BYTES = (2 * FTILE + panel_scratch_doubles(1)) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 2)
+chain_finalize_kernel(const FinalizeTask *__restrict__ tasks, long long bstride) {
+    extern __shared__ __align__(16) double fsm[];
+    double *sL = fsm, *sY = fsm + FTILE, *scr = fsm + 2 * FTILE;
+    double *srinv = scr + 2 * 2 * 4 * FPLD;
+    const int which = blockIdx.x & 1;                    // CTA pair: block 0 / block 1 of the task
+    FinalizeTask T = tasks[blockIdx.x >> 1];
+    const bool parked = T.sq != nullptr;
+    T.sq = lane_ptr(T.sq, bstride); T.P = lane_ptr(T.P, bstride); T.inv0 = lane_ptr(T.inv0, bstride); T.inv1 = lane_ptr(T.inv1, bstride);
+    const int tid = threadIdx.x;
+    const long long ld = T.ld;
+    if (which == 1 && T.nb1 == 0) return;
+    const int nb = which ? T.nb1 : T.nb0, o = which ? FB : 0;
+    double *inv = which ? T.inv1 : T.inv0;
+    for (int e = tid; e < FB * FB; e += 256) {
+        const int i = e & 63, j = e >> 6;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j <= i) v = parked ? T.sq[(o + j) * 128 + o + i] : T.P[(o + i) + (o + j) * ld];
+        sL[j * FLD + i] = v;
+        sY[j * FLD + i] = (i == j) ? 1.0 : 0.0;
+        if (parked) {
+            if (i < nb && j <= i) T.P[(o + i) + (o + j) * ld] = v;
+            if (which == 1 && i < nb) T.P[(FB + i) + j * ld] = T.sq[j * 128 + FB + i];     // the rows under block 0
+        }
+    }
+    __syncthreads();
+    if (tid < FB) srinv[tid] = 1.0 / sL[tid * FLD + tid];
+    __syncthreads();
+    // Y L^T = I  =>  Y = L^-T; the inverse is its transpose
+    const RowTile rt[1] = {{sY, FLD, FB}};
+    panel_solve64<1, false>(sL, scr, rt, nb, 0, nullptr, false);
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int i = e % nb, c = e / nb;
+        inv[e] = (i >= c) ? sY[i * FLD + c] : 0.0;        // inv(i, c) = Y(c, i)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small fronts: one CTA per supernode; the nrow x ns panel lives in shared memory (column-major, leading dimension
+// ldp = nrow rounded up to odd). Extend-add is a GATHER: for every child the inverse of its relative-index list
+// (parent front row -> child update row, -1 if absent) is built in shared memory, and every entry of the parent front
+// sums its children's contributions itself (fixed child order) -- no read-modify-write chains, no atomics, all loads
+// independent. Phases: panel <- Q values already scattered into HBM (cp.async) + children; per 64-column block: potrf,
+// rows below solved (thread per row, values in registers), later columns updated; panel -> HBM; the update matrix
+// U = -L21 L21^T + children goes straight from registers to HBM.
+// ------------------------------------------------------------------------------------------------
+struct FrontTask {
+    int super;
+    int smem_doubles;   // doubles of dynamic shared memory beyond the potrf tile + scratch (panel + inverse maps)
+};
+
+constexpr int FRONT_MAXC = 4;       // children whose inverse row maps are resident at once (more: several passes)
+
+__host__ __device__ __forceinline__ int front_ldp(int nrow) { return (nrow + 1) | 1; }   // odd: conflict-free column walks
+__host__ __device__ __forceinline__ int front_smem_doubles(int nrow, int ns) {
+    return ns * front_ldp(nrow) + (FRONT_MAXC * nrow + 1) / 2;
+}
+
+// (two CTAs per SM: the second one hides the barriers of the small panel steps)
+__global__ void __launch_bounds__(256, 2)
+front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restrict__ meta, const int *__restrict__ child_idx,
+                   const int *__restrict__ relidx, double *__restrict__ Lx0, double *__restrict__ upd0, int *__restrict__ fail_col,
+                   long long bstride) {
+    extern __shared__ __align__(16) double fsm[];
+    __shared__ const double *cU[FRONT_MAXC];
+    __shared__ int cUld[FRONT_MAXC];
+    double *sD = fsm;                       // 64 x 64 tile for the diagonal block
+    double *scr = fsm + FTILE;
+    double *sP = fsm + FTILE + FSCRATCH;    // panel
+    double *__restrict__ Lx = lane_ptr_pinned(Lx0, bstride);
+    double *__restrict__ upd = lane_ptr_pinned(upd0, bstride);
+    fail_col = lane_ptr(fail_col, bstride);
+    const SuperMeta S = meta[tasks[blockIdx.x].super];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ns = S.ns, nrow = S.nrow, nr = nrow - ns;
+    const int ldp = front_ldp(nrow);
+    int *sInv = reinterpret_cast<int *>(sP + ns * ldp);     // [FRONT_MAXC][nrow]
+    const int nch = S.child_end - S.child_begin;
+    double *Lp = Lx + S.panel_off;
+    // ---- panel <- HBM (asynchronous; the strictly upper part of the diagonal block reads as zero) ----
+    for (int c = warp; c < ns; c += 8) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(sP + c * ldp);
+        const double *src = Lp + (long long)c * S.ld;
+        for (int r = lane; r < nrow; r += 32) cp_async8s(sa + r * 8, src + r, r >= c ? 8 : 0);
+    }
+    cp_async_commit();
+    // inverse maps of children [cb, cb + cn)
+    auto build_maps = [&](int cb, int cn) {
+        for (int e = tid; e < cn * nrow; e += 256) sInv[e] = -1;
+        __syncthreads();
+        for (int k = 0; k < cn; k++) {
+            const SuperMeta C = meta[child_idx[S.child_begin + cb + k]];
+            const int cnr = C.nrow - C.ns;
+            const int *rel = relidx + C.rowptr + C.ns;
+            for (int i = tid; i < cnr; i += 256) sInv[k * nrow + rel[i]] = i;
+            if (tid == 0) { cU[k] = upd + C.upd_off; cUld[k] = C.uld; }
+        }
+        __syncthreads();
+    };
+    // ---- children: contributions to the panel ----
+    for (int cb = 0; cb < nch; cb += FRONT_MAXC) {
+        const int cn = min(FRONT_MAXC, nch - cb);
+        build_maps(cb, cn);
+        if (cb == 0) { cp_async_wait<0>(); __syncthreads(); }
+        for (int c = warp; c < ns; c += 8) {
+            double *col = sP + c * ldp;
+            const double *Uck[FRONT_MAXC];
+            bool has[FRONT_MAXC];
+#pragma unroll
+            for (int k = 0; k < FRONT_MAXC; k++) {
+                const int ic = k < cn ? sInv[k * nrow + c] : -1;        // (uniform across the warp)
+                has[k] = ic >= 0;
+                Uck[k] = has[k] ? cU[k] + (long long)ic * cUld[k] : nullptr;
+            }
+            // 8 rows per lane and all children at once: up to 32 independent loads in flight per thread
+            for (int r0 = c; r0 < nrow; r0 += 256) {
+                double v[8][FRONT_MAXC];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + lane + 32 * u;
+#pragma unroll
+                    for (int k = 0; k < FRONT_MAXC; k++) {
+                        const int ir = (has[k] && r < nrow) ? sInv[k * nrow + r] : -1;
+                        v[u][k] = ir >= 0 ? Uck[k][ir] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int r = r0 + lane + 32 * u;
+                    double add = 0.0;
+#pragma unroll
+                    for (int k = 0; k < FRONT_MAXC; k++) add += v[u][k];
+                    if (r < nrow) col[r] += add;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (nch == 0) { cp_async_wait<0>(); __syncthreads(); }
+    // ---- blocked right-looking factorization of the panel ----
+    for (int k0 = 0; k0 < ns; k0 += FB) {
+        const int nb = min(FB, ns - k0), k1 = k0 + nb;
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e & 63, j = e >> 6;
+            double v = (i == j) ? 1.0 : 0.0;
+            if (i < nb && j <= i) v = sP[(k0 + j) * ldp + k0 + i];
+            sD[j * FLD + i] = v;
+        }
+        __syncthreads();
+        // the diagonal block together with the first 128 rows below it, then the remaining rows 128 at a time
+        {
+            const RowTile rt[2] = {{sP + k0 * ldp + k1, ldp, min(FB, nrow - k1)}, {sP + k0 * ldp + k1 + FB, ldp, max(0, min(FB, nrow - k1 - FB))}};
+            panel_solve64<2, true>(sD, scr, rt, nb, S.first + k0, fail_col, true);
+        }
+        for (int e = tid; e < nb * nb; e += 256) {
+            const int i = e % nb, j = e / nb;
+            if (i >= j) sP[(k0 + j) * ldp + k0 + i] = sD[j * FLD + i];
+        }
+        for (int r0 = k1 + 2 * FB; r0 < nrow; r0 += 2 * FB) {
+            const RowTile rt[2] = {{sP + k0 * ldp + r0, ldp, min(FB, nrow - r0)}, {sP + k0 * ldp + r0 + FB, ldp, max(0, min(FB, nrow - r0 - FB))}};
+            panel_solve64<2, false>(sD, scr, rt, nb, 0, nullptr, false);
+        }
+        __syncthreads();
+        // later columns of the panel: A[r, j] -= sum_c X[r, c] X[j, c]  (j in [k1, ns), r >= j), 4 x 4 register tiles
+        if (k1 < ns) {
+            const int nj = ns - k1, ni = nrow - k1;
+            const int tj = (nj + 3) >> 2, ti = (ni + 3) >> 2;
+            for (int tt = tid; tt < tj * ti; tt += 256) {
+                const int bj = tt / ti, bi = tt - bj * ti;
+                if (4 * bi + 3 < 4 * bj) continue;          // tile strictly above the diagonal
+                double acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+                for (int c = 0; c < nb; c++) {
+                    const double *col = sP + (k0 + c) * ldp + k1;
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        a[i] = (4 * bi + i < ni) ? col[4 * bi + i] : 0.0;
+                        b[i] = (4 * bj + i < nj) ? col[4 * bj + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int rr = 4 * bi + i, jj = 4 * bj + j;
+                        if (rr < ni && jj < nj && rr >= jj) sP[(k1 + jj) * ldp + k1 + rr] -= acc[i][j];
+                    }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- panel -> HBM ----
+    for (int c = warp; c < ns; c += 8)
+        for (int r = c + lane; r < nrow; r += 32) Lp[r + (long long)c * S.ld] = sP[c * ldp + r];
+    if (nr == 0) return;
+    // ---- update matrix U = -L21 L21^T + children (lower), registers -> HBM ----
+    double *Up = upd + S.upd_off;
+    const int tn = (nr + 3) >> 2;
+    for (int cb = 0; cb == 0 || cb < nch; cb += FRONT_MAXC) {
+        const int cn = max(0, min(FRONT_MAXC, nch - cb));
+        if (nch > FRONT_MAXC) build_maps(cb, cn);            // (otherwise the maps of the panel phase are still in place)
+        // a warp owns a column of 4 x 4 tiles (round robin), its lanes walk down the rows from the diagonal: the column
+        // operand is a broadcast, the row operand and the stores are contiguous across the lanes, no tile above the
+        // diagonal is ever enumerated
+        for (int bj = warp; bj < tn; bj += 8)
+        for (int bi = bj + lane; bi < tn; bi += 32) {
+            double acc[4][4];
+            if (cb == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+                for (int c = 0; c < ns; c++) {
+                    const double *col = sP + c * ldp + ns;
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        a[i] = (4 * bi + i < nr) ? col[4 * bi + i] : 0.0;
+                        b[i] = (4 * bj + i < nr) ? col[4 * bj + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] -= a[i] * b[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int rr = 4 * bi + i, jj = 4 * bj + j;
+                        acc[i][j] = (rr < nr && jj < nr && rr >= jj) ? Up[rr + (long long)jj * S.uld] : 0.0;
+                    }
+            }
+            for (int k = 0; k < cn; k++) {
+                const int *inv = sInv + k * nrow + ns;
+                const double *Uc = cU[k];
+                const long long uld = cUld[k];
+                int ii[4], ij[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    ii[i] = (4 * bi + i < nr) ? inv[4 * bi + i] : -1;
+                    ij[i] = (4 * bj + i < nr) ? inv[4 * bj + i] : -1;
+                }
+                double g[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        g[i][j] = (ii[i] >= 0 && ij[j] >= 0 && ii[i] >= ij[j]) ? Uc[ii[i] + ij[j] * uld] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[i][j] += g[i][j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int rr = 4 * bi + i, jj = 4 * bj + j;
+                    if (rr < nr && jj < nr && rr >= jj) Up[rr + (long long)jj * S.uld] = acc[i][j];
+                }
+        }
+        if (nch > FRONT_MAXC) __syncthreads();
+    }
+}
+
+}  // namespace gmrf

@@ -7,6 +7,7 @@
 #include "../../include/gmrf_b200.h"
 #include "kernels.cuh"
 #include "solve_kernels.cuh"
+#include "front_kernels.cuh"
 #include "symbolic.hpp"
 
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
@@ -29,13 +30,14 @@ namespace {
 thread_local std::string g_create_error;
 
 enum LaunchKind : int {
-    K_ASSEMBLE, K_UNUSED1, K_UNUSED2, K_UNUSED3, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
+    K_ASSEMBLE, K_CHAIN, K_FINALIZE, K_FRONT, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
     K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE
 };
 
 struct Launch {
     int kind;
-    int aux;            // panel step: NBT bucket
+    int aux;            // panel step: NBT bucket; front launch: dynamic shared memory (bytes)
+    int aux2 = 0;       // front launch: widest diagonal block (selects the kernel instantiation)
     i64 task_off;       // first task in the kind's task array
     int ntasks;
     i64 prefix_off;     // offset into the tile-prefix array (ntasks+1 entries) or -1
@@ -61,6 +63,8 @@ struct gmrf_b200_handle {
     int device = -1;
     std::string err;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;    // side stream: work off the factorization's critical path (block inverses)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool factored = false, selinv_valid = false;
     int fail_col = 0;
@@ -104,6 +108,12 @@ struct gmrf_b200_handle {
     int multi_wcap = 0;                // columns the shared work arrays hold
     TransTask *d_trans = nullptr;
     SplitTask *d_split = nullptr, *d_split_z = nullptr;
+    ChainTask *d_chain = nullptr;      // fused chain steps (front_kernels.cuh)
+    FinalizeTask *d_final = nullptr;
+    FrontTask *d_front = nullptr;
+    double *d_sq = nullptr;            // parked factored diagonal squares of the fused chain steps (128 x 128 each)
+    int front_smem_max = 0;            // dynamic shared memory the one-CTA-per-front kernel was configured for
+    i64 n_large_tile_launches = 0, n_splitk_tasks = 0, n_fast_roots = 0, n_chain_launches = 0, n_front_launches = 0;
     double *d_base = nullptr;          // optional resident copy of a prior's nzval (Newton loops: Q_prior - H on the device)
     double *d_hdiag = nullptr;
     long long *d_diagnz = nullptr;     // nzval position of every diagonal entry of the input pattern (-1: not stored)
@@ -222,6 +232,10 @@ struct Builder {
     std::vector<TransTask> trans;
     std::vector<SplitTask> split;
     std::vector<RowGatherTask> rowgather;
+    std::vector<ChainTask> chain;
+    std::vector<FinalizeTask> finalize;
+    std::vector<FrontTask> front;
+    i64 n_large_tile_launches = 0, n_splitk_tasks = 0;
     double *splitk_base = nullptr;     // device scratch for split-K partial products
     i64 splitk_cap = 0;
     int splitk_min_k = 1024;
@@ -302,8 +316,10 @@ struct Builder {
             if (tot > INT_MAX) throw std::runtime_error("too many GEMM tiles in one launch");
             L.grid = (int)tot;
             plan.launches.push_back(L);
+            if (pass) n_large_tile_launches++;
         }
         tasks.clear();
+        n_splitk_tasks += (i64)reduce.size();
         if (!reduce.empty()) {
             Launch L;
             L.kind = K_SPLIT_REDUCE;
@@ -392,6 +408,55 @@ struct Builder {
         plan.launches.push_back(L);
         tasks.clear();
     }
+    // fused chain step: 1 diagonal CTA + one CTA per 64-row tile below the step's columns
+    void add_chain(Plan &plan, std::vector<ChainTask> &tasks) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = K_CHAIN;
+        L.aux = 0;
+        L.task_off = (i64)chain.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = (i64)prefix.size();
+        i64 tot = 0;
+        for (auto &t : tasks) {
+            prefix.push_back((int)tot);
+            tot += 1 + cdiv(std::max(0, t.nrow - (t.k0 + t.nb0 + t.nb1)), FB);
+            chain.push_back(t);
+        }
+        prefix.push_back((int)tot);
+        if (tot > INT_MAX) throw std::runtime_error("too many tiles in one chain step");
+        L.grid = (int)tot;
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    void add_front(Plan &plan, std::vector<FrontTask> &tasks, int max_nb) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = K_FRONT;
+        L.aux = 0;                                     // dynamic shared memory of the launch (bytes)
+        for (auto &t : tasks) L.aux = std::max(L.aux, (int)((FTILE + FSCRATCH + t.smem_doubles) * sizeof(double)));
+        L.aux2 = max_nb;
+        L.task_off = (i64)front.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = -1;
+        L.grid = (int)tasks.size();
+        front.insert(front.end(), tasks.begin(), tasks.end());
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
+    i64 finalize_done = 0;
+    void add_finalize(Plan &plan) {          // one launch for the tasks pushed since the previous call
+        if ((i64)finalize.size() == finalize_done) return;
+        Launch L;
+        L.kind = K_FINALIZE;
+        L.aux = 0;
+        L.task_off = finalize_done;
+        L.ntasks = (int)((i64)finalize.size() - finalize_done);
+        L.prefix_off = -1;
+        L.grid = L.ntasks;
+        plan.launches.push_back(L);
+        finalize_done = (i64)finalize.size();
+    }
     void add_superlist(Plan &plan, std::vector<int> &lst, int kind) {
         if (lst.empty()) return;
         Launch L;
@@ -409,26 +474,102 @@ struct Builder {
 
 constexpr int NB = POTRF_NB;
 
+// Which path every level of the assembly tree takes in the numeric factorization (decided once per analysis, before the
+// numeric arena is sized):
+//   2  front_small_kernel: every panel of the level fits in shared memory -> ONE launch for the level;
+//   1  fused chain steps (chain_step_kernel): few enough 64-row tiles that the chain's latency dominates -> one launch
+//      per 128 columns (+ the left-looking block-column GEMM) instead of 3 launches per 64 columns;
+//   0  the bulk path: potrf+inverse per 64 columns, TRSM and updates as DMMA GEMM launches (throughput-bound levels).
+struct FusedInfo {
+    std::vector<int> mode;        // per level
+    std::vector<i64> sq_base;     // per supernode: first parked square (units of 128 x 128 doubles), mode 1 only
+    i64 sq_total = 0;
+    int front_smem_max = 0;       // bytes
+};
+
+
+FusedInfo plan_fused(const Symbolic &S, const Options &opt) {
+    FusedInfo F;
+    F.mode.assign((size_t)S.nlevels, 0);
+    F.sq_base.assign((size_t)S.nsuper, -1);
+    if (opt.naive_kernels) return F;
+    const i64 cap = std::min<i64>(220, std::max(40, opt.front_smem_kb)) * 1024;
+    for (i64 l = 0; l < S.nlevels; l++) {
+        bool fit = opt.fused_front != 0;
+        i64 tiles = 0, need_max = 0;
+        for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+            const i64 s = S.level_idx[t], ns = S.ns(s), nrow = S.nrow(s);
+            const i64 need = ns * nrow > (1 << 20) ? (i64)1 << 40 : (i64)(FTILE + FSCRATCH + front_smem_doubles((int)nrow, (int)ns)) * (i64)sizeof(double);
+            need_max = std::max(need_max, need);
+            if (need > cap) fit = false;
+            tiles += 1 + cdiv(std::max<i64>(0, nrow - std::min<i64>(ns, 2 * FB)), FB);
+        }
+        if (fit) {
+            F.mode[l] = 2;
+            F.front_smem_max = std::max(F.front_smem_max, (int)need_max);
+        } else if (opt.fused_chain && tiles <= opt.chain_max_tiles) {
+            F.mode[l] = 1;
+            for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+                const i64 s = S.level_idx[t];
+                F.sq_base[s] = F.sq_total;
+                F.sq_total += cdiv(S.ns(s), 2 * FB);
+            }
+        }
+    }
+    return F;
+}
+
 // Panel factorization of a supernode (nrow x ns, column-major, in place), two-level blocking:
 //   outer blocks of OB columns: left-looking update with ALL previous columns in one large-k DMMA GEMM,
 //   inner blocks of NB=64 columns: single-CTA potrf + inverse, TRSM as a GEMM with the inverted block, then a k=64
-//   trailing update confined to the outer block.
+//   trailing update confined to the outer block (bulk path), or one fused chain step per 128 columns (latency path).
 // All supernodes of a level advance in lockstep, so one launch serves every front of the level.
-void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
+void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
     const Symbolic &S = h->S;
     Plan &plan = h->factor_plan;
-    const i64 OB = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
+    const i64 OB_bulk = std::max<i64>(NB, (i64)h->opt.outer_block / NB * NB);
+    const i64 BBLK = (i64)NB * NB;
     std::vector<AsmItem> its;
     std::vector<PanelTask> pt;
     std::vector<GemmTask> gt, st;
+    std::vector<ChainTask> ct;
+    std::vector<FrontTask> ft;
+    auto push_finalize = [&](i64 s, i64 k0, const double *sq) {
+        const i64 ns = S.ns(s), ld = S.panel_ld[s];
+        FinalizeTask f;
+        f.sq = sq;
+        f.P = h->d_Lx + S.panel_off[s] + k0 * ld + k0;
+        f.inv0 = h->d_Linv + h->inv_base[s] + (k0 / NB) * BBLK;
+        f.inv1 = f.inv0 + BBLK;
+        f.ld = (int)ld;
+        f.nb0 = (int)std::min<i64>(NB, ns - k0);
+        f.nb1 = (int)std::max<i64>(0, std::min<i64>(NB, ns - k0 - NB));
+        f.pad_ = 0;
+        B.finalize.push_back(f);
+    };
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
+        const int mode = F.mode[(size_t)l];
+        if (mode == 2) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                const i64 s = *sp;
+                ft.push_back(FrontTask{(int)s, front_smem_doubles((int)S.nrow(s), (int)S.ns(s))});
+                for (i64 k0 = 0; k0 < S.ns(s); k0 += 2 * NB) push_finalize(s, k0, nullptr);
+            }
+            int max_nb = 0;
+            for (const i64 *sp = sb; sp < se; sp++) max_nb = std::max<int>(max_nb, (int)std::min<i64>(NB, S.ns(*sp)));
+            B.add_front(plan, ft, max_nb);
+            B.add_finalize(plan);
+            h->n_front_launches++;
+            continue;
+        }
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp;
             if (S.child_ptr[s + 1] > S.child_ptr[s])
                 for (i64 c0 = 0; c0 < S.nrow(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
         }
         B.add_items(plan, its, K_ASSEMBLE);
+        const i64 OB = mode == 1 ? 2 * NB : OB_bulk;
         i64 maxouter = 0;
         for (const i64 *sp = sb; sp < se; sp++) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
         for (i64 J = 0; J < maxouter; J++) {
@@ -448,6 +589,24 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                 }
                 B.add_gemm(plan, gt, 0, false, 1.0, /*allow_split=*/true);
             }
+            if (mode == 1) {
+                for (const i64 *sp = sb; sp < se; sp++) {
+                    i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                    if (J0 >= ns) continue;
+                    ChainTask c;
+                    c.P = h->d_Lx + S.panel_off[s];
+                    c.sq = h->d_sq + (F.sq_base[(size_t)s] + J) * (i64)(4 * BBLK);
+                    c.ld = (int)ld; c.nrow = (int)nrow; c.k0 = (int)J0;
+                    c.nb0 = (int)std::min<i64>(NB, ns - J0);
+                    c.nb1 = (int)std::max<i64>(0, std::min<i64>(NB, ns - J0 - NB));
+                    c.col0 = (int)(S.sfirst[s] + J0);
+                    ct.push_back(c);
+                    push_finalize(s, J0, c.sq);
+                }
+                B.add_chain(plan, ct);
+                h->n_chain_launches++;
+                continue;
+            }
             for (i64 jj = 0; jj < OB / NB; jj++) {
                 for (const i64 *sp = sb; sp < se; sp++) {
                     i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
@@ -455,7 +614,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
                     if (k0 >= ns) continue;
                     i64 nb = std::min<i64>(NB, ns - k0), k1 = k0 + nb, J1 = std::min(J0 + OB, ns);
                     double *P = h->d_Lx + S.panel_off[s];
-                    double *inv = h->d_Linv + h->inv_base[s] + (k0 / NB) * (i64)NB * NB;
+                    double *inv = h->d_Linv + h->inv_base[s] + (k0 / NB) * BBLK;
                     pt.push_back(PanelTask{P + k0 * ld + k0, inv, (int)ld, (int)nb, (int)(S.sfirst[s] + k0), 0});
                     if (nrow > k1) {   // rows below the block: X = B * inv(L_kk)^T, in place (one 64-wide tile per row strip)
                         GemmTask g;
@@ -493,6 +652,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B) {
             gt.push_back(g);
         }
         B.add_gemm(plan, gt, 0);
+        B.add_finalize(plan);
     }
 }
 
@@ -745,7 +905,7 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
         for (i64 t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
             i64 s = S.level_idx[t], ns = S.ns(s);
             i64 need = (i64)S.panel_ld[s] * ns;
-            if (S.nr(s) == 0 && ns >= 4 * NB && used + need <= pool) { fast[s] = 1; scratch_off[s] = used; used += need; }
+            if (S.nr(s) == 0 && ns >= 4 * NB && used + need <= pool) { fast[s] = 1; scratch_off[s] = used; used += need; h->n_fast_roots++; }
         }
     }
     for (i64 l = S.nlevels - 1; l >= 0; l--) {
@@ -949,10 +1109,15 @@ cudaError_t configure_gemm_tile() {
     if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, 16, 3, true, true>()))) return e;
     return cudaSuccess;
 }
-cudaError_t configure_kernels() {
+cudaError_t configure_kernels(int front_smem = 0) {
     cudaError_t e;
     if ((e = configure_gemm_tile<128, 64, 2, 2>())) return e;
     if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
+    if ((e = cudaFuncSetAttribute(chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(chain_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FINALIZE_SMEM_BYTES))) return e;
+    // (per device, sticky: handles of one process may need different sizes -> always opt in to the cap)
+    const int fs = std::max(front_smem, 220 * 1024);
+    if ((e = cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs))) return e;
     return cudaSuccess;
 }
 
@@ -962,13 +1127,6 @@ void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefi
     if (naive) gemm_naive_kernel<TA, TB><<<dim3(grid, lanes), 256, 0, st>>>(tasks, prefix, ntasks, bstride);
     else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
     else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
-}
-
-template <int BM, int BN, int WGM, int WGN, int KT, int ST>
-void launch_gemm_exp(const GemmTask *tasks, const int *prefix, int grid) {
-    auto kern = gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, KT, ST>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, KT, ST>());
-    kern<<<grid, WGM * WGN * 32, gemm_smem_bytes<BM, BN, KT, ST>()>>>(tasks, prefix, 1, 0LL);
 }
 
 struct TableSet {
@@ -982,8 +1140,8 @@ struct TableSet {
     int lanes = 1;                          // factorization: lanes advanced per launch (grid.y)
 };
 
-void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs) {
-    cudaStream_t st = h->stream;
+void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs, cudaStream_t stream_override = nullptr) {
+    cudaStream_t st = stream_override ? stream_override : h->stream;
     const bool naive = h->opt.naive_kernels != 0;
     const int *pf = L.prefix_off >= 0 ? T.prefix + L.prefix_off : nullptr;
     const long long bstride = T.lanes > 1 ? h->arena_bytes : 0;
@@ -991,6 +1149,16 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
     switch (L.kind) {
         case K_ASSEMBLE:
             assemble_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd, bstride);
+            break;
+        case K_CHAIN:
+            chain_step_kernel<<<dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st>>>(h->d_chain + L.task_off, pf, L.ntasks, h->d_fail, bstride);
+            break;
+        case K_FRONT:
+            front_small_kernel<<<dim3(L.grid, T.lanes), 256, L.aux, st>>>(h->d_front + L.task_off, h->d_meta, h->d_child, h->d_relidx,
+                                                                          h->d_Lx, h->d_upd, h->d_fail, bstride);
+            break;
+        case K_FINALIZE:
+            chain_finalize_kernel<<<dim3(2 * L.grid, T.lanes), 256, FINALIZE_SMEM_BYTES, st>>>(h->d_final + L.task_off, bstride);
             break;
         case K_PANEL:
             switch (L.aux) {
@@ -1080,7 +1248,24 @@ void enqueue_factor(gmrf_b200_handle *h, int lanes = 1) {
     }
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     T.lanes = lanes;
-    for (const Launch &L : h->factor_plan.launches) run_launch(h, L, T, 0);
+    // The finalize launches (block inverses for the solve / selected-inversion phases, parked diagonal squares -> panels)
+    // feed nothing later in the factorization: they run on a side stream beside the upper tree levels, which leave
+    // most SMs idle, and join before the log-determinant reads the diagonal.
+    bool forked = false;
+    for (const Launch &L : h->factor_plan.launches) {
+        if (L.kind == K_FINALIZE && h->stream2) {
+            cudaEventRecord(h->ev_fork, st);
+            cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+            run_launch(h, L, T, 0, h->stream2);
+            forked = true;
+        } else {
+            run_launch(h, L, T, 0);
+        }
+    }
+    if (forked) {
+        cudaEventRecord(h->ev_join, h->stream2);
+        cudaStreamWaitEvent(st, h->ev_join, 0);
+    }
     logdet_partial_kernel<<<dim3(LOGDET_BLOCKS, lanes), 256, 0, st>>>(h->d_Lx, h->d_diagpos, S.n, h->d_partial, bstride);
     logdet_final_kernel<<<dim3(1, lanes), 256, 0, st>>>(h->d_partial, h->d_scalars, bstride);
 }
@@ -1508,6 +1693,10 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "large_tile_mask") o.large_tile_mask = (int)value & 7;
     else if (k == "lanes") o.lanes = std::max(1, std::min(64, (int)value));
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
+    else if (k == "fused_front") o.fused_front = (int)value;
+    else if (k == "fused_chain") o.fused_chain = (int)value;
+    else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);
+    else if (k == "front_smem_kb") o.front_smem_kb = (int)value;
     else return GMRF_B200_ERR_ARG;
     return 0;
 }
@@ -1571,6 +1760,9 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         }
         if (cudaSetDevice(device) != cudaSuccess) { H->err = "cudaSetDevice failed"; return fail(GMRF_B200_ERR_CUDA); }
         if (cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking) != cudaSuccess) { H->err = "stream creation failed"; return fail(GMRF_B200_ERR_CUDA); }
+        if (cudaStreamCreateWithFlags(&H->stream2, cudaStreamNonBlocking) != cudaSuccess) { H->err = "stream creation failed"; return fail(GMRF_B200_ERR_CUDA); }
+        cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming);
         for (auto &e2 : H->ev) cudaEventCreate(&e2);
         if (configure_kernels() != cudaSuccess) { H->err = "cudaFuncSetAttribute failed (is this an sm_100a device?)"; return fail(GMRF_B200_ERR_CUDA); }
     }
@@ -1588,13 +1780,16 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         }
     }
     H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
+    const FusedInfo fused = plan_fused(S, H->opt);
+    H->front_smem_max = fused.front_smem_max;
     {
         auto al = [](i64 x) { return (std::max<i64>(x, 1) + 31) & ~31LL; };   // 256-byte granules
         // one pool serves the update matrices of the factorization and, afterwards, the gathered Z[R,R] blocks of the
         // selected inversion (the two phases never overlap)
         const i64 n_lx = al(S.panel_total), n_upd = al(std::max(S.upd_total, S.zw_total)), n_nz = al(S.nnzA),
-                  n_inv = al(inv_total), n_split = al(H->splitk_cap), n_part = al(LOGDET_BLOCKS), n_sc = al(8), n_fail = al(2);
-        const i64 arena = n_lx + n_upd + n_nz + n_inv + n_split + n_part + n_sc + n_fail;
+                  n_inv = al(inv_total), n_split = al(H->splitk_cap), n_part = al(LOGDET_BLOCKS), n_sc = al(8), n_fail = al(2),
+                  n_sq = al(fused.sq_total * 4 * (i64)NB * NB);
+        const i64 arena = n_lx + n_upd + n_nz + n_inv + n_split + n_part + n_sc + n_fail + n_sq;
         H->lanes = std::max(1, H->opt.lanes);
         if (H->lanes == 1) {
             // single lane: separate allocations (measured on B200: with panels and update pool inside ONE 78 GB
@@ -1607,6 +1802,7 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
             TRY_RC(dev_alloc(H, &H->d_splitk, (size_t)n_split));
             TRY_RC(dev_alloc(H, &H->d_partial, (size_t)n_part));
             TRY_RC(dev_alloc(H, &H->d_scalars, (size_t)n_sc));
+            TRY_RC(dev_alloc(H, &H->d_sq, (size_t)n_sq));
             double *f = nullptr;
             TRY_RC(dev_alloc(H, &f, (size_t)n_fail));
             H->d_fail = reinterpret_cast<int *>(f);
@@ -1621,6 +1817,7 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
             H->d_splitk = p; p += n_split;
             H->d_partial = p; p += n_part;
             H->d_scalars = p; p += n_sc;
+            H->d_sq = p; p += n_sq;
             H->d_fail = reinterpret_cast<int *>(p);
         }
     }
@@ -1662,13 +1859,18 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         B.naive = H->opt.naive_kernels != 0;
         B.splitk_base = H->d_splitk; B.splitk_cap = H->splitk_cap; B.splitk_min_k = H->opt.splitk_min_k; B.large_tile_mask = H->opt.large_tile_mask;
         try {
-            build_factor_plan(H, B);
+            build_factor_plan(H, B, fused);
             build_solve_plans(H, B);
         } catch (std::exception &e) {
             H->err = e.what();
             return fail(GMRF_B200_ERR_ARG);
         }
         H->gemm_flops_factor = B.gemm_flops;
+        H->n_large_tile_launches = B.n_large_tile_launches;
+        H->n_splitk_tasks = B.n_splitk_tasks;
+        TRY_RC(dev_upload(H, &H->d_chain, B.chain));
+        TRY_RC(dev_upload(H, &H->d_final, B.finalize));
+        TRY_RC(dev_upload(H, &H->d_front, B.front));
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
         TRY_RC(dev_upload(H, &H->d_panel, B.panel));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
@@ -1729,6 +1931,9 @@ void gmrf_b200_destroy(gmrf_b200_handle *h) {
             for (auto &g : m.graph) if (g) cudaGraphExecDestroy(g);
         for (void *p : h->owned) cudaFree(p);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_join) cudaEventDestroy(h->ev_join);
+        if (h->stream2) cudaStreamDestroy(h->stream2);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -2187,6 +2392,11 @@ int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info) {
     v[GMRF_B200_INFO_GRAPH_NODES] = (int64_t)h->factor_plan.launches.size() + 5;
     v[GMRF_B200_INFO_SELINV_NODES] = (int64_t)h->selinv_plan.launches.size();
     v[GMRF_B200_INFO_PATTERN_CACHE_HITS] = (int64_t)h->pp_hits;
+    v[GMRF_B200_INFO_LARGE_TILE_LAUNCHES] = (int64_t)h->n_large_tile_launches;
+    v[GMRF_B200_INFO_SPLITK_TASKS] = (int64_t)h->n_splitk_tasks;
+    v[GMRF_B200_INFO_FAST_ROOTS] = (int64_t)h->n_fast_roots;
+    v[GMRF_B200_INFO_CHAIN_LAUNCHES] = (int64_t)h->n_chain_launches;
+    v[GMRF_B200_INFO_FRONT_LAUNCHES] = (int64_t)h->n_front_launches;
     for (int i = 0; i < n_info && i < GMRF_B200_INFO_COUNT; i++) info[i] = v[i];
     return 0;
 }
@@ -2335,19 +2545,7 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
     T.A = dA; T.B = dB; T.C = dC; T.m = m; T.n = n; T.k = k; T.lda = lda; T.ldb = ldb; T.ldc = ldc;
     T.flags = (flags & 1 ? GEMM_LOWER : 0); T.pad_ = 0;
     const bool large = (flags & 16) != 0;
-    const int variant = (flags >> 8) & 0xff;   // experimental tile configurations (NN only)
     int BM = large ? 128 : 64, BN = 64;
-    switch (variant) {
-        case 1: BM = 128; BN = 64; break;
-        case 2: BM = 128; BN = 128; break;
-        case 3: BM = 64; BN = 64; break;
-        case 4: BM = 128; BN = 64; break;
-        case 5: BM = 64; BN = 128; break;
-        case 6: BM = 128; BN = 128; break;
-        case 7: BM = 64; BN = 64; break;
-        case 8: BM = 128; BN = 64; break;
-        default: break;
-    }
     int tiles = cdiv(m, BM) * cdiv(n, BN);
     int pf[2] = {0, tiles};
     cudaMemcpy(dT, &T, sizeof(T), cudaMemcpyHostToDevice);
@@ -2357,15 +2555,7 @@ int gmrf_b200_bench_gemm(int device, int transa, int transb, int flags, int m, i
     float best = 1e30f;
     for (int r = 0; r < reps + 1; r++) {
         cudaEventRecord(e0, 0);
-        if (variant == 1) launch_gemm_exp<128, 64, 2, 2, 16, 3>(dT, dP, tiles);        // 4 warps, warp tile 64x32
-        else if (variant == 2) launch_gemm_exp<128, 128, 4, 4, 16, 3>(dT, dP, tiles);  // 16 warps, warp tile 32x32
-        else if (variant == 3) launch_gemm_exp<64, 64, 2, 2, 32, 3>(dT, dP, tiles);    // deeper K tile
-        else if (variant == 4) launch_gemm_exp<128, 64, 4, 2, 16, 3>(dT, dP, tiles);   // 8 warps, warp tile 32x32
-        else if (variant == 5) launch_gemm_exp<64, 128, 2, 4, 16, 3>(dT, dP, tiles);   // 8 warps, warp tile 32x32
-        else if (variant == 6) launch_gemm_exp<128, 128, 2, 4, 16, 4>(dT, dP, tiles);  // production large + 4 stages
-        else if (variant == 7) launch_gemm_exp<64, 64, 2, 2, 16, 4>(dT, dP, tiles);    // production small + 4 stages
-        else if (variant == 8) launch_gemm_exp<128, 64, 4, 2, 32, 3>(dT, dP, tiles);
-        else if (!transa && !transb) launch_gemm<false, false>(large, false, dT, dP, 1, tiles, 0);
+        if (!transa && !transb) launch_gemm<false, false>(large, false, dT, dP, 1, tiles, 0);
         else if (!transa && transb) launch_gemm<false, true>(large, false, dT, dP, 1, tiles, 0);
         else launch_gemm<true, true>(large, false, dT, dP, 1, tiles, 0);
         cudaEventRecord(e1, 0);
@@ -2407,7 +2597,8 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, 0LL);
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) {
-        int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0 : L.kind == K_PANEL ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
+        int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0
+                   : (L.kind == K_PANEL || L.kind == K_CHAIN || L.kind == K_FRONT || L.kind == K_FINALIZE) ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
         mark(kind);
         run_launch(h, L, T, 0);
     }

@@ -16,7 +16,8 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_vp = ctypes.c_void_p
 
 INFO_KEYS = ["n", "nnz_q", "nnz_l", "nnz_l_stored", "nsuper", "nlevels", "max_front", "max_ns", "update_pool",
-             "flops_chol", "flops_chol_stored", "device_bytes", "graph_nodes", "selinv_nodes", "pattern_cache_hits"]
+             "flops_chol", "flops_chol_stored", "device_bytes", "graph_nodes", "selinv_nodes", "pattern_cache_hits",
+             "large_tile_launches", "splitk_tasks", "fast_roots", "chain_launches", "front_launches"]
 
 ORDER_NATURAL, ORDER_ND, ORDER_AMD = 0, 1, 2
 

@@ -181,7 +181,12 @@ enum {
     GMRF_B200_INFO_GRAPH_NODES = 12,   /* kernel launches in one refactorization */
     GMRF_B200_INFO_SELINV_NODES = 13,  /* kernel launches in one selected inversion */
     GMRF_B200_INFO_PATTERN_CACHE_HITS = 14, /* selinv_extract / selinv_dot calls that reused the previous pattern's lookup */
-    GMRF_B200_INFO_COUNT = 15
+    GMRF_B200_INFO_LARGE_TILE_LAUNCHES = 15, /* factorization launches of the 128 x 64-tile GEMM (plan introspection for tests) */
+    GMRF_B200_INFO_SPLITK_TASKS = 16,  /* products of the factorization plan that were cut along k */
+    GMRF_B200_INFO_FAST_ROOTS = 17,    /* root supernodes on the triangular route of the selected inversion (after its plan exists) */
+    GMRF_B200_INFO_CHAIN_LAUNCHES = 18, /* fused chain-step launches (one per 128 columns of a level's chains) */
+    GMRF_B200_INFO_FRONT_LAUNCHES = 19, /* one-CTA-per-front launches (one per tree level of small fronts) */
+    GMRF_B200_INFO_COUNT = 20
 };
 int gmrf_b200_info(const gmrf_b200_handle *h, int64_t *info, int n_info);
 int gmrf_b200_get_perm(const gmrf_b200_handle *h, int64_t *perm, int index_base);       /* final elimination order */
@@ -229,7 +234,7 @@ int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`

@@ -409,9 +409,12 @@ def test_schedule_variants_agree():
     base.close()
     assert np.max(np.abs(ref[2] - F.selinv_diag()) / F.selinv_diag()) <= 1e-8
     variants = [{"splitk_min_k": 32}, {"splitk_min_k": 16, "outer_block": 128}, {"selinv_fast_root": 0}, {"use_graph": 0},
-                {"bwd_row_chunk": 64}, {"wide_rhs_min": 1}]
+                {"bwd_row_chunk": 64}, {"wide_rhs_min": 1},
+                # the three factorization paths: bulk only / fused chain steps everywhere / one-CTA fronts where they fit
+                {"fused_front": 0, "fused_chain": 0}, {"fused_front": 0, "chain_max_tiles": 1000000},
+                {"fused_chain": 0}, {"front_smem_kb": 60}, {"fused_front": 0, "chain_max_tiles": 40}]
     defaults = {"splitk_min_k": 1024, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1, "bwd_row_chunk": 2048,
-                "wide_rhs_min": 8}
+                "wide_rhs_min": 8, "fused_front": 1, "fused_chain": 1, "chain_max_tiles": 600, "front_smem_kb": 200}
     try:
         for v in variants:
             for k, val in {**defaults, **v}.items():
