@@ -264,6 +264,10 @@ struct ChainTask {
     int col0;           // global (permuted) column of k0, for pivot reporting
 };
 
+// Phase timestamps (clock64) of tile 1 of the LAST chain launch, for tests/gpu_chain_phases.py: nullptr = off.
+__device__ long long *g_chain_prof = nullptr;
+#define CHAIN_STAMP(i) do { if (prof && tile == 1 && tid == 0) prof[i] = clock64(); } while (0)
+
 constexpr int CHAIN_SMEM_BYTES = (5 * FTILE + FSCRATCH) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(256, 1)
@@ -282,6 +286,8 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
     const int k1 = T.k0 + FB, k2 = T.k0 + T.nb0 + T.nb1;
     const int row0 = k2 + (tile - 1) * FB;
     const int nrv = diag ? 0 : min(FB, T.nrow - row0);
+    long long *prof = g_chain_prof;
+    CHAIN_STAMP(0);
     // ---- loads (asynchronous, all in flight together) ----
     load_tile(sD0, T.P + (long long)T.k0 * ld + T.k0, ld, T.nb0, T.nb0, true);
     load_tile(sH, T.P + (long long)T.k0 * ld + k1, ld, T.nb1, FB, false);
@@ -294,21 +300,26 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
     tile_pad_identity(sD0, T.nb0);
     tile_pad_identity(sD1, T.nb1);
     __syncthreads();
+    CHAIN_STAMP(1);
     // ---- block 0: [D0; H; B0] is one 192 x 64 panel ----
     {
         const RowTile rt[2] = {{sH, FLD, T.nb1}, {sB0, FLD, nrv}};
         panel_solve64<2, true>(sD0, scr, rt, T.nb0, T.col0, fail_col, diag);
     }
+    CHAIN_STAMP(2);
     for (int e = tid; e < FB * FB; e += 256) {          // X0 -> HBM (coalesced along the rows)
         const int i = e & 63, j = e >> 6;
         if (i < nrv && j < T.nb0) T.P[(long long)(T.k0 + j) * ld + row0 + i] = sB0[j * FLD + i];
     }
+    CHAIN_STAMP(3);
     if (two) {
         rank64_update(sD1, sH, sH, true);
         if (!diag) rank64_update(sB1, sB0, sH, false);
         __syncthreads();
+        CHAIN_STAMP(4);
         const RowTile rt[1] = {{sB1, FLD, nrv}};
         panel_solve64<1, true>(sD1, scr, rt, T.nb1, T.col0 + FB, fail_col, diag);
+        CHAIN_STAMP(5);
         for (int e = tid; e < FB * FB; e += 256) {
             const int i = e & 63, j = e >> 6;
             if (i < nrv && j < T.nb1) T.P[(long long)(k1 + j) * ld + row0 + i] = sB1[j * FLD + i];
@@ -325,6 +336,7 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
             }
         }
     }
+    CHAIN_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 #include "solve_kernels.cuh"
 #include "front_kernels.cuh"
+#include "assemble_kernels.cuh"
 #include "symbolic.hpp"
 
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
@@ -31,7 +32,7 @@ thread_local std::string g_create_error;
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_CHAIN, K_FINALIZE, K_FRONT, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE, K_ASSEMBLE_G
 };
 
 struct Launch {
@@ -111,6 +112,9 @@ struct gmrf_b200_handle {
     ChainTask *d_chain = nullptr;      // fused chain steps (front_kernels.cuh)
     FinalizeTask *d_final = nullptr;
     FrontTask *d_front = nullptr;
+    AsmTile *d_asmtiles = nullptr;     // gather extend-add (assemble_kernels.cuh)
+    int *d_relpos = nullptr;           // per child: position in its relative-index list of every 256-row boundary of the parent
+    long long *d_relpos_off = nullptr;
     double *d_sq = nullptr;            // parked factored diagonal squares of the fused chain steps (128 x 128 each)
     int front_smem_max = 0;            // dynamic shared memory the one-CTA-per-front kernel was configured for
     i64 n_large_tile_launches = 0, n_splitk_tasks = 0, n_fast_roots = 0, n_chain_launches = 0, n_front_launches = 0;
@@ -235,6 +239,7 @@ struct Builder {
     std::vector<ChainTask> chain;
     std::vector<FinalizeTask> finalize;
     std::vector<FrontTask> front;
+    std::vector<AsmTile> asmtiles;
     i64 n_large_tile_launches = 0, n_splitk_tasks = 0;
     double *splitk_base = nullptr;     // device scratch for split-K partial products
     i64 splitk_cap = 0;
@@ -408,6 +413,19 @@ struct Builder {
         plan.launches.push_back(L);
         tasks.clear();
     }
+    void add_asm_tiles(Plan &plan, std::vector<AsmTile> &tiles) {
+        if (tiles.empty()) return;
+        Launch L;
+        L.kind = K_ASSEMBLE_G;
+        L.aux = 0;
+        L.task_off = (i64)asmtiles.size();
+        L.ntasks = (int)tiles.size();
+        L.prefix_off = -1;
+        L.grid = (int)tiles.size();
+        asmtiles.insert(asmtiles.end(), tiles.begin(), tiles.end());
+        plan.launches.push_back(L);
+        tiles.clear();
+    }
     // fused chain step: 1 diagonal CTA + one CTA per 64-row tile below the step's columns
     void add_chain(Plan &plan, std::vector<ChainTask> &tasks) {
         if (tasks.empty()) return;
@@ -534,6 +552,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
     std::vector<GemmTask> gt, st;
     std::vector<ChainTask> ct;
     std::vector<FrontTask> ft;
+    std::vector<AsmTile> ats;
     auto push_finalize = [&](i64 s, i64 k0, const double *sq) {
         const i64 ns = S.ns(s), ld = S.panel_ld[s];
         FinalizeTask f;
@@ -565,10 +584,16 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
         }
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp;
-            if (S.child_ptr[s + 1] > S.child_ptr[s])
+            if (S.child_ptr[s + 1] == S.child_ptr[s]) continue;
+            if (h->opt.asm_gather && !B.naive) {
+                for (i64 c0 = 0; c0 < S.nrow(s); c0 += AG_CW)
+                    for (i64 r0 = c0 / AG_RH * AG_RH; r0 < S.nrow(s); r0 += AG_RH) ats.push_back(AsmTile{(int)s, (int)c0, (int)r0, 0});
+            } else {
                 for (i64 c0 = 0; c0 < S.nrow(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
+            }
         }
         B.add_items(plan, its, K_ASSEMBLE);
+        B.add_asm_tiles(plan, ats);
         const i64 OB = mode == 1 ? 2 * NB : OB_bulk;
         i64 maxouter = 0;
         for (const i64 *sp = sb; sp < se; sp++) maxouter = std::max<i64>(maxouter, cdiv(S.ns(*sp), OB));
@@ -1114,6 +1139,7 @@ cudaError_t configure_kernels(int front_smem = 0) {
     if ((e = configure_gemm_tile<128, 64, 2, 2>())) return e;
     if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
     if ((e = cudaFuncSetAttribute(chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(assemble_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(chain_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FINALIZE_SMEM_BYTES))) return e;
     // (per device, sticky: handles of one process may need different sizes -> always opt in to the cap)
     const int fs = std::max(front_smem, 220 * 1024);
@@ -1149,6 +1175,10 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
     switch (L.kind) {
         case K_ASSEMBLE:
             assemble_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd, bstride);
+            break;
+        case K_ASSEMBLE_G:
+            assemble_gather_kernel<<<dim3(L.grid, T.lanes), 256, AG_SMEM_BYTES, st>>>(h->d_asmtiles + L.task_off, h->d_meta, h->d_child, h->d_relidx,
+                                                                                    h->d_relpos, h->d_relpos_off, h->d_Lx, h->d_upd, bstride);
             break;
         case K_CHAIN:
             chain_step_kernel<<<dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st>>>(h->d_chain + L.task_off, pf, L.ntasks, h->d_fail, bstride);
@@ -1693,6 +1723,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "large_tile_mask") o.large_tile_mask = (int)value & 7;
     else if (k == "lanes") o.lanes = std::max(1, std::min(64, (int)value));
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
+    else if (k == "asm_gather") o.asm_gather = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
     else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);
@@ -1846,6 +1877,27 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
             m.child_begin = (int)S.child_ptr[s]; m.child_end = (int)S.child_ptr[s + 1];
         }
         TRY_RC(dev_upload(H, &H->d_meta, meta));
+        // relpos[s][q] = first position in s's relative-index list (rows below its own columns) that lands at or beyond
+        // row 256 q of its parent's front; one extra entry closes the last block
+        std::vector<long long> rpo((size_t)S.nsuper + 1, 0);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            const i64 p = S.sparent[s];
+            rpo[(size_t)s + 1] = rpo[(size_t)s] + (p < 0 ? 0 : cdiv(S.nrow(p), AG_RH) + 1);
+        }
+        std::vector<int> rp((size_t)rpo[(size_t)S.nsuper]);
+        for (i64 s = 0; s < S.nsuper; s++) {
+            const i64 p = S.sparent[s];
+            if (p < 0) continue;
+            const i32 *rel = S.relidx.data() + S.rowptr[s] + S.ns(s);
+            const i64 cnr = S.nr(s), Q = cdiv(S.nrow(p), AG_RH);
+            i64 i = 0;
+            for (i64 q = 0; q <= Q; q++) {
+                while (i < cnr && rel[i] < q * AG_RH) i++;
+                rp[(size_t)(rpo[(size_t)s] + q)] = (int)i;
+            }
+        }
+        TRY_RC(dev_upload(H, &H->d_relpos, rp));
+        TRY_RC(dev_upload(H, &H->d_relpos_off, rpo));
     }
     {
         i64 part_total = 0;   // partial sums of the row-chunked backward products
@@ -1871,6 +1923,7 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         TRY_RC(dev_upload(H, &H->d_chain, B.chain));
         TRY_RC(dev_upload(H, &H->d_final, B.finalize));
         TRY_RC(dev_upload(H, &H->d_front, B.front));
+        TRY_RC(dev_upload(H, &H->d_asmtiles, B.asmtiles));
         TRY_RC(dev_upload(H, &H->d_gemm, B.gemm));
         TRY_RC(dev_upload(H, &H->d_panel, B.panel));
         TRY_RC(dev_upload(H, &H->d_items, B.items));
@@ -2598,7 +2651,8 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     for (const Launch &L : h->factor_plan.launches) {
         int kind = (L.kind >= K_GEMM_NN_S && L.kind <= K_GEMM_TT_L) ? 0
-                   : (L.kind == K_PANEL || L.kind == K_CHAIN || L.kind == K_FRONT || L.kind == K_FINALIZE) ? 1 : L.kind == K_ASSEMBLE ? 2 : 3;
+                   : (L.kind == K_PANEL || L.kind == K_CHAIN || L.kind == K_FRONT || L.kind == K_FINALIZE) ? 1
+                   : (L.kind == K_ASSEMBLE || L.kind == K_ASSEMBLE_G) ? 2 : 3;
         mark(kind);
         run_launch(h, L, T, 0);
     }
@@ -2674,6 +2728,29 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
     return check_launch(h, "profile_plan");
+}
+
+// clock64 stamps of the phases of the last fused chain launch of one refactorization (tile 1): [0] start, [1] tiles
+// loaded, [2] first 64-column panel done, [3] its rows stored, [4] rank-64 updates done, [5] second panel done, [6] end.
+int gmrf_b200_debug_chain_phases(gmrf_b200_handle *h, int64_t *stamps, int n) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->factored || !stamps || n < 7) { h->err = "debug_chain_phases: needs a factored handle and 7 slots"; return GMRF_B200_ERR_ARG; }
+    long long *d = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&d, 8 * sizeof(long long)));
+    cudaMemset(d, 0, 8 * sizeof(long long));
+    CUDA_TRY(h, cudaMemcpyToSymbol(g_chain_prof, &d, sizeof(d)));
+    const int ug = h->opt.use_graph;
+    h->opt.use_graph = 0;
+    rc = do_factor(h);
+    h->opt.use_graph = ug;
+    long long host[8];
+    cudaMemcpy(host, d, sizeof(host), cudaMemcpyDeviceToHost);
+    long long *null = nullptr;
+    cudaMemcpyToSymbol(g_chain_prof, &null, sizeof(null));
+    cudaFree(d);
+    for (int i = 0; i < 7; i++) stamps[i] = host[i];
+    return rc < 0 ? rc : 0;
 }
 
 // ---- factor sharing between the handles of a multi-GPU pool ------------------------------------------------

@@ -33,6 +33,7 @@ EXPORTS = [
     "gmrf_b200_selinv_dot", "gmrf_b200_selinv_dot_basis",
     "gmrf_b200_factor_nnz", "gmrf_b200_factor_pattern", "gmrf_b200_factor_values", "gmrf_b200_pattern_positions",
     "gmrf_b200_create_from_analysis", "gmrf_b200_analysis_export", "gmrf_b200_analysis_equal",
+    "gmrf_b200_debug_chain_phases",
 ]
 
 _lib = None
@@ -151,6 +152,8 @@ def lib():
     L.gmrf_b200_adopt_factor.argtypes = [c_vp, ctypes.c_double, ctypes.c_int]
     L.gmrf_b200_host_register.restype = ctypes.c_int
     L.gmrf_b200_host_register.argtypes = [c_vp, c_i64]
+    L.gmrf_b200_debug_chain_phases.restype = ctypes.c_int
+    L.gmrf_b200_debug_chain_phases.argtypes = [c_vp, c_vp, ctypes.c_int]
     L.gmrf_b200_host_unregister.restype = ctypes.c_int
     L.gmrf_b200_host_unregister.argtypes = [c_vp]
     _lib = L

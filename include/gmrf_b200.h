@@ -216,6 +216,8 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
  * entries of kind[] (internal launch kind), grid[] (CTAs) and ms[] are filled; *count = launches in the phase. */
 int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap, int *kind, int *grid, double *ms,
                            int64_t *count);
+/* Diagnostics: SM clock stamps of the phases of the last fused chain-step launch of one refactorization (7 values). */
+int gmrf_b200_debug_chain_phases(gmrf_b200_handle *h, int64_t *stamps, int n);
 /* Numeric factor / selected inverse panels copied back to the host (tests, CholeskySqrt-style export). */
 int gmrf_b200_get_factor_panels(gmrf_b200_handle *h, double *Lx, int64_t n_doubles);
 int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubles);
@@ -234,7 +236,7 @@ int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`

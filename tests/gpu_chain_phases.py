@@ -1,0 +1,20 @@
+"""Phase timing (SM clocks) inside the fused chain-step kernel, last chain launch of a 2D refactorization (diagnostics):
+   python tests/gpu_chain_phases.py [cells]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200")]
+from gmrf_b200 import spde, _lib
+from gmrf_b200.backend import B200Backend
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 224
+model = spde.MaternSPDE(*spde.mesh2d(cells), 1)
+Q = model.precision(1.0, 0.3)
+b = B200Backend(Q, ordering=spde.geometric_nd_perm((cells + 1, cells + 1), leaf=64, width=3), device=0)
+for _ in range(2):
+    st = np.zeros(7, dtype=np.int64)
+    b._hd.check(_lib.lib().gmrf_b200_debug_chain_phases(b._hd._h, _lib.ptr(st), 7))
+d = np.diff(st)
+names = ["load tiles", "panel 0 (192x64)", "store X0", "rank-64 updates", "panel 1 (128x64)", "store X1 / park"]
+for nm, v in zip(names, d):
+    print(f"{nm:20s} {int(v):8d} cycles  {v / 1.965e3:7.2f} us")
+print("total", int(st[6] - st[0]), "cycles")
