@@ -35,7 +35,7 @@ struct Options {
     int asm_gather = 1;       // extend-add as a gather through TMA-staged shared memory (0: the first, scatter-shaped kernel)
     int fused_front = 1;      // one-CTA-per-front kernel for tree levels whose panels all fit in shared memory
     int fused_chain = 1;      // one launch per 128 columns of a level's supernode chains (redundant diagonal factorization per CTA)
-    int chain_max_tiles = 600;   // a level takes the fused chain path if its first step has at most this many 64-row tiles
+    int chain_max_tiles = 160;   // a level takes the fused chain path if its first step has at most this many 64-row tiles
     int front_smem_kb = 200;  // shared-memory budget of the one-CTA-per-front kernel
 };
 Options &global_options();

@@ -1,7 +1,4 @@
 set -u
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "== $name: $*"; ( time timeout "$TMO" "$@" ) > "gpurun_out/$name.log" 2>&1; echo "   rc=$? ($(tail -n 4 gpurun_out/$name.log | head -n 1 | cut -c1-200))"; }
-TMO=300 run r2f_pytest_ws python -m pytest tests/test_gpu_workspace.py tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -x
-TMO=120 run r2f_plan_2d224 python tests/gpu_plan_profile.py 2d:224 --phase=0 --top=10 --dump=0:70
-TMO=240 run r2f_configs_1_2_3 python tests/gpu_configs.py 1 2 3
-tail -n 5 gpurun_out/r2f_pytest_ws.log
+python bench.py --steps 2 --warmup 3 --cells 40 > gpurun_out/r2_bench_small.json 2> gpurun_out/r2_bench_small.err; echo rc=$?; tail -c 1500 gpurun_out/r2_bench_small.err
+python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err; echo rc=$?; tail -c 800 gpurun_out/r2_bench_b.err

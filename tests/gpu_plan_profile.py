@@ -15,6 +15,10 @@ spec = [a for a in sys.argv[1:] if not a.startswith("--")][0]
 opt = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--") and "=" in a)
 phases = [int(p) for p in opt.get("phase", "3").split(",")]
 top = int(opt.get("top", "30"))
+from gmrf_b200 import _lib  # noqa: E402
+for k, v in opt.items():          # --set:key=value -> library option
+    if k.startswith("set:"):
+        _lib.set_option(k[4:], float(v))
 Q, dims, width, _ = build_problem(spec)
 ordering = spde.geometric_nd_perm(dims, leaf=64, width=width) if opt.get("order", "geo") == "geo" else "nd"
 b = B200Backend(Q, ordering=ordering, device=0)
