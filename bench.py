@@ -458,6 +458,10 @@ def sampling_config5(world, rank, local, small=False):
     if rank == 0:
         be.refactorize(Q)
     fA = be.timings()["factor_ms"] if rank == 0 else 0.0
+    barrier()                               # the peers wait for the factorization here, not inside the timed broadcast
+    if world > 1:                           # (connection set-up of the first broadcast stays outside as well)
+        w = torch.zeros(1 << 20, device=dev)
+        dist.broadcast(w, src=0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()

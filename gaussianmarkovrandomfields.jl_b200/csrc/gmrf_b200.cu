@@ -29,6 +29,7 @@ using namespace gmrf;
 namespace {
 
 thread_local std::string g_create_error;
+int g_alloc_fail_countdown = 0;     // test hook ("debug_alloc_fail_after"): the k-th dev_alloc from now fails
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_CHAIN, K_FINALIZE, K_FRONT, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
@@ -137,6 +138,7 @@ struct gmrf_b200_handle {
     long long *d_zpos = nullptr, *d_zdiagpos = nullptr;
     double *d_zout = nullptr;
     bool z_pattern_built = false;
+    bool selinv_tables_built = false;  // set only after EVERY table of the selected-inversion plan is resident
     // last caller pattern looked up by selinv_extract / selinv_dot (host-side, content-compared): a repeated pattern
     // (gradient loops, linear-predictor marginals) skips the lookup
     std::vector<i64> pp_colptr, pp_rowval;
@@ -144,6 +146,9 @@ struct gmrf_b200_handle {
     int pp_base = 0;
     bool pp_valid = false;
     i64 pp_hits = 0;
+    long long *d_ppos = nullptr;       // the same positions resident in HBM: a repeated pattern costs no upload either
+    i64 d_ppos_cap = 0;
+    bool d_ppos_valid = false;
     unsigned long long pattern_hash = 0;   // of the (0-based) input pattern: ties an exported analysis to its matrix
     // factor export P'L as CSC (lazy; CholeskySqrt-style consumers)
     std::vector<i64> l_colptr, l_rowval;
@@ -189,6 +194,10 @@ template <class T>
 int dev_alloc(gmrf_b200_handle *h, T **p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
+    if (g_alloc_fail_countdown > 0 && --g_alloc_fail_countdown == 0) {
+        h->err = "cudaMalloc failed (injected by debug_alloc_fail_after)";
+        return GMRF_B200_ERR_ALLOC;
+    }
     cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
     if (e != cudaSuccess) {
         h->err = std::string("cudaMalloc failed (") + std::to_string(count * sizeof(T)) + " bytes): " + cudaGetErrorString(e);
@@ -1359,12 +1368,24 @@ int do_factor(gmrf_b200_handle *h, int lanes = 1) {
 }
 
 int build_selinv_tables(gmrf_b200_handle *h) {
-    if (h->d_Zx) return 0;
+    if (h->selinv_tables_built) return 0;
     const Symbolic &S = h->S;
+    // failure-atomic: whatever step fails (Z is a second panel array -- an out-of-memory here is realistic), everything
+    // built so far is released and the plan cleared, so that a retry starts from scratch instead of replaying a
+    // half-built plan or launching kernels on null tables
+    auto rollback = [&](int rc) {
+        if (h->selinv_graph) { cudaGraphExecDestroy(h->selinv_graph); h->selinv_graph = nullptr; }
+        dev_free(h, h->d_Zx); dev_free(h, h->d_gemm_z); dev_free(h, h->d_items_z); dev_free(h, h->d_prefix_z);
+        dev_free(h, h->d_trans); dev_free(h, h->d_split_z); dev_free(h, h->d_zdiagpos);
+        h->selinv_plan.launches.clear();
+        h->n_fast_roots = 0;
+        h->selinv_valid = false;
+        return rc;
+    };
     int rc;
-    if ((rc = dev_alloc(h, &h->d_Zx, (size_t)S.panel_total))) return rc;
+    if ((rc = dev_alloc(h, &h->d_Zx, (size_t)S.panel_total))) return rollback(rc);
     h->d_zw = h->d_upd;
-    CUDA_TRY(h, cudaMemset(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total));
+    if (cudaMemsetAsync(h->d_Zx, 0, sizeof(double) * (size_t)S.panel_total, h->stream) != cudaSuccess) { h->err = "cudaMemset failed"; return rollback(GMRF_B200_ERR_CUDA); }
     Builder B;
     B.naive = h->opt.naive_kernels != 0;
     B.splitk_base = h->d_splitk; B.splitk_cap = h->splitk_cap; B.splitk_min_k = h->opt.splitk_min_k; B.large_tile_mask = h->opt.large_tile_mask;
@@ -1372,18 +1393,21 @@ int build_selinv_tables(gmrf_b200_handle *h) {
         build_selinv_plan(h, B);
     } catch (std::exception &e) {
         h->err = e.what();
-        return GMRF_B200_ERR_ARG;
+        return rollback(GMRF_B200_ERR_ARG);
     }
-    if ((rc = dev_upload(h, &h->d_gemm_z, B.gemm))) return rc;
-    if ((rc = dev_upload(h, &h->d_items_z, B.items))) return rc;
-    if ((rc = dev_upload(h, &h->d_prefix_z, B.prefix))) return rc;
-    if ((rc = dev_upload(h, &h->d_trans, B.trans))) return rc;
-    if ((rc = dev_upload(h, &h->d_split_z, B.split))) return rc;
-    std::vector<long long> dp(S.diag_pos.begin(), S.diag_pos.end());
+    if ((rc = dev_upload(h, &h->d_gemm_z, B.gemm))) return rollback(rc);
+    if ((rc = dev_upload(h, &h->d_items_z, B.items))) return rollback(rc);
+    if ((rc = dev_upload(h, &h->d_prefix_z, B.prefix))) return rollback(rc);
+    if ((rc = dev_upload(h, &h->d_trans, B.trans))) return rollback(rc);
+    if ((rc = dev_upload(h, &h->d_split_z, B.split))) return rollback(rc);
     // diagonal of Z in ORIGINAL ordering: out[perm[k]] = Z[diag_pos[k]]  ->  pos_orig[i] = diag_pos[iperm[i]]
     std::vector<long long> zp(S.n);
     for (i64 i = 0; i < S.n; i++) zp[i] = S.diag_pos[S.iperm[i]];
-    if ((rc = dev_upload(h, &h->d_zdiagpos, zp))) return rc;
+    if ((rc = dev_upload(h, &h->d_zdiagpos, zp))) return rollback(rc);
+    // the uploads above went through the legacy stream from pageable memory: make them (and the memset) visible to the
+    // handle's non-blocking stream before anything is launched on it
+    if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device synchronize failed"; return rollback(GMRF_B200_ERR_CUDA); }
+    h->selinv_tables_built = true;
     return 0;
 }
 
@@ -1436,6 +1460,7 @@ int ensure_multi(gmrf_b200_handle *h, int wi) {
     if ((rc = dev_upload(h, &M.d_prefix, B.prefix))) return rc;
     if ((rc = dev_upload(h, &M.d_superlist, B.superlist))) return rc;
     if ((rc = dev_upload(h, &M.d_rg, B.rowgather))) return rc;
+    CUDA_TRY(h, cudaDeviceSynchronize());      // pageable uploads on the legacy stream -> visible to the handle's stream
     M.built = true;
     return 0;
 }
@@ -1723,6 +1748,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "large_tile_mask") o.large_tile_mask = (int)value & 7;
     else if (k == "lanes") o.lanes = std::max(1, std::min(64, (int)value));
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
+    else if (k == "debug_alloc_fail_after") g_alloc_fail_countdown = std::max(0, (int)value);
     else if (k == "asm_gather") o.asm_gather = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
@@ -1935,6 +1961,9 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
         TRY_RC(dev_upload(H, &H->d_split, B.split));
     }
+    // every table above was copied from pageable memory through the legacy stream; the handle's stream is non-blocking
+    // (not ordered against it), so make the uploads visible before the first launch
+    if (cudaDeviceSynchronize() != cudaSuccess) { H->err = "device synchronize failed after the table uploads"; return fail(GMRF_B200_ERR_CUDA); }
 #undef TRY_RC
     *out = h.release();
     return 0;
@@ -2312,6 +2341,7 @@ static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol,
         return 0;
     }
     h->pp_valid = false;
+    h->d_ppos_valid = false;
     for (i64 j = 0; j < ncol; j++)
         if (colptr[j + 1] < colptr[j] || colptr[j] < index_base) { h->err = std::string(who) + ": colptr must be non-decreasing from index_base"; return GMRF_B200_ERR_ARG; }
     h->pp_pos.assign((size_t)std::max<i64>(cnt, 0), -1LL);
@@ -2325,6 +2355,26 @@ static int pattern_positions(gmrf_b200_handle *h, const char *who, int64_t ncol,
         h->pp_base = index_base;
         h->pp_valid = true;
     }
+    return 0;
+}
+
+// device copy of the positions of the last looked-up pattern (grow-only buffer, reused while the pattern repeats)
+static int resident_positions(gmrf_b200_handle *h, const std::vector<long long> &pos, const long long **d_pos) {
+    const i64 cnt = (i64)pos.size();
+    if (!h->d_ppos_valid) {
+        if (h->d_ppos_cap < cnt) {
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            dev_free(h, h->d_ppos);
+            h->d_ppos_cap = 0;
+            int rc = dev_alloc(h, &h->d_ppos, (size_t)cnt);
+            if (rc) return rc;
+            h->d_ppos_cap = cnt;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_ppos, pos.data(), sizeof(long long) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));       // pos is pageable host memory owned by the handle
+        h->d_ppos_valid = h->pp_valid;
+    }
+    *d_pos = h->d_ppos;
     return 0;
 }
 
@@ -2349,13 +2399,9 @@ int gmrf_b200_selinv_extract(gmrf_b200_handle *h, int64_t ncol, const int64_t *c
     const std::vector<long long> &pos = *ppos;
     const i64 cnt = (i64)pos.size();
     if (cnt <= 0) return 0;
-    long long *d_pos = nullptr;
-    CUDA_TRY(h, cudaMalloc((void **)&d_pos, sizeof(long long) * (size_t)cnt));
-    cudaError_t e = cudaMemcpyAsync(d_pos, pos.data(), sizeof(long long) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) rc = gather_to_host(h, d_pos, cnt, out);
-    else { h->err = "H2D copy failed"; rc = GMRF_B200_ERR_CUDA; }
-    cudaFree(d_pos);
-    return rc;
+    const long long *d_pos = nullptr;
+    if ((rc = resident_positions(h, pos, &d_pos))) return rc;
+    return gather_to_host(h, d_pos, cnt, out);
 }
 
 // ---- traces against the selected inverse, contracted on the device ---------------------------------------------
@@ -2391,14 +2437,12 @@ int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colpt
     if (!values) { h->err = "selinv_dot: null values"; return GMRF_B200_ERR_ARG; }
     if ((rc = ensure_dot(h))) return rc;
     if ((rc = ensure_io(h, cnt))) return rc;
-    long long *d_pos = nullptr;
-    CUDA_TRY(h, cudaMalloc((void **)&d_pos, sizeof(long long) * (size_t)cnt));
-    cudaError_t e = cudaMemcpyAsync(d_pos, pos.data(), sizeof(long long) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_io, values, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
+    const long long *d_pos = nullptr;
+    if ((rc = resident_positions(h, pos, &d_pos))) return rc;
+    cudaError_t e = cudaMemcpyAsync(h->d_io, values, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) rc = run_dot(h, d_pos, nullptr, nullptr, h->d_io, 0, cnt, 1, out);
     else { h->err = "H2D copy failed"; rc = GMRF_B200_ERR_CUDA; }
-    if (rc) cudaStreamSynchronize(h->stream);   // pos / values are pageable host memory: nothing may still be in flight
-    cudaFree(d_pos);
+    if (rc) cudaStreamSynchronize(h->stream);   // values are pageable host memory: nothing may still be in flight
     return rc;
 }
 
@@ -2790,8 +2834,44 @@ int gmrf_b200_adopt_factor(gmrf_b200_handle *h, double logdet, int with_selinv) 
     h->logdet = logdet;
     h->fail_col = 0;
     h->factored = true;
-    h->selinv_valid = with_selinv != 0 && h->d_Zx != nullptr;
+    h->selinv_valid = with_selinv != 0 && h->selinv_tables_built;
     return 0;
+}
+
+// Fingerprint of everything a received factor must agree on with the handle that adopts it: the pattern, the elimination
+// order, the supernode partition and the panel / inverse-block layout (which also encode the relaxation and blocking options).
+int gmrf_b200_analysis_fingerprint(const gmrf_b200_handle *h, uint64_t *out) {
+    if (!h || !out) return GMRF_B200_ERR_ARG;
+    const Symbolic &S = h->S;
+    unsigned long long f = 1469598103934665603ULL ^ h->pattern_hash;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *c = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < bytes; i++) { f ^= c[i]; f *= 1099511628211ULL; }
+    };
+    mix(S.perm.data(), S.perm.size() * sizeof(i64));
+    mix(S.sfirst.data(), S.sfirst.size() * sizeof(i64));
+    mix(S.panel_off.data(), S.panel_off.size() * sizeof(i64));
+    mix(S.panel_ld.data(), S.panel_ld.size() * sizeof(i32));
+    mix(h->inv_base.data(), h->inv_base.size() * sizeof(long long));
+    *out = f;
+    return 0;
+}
+
+// adopt_factor with the sender's fingerprint and pivot status: a peer built with another ordering / other options is
+// refused (GMRF_B200_ERR_ARG) instead of silently solving with foreign panels, and a non-positive pivot travels along.
+int gmrf_b200_adopt_factor_checked(gmrf_b200_handle *h, uint64_t sender_fingerprint, double logdet, int sender_status, int with_selinv) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    uint64_t mine = 0;
+    gmrf_b200_analysis_fingerprint(h, &mine);
+    if (mine != sender_fingerprint) {
+        h->err = "adopt_factor: the sender's symbolic analysis (pattern / ordering / supernodes / panel layout) differs from this handle's";
+        return GMRF_B200_ERR_ARG;
+    }
+    rc = gmrf_b200_adopt_factor(h, logdet, with_selinv);
+    if (rc) return rc;
+    h->fail_col = sender_status > 0 ? sender_status : 0;
+    return h->fail_col;
 }
 
 // Page-lock / unlock a caller-owned host buffer (e.g. the workspace's nzval array) so refactorize() copies it with

@@ -33,7 +33,7 @@ EXPORTS = [
     "gmrf_b200_selinv_dot", "gmrf_b200_selinv_dot_basis",
     "gmrf_b200_factor_nnz", "gmrf_b200_factor_pattern", "gmrf_b200_factor_values", "gmrf_b200_pattern_positions",
     "gmrf_b200_create_from_analysis", "gmrf_b200_analysis_export", "gmrf_b200_analysis_equal",
-    "gmrf_b200_debug_chain_phases",
+    "gmrf_b200_debug_chain_phases", "gmrf_b200_analysis_fingerprint", "gmrf_b200_adopt_factor_checked",
 ]
 
 _lib = None
@@ -154,6 +154,10 @@ def lib():
     L.gmrf_b200_host_register.argtypes = [c_vp, c_i64]
     L.gmrf_b200_debug_chain_phases.restype = ctypes.c_int
     L.gmrf_b200_debug_chain_phases.argtypes = [c_vp, c_vp, ctypes.c_int]
+    L.gmrf_b200_analysis_fingerprint.restype = ctypes.c_int
+    L.gmrf_b200_analysis_fingerprint.argtypes = [c_vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.gmrf_b200_adopt_factor_checked.restype = ctypes.c_int
+    L.gmrf_b200_adopt_factor_checked.argtypes = [c_vp, ctypes.c_uint64, ctypes.c_double, ctypes.c_int, ctypes.c_int]
     L.gmrf_b200_host_unregister.restype = ctypes.c_int
     L.gmrf_b200_host_unregister.argtypes = [c_vp]
     _lib = L

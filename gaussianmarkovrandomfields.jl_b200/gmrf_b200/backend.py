@@ -9,6 +9,7 @@ the `B200Backend <: WorkspaceBackend` glue in julia/B200Backend.jl; both bind th
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -77,6 +78,32 @@ def ordering_permutation(A, ordering) -> np.ndarray:
     return perm
 
 
+# Index base handed to the C-ABI. Python / C callers are 0-based; the Julia glue (julia/B200Backend.jl:59-66,140,156,168,
+# 179) passes `SparseMatrixCSC{Float64,Int}` arrays and permutations as they are, i.e. index_base = 1. With INDEX_BASE = 1
+# this binding shifts every index array on the way in and out exactly like that, so the whole test battery can exercise
+# the entry path the Julia host will take (tests/test_gpu_index_base.py; env GMRF_B200_INDEX_BASE=1 flips it globally).
+INDEX_BASE = int(os.environ.get("GMRF_B200_INDEX_BASE", "0"))
+
+
+class index_base:
+    """Context manager: `with index_base(1): ...` runs the enclosed binding calls through the 1-based C-ABI path."""
+
+    def __init__(self, base: int):
+        if base not in (0, 1):
+            raise ValueError("index base must be 0 or 1")
+        self.base = base
+
+    def __enter__(self):
+        global INDEX_BASE
+        self.prev, INDEX_BASE = INDEX_BASE, self.base
+        return self
+
+    def __exit__(self, *exc):
+        global INDEX_BASE
+        INDEX_BASE = self.prev
+        return False
+
+
 class _Handle:
     """Owns one gmrf_b200_handle*."""
 
@@ -84,14 +111,15 @@ class _Handle:
         L = _lib.lib()
         self._L = L
         self._h = ctypes.c_void_p()
-        cp = np.ascontiguousarray(colptr, dtype=np.int64)
-        rv = np.ascontiguousarray(rowval, dtype=np.int64)
-        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int64)
+        base = INDEX_BASE
+        cp = np.ascontiguousarray(colptr, dtype=np.int64) + base
+        rv = np.ascontiguousarray(rowval, dtype=np.int64) + base
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int64) + base
         if analysis is not None:       # symbolic analysis read from an exported stream instead of recomputed
             blob = np.frombuffer(analysis, dtype=np.uint8)
-            rc = L.gmrf_b200_create_from_analysis(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(blob), blob.size, int(device))
+            rc = L.gmrf_b200_create_from_analysis(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), base, ptr(blob), blob.size, int(device))
         else:
-            rc = L.gmrf_b200_create(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), 0, ptr(pm), int(ordering_code), int(device))
+            rc = L.gmrf_b200_create(ctypes.byref(self._h), int(n), ptr(cp), ptr(rv), base, ptr(pm), int(ordering_code), int(device))
         if rc != 0:
             msg = L.gmrf_b200_last_error(None).decode()
             self._h = None
@@ -117,8 +145,8 @@ class _Handle:
 
     def perm(self) -> np.ndarray:
         p = np.empty(self.n, dtype=np.int64)
-        self.check(self._L.gmrf_b200_get_perm(self._h, ptr(p), 0))
-        return p
+        self.check(self._L.gmrf_b200_get_perm(self._h, ptr(p), INDEX_BASE))
+        return p - INDEX_BASE
 
     def export_analysis(self) -> bytes:
         """The symbolic analysis as a byte stream for `_Handle(..., analysis=...)` / `B200Backend(Q, analysis=...)`."""
@@ -134,8 +162,8 @@ class _Handle:
         self.check(self._L.gmrf_b200_factor_nnz(self._h, ctypes.byref(nnz)))
         cp = np.empty(self.n + 1, dtype=np.int64)
         rv = np.empty(nnz.value, dtype=np.int64)
-        self.check(self._L.gmrf_b200_factor_pattern(self._h, ptr(cp), ptr(rv), 0))
-        return cp, rv
+        self.check(self._L.gmrf_b200_factor_pattern(self._h, ptr(cp), ptr(rv), INDEX_BASE))
+        return cp - INDEX_BASE, rv - INDEX_BASE
 
     def close(self):
         if self._h is not None and self._h.value:
@@ -233,8 +261,8 @@ class B200Backend:
                 self._hd.check(self._L.gmrf_b200_selinv_nnz(self._hd._h, ctypes.byref(nnz)))
                 cp = np.empty(self.n + 1, dtype=np.int64)
                 rv = np.empty(nnz.value, dtype=np.int64)
-                self._hd.check(self._L.gmrf_b200_selinv_pattern(self._hd._h, ptr(cp), ptr(rv), 0))
-                self._selinv_pattern = (cp, rv)
+                self._hd.check(self._L.gmrf_b200_selinv_pattern(self._hd._h, ptr(cp), ptr(rv), INDEX_BASE))
+                self._selinv_pattern = (cp - INDEX_BASE, rv - INDEX_BASE)
             cp, rv = self._selinv_pattern
             vals = np.empty(rv.size, dtype=np.float64)
             self._hd.check(self._L.gmrf_b200_selinv_values(self._hd._h, ptr(vals)))
@@ -257,10 +285,10 @@ class B200Backend:
         B = _csc(B)
         if B.shape != (self.n, self.n):
             raise ValueError("pattern matrix has the wrong shape")
-        cp = B.indptr.astype(np.int64)
-        rv = B.indices.astype(np.int64)
+        cp = B.indptr.astype(np.int64) + INDEX_BASE
+        rv = B.indices.astype(np.int64) + INDEX_BASE
         out = np.empty(rv.size, dtype=np.float64)
-        self._hd.check(self._L.gmrf_b200_selinv_extract(self._hd._h, self.n, ptr(cp), ptr(rv), 0, ptr(out)))
+        self._hd.check(self._L.gmrf_b200_selinv_extract(self._hd._h, self.n, ptr(cp), ptr(rv), INDEX_BASE, ptr(out)))
         return sp.csc_matrix((out, B.indices.copy(), B.indptr.copy()), shape=B.shape)
 
     def selinv_dot(self, B) -> float:
@@ -269,11 +297,11 @@ class B200Backend:
         B = _csc(B)
         if B.shape != (self.n, self.n):
             raise ValueError("pattern matrix has the wrong shape")
-        cp = B.indptr.astype(np.int64)
-        rv = B.indices.astype(np.int64)
+        cp = B.indptr.astype(np.int64) + INDEX_BASE
+        rv = B.indices.astype(np.int64) + INDEX_BASE
         vals = np.ascontiguousarray(B.data, dtype=np.float64)
         out = ctypes.c_double()
-        self._hd.check(self._L.gmrf_b200_selinv_dot(self._hd._h, self.n, ptr(cp), ptr(rv), 0, ptr(vals), ctypes.byref(out)))
+        self._hd.check(self._L.gmrf_b200_selinv_dot(self._hd._h, self.n, ptr(cp), ptr(rv), INDEX_BASE, ptr(vals), ctypes.byref(out)))
         return float(out.value)
 
     def selinv_dot_basis(self) -> np.ndarray:
@@ -412,10 +440,24 @@ class B200Backend:
         self._hd.check(self._L.gmrf_b200_device_array(self._hd._h, which, ctypes.byref(p), ctypes.byref(n)))
         return int(p.value or 0), int(n.value)
 
-    def adopt_factor(self, logdet: float, with_selinv: bool = False):
-        """Declare the factor arrays received from a peer GPU (sharding.broadcast_factor) to be this backend's factor."""
-        self._hd.check(self._L.gmrf_b200_adopt_factor(self._hd._h, float(logdet), int(bool(with_selinv))))
-        self.status = 0
+    def analysis_fingerprint(self) -> int:
+        """64-bit fingerprint of pattern + elimination order + supernode partition + panel layout: what two handles must
+        share before one can adopt the other's numeric factor."""
+        f = ctypes.c_uint64()
+        self._hd.check(self._L.gmrf_b200_analysis_fingerprint(self._hd._h, ctypes.byref(f)))
+        return int(f.value)
+
+    def adopt_factor(self, logdet: float, with_selinv: bool = False, fingerprint: int | None = None, status: int = 0):
+        """Declare the factor arrays received from a peer GPU (sharding.broadcast_factor) to be this backend's factor.
+        With the sender's `fingerprint` the library refuses a factor built on another analysis (ValueError) and the
+        sender's pivot `status` becomes this backend's."""
+        if fingerprint is None:
+            self._hd.check(self._L.gmrf_b200_adopt_factor(self._hd._h, float(logdet), int(bool(with_selinv))))
+            self.status = 0
+        else:
+            rc = self._L.gmrf_b200_adopt_factor_checked(self._hd._h, ctypes.c_uint64(fingerprint), float(logdet), int(status),
+                                                        int(bool(with_selinv)))
+            self.status = self._hd.check(rc, allow_positive=not self.check_pd)
         self.selinv_cache = None
         self.selinv_diag_cache = None
 

@@ -76,7 +76,8 @@ def pad_to_workspace_pattern(Q, ws: GMRFWorkspace) -> sp.csc_matrix:
 
 def copy_values_into(dst: sp.csc_matrix, src: sp.csc_matrix) -> None:
     """dst.nzval := src at matching positions, zero elsewhere (`_copy_values_into!`, :252-275)."""
-    pos = _positions_in(dst, _csc(src), "src")
+    src = _csc(src)            # positions and values must come from the SAME (sorted CSC) object
+    pos = _positions_in(dst, src, "src")
     dst.data[:] = 0.0
     dst.data[pos] = src.data
 

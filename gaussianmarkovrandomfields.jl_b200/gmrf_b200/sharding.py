@@ -123,13 +123,24 @@ def broadcast_factor(backend, src: int = 0, group=None, with_selinv: bool = Fals
     if dist is None or dist.get_world_size(group) == 1:
         return
     dev = torch.device("cuda", backend.device)
+    is_src = dist.get_rank(group) == src
+    # header first: the sender's analysis fingerprint (split into two exactly representable doubles), its pivot status
+    # and log-determinant -- a peer created with another ordering / other options must refuse the panels, not solve
+    # with them, and a failed factorization must not look healthy on the receivers
+    fp = backend.analysis_fingerprint()
+    head = torch.tensor([float(fp >> 32), float(fp & 0xFFFFFFFF), float(backend.status), backend.compute_logdet()] if is_src
+                        else [0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+    dist.broadcast(head, src=src, group=group)
+    hi, lo, status, logdet = head.tolist()
+    sender_fp = (int(hi) << 32) | int(lo)
+    if not is_src and sender_fp != fp:
+        raise ValueError("broadcast_factor: this rank's symbolic analysis (pattern / ordering / supernodes / options) differs "
+                         "from the sender's; create every handle from the same ordering or analysis blob")
     which = [0, 1] + ([2] if with_selinv else [])
     for w in which:
         ptr, n = backend.device_array(w)
         t = torch.as_tensor(_DeviceArray(ptr, n), device=dev)
         dist.broadcast(t, src=src, group=group)
-    meta = torch.tensor([backend.compute_logdet() if dist.get_rank(group) == src else 0.0], dtype=torch.float64, device=dev)
-    dist.broadcast(meta, src=src, group=group)
     torch.cuda.synchronize(dev)
-    if dist.get_rank(group) != src:
-        backend.adopt_factor(float(meta.item()), with_selinv)
+    if not is_src:
+        backend.adopt_factor(float(logdet), with_selinv, fingerprint=sender_fp, status=int(status))

@@ -119,7 +119,10 @@ int gmrf_b200_solve(gmrf_b200_handle *h, const double *B, double *X, int64_t ld,
 /* replaces  backend_backward_solve(b, x) = factor.UP \ x   backend.jl:281-284
  * X = P' L^-T Z so that Cov(X) = Q^-1 for Z ~ N(0, I) (sampling). */
 int gmrf_b200_solve_Lt(gmrf_b200_handle *h, const double *Z, double *X, int64_t ld, int64_t nrhs);
-/* Same two operations on buffers resident in this device's HBM. */
+/* Same two operations on buffers resident in this device's HBM. Stream contract of every *_device entry point: the
+ * library works on the handle's own (non-blocking) stream and returns after that stream has drained; it does NOT wait
+ * for work the caller queued on other streams, so buffers produced elsewhere (e.g. on torch's current stream) must be
+ * complete -- synchronize that stream or the device -- before the call. */
 int gmrf_b200_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, int64_t ld, int64_t nrhs);
 int gmrf_b200_solve_Lt_device(gmrf_b200_handle *h, const double *dZ, double *dX, int64_t ld, int64_t nrhs);
 
@@ -229,6 +232,12 @@ int gmrf_b200_get_selinv_panels(gmrf_b200_handle *h, double *Zx, int64_t n_doubl
  * of their own (right-hand-side blocks sharded over GPUs). */
 int gmrf_b200_device_array(gmrf_b200_handle *h, int which, void **ptr, int64_t *n_doubles);
 int gmrf_b200_adopt_factor(gmrf_b200_handle *h, double logdet, int with_selinv);
+/* The same with a guard: `fingerprint` (gmrf_b200_analysis_fingerprint of the SENDER: pattern, elimination order,
+ * supernode partition, panel and inverse-block layout) must equal the receiver's, else GMRF_B200_ERR_ARG; the sender's
+ * factorization status (0 / first non-positive pivot) becomes the receiver's and is returned. */
+int gmrf_b200_analysis_fingerprint(const gmrf_b200_handle *h, uint64_t *fingerprint);
+int gmrf_b200_adopt_factor_checked(gmrf_b200_handle *h, uint64_t sender_fingerprint, double logdet, int sender_status,
+                                   int with_selinv);
 
 /* Page-lock / unlock a caller-owned host buffer (typically the workspace's nzval array, `ws.Q.nzval`) so that
  * gmrf_b200_refactorize moves it with an asynchronous DMA. Optional; ownership stays with the caller. */

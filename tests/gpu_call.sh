@@ -1,4 +1,5 @@
 set -u
 mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 3 --cells 40 > gpurun_out/r2_bench_small.json 2> gpurun_out/r2_bench_small.err; echo rc=$?; tail -c 1500 gpurun_out/r2_bench_small.err
-python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err; echo rc=$?; tail -c 800 gpurun_out/r2_bench_b.err
+run() { name=$1; shift; echo "== $name: $*"; ( time timeout "$TMO" "$@" ) > "gpurun_out/$name.log" 2>&1; echo "   rc=$? ($(tail -n 4 gpurun_out/$name.log | head -n 1 | cut -c1-200))"; }
+TMO=900 run r2g_pytest_gpu python -m pytest tests -m gpu -q -p no:cacheprovider -x --durations=8
+tail -n 14 gpurun_out/r2g_pytest_gpu.log

@@ -450,3 +450,26 @@ def test_pool_can_share_one_analysis():
     assert all(np.array_equal(ws.backend.permutation(), pool.workspaces[0].backend.permutation()) for ws in pool.workspaces)
     plain = WorkspacePool(Q, size=2, devices=(-1,), factorize=False)
     assert hs[0]._L.gmrf_b200_analysis_equal(hs[0]._h, plain.workspaces[1].backend._hd._h) == 1    # same result either way
+
+
+def test_one_based_create_gives_the_same_analysis():
+    """index_base = 1 (the Julia glue's arrays) and index_base = 0 describe the same matrix: identical tables, identical
+    (0-based) permutation, identical exported patterns -- host-side, no GPU."""
+    from gmrf_b200.backend import index_base
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    A = sp.random(60, 60, density=0.08, random_state=rng, format="csc")
+    Q = sp.csc_matrix(A + A.T + 10 * sp.identity(60)); Q.sort_indices()
+    user = rng.permutation(60)
+    for ordering in (None, user):
+        hs = []
+        for base in (0, 1):
+            with index_base(base):
+                h = _Handle(60, Q.indptr, Q.indices, ordering, _lib.ORDER_AMD, device=-1)
+                hs.append((h, h.perm(), h.factor_pattern()))
+        (h0, p0, f0), (h1, p1, f1) = hs
+        assert h0._L.gmrf_b200_analysis_equal(h0._h, h1._h) == 1
+        assert np.array_equal(p0, p1) and np.array_equal(f0[0], f1[0]) and np.array_equal(f0[1], f1[1])
+        if ordering is not None:
+            assert np.array_equal(np.sort(p0), np.arange(60))
+        h0.close(); h1.close()
