@@ -1750,6 +1750,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "splitk_min_k") o.splitk_min_k = std::max(16, (int)value);
     else if (k == "debug_alloc_fail_after") g_alloc_fail_countdown = std::max(0, (int)value);
     else if (k == "asm_gather") o.asm_gather = (int)value;
+    else if (k == "level_alap") o.level_alap = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
     else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);
@@ -1837,6 +1838,14 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         }
     }
     H->splitk_cap = std::min<i64>(32LL << 20, std::max<i64>(1, 24 * S.max_front * (i64)H->opt.outer_block));
+    H->lanes = std::max(1, H->opt.lanes);
+    if (H->lanes >= 4) {
+        // A handle with lanes exists for THROUGHPUT (a sweep of independent value sets fills the GPU by itself): the
+        // latency-oriented paths cost it 5 % each (measured, profiles/r02_sweep_lanes.log: redundant diagonal factorization
+        // in every chain CTA; the gather extend-add's per-tile set-up), so such a handle takes the bulk path for those.
+        H->opt.fused_chain = 0;
+        H->opt.asm_gather = 0;
+    }
     const FusedInfo fused = plan_fused(S, H->opt);
     H->front_smem_max = fused.front_smem_max;
     {
@@ -1847,7 +1856,6 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
                   n_inv = al(inv_total), n_split = al(H->splitk_cap), n_part = al(LOGDET_BLOCKS), n_sc = al(8), n_fail = al(2),
                   n_sq = al(fused.sq_total * 4 * (i64)NB * NB);
         const i64 arena = n_lx + n_upd + n_nz + n_inv + n_split + n_part + n_sc + n_fail + n_sq;
-        H->lanes = std::max(1, H->opt.lanes);
         if (H->lanes == 1) {
             // single lane: separate allocations (measured on B200: with panels and update pool inside ONE 78 GB
             // allocation the extend-add kernel ran 91 ms instead of 55 ms per 1 M-dof refactorization)

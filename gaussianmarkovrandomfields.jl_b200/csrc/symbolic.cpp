@@ -744,6 +744,15 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
     }
     S.nlevels = 0;
     for (i64 s = 0; s < S.nsuper; s++) S.nlevels = std::max<i64>(S.nlevels, S.level[s] + 1);
+    if (opt.level_alap) {
+        // as late as possible: a supernode runs one level below its parent (the roots at the height of the forest), so
+        // siblings with subtrees of different height share a launch instead of each paying its own chain of block steps,
+        // and every update matrix lives for exactly one level (smaller pool). Children precede parents in the numbering.
+        for (i64 s = S.nsuper - 1; s >= 0; s--) {
+            i64 p = S.sparent[s];
+            S.level[s] = (i32)(p == -1 ? S.nlevels - 1 : S.level[p] - 1);
+        }
+    }
     S.level_ptr.assign(S.nlevels + 1, 0);
     for (i64 s = 0; s < S.nsuper; s++) S.level_ptr[S.level[s] + 1]++;
     for (i64 l = 0; l < S.nlevels; l++) S.level_ptr[l + 1] += S.level_ptr[l];
