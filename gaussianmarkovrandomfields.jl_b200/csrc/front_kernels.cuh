@@ -24,8 +24,9 @@
 namespace gmrf {
 
 constexpr int FB = 64;                 // block order
-constexpr int FLD = 66;                // leading dimension of a 64 x 64 tile in shared memory (column-major; even ->
-                                       // 16-byte aligned row pairs, 66 mod 32 banks spreads the columns)
+constexpr int FLD = 72;                // leading dimension of a 64 x 64 tile in shared memory (column-major; even ->
+                                       // 16-byte aligned row pairs; 72 = 8 mod 16 makes the DMMA fragment loads -- 8 rows
+                                       // of 4 consecutive columns per warp -- hit every bank exactly twice, the minimum)
 constexpr int FTILE = FB * FLD;        // doubles per tile
 constexpr int FPLD = 68;               // leading dimension of the published 4-column panel (k-major)
 constexpr int FSCRATCH = 2 * 3 * 4 * FPLD + FB;   // panel-step scratch: double-buffered published panel (diagonal tile + 2 row tiles) + reciprocal pivots
@@ -206,30 +207,54 @@ __device__ __forceinline__ void panel_solve64(double *__restrict__ sD, double *_
     __syncthreads();
 }
 
-// C[64 x 64] -= A[64 x 64] B[64 x 64]^T on column-major shared-memory tiles (C(i,j) at sC[j*FLD+i], A(i,k) at sA[k*FLD+i],
-// B(j,k) at sB[k*FLD+j]); 256 threads x 4 x 4 register tiles; lower: only tiles on / below the diagonal.
-__device__ __forceinline__ void rank64_update(double *__restrict__ sC, const double *__restrict__ sA, const double *__restrict__ sB, bool lower) {
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    if (lower && ty < tx) return;
-    double c[4][4];
+// Warp-level FP64 tensor-core product on shared-memory operands (mma.sync.m8n8k4.f64 -> DMMA.8x8x4): the warp accumulates
+// a 32 x 16 tile  acc += A[r0.., :K] * B[c0.., :K]^T  with A(r, k) at A[k * lda + r] and B(c, k) at B[k * ldb + c]
+// (both column-major in k); rows >= arows / brows and columns k >= K read as zero. Fragment layout as in gemm_dmma_kernel:
+// lane = 4 grp + tig holds acc[i][j][e] = C[8 i + grp][8 j + 2 tig + e]. Per 4 k's: 6 fragment loads, 8 DMMA -- the
+// 4 x 4 register-tile FMA loops this replaces were bound by shared-memory bandwidth (8 loads per 16 FMA: ncu, 10 us for
+// the two rank-64 updates of a chain step against 2 us of FP64 issue time).
+__device__ __forceinline__ void warp_dmma_32x16(const double *__restrict__ A, int lda, int r0, int arows, const double *__restrict__ B, int ldb,
+                                                int c0, int brows, int K, double (&acc)[4][2][2]) {
+    const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
+    bool aok[4], bok[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) aok[i] = r0 + 8 * i + grp < arows;
 #pragma unroll
-        for (int i = 0; i < 4; i++) c[i][j] = sC[(4 * tx + j) * FLD + 4 * ty + i];
-#pragma unroll 8
-    for (int k = 0; k < FB; k++) {
-        double a[4], b[4];
+    for (int j = 0; j < 2; j++) bok[j] = c0 + 8 * j + grp < brows;
+    const double *ap = A + r0 + grp + tig * lda, *bp = B + c0 + grp + tig * ldb;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const bool kok = k0 + tig < K;
+        double a[4], b[2];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { a[i] = sA[k * FLD + 4 * ty + i]; b[i] = sB[k * FLD + 4 * tx + i]; }
+        for (int i = 0; i < 4; i++) a[i] = (aok[i] && kok) ? ap[k0 * lda + 8 * i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = (bok[j] && kok) ? bp[k0 * ldb + 8 * j] : 0.0;
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) c[i][j] -= a[i] * b[j];
+            for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+}
+
+// C[64 x 64] -= A[64 x 64] B[64 x 64]^T on column-major shared-memory tiles (leading dimension FLD), 8 warps x (32 x 16);
+// lower: warp tiles strictly above the diagonal are skipped (entries above the diagonal inside the others are computed
+// and ignored by the caller).
+__device__ __forceinline__ void rank64_update(double *__restrict__ sC, const double *__restrict__ sA, const double *__restrict__ sB, bool lower) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
+    const int r0 = (warp & 1) * 32, c0 = (warp >> 1) * 16;
+    if (lower && c0 >= r0 + 32) return;
+    double acc[4][2][2];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int i = 0; i < 4; i++) sC[(4 * tx + j) * FLD + 4 * ty + i] = c[i][j];
+        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    warp_dmma_32x16(sA, FLD, r0, FB, sB, FLD, c0, FB, FB, acc);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) sC[(c0 + 8 * j + 2 * tig + e) * FLD + r0 + 8 * i + grp] -= acc[i][j][e];
 }
 
 // global (column-major, leading dimension ld) -> shared tile; entries outside nr x nc read as 0 (tri: only i >= j is
@@ -405,7 +430,8 @@ struct FrontTask {
 
 constexpr int FRONT_MAXC = 4;       // children whose inverse row maps are resident at once (more: several passes)
 
-__host__ __device__ __forceinline__ int front_ldp(int nrow) { return (nrow + 1) | 1; }   // odd: conflict-free column walks
+// panel stride: the smallest value >= nrow that is 8 mod 16 (the DMMA fragment loads of the update matrix then touch every bank twice)
+__host__ __device__ __forceinline__ int front_ldp(int nrow) { return ((nrow + 7) & ~15) + 8; }
 __host__ __device__ __forceinline__ int front_smem_doubles(int nrow, int ns) {
     return ns * front_ldp(nrow) + (FRONT_MAXC * nrow + 1) / 2;
 }
@@ -561,67 +587,70 @@ front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restr
     for (int cb = 0; cb == 0 || cb < nch; cb += FRONT_MAXC) {
         const int cn = max(0, min(FRONT_MAXC, nch - cb));
         if (nch > FRONT_MAXC) build_maps(cb, cn);            // (otherwise the maps of the panel phase are still in place)
-        // a warp owns a column of 4 x 4 tiles (round robin), its lanes walk down the rows from the diagonal: the column
-        // operand is a broadcast, the row operand and the stores are contiguous across the lanes, no tile above the
-        // diagonal is ever enumerated
-        for (int bj = warp; bj < tn; bj += 8)
-        for (int bi = bj + lane; bi < tn; bi += 32) {
-            double acc[4][4];
+        // FP64 tensor cores: the warps take 32 x 16 tiles of the lower triangle round robin (column-major over the tile
+        // grid, so the warps of a round share the column operand); the children's contributions are gathered straight
+        // into the accumulator fragments and every entry is stored once
+        const int tr = (nr + 31) >> 5, tc = (nr + 15) >> 4;
+        const int grp = lane >> 2, tig = lane & 3;
+        for (int t = warp; t < tr * tc; t += 8) {
+            const int bj = t / tr, bi = t - bj * tr;
+            const int r0 = 32 * bi, c0 = 16 * bj;
+            if (c0 >= r0 + 32) continue;                                   // tile strictly above the diagonal
+            double acc[4][2][2];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
             if (cb == 0) {
+                warp_dmma_32x16(sP + ns, ldp, r0, nr, sP + ns, ldp, c0, nr, ns, acc);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-                for (int c = 0; c < ns; c++) {
-                    const double *col = sP + c * ldp + ns;
-                    double a[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        a[i] = (4 * bi + i < nr) ? col[4 * bi + i] : 0.0;
-                        b[i] = (4 * bj + i < nr) ? col[4 * bj + i] : 0.0;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[i][j] -= a[i] * b[j];
-                }
+                    for (int j = 0; j < 2; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int rr = 4 * bi + i, jj = 4 * bj + j;
-                        acc[i][j] = (rr < nr && jj < nr && rr >= jj) ? Up[rr + (long long)jj * S.uld] : 0.0;
-                    }
+                    for (int j = 0; j < 2; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int rr = r0 + 8 * i + grp, jj = c0 + 8 * j + 2 * tig + e;
+                            acc[i][j][e] = (rr < nr && jj < nr && rr >= jj) ? Up[rr + (long long)jj * S.uld] : 0.0;
+                        }
             }
             for (int k = 0; k < cn; k++) {
                 const int *inv = sInv + k * nrow + ns;
                 const double *Uc = cU[k];
                 const long long uld = cUld[k];
-                int ii[4], ij[4];
+                int ii[4], ij[2][2];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    ii[i] = (4 * bi + i < nr) ? inv[4 * bi + i] : -1;
-                    ij[i] = (4 * bj + i < nr) ? inv[4 * bj + i] : -1;
-                }
-                double g[4][4];
+                for (int i = 0; i < 4; i++) ii[i] = (r0 + 8 * i + grp < nr) ? inv[r0 + 8 * i + grp] : -1;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < 2; j++)
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        g[i][j] = (ii[i] >= 0 && ij[j] >= 0 && ii[i] >= ij[j]) ? Uc[ii[i] + ij[j] * uld] : 0.0;
+                    for (int e = 0; e < 2; e++) ij[j][e] = (c0 + 8 * j + 2 * tig + e < nr) ? inv[c0 + 8 * j + 2 * tig + e] : -1;
+                double g[4][2][2];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int i = 0; i < 4; i++) acc[i][j] += g[i][j];
+                    for (int j = 0; j < 2; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++)
+                            g[i][j][e] = (ii[i] >= 0 && ij[j][e] >= 0 && ii[i] >= ij[j][e]) ? Uc[ii[i] + ij[j][e] * uld] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { acc[i][j][0] += g[i][j][0]; acc[i][j][1] += g[i][j][1]; }
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int rr = 4 * bi + i, jj = 4 * bj + j;
-                    if (rr < nr && jj < nr && rr >= jj) Up[rr + (long long)jj * S.uld] = acc[i][j];
-                }
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int rr = r0 + 8 * i + grp, jj = c0 + 8 * j + 2 * tig + e;
+                        if (rr < nr && jj < nr && rr >= jj) Up[rr + (long long)jj * S.uld] = acc[i][j][e];
+                    }
         }
         if (nch > FRONT_MAXC) __syncthreads();
     }

@@ -344,7 +344,16 @@ def test_lanes_factorize_a_sweep_side_by_side():
     assert be.lane_capacity() == 6 and single.lane_capacity() == 1
     nz = np.stack([model.values(*th) for th in thetas])
     ld, st = be.refactorize_lanes(nz)
-    assert np.array_equal(ld, np.array(want)) and not st.any()              # deterministic: identical bits per lane
+    # identical bits per lane: the same launches advance every lane, so a lane reproduces what the handle computes for
+    # that value set alone (a lane handle schedules for throughput -- bulk path instead of the latency-oriented fused
+    # chain steps -- so against a single-lane HANDLE the agreement is to rounding, not to the bit)
+    own = []
+    for th in thetas:
+        be.refactorize(model.precision(*th))
+        own.append(be.compute_logdet())
+    assert np.array_equal(ld, np.array(own)) and not st.any()
+    assert np.allclose(ld, want, rtol=1e-12, atol=0)
+    want = own
     be.set_value_basis(model.basis())
     ld2, st2 = be.refactorize_combination_lanes(np.stack([model.coefficients(*th) for th in thetas]))
     assert np.allclose(ld2, want, rtol=1e-12) and not st2.any()
