@@ -35,10 +35,13 @@ struct AsmTile {
 
 struct AgChild {
     const double *U;    // child's update matrix (lane 0)
+    const int *rel;     // its relative-index list (rows below its own columns)
     int uld;
     int a, b;           // run [a, b) of the child's row list that lands in the tile's rows
     int a_base;         // a rounded down to even (16-byte aligned staging)
-    int ca, cb;         // run of the child's row list (= its update columns) that lands in the tile's columns
+    int pa, pb;         // run that lands in the 256-row block holding the tile's columns
+    int ca, cb;         // run that lands in the tile's columns proper (= the child's update columns to fetch): first as
+                        // counts of entries below c0 / below c0 + 32, then turned into positions
 };
 
 constexpr int AG_SMEM_BYTES = AG_CW * AG_LDS * 8 + AG_MAXCH * (AG_RH + AG_CW) * 4 + AG_MAXCH * (int)sizeof(AgChild) + 16;
@@ -98,27 +101,35 @@ assemble_gather_kernel(const AsmTile *__restrict__ tiles, const SuperMeta *__res
     for (int cb0 = 0; cb0 < nch; cb0 += AG_MAXCH) {
         const int cn = min(AG_MAXCH, nch - cb0);
         // ---- maps and runs of this group of children ----
+        // one thread per child walks the dependent chain child -> meta -> relpos (all children in parallel: the first
+        // version did it child after child on every thread, ~5 dependent global round trips per child and tile)
+        if (tid < cn) {
+            const int cs = child_idx[P.child_begin + cb0 + tid];
+            const SuperMeta C = meta[cs];
+            const int *rp = relpos + relpos_off[cs];
+            AgChild c;
+            c.U = upd + C.upd_off; c.rel = relidx + C.rowptr + C.ns; c.uld = C.uld;
+            c.a = rp[qr]; c.b = rp[qr + 1]; c.a_base = c.a & ~1;
+            c.pa = rp[qc]; c.pb = rp[qc + 1];
+            c.ca = 0; c.cb = 0;
+            ch[tid] = c;
+        }
         for (int e = tid; e < cn * AG_RH; e += 256) invRow[e] = -1;
         for (int e = tid; e < cn * AG_CW; e += 256) invCol[e] = -1;
         __syncthreads();
-        for (int k = 0; k < cn; k++) {
-            const int cs = child_idx[P.child_begin + cb0 + k];
-            const SuperMeta C = meta[cs];
-            const int *rel = relidx + C.rowptr + C.ns;
-            const int *rp = relpos + relpos_off[cs];
-            const int a = rp[qr], b = rp[qr + 1];                // child rows landing in parent rows [r0, r0 + 256)
-            const int pa = rp[qc], pb = rp[qc + 1];              // ... in the 256-row block that holds the tile's columns
-            if (a + tid < b) invRow[k * AG_RH + rel[a + tid] - r0] = a + tid;
-            int jc = -1;
-            if (pa + tid < pb) {
-                const int p = rel[pa + tid];
-                if (p >= c0 && p < c0 + AG_CW) { jc = pa + tid; invCol[k * AG_CW + p - c0] = jc; }
+        for (int e = tid; e < cn * AG_RH; e += 256) {           // (both runs are at most 256 entries long)
+            const int k = e >> 8, t = e & 255;
+            const AgChild &c = ch[k];
+            if (c.a + t < c.b) invRow[k * AG_RH + c.rel[c.a + t] - r0] = c.a + t;
+            if (c.pa + t < c.pb) {
+                const int p = c.rel[c.pa + t];
+                if (p < c0) atomicAdd(&ch[k].ca, 1);
+                if (p < c0 + AG_CW) atomicAdd(&ch[k].cb, 1);
+                if (p >= c0 && p < c0 + AG_CW) invCol[k * AG_CW + p - c0] = c.pa + t;
             }
-            // first / one-past-last child column of the tile: block-wide min / max through shared memory ints
-            if (tid == 0) { ch[k].U = upd + C.upd_off; ch[k].uld = C.uld; ch[k].a = a; ch[k].b = b; ch[k].a_base = a & ~1; ch[k].ca = 0x7fffffff; ch[k].cb = -1; }
-            __syncthreads();
-            if (jc >= 0) { atomicMin(&ch[k].ca, jc); atomicMax(&ch[k].cb, jc + 1); }
         }
+        __syncthreads();
+        if (tid < cn) { ch[tid].ca += ch[tid].pa; ch[tid].cb += ch[tid].pa; }     // counts -> positions (the list is sorted)
         __syncthreads();
         // ---- children one after the other: bulk copies into the stage, gather from it ----
         for (int k = 0; k < cn; k++) {
