@@ -30,7 +30,7 @@ struct AsmTile {
     int super;      // parent supernode
     int col0;       // first front column of the tile (multiple of 32)
     int row0;       // first front row of the tile (multiple of 256)
-    int pad_;
+    int pad_;       // 1: panel columns only
 };
 
 struct AgChild {
@@ -184,7 +184,7 @@ assemble_gather_kernel(const AsmTile *__restrict__ tiles, const SuperMeta *__res
             if (r >= P.nrow || r < c) continue;
             if (c < P.ns) {
                 if (acc[j][u] != 0.0) Lp[r + (long long)c * P.ld] += acc[j][u];
-            } else {
+            } else if (!it.pad_) {            // (pad_ = 1: the update part is gathered by the update-matrix product itself)
                 Up[(r - P.ns) + (long long)(c - P.ns) * P.uld] = acc[j][u];
             }
         }

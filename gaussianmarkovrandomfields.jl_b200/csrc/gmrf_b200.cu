@@ -113,6 +113,7 @@ struct gmrf_b200_handle {
     ChainTask *d_chain = nullptr;      // fused chain steps (front_kernels.cuh)
     FinalizeTask *d_final = nullptr;
     FrontTask *d_front = nullptr;
+    GatherCtx *d_gctx = nullptr;       // tables of the gathering epilogue of the update-matrix products
     AsmTile *d_asmtiles = nullptr;     // gather extend-add (assemble_kernels.cuh)
     int *d_relpos = nullptr;           // per child: position in its relative-index list of every 256-row boundary of the parent
     long long *d_relpos_off = nullptr;
@@ -316,7 +317,8 @@ struct Builder {
             int BM = naive ? 16 : (pass ? 128 : 64), BN = naive ? 16 : 64;
             Launch L;
             L.kind = (variant == 0 ? K_GEMM_NN_S : variant == 1 ? K_GEMM_NT_S : K_GEMM_TT_S) + pass;
-            L.aux = 0;
+            L.aux = 0;                                     // 1: the launch holds gathering update-matrix products
+            for (auto &t : v) if (t.flags & GEMM_GATHER) L.aux = 1;
             L.task_off = (i64)gemm.size();
             L.ntasks = (int)v.size();
             L.prefix_off = (i64)prefix.size();
@@ -562,6 +564,8 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
     std::vector<ChainTask> ct;
     std::vector<FrontTask> ft;
     std::vector<AsmTile> ats;
+    // the update part of the extend-add moves into the epilogue of the update-matrix product (needs the gather tables)
+    const bool syrk_gather = h->opt.syrk_gather && h->opt.asm_gather && !B.naive;
     auto push_finalize = [&](i64 s, i64 k0, const double *sq) {
         const i64 ns = S.ns(s), ld = S.panel_ld[s];
         FinalizeTask f;
@@ -595,8 +599,9 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
             i64 s = *sp;
             if (S.child_ptr[s + 1] == S.child_ptr[s]) continue;
             if (h->opt.asm_gather && !B.naive) {
-                for (i64 c0 = 0; c0 < S.nrow(s); c0 += AG_CW)
-                    for (i64 r0 = c0 / AG_RH * AG_RH; r0 < S.nrow(s); r0 += AG_RH) ats.push_back(AsmTile{(int)s, (int)c0, (int)r0, 0});
+                const i64 cend = syrk_gather ? S.ns(s) : S.nrow(s);        // panel columns only / the whole front
+                for (i64 c0 = 0; c0 < cend; c0 += AG_CW)
+                    for (i64 r0 = c0 / AG_RH * AG_RH; r0 < S.nrow(s); r0 += AG_RH) ats.push_back(AsmTile{(int)s, (int)c0, (int)r0, syrk_gather ? 1 : 0});
             } else {
                 for (i64 c0 = 0; c0 < S.nrow(s); c0 += ASM_CW) its.push_back(AsmItem{(int)s, (int)c0});
             }
@@ -681,8 +686,9 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
             g.C = h->d_upd + S.upd_off[s];
             g.m = g.n = (int)nr; g.k = (int)ns;
             g.lda = g.ldb = (int)ld; g.ldc = S.upd_ld[s];
-            g.flags = GEMM_LOWER | ((S.child_ptr[s + 1] > S.child_ptr[s]) ? 0 : GEMM_BETA0);
-            g.pad_ = 0;
+            const bool kids = S.child_ptr[s + 1] > S.child_ptr[s];
+            g.flags = GEMM_LOWER | (kids ? (syrk_gather ? GEMM_GATHER : 0) : GEMM_BETA0);
+            g.pad_ = (kids && syrk_gather) ? (int)s + 1 : 0;
             gt.push_back(g);
         }
         B.add_gemm(plan, gt, 0);
@@ -1130,8 +1136,12 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
 // Launch dispatch
 // ------------------------------------------------------------------------------------------------
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
-void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st, int lanes, long long bstride) {
-    gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks, bstride);
+void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st, int lanes, long long bstride,
+                   const GatherCtx *gctx = nullptr) {
+    if (!TA && !TB && gctx)      // update-matrix products whose epilogue gathers the children's contributions
+        gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, 16, 3, true><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN>(), st>>>(tasks, prefix, ntasks, bstride, gctx);
+    else
+        gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks, bstride);
 }
 
 // Opt in to > 48 KB dynamic shared memory for every GEMM instantiation (per device; must run outside stream capture).
@@ -1139,6 +1149,7 @@ template <int BM, int BN, int WGM, int WGN>
 cudaError_t configure_gemm_tile() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
+    if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, 16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN>()))) return e;
     if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, 16, 3, false, true>()))) return e;
     if ((e = cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WGM, WGN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BM, BN, 16, 3, true, true>()))) return e;
     return cudaSuccess;
@@ -1158,10 +1169,10 @@ cudaError_t configure_kernels(int front_smem = 0) {
 
 template <bool TA, bool TB>
 void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st,
-                 int lanes = 1, long long bstride = 0) {
+                 int lanes = 1, long long bstride = 0, const GatherCtx *gctx = nullptr) {
     if (naive) gemm_naive_kernel<TA, TB><<<dim3(grid, lanes), 256, 0, st>>>(tasks, prefix, ntasks, bstride);
-    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
-    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride);
+    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx);
+    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx);
 }
 
 struct TableSet {
@@ -1208,7 +1219,9 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             }
             break;
         case K_GEMM_NN_S: case K_GEMM_NN_L:
-            launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
+            launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride,
+                                      L.aux ? h->d_gctx : nullptr);
+            break;
         case K_GEMM_NT_S: case K_GEMM_NT_L:
             launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
         case K_GEMM_TT_S: case K_GEMM_TT_L:
@@ -1751,6 +1764,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "debug_alloc_fail_after") g_alloc_fail_countdown = std::max(0, (int)value);
     else if (k == "asm_gather") o.asm_gather = (int)value;
     else if (k == "level_alap") o.level_alap = (int)value;
+    else if (k == "syrk_gather") o.syrk_gather = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
     else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);
@@ -1845,6 +1859,7 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         // in every chain CTA; the gather extend-add's per-tile set-up), so such a handle takes the bulk path for those.
         H->opt.fused_chain = 0;
         H->opt.asm_gather = 0;
+        H->opt.syrk_gather = 0;
     }
     const FusedInfo fused = plan_fused(S, H->opt);
     H->front_smem_max = fused.front_smem_max;
@@ -1932,6 +1947,9 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         }
         TRY_RC(dev_upload(H, &H->d_relpos, rp));
         TRY_RC(dev_upload(H, &H->d_relpos_off, rpo));
+        std::vector<GatherCtx> gc(1);
+        gc[0] = GatherCtx{H->d_meta, H->d_child, H->d_relidx, H->d_relpos, H->d_relpos_off, H->d_upd};
+        TRY_RC(dev_upload(H, &H->d_gctx, gc));
     }
     {
         i64 part_total = 0;   // partial sums of the row-chunked backward products

@@ -23,7 +23,9 @@ enum : int {
     GEMM_LOWER = 1,      // write only entries with local row >= local col
     GEMM_BETA0 = 2,      // C = alpha*op(A)op(B) (+I) instead of C += ...
     GEMM_ALPHA_POS = 4,  // alpha = +1 (default alpha = -1)
-    GEMM_ADD_I = 8       // add the identity on the local diagonal
+    GEMM_ADD_I = 8,      // add the identity on the local diagonal
+    GEMM_GATHER = 16     // (GATHER instantiation, C = update matrix of supernode pad_ - 1) C = children's contributions - A B^T,
+                         // written once: the extend-add of the update matrix happens in this epilogue
 };
 
 struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
@@ -33,7 +35,7 @@ struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
     int m, n, k;
     int lda, ldb, ldc;
     int flags;
-    int pad_;
+    int pad_;            // GEMM_GATHER: parent supernode + 1
 };
 
 struct PanelTask {       // diagonal block step: D := chol(D) (nb x nb, in place, lower) and inv := D^-1
@@ -58,6 +60,17 @@ struct SuperMeta {
     int first, ns, nrow, ld, uld, parent;
     int child_begin, child_end;   // range in child_idx
 };
+
+// Tables the gathering epilogue of the update-matrix products reads (one copy per handle, in HBM).
+struct GatherCtx {
+    const SuperMeta *meta;
+    const int *child_idx;
+    const int *relidx;
+    const int *relpos;            // per child: position in its relative-index list of every 256-row boundary of the parent
+    const long long *relpos_off;
+    double *upd;                  // update pool (lane 0)
+};
+constexpr int GATHER_MAXC = 4;    // children whose inverse maps are resident at once
 
 // ------------------------------------------------------------------------------------------------
 // Batched factorization: a handle may hold several numeric "lanes" (independent value sets on the same pattern, e.g.
@@ -229,9 +242,93 @@ struct TileLoader {
     }
 };
 
-template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, int GEMM_STAGES = 3>
+// Tail of an update-matrix product of a supernode with children (GEMM_GATHER): the extend-add of the update part happens
+// HERE. The tile holds -L21 L21^T (just written by this CTA, still in L2); every entry adds what the children contribute
+// to it and is stored once more -- HBM sees the children's entries read once and the parent's written once (the scatter
+// form wrote the parent's update matrix -- zeros included --, and this product read and rewrote it: 24 B per entry where
+// 8 B suffice). Per child the rows / columns that land in the tile are found by scanning the (<= 512-entry) stretch of
+// its relative-index list that the 256-row position table brackets; the inverse maps live in the pipeline's shared
+// memory, free by now. A separate function on purpose: nothing of it may cost the main loop a register.
+struct GatherChild {          // per child of the tile's supernode (shared memory)
+    const double *U;
+    const int *rel;
+    long long uld;
+    int rlo, rhi, clo, chi;   // stretches of the child's relative-index list bracketing the tile's rows / columns
+};
+
+template <int BM, int BN, int NT>
+__device__ __noinline__ void gather_children_into_tile(const GemmTask &T, int m0, int n0, const GatherCtx *__restrict__ gctx, long long bstride,
+                                                       int *__restrict__ smem_i) {
+    int *invR = smem_i;                         // [GATHER_MAXC][BM]
+    int *invC = smem_i + GATHER_MAXC * BM;      // [GATHER_MAXC][BN]
+    GatherChild *ch = reinterpret_cast<GatherChild *>(smem_i + GATHER_MAXC * (BM + BN));
+    const int tid = threadIdx.x;
+    const GatherCtx G = *gctx;
+    const SuperMeta P = G.meta[T.pad_ - 1];
+    const double *upd = lane_ptr(G.upd, bstride);
+    const int fr0 = P.ns + m0, fc0 = P.ns + n0;                  // first front row / column of the tile
+    const int nch = P.child_end - P.child_begin;
+    const int qmax = (P.nrow - 1) >> 8;
+    for (int cb = 0; cb < nch; cb += GATHER_MAXC) {
+        const int cn = min(GATHER_MAXC, nch - cb);
+        if (tid < cn) {                          // one thread per child walks child -> meta -> position table
+            const int cs = G.child_idx[P.child_begin + cb + tid];
+            const SuperMeta C = G.meta[cs];
+            const int *rp = G.relpos + G.relpos_off[cs];
+            GatherChild c;
+            c.U = upd + C.upd_off; c.rel = G.relidx + C.rowptr + C.ns; c.uld = C.uld;
+            c.rlo = rp[fr0 >> 8]; c.rhi = rp[min((fr0 + BM - 1) >> 8, qmax) + 1];
+            c.clo = rp[fc0 >> 8]; c.chi = rp[min((fc0 + BN - 1) >> 8, qmax) + 1];
+            ch[tid] = c;
+        }
+        for (int e = tid; e < GATHER_MAXC * (BM + BN); e += NT) invR[e] = -1;
+        __syncthreads();
+        for (int k = 0; k < cn; k++) {
+            const GatherChild c = ch[k];
+            for (int i = c.rlo + tid; i < c.rhi; i += NT) {
+                const int p = c.rel[i];
+                if (p >= fr0 && p < fr0 + BM) invR[k * BM + p - fr0] = i;
+            }
+            for (int i = c.clo + tid; i < c.chi; i += NT) {
+                const int p = c.rel[i];
+                if (p >= fc0 && p < fc0 + BN) invC[k * BN + p - fc0] = i;
+            }
+        }
+        __syncthreads();
+        // rows across the threads (coalesced), eight columns per pass and all children at once: up to 32 loads in flight
+        constexpr int UN = 8;
+        for (int e0 = tid; e0 < BM * BN; e0 += UN * NT) {
+            double v[UN][GATHER_MAXC];
+            bool ok[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int e = e0 + u * NT, rr = e % BM, cc = e / BM;
+                const int r = m0 + rr, c = n0 + cc;
+                ok[u] = e < BM * BN && r < T.m && c < T.n && r >= c;
+#pragma unroll
+                for (int k = 0; k < GATHER_MAXC; k++) {
+                    v[u][k] = 0.0;
+                    if (k < cn && ok[u]) {
+                        const int ir = invR[k * BM + rr], ic = invC[k * BN + cc];
+                        if (ic >= 0 && ir >= ic) v[u][k] = ch[k].U[ir + ic * ch[k].uld];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int e = e0 + u * NT, rr = e % BM, cc = e / BM;
+                const double add = (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+                if (ok[u] && add != 0.0) T.C[(m0 + rr) + (long long)(n0 + cc) * T.ldc] += add;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BM, int BN, int WGM, int WGN, bool TA, bool TB, int GEMM_KT = 16, int GEMM_STAGES = 3, bool GATHER = false>
 __global__ void __launch_bounds__(WGM *WGN * 32, (WGM * WGN == 4) ? ((BM * BN <= 64 * 64) ? 4 : 3) : 1)
-gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride) {
+gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride,
+                 const GatherCtx *__restrict__ gctx = nullptr) {
     constexpr int NT = WGM * WGN * 32;
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4, LDK = GEMM_KT + 4;
     constexpr int A_TILE = gemm_tile_doubles<BM, GEMM_KT, TA>(), B_TILE = gemm_tile_doubles<BN, GEMM_KT, TB>();
@@ -315,7 +412,8 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     cp_async_wait<0>();
 
     const double alpha = (T.flags & GEMM_ALPHA_POS) ? 1.0 : -1.0;
-    const bool beta0 = T.flags & GEMM_BETA0, lower = T.flags & GEMM_LOWER, addi = T.flags & GEMM_ADD_I;
+    const bool gather = GATHER && (T.flags & GEMM_GATHER);
+    const bool beta0 = (T.flags & GEMM_BETA0) || gather, lower = T.flags & GEMM_LOWER, addi = T.flags & GEMM_ADD_I;
     // Epilogue in chunks of 16 outputs: all reads of C are issued before the first store of the chunk, so a tile pays
     // one memory round trip per chunk instead of one per element (loads could not be hoisted over the stores otherwise;
     // with k = 64 the element-wise read-modify-write chain cost more than the tile's arithmetic).
@@ -343,6 +441,10 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
                 Cb[8 * i + (long long)(8 * j + e) * T.ldc] = v;
             }
         }
+    }
+    if (gather) {
+        __syncthreads();           // the tile is written (-A B^T) and the operand stages are free
+        gather_children_into_tile<BM, BN, NT>(T, m0, n0, gctx, bstride, reinterpret_cast<int *>(gemm_smem));
     }
 }
 

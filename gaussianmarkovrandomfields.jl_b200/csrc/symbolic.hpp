@@ -32,6 +32,7 @@ struct Options {
     int large_tile_mask = 1;  // GEMM operand-layout variants (bit 0 NN, 1 NT, 2 TT) allowed to use the 128 x 64 tile (measured: only NN gains)
     int lanes = 1;            // value sets a handle can factorize side by side (batched hyperparameter evaluations)
     int selinv_fast_root = 1; // triangular (trtri + lauum) route for top-level root supernodes in the selected inversion
+    int syrk_gather = 0;      // update-matrix products gather their children's contributions in a tail of the GEMM (U written once). Measured at 1 M dofs (profiles/r02_plan_3d100_syrk_gather.log): extend-add 60 -> 33 ms but the products +50 ms (the tail is not hidden behind the other CTAs), so off by default
     int level_alap = 1;       // assembly-tree levels counted from the roots (as late as possible) instead of from the leaves
     int asm_gather = 1;       // extend-add as a gather through TMA-staged shared memory (0: the first, scatter-shaped kernel)
     int fused_front = 1;      // one-CTA-per-front kernel for tree levels whose panels all fit in shared memory
