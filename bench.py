@@ -147,7 +147,19 @@ def cpu_baseline_run(sample_cells: int, full_flops: float, reps: int = 1):
     h.close()
     return {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port", "sample": sample,
             "gflops": gflops, "sample_seconds": best, "same_config": False,
-            "note": "bounded sample scaled by flops (extrapolated); `bench.py --impl reference` measures the full problem"}
+            "note": "bounded sample scaled by flops (extrapolated); `bench.py --impl reference` measures the full problem",
+            "full_problem_measured": _recorded_reference()}
+
+
+def _recorded_reference():
+    """The committed record of the reference arm on this pool's box (whole 100^3 factorizations, measured -- not scaled)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json")) as f:
+            d = json.loads(f.read().strip().splitlines()[-1])
+        return {"value": d["value"], "unit": d["unit"], "seconds_per_factorization": d["ms_per_step"] / 1e3,
+                "cores": d["cpu_baseline"]["cores"], "source": "profiles/r02_bench_reference_arm.json"}
+    except Exception:
+        return None
 
 
 def full_flops_estimate(cells: int) -> float:
