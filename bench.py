@@ -453,8 +453,9 @@ def sampling_config5(world, rank, local, small=False):
         be.solve_device(Z.data_ptr(), X.data_ptr(), n, mine, half=True)
         return be.timings()["solve_ms"]
 
-    # ---- variant B first (it also warms the graphs): everybody factorizes ----
+    # ---- variant B first: everybody factorizes ----
     be.refactorize(Q)
+    draw()                                   # (plans and graphs of this block width are built outside the timed regions)
     barrier()
     t1 = time.perf_counter()
     be.refactorize(Q)
@@ -527,7 +528,28 @@ def run_gpu(args):
     # two hyperparameter points are kept resident and alternated; every step re-factorizes different values
     nz_host = [np.ascontiguousarray(model.values(*theta_for(k, rank))) for k in range(2)]
     Q0 = model.precision(*theta_for(0, rank))
-    ws = GMRFWorkspace(Q0, ordering=perm, device=local)           # symbolic analysis + first factorization
+    # ONE symbolic analysis per node (workspace_pool.jl:55-58 "resolve the permutation ONCE"): rank 0 analyses on all host
+    # threads (torchrun pins OMP_NUM_THREADS=1; every rank analysing at once doubled the set-up in round 1), the blob
+    # travels over NCCL and the peers restore it (gmrf_b200_create_from_analysis)
+    if world > 1:
+        from gmrf_b200.backend import B200Backend
+        blob = None
+        if rank == 0:
+            import contextlib
+            try:
+                from threadpoolctl import threadpool_limits
+                ctx = threadpool_limits(limits=os.cpu_count() or 1, user_api="openmp")
+            except Exception:
+                ctx = contextlib.nullcontext()
+            with ctx:
+                ws = GMRFWorkspace(Q0, ordering=perm, device=local)
+            blob = ws.backend.export_analysis()
+        blob = _bcast_bytes(blob, dist, torch.device("cuda", local))
+        if rank != 0:
+            ws = GMRFWorkspace(Q0, analysis=blob, device=local)
+        del blob
+    else:
+        ws = GMRFWorkspace(Q0, ordering=perm, device=local)       # symbolic analysis + first factorization
     be = ws.backend
     info = be.info()
     setup_s = time.time() - t0
