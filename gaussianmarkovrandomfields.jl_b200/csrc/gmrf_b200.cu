@@ -33,7 +33,8 @@ int g_alloc_fail_countdown = 0;     // test hook ("debug_alloc_fail_after"): the
 
 enum LaunchKind : int {
     K_ASSEMBLE, K_CHAIN, K_FINALIZE, K_FRONT, K_GEMM_NN_S, K_GEMM_NN_L, K_GEMM_NT_S, K_GEMM_NT_L, K_GEMM_TT_S, K_GEMM_TT_L,
-    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE, K_ASSEMBLE_G
+    K_GATHER, K_TRANSPOSE, K_FWD_ASM, K_FWD_STEP, K_BWD_GATHER, K_BWD_STEP, K_PANEL, K_SPLIT_REDUCE, K_FWD_ASM_M, K_ROWS_GATHER, K_BWD_REDUCE, K_ASSEMBLE_G,
+    K_FWD_WSTEP, K_FWD_WDIAG, K_BWD_WSTEP, K_BWD_WDIAG
 };
 
 struct Launch {
@@ -90,6 +91,8 @@ struct gmrf_b200_handle {
     BwdGatherTask *d_bwdg = nullptr;
     BwdStepTask *d_bwds = nullptr;
     BwdReduceTask *d_bwdr = nullptr;
+    WideStepTask *d_wstep = nullptr;   // 256-column steps of the long chains (solve_kernels.cuh)
+    WideDiagTask *d_wdiag = nullptr;
     double *d_bwdpart = nullptr;       // partial sums of the row-chunked L21' x_R products (backward sweep)
     double *d_Linv = nullptr;          // inverted 64-column diagonal blocks: written by the factorization (TRSM by
                                        // GEMM), reused by the solve phase
@@ -243,6 +246,8 @@ struct Builder {
     std::vector<BwdGatherTask> bwdg;
     std::vector<BwdStepTask> bwds;
     std::vector<BwdReduceTask> bwdr;
+    std::vector<WideStepTask> wstep;
+    std::vector<WideDiagTask> wdiag;
     std::vector<TransTask> trans;
     std::vector<SplitTask> split;
     std::vector<RowGatherTask> rowgather;
@@ -486,6 +491,19 @@ struct Builder {
         plan.launches.push_back(L);
         finalize_done = (i64)finalize.size();
     }
+    void add_wdiag(Plan &plan, std::vector<WideDiagTask> &tasks, int kind) {
+        if (tasks.empty()) return;
+        Launch L;
+        L.kind = kind;
+        L.aux = 0;
+        L.task_off = (i64)wdiag.size();
+        L.ntasks = (int)tasks.size();
+        L.prefix_off = -1;
+        L.grid = (int)tasks.size();
+        wdiag.insert(wdiag.end(), tasks.begin(), tasks.end());
+        plan.launches.push_back(L);
+        tasks.clear();
+    }
     void add_superlist(Plan &plan, std::vector<int> &lst, int kind) {
         if (lst.empty()) return;
         Launch L;
@@ -706,6 +724,9 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     std::vector<BwdGatherTask> gt;
     std::vector<BwdReduceTask> rt;
     std::vector<BwdStepTask> bt;
+    std::vector<WideStepTask> wt;
+    std::vector<WideDiagTask> wd;
+    auto is_wide = [&](i64 s) { return h->opt.wide_steps && S.ns(s) > SOLVE_WIDE_MIN; };
     i64 part_off = 0;
     const i64 RCH = std::max(32, h->opt.bwd_row_chunk);
     const i64 BB = (i64)SOLVE_NB * SOLVE_NB;
@@ -715,13 +736,32 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
         for (const i64 *sp = sb; sp < se; sp++) lst.push_back((int)*sp);
         B.add_superlist(h->fwd_plan, lst, K_FWD_ASM);
-        i64 maxsteps = 0;
-        for (const i64 *sp = sb; sp < se; sp++) maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), SOLVE_NB));
+        i64 maxsteps = 0, maxwide = 0;
+        for (const i64 *sp = sb; sp < se; sp++) {
+            if (is_wide(*sp)) maxwide = std::max<i64>(maxwide, cdiv(S.ns(*sp), SOLVE_WB));
+            else maxsteps = std::max<i64>(maxsteps, cdiv(S.ns(*sp), SOLVE_NB));
+        }
+        // long chains: per 256 columns one diagonal-block solve (one CTA per supernode), then one update of everything below
+        for (i64 J = 0; J < maxwide; J++) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
+                i64 k0 = J * SOLVE_WB;
+                if (!is_wide(s) || k0 >= ns) continue;
+                i64 nbw = std::min<i64>(SOLVE_WB, ns - k0), k1 = k0 + nbw;
+                const double *P = h->d_Lx + S.panel_off[s];
+                wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
+                if (nrow > k1)
+                    wt.push_back(WideStepTask{P + k0 * ld + k1, h->d_y + S.sfirst[s] + k0, h->d_y + S.sfirst[s] + k1, h->d_uvec + S.uvec_off[s],
+                                              (int)ld, (int)nbw, (int)(ns - k1), (int)(nrow - k1)});
+            }
+            B.add_wdiag(h->fwd_plan, wd, K_FWD_WDIAG);
+            B.add_tiled(h->fwd_plan, wt, B.wstep, K_FWD_WSTEP, [](const WideStepTask &t) { return (i64)cdiv(t.m, SOLVE_NB); });
+        }
         for (i64 j = 0; j < maxsteps; j++) {
             for (const i64 *sp = sb; sp < se; sp++) {
                 i64 s = *sp, ns = S.ns(s), nrow = S.nrow(s), ld = S.panel_ld[s];
                 i64 k0 = j * SOLVE_NB;
-                if (k0 >= ns) continue;
+                if (k0 >= ns || is_wide(s)) continue;
                 i64 nb = std::min<i64>(SOLVE_NB, ns - k0), k1 = k0 + nb;
                 if (nrow == k1) continue;
                 const double *P = h->d_Lx + S.panel_off[s];
@@ -742,11 +782,12 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     // backward: L^T x = y
     for (i64 l = S.nlevels - 1; l >= 0; l--) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
-        i64 maxsteps = 0;
+        i64 maxsteps = 0, maxwide = 0;
         for (const i64 *sp = sb; sp < se; sp++) {
             i64 s = *sp, ns = S.ns(s), nr = S.nr(s), ld = S.panel_ld[s];
             i64 nblk = cdiv(ns, SOLVE_NB);
-            maxsteps = std::max(maxsteps, nblk);
+            if (is_wide(s)) maxwide = std::max<i64>(maxwide, cdiv(ns, SOLVE_WB));
+            else maxsteps = std::max(maxsteps, nblk);
             BwdGatherTask t;
             t.L21 = h->d_Lx + S.panel_off[s] + ns;
             t.idx = h->d_rowidx + S.rowptr[s] + ns;
@@ -754,7 +795,7 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
             t.y = h->d_y + S.sfirst[s];
             t.ld = (int)ld; t.ns = (int)ns; t.nr = (int)nr; t.nb_last = (int)(ns - (nblk - 1) * SOLVE_NB);
             t.tile0 = nr > 0 ? 0 : (int)(nblk - 1);
-            t.pad_ = 0;
+            t.pad_ = is_wide(s) ? 1 : 0;          // long chain: the last block is solved by the wide diagonal kernel
             t.part = nullptr;
             if (nr > RCH) {
                 // tall L21: row chunks write partial sums, a second pass folds them (fixed order) and finishes t_S
@@ -769,7 +810,7 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
                     c.part = part + k * BWD_PART_Q * ns;
                     gt.push_back(c);
                 }
-                rt.push_back(BwdReduceTask{part, t.inv_last, t.y, (int)ns, (int)nch, t.nb_last, 0});
+                rt.push_back(BwdReduceTask{part, t.inv_last, t.y, (int)ns, (int)nch, t.nb_last, t.pad_});
             } else {
                 gt.push_back(t);
             }
@@ -778,12 +819,27 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
             return (i64)(cdiv(t.ns, SOLVE_NB) - t.tile0);
         });
         B.add_tiled(h->bwd_plan, rt, B.bwdr, K_BWD_REDUCE, [](const BwdReduceTask &t) { return (i64)cdiv(t.ns, SOLVE_NB); });
+        for (i64 tJ = 0; tJ < maxwide; tJ++) {
+            for (const i64 *sp = sb; sp < se; sp++) {
+                i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
+                if (!is_wide(s)) continue;
+                i64 J = cdiv(ns, SOLVE_WB) - 1 - tJ;
+                if (J < 0) continue;
+                i64 k0 = J * SOLVE_WB, nbw = std::min<i64>(SOLVE_WB, ns - k0);
+                const double *P = h->d_Lx + S.panel_off[s];
+                wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
+                if (k0 > 0)
+                    wt.push_back(WideStepTask{P + k0, h->d_y + S.sfirst[s] + k0, h->d_y + S.sfirst[s], nullptr, (int)ld, (int)nbw, 0, (int)k0});
+            }
+            B.add_wdiag(h->bwd_plan, wd, K_BWD_WDIAG);
+            B.add_tiled(h->bwd_plan, wt, B.wstep, K_BWD_WSTEP, [](const WideStepTask &t) { return (i64)cdiv(t.m, SOLVE_NB); });
+        }
         for (i64 tt = 0; tt + 1 < maxsteps; tt++) {
             for (const i64 *sp = sb; sp < se; sp++) {
                 i64 s = *sp, ns = S.ns(s), ld = S.panel_ld[s];
                 i64 nblk = cdiv(ns, SOLVE_NB);
                 i64 j = nblk - 1 - tt;
-                if (j < 1) continue;
+                if (j < 1 || is_wide(s)) continue;
                 i64 k0 = j * SOLVE_NB, nb = std::min<i64>(SOLVE_NB, ns - k0);
                 BwdStepTask t;
                 t.L = h->d_Lx + S.panel_off[s] + k0;
@@ -1270,6 +1326,18 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_BWD_STEP:
             SOLVE_RB_DISPATCH(bwd_step_kernel, h->d_bwds + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
+            break;
+        case K_FWD_WSTEP:
+            SOLVE_RB_DISPATCH(fwd_wide_step_kernel, h->d_wstep + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
+            break;
+        case K_BWD_WSTEP:
+            SOLVE_RB_DISPATCH(bwd_wide_step_kernel, h->d_wstep + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
+            break;
+        case K_FWD_WDIAG:
+            SOLVE_RB_DISPATCH(fwd_wide_diag_kernel, h->d_wdiag + L.task_off, nrhs, (long long)h->S.n);
+            break;
+        case K_BWD_WDIAG:
+            SOLVE_RB_DISPATCH(bwd_wide_diag_kernel, h->d_wdiag + L.task_off, nrhs, (long long)h->S.n);
             break;
 #undef SOLVE_RB_DISPATCH
     }
@@ -1765,6 +1833,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "asm_gather") o.asm_gather = (int)value;
     else if (k == "level_alap") o.level_alap = (int)value;
     else if (k == "syrk_gather") o.syrk_gather = (int)value;
+    else if (k == "wide_steps") o.wide_steps = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
     else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);
@@ -1924,6 +1993,7 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
             m.first = (int)S.sfirst[s]; m.ns = (int)S.ns(s); m.nrow = (int)S.nrow(s);
             m.ld = S.panel_ld[s]; m.uld = S.upd_ld[s]; m.parent = (int)S.sparent[s];
             m.child_begin = (int)S.child_ptr[s]; m.child_end = (int)S.child_ptr[s + 1];
+            m.wide = (H->opt.wide_steps && S.ns(s) > SOLVE_WIDE_MIN) ? 1 : 0; m.pad_ = 0;
         }
         TRY_RC(dev_upload(H, &H->d_meta, meta));
         // relpos[s][q] = first position in s's relative-index list (rows below its own columns) that lands at or beyond
@@ -1983,6 +2053,8 @@ static int create_impl(gmrf_b200_handle **out, int64_t n, const int64_t *colptr,
         TRY_RC(dev_upload(H, &H->d_bwdg, B.bwdg));
         TRY_RC(dev_upload(H, &H->d_bwds, B.bwds));
         TRY_RC(dev_upload(H, &H->d_bwdr, B.bwdr));
+        TRY_RC(dev_upload(H, &H->d_wstep, B.wstep));
+        TRY_RC(dev_upload(H, &H->d_wdiag, B.wdiag));
         TRY_RC(dev_upload(H, &H->d_superlist, B.superlist));
         TRY_RC(dev_upload(H, &H->d_prefix, B.prefix));
         TRY_RC(dev_upload(H, &H->d_split, B.split));

@@ -59,6 +59,7 @@ struct SuperMeta {
     long long uvec_off;    // rows
     int first, ns, nrow, ld, uld, parent;
     int child_begin, child_end;   // range in child_idx
+    int wide, pad_;               // wide = 1: a long chain whose triangular solves advance 256 columns per step
 };
 
 // Tables the gathering epilogue of the update-matrix products reads (one copy per handle, in HBM).

@@ -176,8 +176,9 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
     const int nr = P.nrow - P.ns;
     const int r = blockIdx.y;
     const int nb0 = min(P.ns, SOLVE_NB);
+    const bool wide = P.wide != 0;           // long chains: the first 256-column block is solved by fwd_wide_diag_kernel
     double g[16];
-    load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
+    if (!wide) load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
     double *us = uvec + P.uvec_off + (long long)r * ldu;
     for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
     __syncthreads();
@@ -193,6 +194,7 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
         }
         __syncthreads();
     }
+    if (wide) return;
     if (threadIdx.x < SOLVE_NB) sb[threadIdx.x][0] = threadIdx.x < nb0 ? ys[threadIdx.x] : 0.0;
     __syncthreads();
     apply_inv_lower<1>(g, nb0, sb, sp, ys, 0, 1, threadIdx.x);
@@ -279,7 +281,7 @@ bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = tile * SOLVE_NB + warp * 8;
     const int nblk = (T.ns + SOLVE_NB - 1) / SOLVE_NB;
-    const bool tail = (tile == nblk - 1);
+    const bool tail = (tile == nblk - 1) && !T.pad_;      // pad_ = 1: long chain, bwd_wide_diag_kernel solves the last block
     double g[16];
     if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
     double acc[8][RB];
@@ -352,7 +354,7 @@ bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict
     const int tile = blockIdx.x - tile_prefix[t];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = (T.ns + SOLVE_NB - 1) / SOLVE_NB;
-    const bool tail = (tile == nblk - 1);
+    const bool tail = (tile == nblk - 1) && !T.pad_;
     double g[16];
     if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
     for (int e = tid; e < SOLVE_NB * RB; e += 256) {
@@ -419,6 +421,260 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
     if (!tail) return;
     __syncthreads();
     apply_inv_lower_t<RB>(g, SOLVE_NB, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide steps for long supernode chains (ns > 256): the sweeps above advance 64 columns per launch, so the top separators
+// of a 3D problem (30,000 columns) cost ~480 dependent launches per direction whose ~10 us of latency each -- not the
+// 15 MB they stream -- bound the 1 M-dof solve (18.7 ms against 10 ms of pure streaming). Here a step is 256 columns and two
+// launches: (A) every 64-row (forward) / 64-column (backward) tile applies the whole 256-column block of already final
+// unknowns, 64 independent loads per thread in flight; (B) ONE CTA per supernode solves the next 256 x 256 diagonal block
+// (four inverse-block products with the updates in between; 260 KB, L2-resident right after the factorization's writes).
+// A quarter of the dependent launches, each moving four times the bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int SOLVE_WB = 256;          // columns per wide step
+constexpr int SOLVE_WIDE_MIN = 256;    // supernodes with more own columns than this take the wide steps
+
+struct WideStepTask {     // forward: rows below block column K = [k0, k0 + nbw): dst[r] -= L[r, K] x_K
+    const double *L;      // forward: panel + k0*ld + k1 (k1 = k0 + nbw);  backward: panel + k0 (row k0, column 0)
+    const double *x;      // x_K (nbw entries per right-hand side, stride ldy)
+    double *y;            // forward: own rows k1.. of the supernode;  backward: own columns 0.. of the supernode
+    double *u;            // forward: update vector of the supernode (rows beyond ns)
+    int ld, nbw;          // nbw <= 256
+    int ms, m;            // forward: own rows below / all rows below;  backward: m = columns left of K (a multiple of 64 tiles)
+};
+
+struct WideDiagTask {     // the 256 x 256 diagonal block D = L[K, K] with its (up to four) inverted 64 x 64 blocks
+    const double *D;      // panel + k0*ld + k0
+    const double *inv;    // inverse of the first 64-column block of K (the others follow at stride 64*64)
+    double *y;            // the nbw unknowns of K (stride ldy)
+    int ld, nbw;
+};
+
+template <int RB>
+__global__ void __launch_bounds__(256)
+fwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
+                     long long ldy, long long ldu) {
+    __shared__ double xs[SOLVE_WB][RB];
+    __shared__ double part[8][SOLVE_NB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const WideStepTask T = tasks[t];
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = tile * SOLVE_NB;
+    // all 64 loads of the thread's 2 rows x 32 columns are issued before anything waits on them
+    double l[4][8][2];
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int kk = b * SOLVE_NB + warp * 8 + i;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = row0 + lane + 32 * h;
+                l[b][i][h] = (kk < T.nbw && r < T.m) ? T.L[r + (long long)kk * T.ld] : 0.0;
+            }
+        }
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        xs[kk][q] = (kk < T.nbw && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double xv = xs[b * SOLVE_NB + warp * 8 + i][q];
+                a0 += l[b][i][0] * xv;
+                a1 += l[b][i][1] * xv;
+            }
+        part[warp][lane][q] = a0;
+        part[warp][lane + 32][q] = a1;
+    }
+    __syncthreads();
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+        const int r = row0 + rr;
+        if (r >= T.m || q >= nrhs) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += part[w][rr][q];
+        double *dst = (r < T.ms) ? (T.y + r + q * ldy) : (T.u + (r - T.ms) + q * ldu);
+        *dst -= s;
+    }
+}
+
+// x_K := L[K, K]^-1 y_K, block by block: x_b = inv_b y_b, then y_c -= L[c, b] x_b for the later blocks c of K
+template <int RB>
+__global__ void __launch_bounds__(256)
+fwd_wide_diag_kernel(const WideDiagTask *__restrict__ tasks, int nrhs, long long ldy) {
+    __shared__ double ys[SOLVE_WB][RB];
+    __shared__ double sp[4][SOLVE_NB][RB];
+    const WideDiagTask T = tasks[blockIdx.x];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        ys[kk][q] = (kk < T.nbw && q < nrhs) ? T.y[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+    const int nblk = (T.nbw + SOLVE_NB - 1) / SOLVE_NB;
+    for (int b = 0; b < nblk; b++) {
+        const int c0 = b * SOLVE_NB, nb = min(SOLVE_NB, T.nbw - c0);
+        // the rows of the later blocks against this block's columns: issued now, used after the block solve
+        const int r = c0 + SOLVE_NB + tid;                     // one thread per later row (<= 192 of them)
+        double lrow[SOLVE_NB];
+        const bool has = r < T.nbw;
+#pragma unroll
+        for (int c = 0; c < SOLVE_NB; c++) lrow[c] = (has && c < nb) ? T.D[r + (long long)(c0 + c) * T.ld] : 0.0;
+        double g[16];
+        load_inv_lower(g, T.inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, tid);
+        {
+            const int rr = tid & 63, prt = tid >> 6;
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    s0 += g[i] * ys[c0 + prt * 16 + i][q];
+                    s1 += g[i + 1] * ys[c0 + prt * 16 + i + 1][q];
+                }
+                sp[prt][rr][q] = s0 + s1;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+            const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+            if (rr < nb) ys[c0 + rr][q] = (sp[0][rr][q] + sp[1][rr][q]) + (sp[2][rr][q] + sp[3][rr][q]);
+        }
+        __syncthreads();
+        if (has) {
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < SOLVE_NB; c += 2) { s0 += lrow[c] * ys[c0 + c][q]; s1 += lrow[c + 1] * ys[c0 + c + 1][q]; }
+                ys[r][q] -= s0 + s1;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        if (kk < T.nbw && q < nrhs) T.y[kk + q * ldy] = ys[kk][q];
+    }
+}
+
+// backward: columns left of block row K = [k0, k0 + nbw): t[c] -= sum_{r in K} L[r, c] x_K[r]; a CTA owns 64 columns
+template <int RB>
+__global__ void __launch_bounds__(256)
+bwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs, long long ldy) {
+    __shared__ double xs[SOLVE_WB][RB];
+    const int t = find_task(tile_prefix, ntasks, blockIdx.x);
+    const WideStepTask T = tasks[t];
+    const int tile = blockIdx.x - tile_prefix[t];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = tile * SOLVE_NB + warp * 8;
+    double l[8][8];                                            // 8 columns x 8 rows (lane, lane + 32, ...)
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const int r = lane + 32 * h;
+            l[i][h] = (r < T.nbw && c0 + i < T.m) ? T.L[r + (long long)(c0 + i) * T.ld] : 0.0;
+        }
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        xs[kk][q] = (kk < T.nbw && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        if (q >= nrhs) break;
+        double xv[8];
+#pragma unroll
+        for (int h = 0; h < 8; h++) xv[h] = xs[lane + 32 * h][q];
+        double p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int h = 0; h < 8; h += 2) { s0 += l[i][h] * xv[h]; s1 += l[i][h + 1] * xv[h + 1]; }
+            p[i] = s0 + s1;
+        }
+        const double sum = warp_reduce8(p, lane);
+        const int cl = warp * 8 + warp_reduce8_index(lane);
+        const int c = tile * SOLVE_NB + cl;
+        if ((lane & 3) == 0 && c < T.m) T.y[c + q * ldy] -= sum;
+    }
+}
+
+// x_K := L[K, K]^-T t_K, blocks in reverse: x_b = inv_b^T t_b, then t_c -= L[b, c]^T x_b for the earlier blocks c of K
+template <int RB>
+__global__ void __launch_bounds__(256)
+bwd_wide_diag_kernel(const WideDiagTask *__restrict__ tasks, int nrhs, long long ldy) {
+    __shared__ double ys[SOLVE_WB][RB];
+    __shared__ double st[SOLVE_NB][RB];
+    const WideDiagTask T = tasks[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        ys[kk][q] = (kk < T.nbw && q < nrhs) ? T.y[kk + q * ldy] : 0.0;
+    }
+    __syncthreads();
+    const int nblk = (T.nbw + SOLVE_NB - 1) / SOLVE_NB;
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int r0 = b * SOLVE_NB, nb = min(SOLVE_NB, T.nbw - r0);
+        // x_b = inv_b^T t_b: warp owns 8 columns of the inverse, lanes own rows lane, lane + 32
+        double g[16];
+        load_inv_lower_t(g, T.inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, warp, lane);
+        // rows r0.. of the earlier columns: warp w takes columns w, w + 8, ... of [0, r0), lanes the rows of the block
+        for (int e = tid; e < SOLVE_NB * RB; e += 256) st[e % SOLVE_NB][e / SOLVE_NB] = ys[r0 + e % SOLVE_NB][e / SOLVE_NB];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            if (q >= nrhs) break;
+            double p[8];
+            const double t0 = lane < nb ? st[lane][q] : 0.0, t1 = lane + 32 < nb ? st[lane + 32][q] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = g[2 * i] * t0 + g[2 * i + 1] * t1;
+            const double sum = warp_reduce8(p, lane);
+            const int c = warp * 8 + warp_reduce8_index(lane);
+            if ((lane & 3) == 0 && c < nb) ys[r0 + c][q] = sum;
+        }
+        __syncthreads();
+        if (b > 0) {
+            // t_c -= L[b-rows, c]^T x_b for the r0 earlier columns (r0 is a multiple of 64): 64 columns per pass, a warp
+            // takes 8 of them with two rows per lane -- 16 loads in flight, then the fixed 8-way shuffle tree
+            for (int cb = 0; cb < r0; cb += SOLVE_NB) {
+                double l[8][2];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const double *col = T.D + (long long)(cb + warp * 8 + i) * T.ld + r0;
+                    l[i][0] = lane < nb ? col[lane] : 0.0;
+                    l[i][1] = lane + 32 < nb ? col[lane + 32] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < RB; q++) {
+                    if (q >= nrhs) break;
+                    const double x0 = lane < nb ? ys[r0 + lane][q] : 0.0, x1 = lane + 32 < nb ? ys[r0 + lane + 32][q] : 0.0;
+                    double p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) p[i] = l[i][0] * x0 + l[i][1] * x1;
+                    const double sum = warp_reduce8(p, lane);
+                    const int c = cb + warp * 8 + warp_reduce8_index(lane);
+                    if ((lane & 3) == 0) ys[c][q] -= sum;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+        const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+        if (kk < T.nbw && q < nrhs) T.y[kk + q * ldy] = ys[kk][q];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -462,7 +462,7 @@ class B200Backend:
         self.selinv_diag_cache = None
 
     LAUNCH_KINDS = ("assemble", "chain", "finalize", "front", "gemm_nn_s", "gemm_nn_l", "gemm_nt_s", "gemm_nt_l", "gemm_tt_s",
-                    "gemm_tt_l", "gather", "transpose", "fwd_asm", "fwd_step", "bwd_gather", "bwd_step", "panel", "split_reduce", "fwd_asm_wide", "rows_gather", "bwd_reduce", "assemble_g")
+                    "gemm_tt_l", "gather", "transpose", "fwd_asm", "fwd_step", "bwd_gather", "bwd_step", "panel", "split_reduce", "fwd_asm_wide", "rows_gather", "bwd_reduce", "assemble_g", "fwd_wstep", "fwd_wdiag", "bwd_wstep", "bwd_wdiag")
 
     def profile_plan(self, phase: int, nrhs: int = 1):
         """Per-launch (kind, grid, ms) of one phase: 0 factorization, 1 selinv, 2 forward sweep, 3 backward sweep."""

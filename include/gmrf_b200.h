@@ -245,7 +245,7 @@ int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather","syrk_gather","level_alap"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather","syrk_gather","level_alap","wide_steps"}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`
