@@ -125,6 +125,8 @@ struct gmrf_b200_handle {
     i64 n_large_tile_launches = 0, n_splitk_tasks = 0, n_fast_roots = 0, n_chain_launches = 0, n_front_launches = 0;
     double *d_base = nullptr;          // optional resident copy of a prior's nzval (Newton loops: Q_prior - H on the device)
     double *d_hdiag = nullptr;
+    long long *d_hpos = nullptr;       // nzval positions of a sparse observation Hessian (set_hessian_pattern)
+    i64 hpos_count = 0;
     long long *d_diagnz = nullptr;     // nzval position of every diagonal entry of the input pattern (-1: not stored)
     std::vector<long long> diag_nzpos;
     double *d_basis = nullptr;         // optional value basis (nbasis x nnz) for device-side assembly of nzval
@@ -2226,6 +2228,54 @@ int gmrf_b200_refactorize_base_minus_diag(gmrf_b200_handle *h, const double *dia
     return rc;
 }
 
+// Sparse observation Hessians (replaces _sparse_hessian_map + _subtract_sparse_hessian! + refactorize!,
+// src/workspace/gaussian_approximation.jl:31-83, backend.jl:178-189): the nzval positions of the Hessian's stored entries
+// are uploaded once per Newton loop, an iterate then moves nnz(H) doubles and forms Q_prior - H in HBM.
+int gmrf_b200_set_hessian_pattern(gmrf_b200_handle *h, const int64_t *nzpos, int64_t count, int index_base) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (count < 0 || (!nzpos && count > 0) || (index_base != 0 && index_base != 1)) { h->err = "set_hessian_pattern: bad arguments"; return GMRF_B200_ERR_ARG; }
+    std::vector<long long> p((size_t)count);
+    for (i64 k = 0; k < count; k++) {
+        p[(size_t)k] = nzpos[k] - index_base;
+        if (p[(size_t)k] < 0 || p[(size_t)k] >= h->S.nnzA) { h->err = "set_hessian_pattern: position outside the workspace pattern"; return GMRF_B200_ERR_ARG; }
+    }
+    {   // one owner per entry (no floating-point atomics): duplicates must be summed by the caller (a CSC matrix has none)
+        std::vector<long long> q(p);
+        std::sort(q.begin(), q.end());
+        if (std::adjacent_find(q.begin(), q.end()) != q.end()) { h->err = "set_hessian_pattern: duplicate positions"; return GMRF_B200_ERR_ARG; }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    dev_free(h, h->d_hpos);
+    h->hpos_count = 0;
+    if ((rc = dev_upload(h, &h->d_hpos, p))) return rc;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->hpos_count = count;
+    return 0;
+}
+
+int gmrf_b200_refactorize_base_minus_sparse(gmrf_b200_handle *h, const double *values, int64_t count) {
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (!h->d_base) { h->err = "refactorize_base_minus_sparse: call set_base_values first"; return GMRF_B200_ERR_STATE; }
+    if (count != h->hpos_count || (!values && count > 0)) { h->err = "refactorize_base_minus_sparse: values must match set_hessian_pattern"; return GMRF_B200_ERR_ARG; }
+    cudaStream_t st = h->stream;
+    if ((rc = ensure_io(h, std::max<i64>(count, 1)))) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_nz, h->d_base, sizeof(double) * (size_t)h->S.nnzA, cudaMemcpyDeviceToDevice, st));
+    if (count > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_io, values, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, st));
+        minus_sparse_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(h->d_nz, h->d_hpos, h->d_io, count);
+        if ((rc = check_launch(h, "sparse Hessian update"))) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], st));
+    rc = do_factor(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+    h->t_ms[0] = ms;
+    return rc;
+}
+
 // ---- lanes: several value sets factorized side by side ------------------------------------------------------
 // The workload of a hyperparameter sweep (`WorkspacePool` + `(model)(ws; theta...)`, workspace_pool.jl:42-119): many
 // independent numeric factorizations of ONE pattern whose only outputs are log-determinants. A handle created with the
@@ -2565,6 +2615,53 @@ int gmrf_b200_selinv_dot_basis(gmrf_b200_handle *h, double *out, int nbasis) {
         if ((rc = dev_upload(h, &h->d_qzw, w))) return rc;
     }
     return run_dot(h, h->d_qdst, h->d_qsrc, h->d_qzw, h->d_basis, (long long)S.nnzA, cnt, nbasis, out);
+}
+
+// diag(A Sigma A') for a sparse m x n design matrix A in CSR (replaces _row_diag_AΣAt, src/linear_predictor_marginals.jl:
+// 137-165: Sigma read at the pattern of A'A and contracted row by row): the panel positions of every index pair of a row
+// are looked up on the host (OpenMP over rows), positions and weights A_ia * A_ib go to the device, one warp per row
+// contracts them against Z in HBM. Pairs outside the factor's pattern count 0, like selinv_extract.
+int gmrf_b200_selinv_quadform_rows(gmrf_b200_handle *h, int64_t m, const int64_t *rowptr, const int64_t *colidx, const double *values,
+                                   int index_base, double *out) {
+    int rc = gmrf_b200_selinv_compute(h);
+    if (rc) return rc;
+    if (m < 0 || !rowptr || !out || (index_base != 0 && index_base != 1)) { h->err = "selinv_quadform_rows: bad arguments"; return GMRF_B200_ERR_ARG; }
+    if (m == 0) return 0;
+    const Symbolic &S = h->S;
+    const i64 nnz = rowptr[m] - index_base;
+    if (nnz < 0 || (nnz > 0 && (!colidx || !values))) { h->err = "selinv_quadform_rows: bad arguments"; return GMRF_B200_ERR_ARG; }
+    std::vector<long long> seg((size_t)m + 1, 0);
+    for (i64 i = 0; i < m; i++) {
+        const i64 c = rowptr[i + 1] - rowptr[i];
+        if (c < 0) { h->err = "selinv_quadform_rows: rowptr must be non-decreasing"; return GMRF_B200_ERR_ARG; }
+        seg[(size_t)i + 1] = seg[(size_t)i] + c * c;
+    }
+    for (i64 p = 0; p < nnz; p++)
+        if (colidx[p] - index_base < 0 || colidx[p] - index_base >= S.n) { h->err = "selinv_quadform_rows: column index out of range"; return GMRF_B200_ERR_ARG; }
+    const i64 tot = seg[(size_t)m];
+    std::vector<long long> pos((size_t)tot);
+    std::vector<double> w((size_t)tot);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (i64 i = 0; i < m; i++) {
+        const i64 lo = rowptr[i] - index_base, c = rowptr[i + 1] - rowptr[i];
+        long long q = seg[(size_t)i];
+        for (i64 a = 0; a < c; a++)
+            for (i64 b = 0; b < c; b++, q++) {
+                pos[(size_t)q] = gmrf::entry_position(S, colidx[lo + a] - index_base, colidx[lo + b] - index_base);
+                w[(size_t)q] = values[lo + a] * values[lo + b];
+            }
+    }
+    long long *d_pos = nullptr, *d_seg = nullptr;
+    double *d_w = nullptr, *d_out = nullptr;
+    auto cleanup = [&](int r) { dev_free(h, d_pos); dev_free(h, d_seg); dev_free(h, d_w); dev_free(h, d_out); return r; };
+    if ((rc = dev_upload(h, &d_pos, pos)) || (rc = dev_upload(h, &d_seg, seg)) || (rc = dev_upload(h, &d_w, w)) || (rc = dev_alloc(h, &d_out, (size_t)m)))
+        return cleanup(rc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device synchronize failed"; return cleanup(GMRF_B200_ERR_CUDA); }
+    segment_dot_kernel<<<(unsigned)((m * 32 + 255) / 256), 256, 0, h->stream>>>(h->d_Zx, d_pos, d_w, d_seg, m, d_out);
+    if ((rc = check_launch(h, "selinv_quadform_rows"))) return cleanup(rc);
+    if (cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "D2H copy failed"; return cleanup(GMRF_B200_ERR_CUDA); }
+    return cleanup(0);
 }
 
 // ---- introspection -------------------------------------------------------------------------------

@@ -1001,4 +1001,34 @@ __global__ void __launch_bounds__(256) gather_dot_final_kernel(const double *__r
     if (threadIdx.x == 0) out[blockIdx.y] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// out[i] = sum over the entries p of segment i of w[p] * Z[pos[p]] (pos < 0: outside the factor's pattern, counts 0):
+// diag(A Sigma A') of a sparse design matrix, one segment per row of A holding its nnz^2 index pairs
+// (_row_diag_AΣAt, src/linear_predictor_marginals.jl:137-165). One warp per row, lanes stride the segment, fixed
+// shuffle tree: bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+segment_dot_kernel(const double *__restrict__ Zx, const long long *__restrict__ pos, const double *__restrict__ w,
+                   const long long *__restrict__ segptr, long long nseg, double *__restrict__ out) {
+    const long long i = (blockIdx.x * 256LL + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= nseg) return;
+    double acc = 0.0;
+    for (long long p = segptr[i] + lane; p < segptr[i + 1]; p += 32) {
+        const long long q = pos[p];
+        if (q >= 0) acc += w[p] * Zx[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[i] = acc;
+}
+
+// nz[pos[k]] -= v[k] (positions unique): the Newton iterate Q_prior - H(x_k) for a SPARSE observation Hessian
+// (_subtract_sparse_hessian!, src/workspace/gaussian_approximation.jl:74-83) formed on values resident in HBM.
+__global__ void __launch_bounds__(256)
+minus_sparse_kernel(double *__restrict__ nz, const long long *__restrict__ pos, const double *__restrict__ v, long long cnt) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k < cnt) nz[pos[k]] -= v[k];
+}
+
 }  // namespace gmrf

@@ -855,6 +855,15 @@ void analyze(Symbolic &S, i64 n, const i64 *Ap, const i64 *Ai, const i64 *user_p
 // caller pattern -> panel offsets (selinv_extract / selinv_dot): one binary search in the owning supernode's row list
 // per entry, ~40 ns each single-threaded (cache-missing), so the columns are spread over the host cores
 // ------------------------------------------------------------------------------------------------
+long long entry_position(const Symbolic &S, i64 i, i64 j) {
+    const i64 a = S.iperm[i], b = S.iperm[j];
+    const i64 col = std::min(a, b), row = std::max(a, b);
+    const i64 s = S.col2super[col];
+    const i32 *rb = S.rowidx.data() + S.rowptr[s], *re = S.rowidx.data() + S.rowptr[s + 1];
+    const i32 *it = std::lower_bound(rb, re, (i32)row);
+    return (it != re && *it == (i32)row) ? (long long)(S.panel_off[s] + (col - S.sfirst[s]) * (i64)S.panel_ld[s] + (it - rb)) : -1LL;
+}
+
 i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i64 index_base, long long *pos) {
     const i64 n = S.n;
     i64 bad = -1;

@@ -102,6 +102,10 @@ void analyze(Symbolic &S, i64 n, const i64 *colptr, const i64 *rowval, const i64
 // Returns -1, or the index p of the first entry whose row index is out of range.
 i64 pattern_positions(const Symbolic &S, const i64 *colptr, const i64 *rowval, i64 index_base, long long *pos);
 
+// Offset in the panel array of entry (i, j) = (j, i) (ORIGINAL 0-based indices) of a symmetric matrix on the factor's stored
+// pattern, -1 outside it.
+long long entry_position(const Symbolic &S, i64 i, i64 j);
+
 // Persisting the analysis (the only state worth keeping across sessions / sharing between the handles of a pool):
 // a self-describing little-endian byte stream of every member of Symbolic plus a hash of the pattern it belongs to.
 // deserialize throws std::runtime_error on a malformed / truncated stream or a pattern mismatch.

@@ -387,6 +387,35 @@ class B200Backend:
         self.selinv_cache = None
         self.selinv_diag_cache = None
 
+    def set_hessian_pattern(self, nzpos: np.ndarray):
+        """nzval positions (0-based, distinct) of a sparse observation Hessian's stored entries -- `_sparse_hessian_map`
+        (src/workspace/gaussian_approximation.jl:31-61), uploaded once per Newton loop."""
+        p = np.ascontiguousarray(nzpos, dtype=np.int64) + INDEX_BASE
+        self._hd.check(self._L.gmrf_b200_set_hessian_pattern(self._hd._h, ptr(p), p.size, INDEX_BASE))
+
+    def refactorize_minus_sparse(self, values: np.ndarray):
+        """Refactorize Q_prior - H with H given by its stored values on the pattern of `set_hessian_pattern` (iterate formed in
+        HBM from the resident prior values of `set_base_values`): `_subtract_sparse_hessian!` (:74-83) + `refactorize!`."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        rc = self._L.gmrf_b200_refactorize_base_minus_sparse(self._hd._h, ptr(v), v.size)
+        self.status = self._hd.check(rc, allow_positive=not self.check_pd)
+        self.selinv_cache = None
+        self.selinv_diag_cache = None
+
+    def selinv_quadform_rows(self, A) -> np.ndarray:
+        """diag(A Sigma A') for a sparse design matrix A (m x n): `_row_diag_AΣAt` (src/linear_predictor_marginals.jl:137-165)
+        with Sigma contracted on the device; nothing but the m results comes back."""
+        A = sp.csr_matrix(A, dtype=np.float64)
+        A.sort_indices()
+        if A.shape[1] != self.n:
+            raise ValueError(f"design matrix has {A.shape[1]} columns but the field has {self.n} components")
+        rp = A.indptr.astype(np.int64) + INDEX_BASE
+        ci = A.indices.astype(np.int64) + INDEX_BASE
+        vals = np.ascontiguousarray(A.data, dtype=np.float64)
+        out = np.empty(A.shape[0], dtype=np.float64)
+        self._hd.check(self._L.gmrf_b200_selinv_quadform_rows(self._hd._h, A.shape[0], ptr(rp), ptr(ci), ptr(vals), INDEX_BASE, ptr(out)))
+        return out
+
     def lane_capacity(self) -> int:
         return int(self._L.gmrf_b200_lane_capacity(self._hd._h))
 

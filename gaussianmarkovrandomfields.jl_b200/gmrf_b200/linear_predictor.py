@@ -30,10 +30,17 @@ def linear_predictor_variances(ga: WorkspaceGMRF, A) -> np.ndarray:
     if A.shape[1] != len(ga):
         raise ValueError(f"design matrix has {A.shape[1]} columns but the field has {len(ga)} components")
     ga.ensure_loaded()
-    pattern = sp.csc_matrix(A.T @ A)
-    pattern.sort_indices()
-    sigma_local = ga.workspace.selinv_extract_at(pattern)
-    v = _row_diag_A_sigma_At(A, sigma_local)
+    be = ga.workspace.backend
+    if hasattr(be, "selinv_quadform_rows"):
+        # B200 backend: positions of the index pairs looked up on the host, Sigma contracted against them on the device
+        # (gmrf_b200_selinv_quadform_rows) -- Sigma never leaves HBM
+        ga.workspace.ensure_selinv()
+        v = be.selinv_quadform_rows(A)
+    else:
+        pattern = sp.csc_matrix(A.T @ A)
+        pattern.sort_indices()
+        sigma_local = ga.workspace.selinv_extract_at(pattern)
+        v = _row_diag_A_sigma_At(A, sigma_local)
     ci = ga.constraints
     if ci is not None:                                   # _subtract_constraint_correction! (:189-195)
         M = A @ ci.A_tilde_T

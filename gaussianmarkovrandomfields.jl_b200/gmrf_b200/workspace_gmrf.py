@@ -366,6 +366,7 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
         return _constrain_step(ws.workspace_solve(g), ws, constraints)
 
     hess_map = [None]                                                # sparse Hessians: index map built once (:257)
+    sparse_on_device = [False]
 
     def build_result(x_final):
         Q_p, _, _ = _prior_local(prior, x_final)
@@ -385,6 +386,13 @@ def gaussian_approximation(prior: WorkspaceGMRF, obs_lik, x0=None, max_iter: int
         hess_map[0] = _update_hessian(ws, H_k, Q_p.data, diag_idx, hess_map[0])
         if on_device and isinstance(H_k, np.ndarray) and H_k.ndim == 1:
             ws.backend.refactorize_minus_diag(H_k)          # same values as ws.Q, formed in HBM
+            ws.numeric_valid, ws.selinv_valid, ws.logdet_valid = True, False, False
+        elif on_device and hasattr(ws.backend, "refactorize_minus_sparse") and not isinstance(H_k, np.ndarray):
+            H_sparse = _csc(H_k)
+            if not sparse_on_device[0]:                      # positions uploaded once per loop (pattern is fixed, :257)
+                ws.backend.set_hessian_pattern(hess_map[0])
+                sparse_on_device[0] = True
+            ws.backend.refactorize_minus_sparse(H_sparse.data)   # nnz(H) doubles per iterate instead of nnz(Q)
             ws.numeric_valid, ws.selinv_valid, ws.logdet_valid = True, False, False
         else:
             ws.ensure_numeric()

@@ -253,6 +253,27 @@ function refactorize_minus_diag!(b::B200Backend, hdiag::Vector{Float64})
     return nothing
 end
 
+# ... and a SPARSE observation Hessian: `_sparse_hessian_map` (src/workspace/gaussian_approximation.jl:31-61) is uploaded once per
+# Newton loop as 1-based nzval positions, every iterate moves nnz(H) values (`_subtract_sparse_hessian!` :74-83 in HBM).
+set_hessian_pattern!(b::B200Backend, nzpos::Vector{Int}) =
+    _check(b, ccall((:gmrf_b200_set_hessian_pattern, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Cint), b.handle, nzpos, length(nzpos), 1))
+function refactorize_minus_sparse!(b::B200Backend, hvals::Vector{Float64})
+    _check(b, ccall((:gmrf_b200_refactorize_base_minus_sparse, libgmrf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), b.handle, hvals, length(hvals)))
+    b.selinv_cache = nothing; b.selinv_diag_cache = nothing
+    return nothing
+end
+
+# diag(A Sigma A') of a sparse design matrix, contracted on the device: the workspace method of `_row_diag_AΣAt`
+# (src/linear_predictor_marginals.jl:137-141). A is handed over as CSR = the CSC arrays of its transpose.
+function row_diag_AΣAt(b::B200Backend, A::SparseMatrixCSC{Float64,Int})
+    At = sparse(transpose(A))
+    out = Vector{Float64}(undef, size(A, 1))
+    _check(b, GC.@preserve At ccall((:gmrf_b200_selinv_quadform_rows, libgmrf), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Ptr{Float64}),
+        b.handle, size(A, 1), SparseArrays.getcolptr(At), rowvals(At), nonzeros(At), 1, out))
+    return out
+end
+
 # Lanes: B value sets of the same pattern per launch (handle created after `set_option("lanes", B)`); returns the B
 # log-determinants and status words. Lane 0 stays the backend's factor.
 set_option(key::AbstractString, value::Real) = ccall((:gmrf_b200_set_option, libgmrf), Cint, (Cstring, Cdouble), key, value)
@@ -284,5 +305,14 @@ function device_array(b::B200Backend, which::Integer)
 end
 adopt_factor!(b::B200Backend, logdet::Float64; with_selinv::Bool = false) =
     _check(b, ccall((:gmrf_b200_adopt_factor, libgmrf), Cint, (Ptr{Cvoid}, Cdouble, Cint), b.handle, logdet, with_selinv))
+# ... guarded: the sender's analysis fingerprint must equal the receiver's, its pivot status travels along
+function analysis_fingerprint(b::B200Backend)
+    f = Ref{UInt64}(0)
+    _check(b, ccall((:gmrf_b200_analysis_fingerprint, libgmrf), Cint, (Ptr{Cvoid}, Ref{UInt64}), b.handle, f))
+    return f[]
+end
+adopt_factor!(b::B200Backend, fingerprint::UInt64, logdet::Float64, status::Integer; with_selinv::Bool = false) =
+    _check(b, ccall((:gmrf_b200_adopt_factor_checked, libgmrf), Cint, (Ptr{Cvoid}, UInt64, Cdouble, Cint, Cint),
+                    b.handle, fingerprint, logdet, status, with_selinv))
 
 end # module

@@ -96,6 +96,13 @@ int gmrf_b200_refactorize_combination(gmrf_b200_handle *h, const double *coeff, 
  * (src/workspace/gaussian_approximation.jl:96-129, _subtract_diagonal_hessian! :63-72) + refactorize! (backend.jl:178-189). */
 int gmrf_b200_set_base_values(gmrf_b200_handle *h, const double *nzval, int64_t nnz);
 int gmrf_b200_refactorize_base_minus_diag(gmrf_b200_handle *h, const double *diag, int64_t n);
+/* The same for a SPARSE observation Hessian whose pattern lies inside the workspace's. replaces _sparse_hessian_map (built
+ * once per Newton loop, gaussian_approximation.jl:31-61) + _subtract_sparse_hessian! (:74-83) + refactorize!:
+ * set_hessian_pattern uploads the nzval positions (in `index_base`) of the Hessian's stored entries once -- they must be
+ * distinct (a CSC matrix has no duplicates; one owner per entry, no floating-point atomics) --, every iterate then moves
+ * `count` values and refactorizes Q_prior - H formed in HBM. */
+int gmrf_b200_set_hessian_pattern(gmrf_b200_handle *h, const int64_t *nzpos, int64_t count, int index_base);
+int gmrf_b200_refactorize_base_minus_sparse(gmrf_b200_handle *h, const double *values, int64_t count);
 
 /* Lanes: B independent value sets of the SAME pattern factorized side by side by the same launches -- the workload of a
  * hyperparameter sweep over a `WorkspacePool` (src/workspace/workspace_pool.jl:42-119, `(model)(ws; theta...)`
@@ -155,6 +162,13 @@ int gmrf_b200_selinv_dot(gmrf_b200_handle *h, int64_t ncol, const int64_t *colpt
  * when Q is a fixed-pattern combination. The B_j are read as symmetric matrices through their stored upper
  * triangle, like the factorization reads Q. Nothing but nbasis doubles crosses PCIe. */
 int gmrf_b200_selinv_dot_basis(gmrf_b200_handle *h, double *out, int nbasis);
+
+/* replaces  _row_diag_AΣAt(ws, A)   src/linear_predictor_marginals.jl:137-165 : out[i] = sum_{j,k} A_ij A_ik Sigma_jk for
+ * the m rows of a sparse design matrix A (CSR, m x n, indices in `index_base`) -- the marginal variances of a linear
+ * predictor eta = A x -- contracted against Z on the device (one warp per row, fixed reduction order). Sigma entries
+ * outside the factor's pattern count 0, like selinv_extract. */
+int gmrf_b200_selinv_quadform_rows(gmrf_b200_handle *h, int64_t m, const int64_t *rowptr, const int64_t *colidx,
+                                   const double *values, int index_base, double *out);
 
 /* ---- factor export ------------------------------------------------------------------------------
  * replaces  sparse_cho_sqrt(cho) = sparse(cho.L)[invperm(cho.p), :]   src/linear_maps/cholesky_sqrt.jl:6-21

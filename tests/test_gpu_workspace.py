@@ -566,3 +566,80 @@ def test_adopting_a_factor_from_a_different_analysis_is_refused():
     assert twin.status == 17
     for x in (a, b, twin):
         x.close()
+
+
+def test_linear_predictor_rows_contracted_on_the_device():
+    """diag(A Sigma A') (`_row_diag_AΣAt`, src/linear_predictor_marginals.jl:137-165) through gmrf_b200_selinv_quadform_rows:
+    the index pairs of every row are looked up on the host, Sigma is contracted against them in HBM. Rows whose pairs all
+    lie inside the factor's pattern (point and local-stencil observations) must match the dense answer to the marginal-
+    variance tolerance; 0- and 1-based entry give identical bits; an empty row gives 0."""
+    from gmrf_b200.backend import index_base
+    Q = FIX["grid3d_12"]
+    n = Q.shape[0]
+    Sigma = np.linalg.inv(Q.toarray())
+    rng = np.random.default_rng(8)
+    rows = []
+    for i in range(40):
+        if i == 7:
+            rows.append(np.zeros(n))                                  # an empty row
+            continue
+        r = np.zeros(n)
+        j = rng.integers(n)
+        nb = Q[:, [j]].nonzero()[0]                                   # j and its stencil neighbours: pairs inside pattern(Q^2) at most
+        pick = rng.choice(nb, size=min(len(nb), rng.integers(1, 4)), replace=False)
+        r[pick] = rng.standard_normal(pick.size)
+        rows.append(r)
+    A = sp.csr_matrix(np.array(rows))
+    be = B200Backend(Q, device=0)
+    v = be.selinv_quadform_rows(A)
+    Z = be.get_selinv()
+    inside = np.array([all(Z[a, b] != 0.0 for a in A[i].indices for b in A[i].indices) for i in range(A.shape[0])])
+    want = np.einsum("ij,jk,ik->i", A.toarray(), Sigma, A.toarray())
+    assert inside.sum() >= 20 and v[7] == 0.0
+    assert np.allclose(v[inside], want[inside], rtol=1e-8, atol=0)
+    # every row equals the contraction of the materialised selected inverse (zeros outside the pattern), whatever the row
+    ref = np.array([A[i].data @ (Z[A[i].indices][:, A[i].indices].toarray() @ A[i].data) if A[i].nnz else 0.0 for i in range(A.shape[0])])
+    assert np.allclose(v, ref, rtol=1e-12, atol=1e-300)
+    with index_base(1):
+        be1 = B200Backend(Q, ordering=be.permutation(), device=0)
+        assert np.array_equal(be1.selinv_quadform_rows(A), v)
+        be1.close()
+    with pytest.raises(ValueError):
+        be.selinv_quadform_rows(sp.csr_matrix((3, n + 1)))
+    be.close()
+
+
+def test_sparse_hessian_iterate_formed_on_the_device():
+    """Q_k = Q_prior - H_k for a SPARSE observation Hessian (`_subtract_sparse_hessian!`, gaussian_approximation.jl:74-83)
+    formed in HBM from nnz(H) uploaded values must equal the host-assembled iterate bit for bit."""
+    from gmrf_b200.workspace_gmrf import _sparse_hessian_map
+    model = spde.MaternSPDE(*spde.mesh2d(20), 1)
+    Q = model.precision(1.0, 0.5)
+    n = Q.shape[0]
+    rng = np.random.default_rng(9)
+    # a Hessian pattern inside Q's: the diagonal plus a random third of the off-diagonal entries, symmetric
+    M = sp.triu(Q, 1).tocoo()
+    keep = rng.random(M.nnz) < 0.33
+    U = sp.csc_matrix((np.ones(keep.sum()), (M.row[keep], M.col[keep])), shape=(n, n))
+    P = sp.csc_matrix(U + U.T + sp.identity(n)); P.sort_indices()
+    be = B200Backend(Q, device=0)
+    be.set_base_values(Q.data)
+    hmap = _sparse_hessian_map(Q, P)
+    be.set_hessian_pattern(hmap)
+    b = rng.standard_normal(n)
+    for _ in range(3):
+        H = P.copy()
+        H.data = -0.05 * np.abs(rng.standard_normal(H.nnz))          # negative semi-definite-ish: Q - H stays SPD here
+        H = sp.csc_matrix((H + H.T) * 0.5); H.sort_indices()
+        assert np.array_equal(H.indices, P.indices)
+        Qk = Q.copy()
+        np.subtract.at(Qk.data, hmap, H.data)
+        be.refactorize(Qk)
+        ld, x = be.compute_logdet(), be.backend_solve(b)
+        be.refactorize_minus_sparse(H.data)
+        assert be.status == 0 and be.compute_logdet() == ld and np.array_equal(be.backend_solve(b), x)
+    with pytest.raises(ValueError):
+        be.set_hessian_pattern(np.array([0, 0]))                      # duplicates have no single owner
+    with pytest.raises(ValueError):
+        be.refactorize_minus_sparse(np.ones(3))
+    be.close()
