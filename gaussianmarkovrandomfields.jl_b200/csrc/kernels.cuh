@@ -929,13 +929,11 @@ transpose_inplace_kernel(const TransTask *__restrict__ tasks, const int *__restr
     __shared__ double s1[32][33], s2[32][33];
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const TransTask T = tasks[t];
-    const int nt = (T.n + 31) / 32;
     // enumerate tile pairs (ti >= tj) from the linear index
     int local = blockIdx.x - tile_prefix[t];
     int ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= local) ti++;
     const int tj = local - ti * (ti + 1) / 2;
-    (void)nt;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int yy = ty; yy < 32; yy += 8) {
         int r = ti * 32 + tx, c = tj * 32 + yy;

@@ -7,6 +7,8 @@
  *   factor_nnz + factor_pattern(…, 1) + factor_values                         :177-184
  *   analysis_export (size query, then the blob) + create_from_analysis(…, 1)  :192-194, :59-61
  *   get_perm(…, 1), destroy                                                    :70
+ *   selinv_quadform_rows(…, 1), set_base_values / refactorize_base_minus_diag, set_hessian_pattern(…, 1) /
+ *   refactorize_base_minus_sparse                                            (the device-side consumers of the glue)
  * The matrix is the reference's first deterministic fixture (test/workspace/test_backend_ordering.jl:9-17: 12 x 12 grid
  * Laplacian + 0.1 I with a dense border row/column), answers are checked against a dense Cholesky written here.
  * Exit code 0 = every check passed.  cc julia_ccall_replay.c -I include -L lib -lgmrf_b200 -lm */
@@ -142,6 +144,39 @@ int main(void) {
         if (gmrf_b200_refactorize(h2, nzval, nnz) != 0) { fprintf(stderr, "refactorize (restored handle) failed\n"); return 1; }
         double ld2 = 0.0; gmrf_b200_logdet(h2, &ld2);
         REQUIRE(ld2 == ld, "restored analysis reproduces the log-determinant bit for bit");
+        /* diag(A Sigma A') of a sparse design matrix in CSR, 1-based (row_diag_AΣAt in the glue): point observations and
+         * one two-point row on grid neighbours (pairs inside Q's pattern, hence inside the factor's) */
+        {
+            int64_t rp[5] = {1, 2, 3, 5, 5}, ci[4] = {1, 77, 10, 11};          /* 4 rows; the last one is empty */
+            double av[4] = {1.0, 2.0, 0.5, -1.5}, qf[4];
+            CHECK(gmrf_b200_selinv_quadform_rows(h, 4, rp, ci, av, 1, qf), "selinv_quadform_rows");
+            double want2 = 0.25 * inv[9 + 9 * (size_t)n] + 2.25 * inv[10 + 10 * (size_t)n] + 2.0 * 0.5 * -1.5 * inv[9 + 10 * (size_t)n];
+            REQUIRE(fabs(qf[0] - inv[0]) <= 1e-8 * inv[0], "quadform row 1 = Sigma_11");
+            REQUIRE(fabs(qf[1] - 4.0 * inv[76 + 76 * (size_t)n]) <= 1e-8 * 4.0 * inv[76 + 76 * (size_t)n], "quadform row 2 = 4 Sigma_77,77");
+            REQUIRE(fabs(qf[2] - want2) <= 1e-8 * fabs(want2) + 1e-14, "quadform row 3 (two neighbouring sites)");
+            REQUIRE(qf[3] == 0.0, "quadform of an empty row");
+        }
+        /* Newton iterates formed in HBM: prior values resident, a diagonal and a sparse Hessian update (1-based positions) */
+        {
+            CHECK(gmrf_b200_set_base_values(h, nzval, nnz), "set_base_values");
+            double *hd = malloc(sizeof(double) * n), *nz2 = malloc(sizeof(double) * nnz);
+            memcpy(nz2, nzval, sizeof(double) * nnz);
+            int64_t *hp = malloc(sizeof(int64_t) * n);
+            for (int j = 0; j < n; j++) {
+                hd[j] = -0.25 - 0.01 * j;
+                for (int64_t k = colptr[j] - 1; k < colptr[j + 1] - 1; k++) if (rowval[k] - 1 == j) { nz2[k] -= hd[j]; hp[j] = k + 1; }
+            }
+            double ld_host = 0.0, ld_dev = 0.0, ld_sp = 0.0;
+            CHECK(gmrf_b200_refactorize(h, nz2, nnz), "refactorize (host-assembled iterate)");
+            gmrf_b200_logdet(h, &ld_host);
+            CHECK(gmrf_b200_refactorize_base_minus_diag(h, hd, n), "refactorize_base_minus_diag");
+            gmrf_b200_logdet(h, &ld_dev);
+            CHECK(gmrf_b200_set_hessian_pattern(h, hp, n, 1), "set_hessian_pattern");
+            CHECK(gmrf_b200_refactorize_base_minus_sparse(h, hd, n), "refactorize_base_minus_sparse");
+            gmrf_b200_logdet(h, &ld_sp);
+            REQUIRE(ld_dev == ld_host && ld_sp == ld_host, "device-formed iterates are bit-identical to the host-assembled one");
+            CHECK(gmrf_b200_refactorize(h, nzval, nnz), "refactorize (back to Q)");
+        }
         /* error behaviour the glue maps to ArgumentError: nnz mismatch */
         REQUIRE(gmrf_b200_refactorize(h, nzval, nnz - 1) == GMRF_B200_ERR_ARG, "nnz mismatch is GMRF_B200_ERR_ARG");
         gmrf_b200_destroy(h2);
