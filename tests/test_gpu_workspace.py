@@ -643,3 +643,41 @@ def test_sparse_hessian_iterate_formed_on_the_device():
     with pytest.raises(ValueError):
         be.refactorize_minus_sparse(np.ones(3))
     be.close()
+
+
+@pytest.mark.parametrize("opts", [{}, {"fused_front": 0}, {"fused_front": 0, "fused_chain": 0}, {"fused_front": 0, "asm_gather": 0},
+                                  {"fused_front": 0, "syrk_gather": 1}])
+def test_supernode_with_many_children(opts):
+    """A root with 14 children (more than the 4 whose inverse maps the fused kernels keep resident at once): 14 dense
+    blocks of different sizes coupled only through a 9-variable border. Exercises the multi-pass paths of the one-CTA front
+    kernel, of the gather extend-add and of the gathering SYRK tail against dense LinearAlgebra."""
+    rng = np.random.default_rng(21)
+    sizes = [5, 9, 17, 33, 12, 7, 21, 40, 6, 14, 27, 8, 19, 11]
+    nb = 9
+    n = sum(sizes) + nb
+    D = np.zeros((n, n))
+    o = 0
+    for m in sizes:
+        B = rng.standard_normal((m, m))
+        D[o:o + m, o:o + m] = B @ B.T + m * np.eye(m)
+        C = 0.3 * rng.standard_normal((m, nb)) * (rng.random((m, nb)) < 0.7)
+        D[o:o + m, n - nb:] = C
+        D[n - nb:, o:o + m] = C.T
+        o += m
+    Bb = rng.standard_normal((nb, nb))
+    D[n - nb:, n - nb:] = Bb @ Bb.T + 40.0 * np.eye(nb)
+    Q = sp.csc_matrix(D); Q.sort_indices()
+    perm = np.arange(n)                                       # natural order: blocks first, border last -> one root, 14 children
+    defaults = {"fused_front": 1, "fused_chain": 1, "asm_gather": 1, "syrk_gather": 0}
+    try:
+        for k, v in {**defaults, **opts}.items():
+            _lib.set_option(k, v)
+        be = B200Backend(Q, ordering=perm, device=0)
+    finally:
+        for k, v in defaults.items():
+            _lib.set_option(k, v)
+    assert abs(be.compute_logdet() - np.linalg.slogdet(D)[1]) <= 1e-10 * abs(np.linalg.slogdet(D)[1])
+    b = rng.standard_normal(n)
+    assert _rel(be.backend_solve(b), np.linalg.solve(D, b)) <= 1e-10
+    assert np.allclose(be.get_selinv_diag(), np.diag(np.linalg.inv(D)), rtol=1e-8)
+    be.close()
