@@ -711,7 +711,7 @@ void build_factor_plan(gmrf_b200_handle *h, Builder &B, const FusedInfo &F) {
             g.pad_ = (kids && syrk_gather) ? (int)s + 1 : 0;
             gt.push_back(g);
         }
-        B.add_gemm(plan, gt, 0);
+        B.add_gemm(plan, gt, 0, false, 1.0, /*allow_split=*/h->opt.syrk_split != 0);
         B.add_finalize(plan);
     }
 }
@@ -1836,6 +1836,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "level_alap") o.level_alap = (int)value;
     else if (k == "syrk_gather") o.syrk_gather = (int)value;
     else if (k == "wide_steps") o.wide_steps = (int)value;
+    else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
     else if (k == "chain_max_tiles") o.chain_max_tiles = std::max(0, (int)value);

@@ -26,7 +26,7 @@ struct Options {
     int use_graph = 1;
     int outer_block = 256;   // outer panel block (columns) of the two-level blocked factorization
     int naive_kernels = 0;
-    int splitk_min_k = 1024;  // split-K: a k-slice is at least this long (tests lower it to reach the path on small inputs)
+    int splitk_min_k = 128;   // split-K: a k-slice is at least this long (1024 in round 1; 128 measured 4-7 % faster on the 2D configs, neutral at 1 M dofs: profiles/r02_sweep_opts_splitk.log)
     int wide_rhs_min = 8;     // more right-hand sides than this take the GEMM (wide) solve path in blocks of 64 columns
     int bwd_row_chunk = 2048; // backward sweep: rows of L21 per partial task (taller panels are reduced in a second pass)
     int large_tile_mask = 1;  // GEMM operand-layout variants (bit 0 NN, 1 NT, 2 TT) allowed to use the 128 x 64 tile (measured: only NN gains)
@@ -34,6 +34,7 @@ struct Options {
     int selinv_fast_root = 1; // triangular (trtri + lauum) route for top-level root supernodes in the selected inversion
     int syrk_gather = 0;      // update-matrix products gather their children's contributions in a tail of the GEMM (U written once). Measured at 1 M dofs (profiles/r02_plan_3d100_syrk_gather.log): extend-add 60 -> 33 ms but the products +50 ms (the tail is not hidden behind the other CTAs), so off by default
     int wide_steps = 0;       // few-RHS triangular solves advance 256 columns per step on supernodes with more than 256 columns (two launches per step: update + one-CTA diagonal-block solve). Measured at 1 M dofs (profiles/r02_plan_solve_3d100_wide_vs_narrow.log): 20.3 ms against 18.7 ms for the 64-column steps with their look-ahead block solve -- the serial diagonal kernels (15 us x 222 per direction) cost more than the halved launch count saves; off by default
+    int syrk_split = 0;       // allow split-K on the update-matrix products as well (few-tile launches at the top of 2D trees)
     int level_alap = 1;       // assembly-tree levels counted from the roots (as late as possible) instead of from the leaves
     int asm_gather = 1;       // extend-add as a gather through TMA-staged shared memory (0: the first, scatter-shaped kernel)
     int fused_front = 1;      // one-CTA-per-front kernel for tree levels whose panels all fit in shared memory

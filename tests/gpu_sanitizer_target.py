@@ -14,7 +14,7 @@ cases = [("3d:12 default", spde.MaternSPDE(*spde.mesh3d(12), 0), {}),
          ("2d:48 chain everywhere", spde.MaternSPDE(*spde.mesh2d(48), 1), {"fused_front": 0, "chain_max_tiles": 100000}),
          ("3d:12 bulk path, scatter extend-add, split-K", spde.MaternSPDE(*spde.mesh3d(12), 0),
           {"fused_front": 0, "fused_chain": 0, "asm_gather": 0, "splitk_min_k": 32})]
-defaults = {"fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "asm_gather": 1, "splitk_min_k": 1024}
+defaults = {"fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "asm_gather": 1, "splitk_min_k": 128}
 for name, model, opts in cases:
     for k, v in {**defaults, **opts}.items():
         _lib.set_option(k, v)

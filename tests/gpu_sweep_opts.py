@@ -5,9 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "gaussianmarkovrandomfields.jl_b200")]
 from gmrf_b200 import spde, _lib
 from gmrf_b200.backend import B200Backend
-defaults = {"fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "asm_gather": 1, "level_alap": 1, "front_smem_kb": 200}
-variants = [{}, {"chain_max_tiles": 400}, {"chain_max_tiles": 800}, {"chain_max_tiles": 2000}, {"front_smem_kb": 100}, {"front_smem_kb": 70},
-            {"fused_front": 0}, {"fused_chain": 0}, {"fused_front": 0, "fused_chain": 0}, {"asm_gather": 0}, {"level_alap": 0},
+defaults = {"fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "asm_gather": 1, "level_alap": 1, "front_smem_kb": 200, "splitk_min_k": 128, "outer_block": 256, "syrk_split": 0}
+variants = [{}, {"splitk_min_k": 64}, {"splitk_min_k": 128}, {"splitk_min_k": 256}, {"splitk_min_k": 64, "syrk_split": 1},
+            {"splitk_min_k": 128, "syrk_split": 1}, {"splitk_min_k": 256, "syrk_split": 1},
             {"fused_front": 0, "fused_chain": 0, "asm_gather": 0, "level_alap": 0}]
 for cells in (224, 316, 500):
     model = spde.MaternSPDE(*spde.mesh2d(cells), 1)
