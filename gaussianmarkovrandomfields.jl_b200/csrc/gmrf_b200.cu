@@ -41,6 +41,8 @@ struct Launch {
     int kind;
     int aux;            // panel step: NBT bucket; front launch: dynamic shared memory (bytes)
     int aux2 = 0;       // front launch: widest diagonal block (selects the kernel instantiation)
+    double flops = 0;   // GEMM launches: algorithmic flops of the launch's tasks (diagnostics)
+    int kmax = 0;       // GEMM launches: longest contraction
     i64 task_off;       // first task in the kind's task array
     int ntasks;
     i64 prefix_off;     // offset into the tile-prefix array (ntasks+1 entries) or -1
@@ -334,6 +336,8 @@ struct Builder {
                 prefix.push_back((int)tot);
                 tot += (i64)cdiv(t.m, BM) * cdiv(t.n, BN);
                 gemm.push_back(t);
+                L.flops += 2.0 * t.m * (double)t.n * t.k * ((t.flags & GEMM_LOWER) ? 0.5 * ((double)t.n <= t.m ? (2.0 - (double)t.n / t.m) : 1.0) : 1.0);
+                L.kmax = std::max(L.kmax, t.k);
             }
             prefix.push_back((int)tot);
             if (tot > INT_MAX) throw std::runtime_error("too many GEMM tiles in one launch");
@@ -2968,6 +2972,21 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
         CUDA_TRY(h, cudaStreamSynchronize(st));
     }
     return check_launch(h, "profile_plan");
+}
+
+// Static facts of the launches of a phase (same order as profile_plan): flops = algorithmic flops of GEMM launches, kmax
+// = their longest contraction, ntasks = tasks in the launch.
+int gmrf_b200_plan_launch_info(gmrf_b200_handle *h, int phase, int64_t cap, double *flops, int *kmax, int *ntasks, int64_t *count) {
+    if (!h || !count) return GMRF_B200_ERR_ARG;
+    const Plan *plan = phase == 0 ? &h->factor_plan : phase == 1 ? &h->selinv_plan : phase == 2 ? &h->fwd_plan : phase == 3 ? &h->bwd_plan : nullptr;
+    if (!plan) { h->err = "plan_launch_info: phase must be 0..3"; return GMRF_B200_ERR_ARG; }
+    *count = (int64_t)plan->launches.size();
+    for (size_t i = 0; i < plan->launches.size() && (int64_t)i < cap; i++) {
+        if (flops) flops[i] = plan->launches[i].flops;
+        if (kmax) kmax[i] = plan->launches[i].kmax;
+        if (ntasks) ntasks[i] = plan->launches[i].ntasks;
+    }
+    return 0;
 }
 
 // clock64 stamps of the phases of the last fused chain launch of one refactorization (tile 1): [0] start, [1] tiles

@@ -34,7 +34,7 @@ EXPORTS = [
     "gmrf_b200_factor_nnz", "gmrf_b200_factor_pattern", "gmrf_b200_factor_values", "gmrf_b200_pattern_positions",
     "gmrf_b200_create_from_analysis", "gmrf_b200_analysis_export", "gmrf_b200_analysis_equal",
     "gmrf_b200_debug_chain_phases", "gmrf_b200_analysis_fingerprint", "gmrf_b200_adopt_factor_checked",
-    "gmrf_b200_set_hessian_pattern", "gmrf_b200_refactorize_base_minus_sparse", "gmrf_b200_selinv_quadform_rows",
+    "gmrf_b200_plan_launch_info", "gmrf_b200_set_hessian_pattern", "gmrf_b200_refactorize_base_minus_sparse", "gmrf_b200_selinv_quadform_rows",
 ]
 
 _lib = None
@@ -159,6 +159,8 @@ def lib():
     L.gmrf_b200_analysis_fingerprint.argtypes = [c_vp, ctypes.POINTER(ctypes.c_uint64)]
     L.gmrf_b200_adopt_factor_checked.restype = ctypes.c_int
     L.gmrf_b200_adopt_factor_checked.argtypes = [c_vp, ctypes.c_uint64, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+    L.gmrf_b200_plan_launch_info.restype = ctypes.c_int
+    L.gmrf_b200_plan_launch_info.argtypes = [c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.gmrf_b200_set_hessian_pattern.restype = ctypes.c_int
     L.gmrf_b200_set_hessian_pattern.argtypes = [c_vp, c_vp, c_i64, ctypes.c_int]
     L.gmrf_b200_refactorize_base_minus_sparse.restype = ctypes.c_int

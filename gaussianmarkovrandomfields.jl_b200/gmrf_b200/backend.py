@@ -502,6 +502,15 @@ class B200Backend:
         self._hd.check(self._L.gmrf_b200_profile_plan(self._hd._h, phase, nrhs, n, ptr(kind), ptr(grid), ptr(ms), ctypes.byref(cnt)))
         return [(self.LAUNCH_KINDS[k], int(g), float(t)) for k, g, t in zip(kind, grid, ms)]
 
+    def plan_launch_info(self, phase: int):
+        """(flops, kmax, ntasks) arrays of the launches of a phase, in `profile_plan`'s order (GEMM launches only carry flops)."""
+        cnt = ctypes.c_int64()
+        self._hd.check(self._L.gmrf_b200_plan_launch_info(self._hd._h, phase, 0, None, None, None, ctypes.byref(cnt)))
+        n = cnt.value
+        fl = np.zeros(n); km = np.zeros(n, dtype=np.int32); nt = np.zeros(n, dtype=np.int32)
+        self._hd.check(self._L.gmrf_b200_plan_launch_info(self._hd._h, phase, n, ptr(fl), ptr(km), ptr(nt), ctypes.byref(cnt)))
+        return fl, km, nt
+
     def pin_host_buffer(self, arr: np.ndarray) -> bool:
         """Page-lock a caller-owned numpy buffer for asynchronous H2D copies (no-op without a device)."""
         # Only large buffers are registered: they are mmap-backed (own pages), whereas page-locking a small heap

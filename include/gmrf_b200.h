@@ -233,6 +233,9 @@ int gmrf_b200_profile_refactorize(gmrf_b200_handle *h, double *ms, int64_t *coun
  * entries of kind[] (internal launch kind), grid[] (CTAs) and ms[] are filled; *count = launches in the phase. */
 int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap, int *kind, int *grid, double *ms,
                            int64_t *count);
+/* Static facts of the launches of a phase, in profile_plan's order: algorithmic flops and longest contraction of the GEMM
+ * launches, tasks per launch (diagnostics: per-launch TFLOP/s = flops / ms). */
+int gmrf_b200_plan_launch_info(gmrf_b200_handle *h, int phase, int64_t cap, double *flops, int *kmax, int *ntasks, int64_t *count);
 /* Diagnostics: SM clock stamps of the phases of the last fused chain-step launch of one refactorization (7 values). */
 int gmrf_b200_debug_chain_phases(gmrf_b200_handle *h, int64_t *stamps, int n);
 /* Numeric factor / selected inverse panels copied back to the host (tests, CholeskySqrt-style export). */

@@ -41,6 +41,18 @@ for phase in phases:
         print(f"   launches {a}..{b_} (index kind grid ms):")
         for i in range(a, min(b_, len(rows))):
             print(f"     {i:6d} {rows[i][0]:12s} {rows[i][1]:8d} {rows[i][2]:9.4f}")
+    if phase in (0, 1):
+        # GEMM launches by contraction length: time, algorithmic flops, TFLOP/s
+        fl, km, nt = b.plan_launch_info(phase)
+        if len(fl) == len(rows):
+            classes = [(0, 64), (65, 128), (129, 256), (257, 512), (513, 1024), (1025, 4096), (4097, 10 ** 9)]
+            print("   GEMM launches by longest contraction k (launches, ms, Gflop, TFLOP/s, avg tiles):")
+            for lo, hi in classes:
+                sel = [i for i in range(len(rows)) if rows[i][0].startswith("gemm") and lo <= km[i] <= hi]
+                if not sel:
+                    continue
+                tms = sum(rows[i][2] for i in sel); f = sum(fl[i] for i in sel)
+                print(f"     k in [{lo:5d}, {hi if hi < 10 ** 9 else 'inf':>5}] {len(sel):6d} {tms:10.3f} {f / 1e9:12.2f} {f / (tms * 1e-3) / 1e12 if tms > 0 else 0:8.2f} {sum(rows[i][1] for i in sel) / len(sel):10.1f}")
     # cumulative time by position (coarse timeline in 20 buckets)
     nb = 20
     step = max(1, len(rows) // nb)
