@@ -408,7 +408,7 @@ def sweep_config3(world, rank, local, small=False):
             "limiter": "device time of the lane-batched factorizations (latency-bound 2D fronts); host side = 16 coefficient triples per call"}
 
 
-def sampling_config5(world, rank, local, small=False):
+def sampling_config5(world, rank, local, small=False, nt=None):
     """BASELINE config 5 at 101^2 x 50 = 510,050 latent dofs (the 2 M-latent size does not fit one B200 in this layout):
     space-time advection-diffusion posterior, 1024 posterior samples. Variant A: rank 0 factorizes, the numeric factor
     travels to the peers by NCCL broadcast out of / into the handles' HBM, every rank draws 1024 / N samples (one blocked
@@ -418,7 +418,8 @@ def sampling_config5(world, rank, local, small=False):
     from gmrf_b200 import spde
     from gmrf_b200.backend import B200Backend
     from gmrf_b200.sharding import broadcast_factor, shard_range
-    cells, nt, m = (24, 10, 256) if small else (100, 50, 1024)
+    cells, nt_default, m = (24, 10, 256) if small else (100, 50, 1024)
+    nt = nt or nt_default
     dev = torch.device("cuda", local)
     t0 = time.perf_counter()
     coords, tri = spde.mesh2d(cells)

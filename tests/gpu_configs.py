@@ -179,7 +179,7 @@ def config3():
 
 
 def config5():
-    cells, nt = (40, 20) if small else (100, 50)
+    cells, nt = (40, 20) if small else (100, 100) if "--big5" in sys.argv else (100, 50)    # --big5: 101^2 x 100 = 1,020,100 latent
     coords, tri = spde.mesh2d(cells)
     model = spde.AdvectionDiffusionSSM(coords, tri, nt=nt)
     rng = np.random.default_rng(3)
