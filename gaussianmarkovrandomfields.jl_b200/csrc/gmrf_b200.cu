@@ -169,6 +169,7 @@ struct gmrf_b200_handle {
     // lanes: independent value sets on the same pattern factorized by the same launches (blockIdx.y); every numeric
     // array of the factorization lives in one arena per lane, lane b starts arena_bytes * b after lane 0
     int lanes = 1;
+    int last_lanes = 1;     // lanes advanced by the last factorization
     long long arena_bytes = 0;
     double *d_arena = nullptr;
     std::vector<double> lane_logdet;
@@ -1434,6 +1435,7 @@ int do_factor(gmrf_b200_handle *h, int lanes = 1) {
         if (rc) return rc;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
+    h->last_lanes = lanes;
     h->lane_logdet.assign(lanes, 0.0);
     h->lane_fail.assign(lanes, 0);
     for (int b = 0; b < lanes; b++) {      // (a strided 2-D copy would exceed the pitch limit for multi-GB arenas)
@@ -2930,10 +2932,15 @@ int gmrf_b200_profile_plan(gmrf_b200_handle *h, int phase, int nrhs, int64_t cap
     cudaStream_t st = h->stream;
     if (phase == 0) {
         plan = &h->factor_plan;
-        cudaMemsetAsync(h->d_Lx, 0, sizeof(double) * (size_t)h->S.panel_total, st);
-        cudaMemsetAsync(h->d_fail, 0x7f, sizeof(int), st);
+        // (a lane handle is profiled with the lanes of its last sweep: same grids as the sweep itself)
+        T.lanes = std::max(1, h->last_lanes);
+        const long long bstride = T.lanes > 1 ? h->arena_bytes : 0;
+        for (int b = 0; b < T.lanes; b++) {
+            cudaMemsetAsync(reinterpret_cast<char *>(h->d_Lx) + (long long)b * h->arena_bytes, 0, sizeof(double) * (size_t)h->S.panel_total, st);
+            cudaMemsetAsync(reinterpret_cast<char *>(h->d_fail) + (long long)b * h->arena_bytes, 0x7f, sizeof(int), st);
+        }
         i64 cnt = (i64)h->S.q_src.size();
-        if (cnt > 0) scatter_q_kernel<<<(int)std::min<i64>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, 0LL);
+        if (cnt > 0) scatter_q_kernel<<<dim3((int)std::min<i64>((cnt + 255) / 256, 148 * 16), T.lanes), 256, 0, st>>>(h->d_Lx, h->d_nz, h->d_qsrc, h->d_qdst, cnt, bstride);
         h->selinv_valid = false;
     } else if (phase == 1) {
         if ((rc = build_selinv_tables(h))) return rc;

@@ -1,6 +1,6 @@
 """Per-launch profile of one phase on the GPU box (diagnostics, not a pytest file):
     python tests/gpu_plan_profile.py 3d:100 --phase=3 [--order=geo] [--top=40]
-phase 0 factorization, 1 selinv, 2 forward sweep, 3 backward sweep."""
+phase 0 factorization, 1 selinv, 2 forward sweep, 3 backward sweep; --lanes=16 profiles a lane sweep (phase 0 only)."""
 import collections
 import os
 import sys
@@ -21,7 +21,19 @@ for k, v in opt.items():          # --set:key=value -> library option
         _lib.set_option(k[4:], float(v))
 Q, dims, width, _ = build_problem(spec)
 ordering = spde.geometric_nd_perm(dims, leaf=64, width=width) if opt.get("order", "geo") == "geo" else "nd"
-b = B200Backend(Q, ordering=ordering, device=0)
+lanes = int(opt.get("lanes", "1"))
+if lanes > 1:                      # lane handle: profile one sweep of `lanes` value sets (grid.y = lanes on every launch)
+    import numpy as np
+    _lib.set_option("lanes", lanes)
+    b = B200Backend(Q, ordering=ordering, device=0, factorize=False)
+    _lib.set_option("lanes", 1)
+    Qc = Q.tocsc()
+    for _ in range(2):
+        ld, st = b.refactorize_lanes(np.tile(Qc.data, (lanes, 1)))
+    print(f"lanes {lanes}: sweep {b.timings()['factor_ms']:.3f} ms on the device = {b.timings()['factor_ms'] / lanes:.3f} ms per value set; "
+          f"logdets agree: {bool(np.all(ld == ld[0]))}")
+else:
+    b = B200Backend(Q, ordering=ordering, device=0)
 for phase in phases:
     b.profile_plan(phase)                       # warm-up
     rows = b.profile_plan(phase)
