@@ -85,6 +85,7 @@ assemble_gather_kernel(const AsmTile *__restrict__ tiles, const SuperMeta *__res
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(ch + AG_MAXCH);
     double *__restrict__ Lx = lane_ptr_pinned(Lx0, bstride);
     double *__restrict__ upd = lane_ptr_pinned(upd0, bstride);
+    pdl_launch_dependents();
     const AsmTile it = tiles[blockIdx.x];
     const SuperMeta P = meta[it.super];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -132,6 +133,7 @@ assemble_gather_kernel(const AsmTile *__restrict__ tiles, const SuperMeta *__res
         if (tid < cn) { ch[tid].ca += ch[tid].pa; ch[tid].cb += ch[tid].pa; }     // counts -> positions (the list is sorted)
         __syncthreads();
         // ---- children one after the other: bulk copies into the stage, gather from it ----
+        pdl_wait();          // (the maps above come from the symbolic tables only; the update matrices are the predecessor's)
         for (int k = 0; k < cn; k++) {
             const AgChild c = ch[k];
             const bool any = c.cb > c.ca && c.b > c.a;

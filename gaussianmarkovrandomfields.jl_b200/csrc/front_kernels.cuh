@@ -301,6 +301,7 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
     extern __shared__ __align__(16) double fsm[];
     double *sD0 = fsm, *sH = fsm + FTILE, *sD1 = fsm + 2 * FTILE, *sB0 = fsm + 3 * FTILE, *sB1 = fsm + 4 * FTILE;
     double *scr = fsm + 5 * FTILE;
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     ChainTask T = tasks[t];
     T.P = lane_ptr(T.P, bstride); T.sq = lane_ptr(T.sq, bstride); fail_col = lane_ptr(fail_col, bstride);
@@ -312,6 +313,7 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
     const int row0 = k2 + (tile - 1) * FB;
     const int nrv = diag ? 0 : min(FB, T.nrow - row0);
     long long *prof = g_chain_prof;
+    pdl_wait();
     CHAIN_STAMP(0);
     // ---- loads (asynchronous, all in flight together) ----
     load_tile(sD0, T.P + (long long)T.k0 * ld + T.k0, ld, T.nb0, T.nb0, true);
@@ -450,6 +452,7 @@ front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restr
     double *__restrict__ Lx = lane_ptr_pinned(Lx0, bstride);
     double *__restrict__ upd = lane_ptr_pinned(upd0, bstride);
     fail_col = lane_ptr(fail_col, bstride);
+    pdl_launch_dependents();
     const SuperMeta S = meta[tasks[blockIdx.x].super];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ns = S.ns, nrow = S.nrow, nr = nrow - ns;
@@ -457,6 +460,7 @@ front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restr
     int *sInv = reinterpret_cast<int *>(sP + ns * ldp);     // [FRONT_MAXC][nrow]
     const int nch = S.child_end - S.child_begin;
     double *Lp = Lx + S.panel_off;
+    pdl_wait();
     // ---- panel <- HBM (asynchronous; the strictly upper part of the diagonal block reads as zero) ----
     for (int c = warp; c < ns; c += 8) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(sP + c * ldp);

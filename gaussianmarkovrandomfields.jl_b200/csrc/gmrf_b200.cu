@@ -734,6 +734,7 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     std::vector<WideStepTask> wt;
     std::vector<WideDiagTask> wd;
     auto is_wide = [&](i64 s) { return h->opt.wide_steps && S.ns(s) > SOLVE_WIDE_MIN; };
+    const bool lookahead = h->opt.wide_steps >= 2;
     i64 part_off = 0;
     const i64 RCH = std::max(32, h->opt.bwd_row_chunk);
     const i64 BB = (i64)SOLVE_NB * SOLVE_NB;
@@ -756,13 +757,18 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
                 if (!is_wide(s) || k0 >= ns) continue;
                 i64 nbw = std::min<i64>(SOLVE_WB, ns - k0), k1 = k0 + nbw;
                 const double *P = h->d_Lx + S.panel_off[s];
-                wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
-                if (nrow > k1)
+                // wide_steps = 2: the step's head CTA solves the NEXT diagonal block, only the first one needs a launch
+                if (!lookahead || J == 0)
+                    wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
+                if (nrow > k1) {
+                    const i64 hrows = lookahead ? std::min<i64>(SOLVE_WB, ns - k1) : 0;
                     wt.push_back(WideStepTask{P + k0 * ld + k1, h->d_y + S.sfirst[s] + k0, h->d_y + S.sfirst[s] + k1, h->d_uvec + S.uvec_off[s],
-                                              (int)ld, (int)nbw, (int)(ns - k1), (int)(nrow - k1)});
+                                              hrows > 0 ? inv_ptr(s, k1 / SOLVE_NB) : nullptr, (int)ld, (int)nbw, (int)(ns - k1),
+                                              (int)(nrow - k1), (int)hrows, 0});
+                }
             }
             B.add_wdiag(h->fwd_plan, wd, K_FWD_WDIAG);
-            B.add_tiled(h->fwd_plan, wt, B.wstep, K_FWD_WSTEP, [](const WideStepTask &t) { return (i64)cdiv(t.m, SOLVE_NB); });
+            B.add_tiled(h->fwd_plan, wt, B.wstep, K_FWD_WSTEP, [](const WideStepTask &t) { return (i64)((t.hrows > 0) + cdiv(t.m - t.hrows, SOLVE_NB)); });
         }
         for (i64 j = 0; j < maxsteps; j++) {
             for (const i64 *sp = sb; sp < se; sp++) {
@@ -834,12 +840,15 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
                 if (J < 0) continue;
                 i64 k0 = J * SOLVE_WB, nbw = std::min<i64>(SOLVE_WB, ns - k0);
                 const double *P = h->d_Lx + S.panel_off[s];
-                wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
-                if (k0 > 0)
-                    wt.push_back(WideStepTask{P + k0, h->d_y + S.sfirst[s] + k0, h->d_y + S.sfirst[s], nullptr, (int)ld, (int)nbw, 0, (int)k0});
+                if (!lookahead || tJ == 0)
+                    wd.push_back(WideDiagTask{P + k0 * ld + k0, inv_ptr(s, k0 / SOLVE_NB), h->d_y + S.sfirst[s] + k0, (int)ld, (int)nbw});
+                if (k0 > 0)     // (k0 is a multiple of 256: the head's previous block is always a full one)
+                    wt.push_back(WideStepTask{P + k0, h->d_y + S.sfirst[s] + k0, h->d_y + S.sfirst[s], nullptr,
+                                              lookahead ? inv_ptr(s, (k0 - SOLVE_WB) / SOLVE_NB) : nullptr, (int)ld, (int)nbw, 0, (int)k0,
+                                              lookahead ? SOLVE_WB : 0, 0});
             }
             B.add_wdiag(h->bwd_plan, wd, K_BWD_WDIAG);
-            B.add_tiled(h->bwd_plan, wt, B.wstep, K_BWD_WSTEP, [](const WideStepTask &t) { return (i64)cdiv(t.m, SOLVE_NB); });
+            B.add_tiled(h->bwd_plan, wt, B.wstep, K_BWD_WSTEP, [](const WideStepTask &t) { return (i64)((t.hrows > 0) + cdiv(t.m - t.hrows, SOLVE_NB)); });
         }
         for (i64 tt = 0; tt + 1 < maxsteps; tt++) {
             for (const i64 *sp = sb; sp < se; sp++) {
@@ -1249,6 +1258,19 @@ struct TableSet {
     int lanes = 1;                          // factorization: lanes advanced per launch (grid.y)
 };
 
+// Kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may become resident while
+// its predecessor in the stream still runs and synchronizes itself with griddepcontrol.wait (solve_kernels.cuh).
+template <typename... KA, typename... A>
+static inline void launch_k(bool pdl, void (*kern)(KA...), dim3 grid, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+
 void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs, cudaStream_t stream_override = nullptr) {
     cudaStream_t st = stream_override ? stream_override : h->stream;
     const bool naive = h->opt.naive_kernels != 0;
@@ -1300,8 +1322,8 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_FWD_ASM: {
             dim3 g(L.grid, nrhs);
-            fwd_assemble_x0_kernel<<<g, 256, 0, st>>>(h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
-                                                      h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
+            launch_k(h->opt.pdl != 0, fwd_assemble_x0_kernel, g, st, h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
+                     h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
             break;
         }
         case K_FWD_ASM_M: {
@@ -1322,17 +1344,27 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
         else if (nrhs <= 4) KERNEL<4><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                    \
         else KERNEL<8><<<L.grid, 256, 0, st>>>(__VA_ARGS__);                                   \
     } while (0)
+// the kernels of the few-RHS sweeps: programmatic dependent launch (solve_kernels.cuh) -- the next step's CTAs may start
+// loading their factor tiles while this one finishes
+#define SOLVE_RB_DISPATCH_PDL(KERNEL, ...)                                                    \
+    do {                                                                                       \
+        const bool pdl = h->opt.pdl != 0;                                                      \
+        if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), st, __VA_ARGS__);                \
+        else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), st, __VA_ARGS__);           \
+        else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), st, __VA_ARGS__);           \
+        else launch_k(pdl, KERNEL<8>, dim3(L.grid), st, __VA_ARGS__);                          \
+    } while (0)
         case K_FWD_STEP:
-            SOLVE_RB_DISPATCH(fwd_step_kernel, h->d_fwd + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
+            SOLVE_RB_DISPATCH_PDL(fwd_step_kernel, (const FwdStepTask *)(h->d_fwd + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
             break;
         case K_BWD_GATHER:
-            SOLVE_RB_DISPATCH(bwd_gather_kernel, h->d_bwdg + L.task_off, pf, L.ntasks, nrhs, h->d_y, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(bwd_gather_kernel, h->d_bwdg + L.task_off, pf, (int)L.ntasks, nrhs, h->d_y, (long long)h->S.n);
             break;
         case K_BWD_REDUCE:
-            SOLVE_RB_DISPATCH(bwd_reduce_kernel, h->d_bwdr + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(bwd_reduce_kernel, h->d_bwdr + L.task_off, pf, (int)L.ntasks, nrhs, (long long)h->S.n);
             break;
         case K_BWD_STEP:
-            SOLVE_RB_DISPATCH(bwd_step_kernel, h->d_bwds + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(bwd_step_kernel, (const BwdStepTask *)(h->d_bwds + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n);
             break;
         case K_FWD_WSTEP:
             SOLVE_RB_DISPATCH(fwd_wide_step_kernel, h->d_wstep + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
@@ -1347,6 +1379,7 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             SOLVE_RB_DISPATCH(bwd_wide_diag_kernel, h->d_wdiag + L.task_off, nrhs, (long long)h->S.n);
             break;
 #undef SOLVE_RB_DISPATCH
+#undef SOLVE_RB_DISPATCH_PDL
     }
 }
 
@@ -1842,6 +1875,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "level_alap") o.level_alap = (int)value;
     else if (k == "syrk_gather") o.syrk_gather = (int)value;
     else if (k == "wide_steps") o.wide_steps = (int)value;
+    else if (k == "pdl") o.pdl = value != 0;
     else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;

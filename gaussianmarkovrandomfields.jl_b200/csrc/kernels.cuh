@@ -74,6 +74,16 @@ struct GatherCtx {
 constexpr int GATHER_MAXC = 4;    // children whose inverse maps are resident at once
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol). A kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream still runs: it reads its task tables (and whatever else no kernel
+// of the same graph writes -- for the triangular sweeps that is the whole factor) and then waits for the predecessor's
+// completion before touching anything the predecessor produces. The few-RHS sweeps are ~900 dependent launches per
+// direction whose factor tiles do NOT depend on the previous step, only the 64 unknowns x_j do: their HBM latency
+// overlaps the previous step. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // Batched factorization: a handle may hold several numeric "lanes" (independent value sets on the same pattern, e.g.
 // the points of a hyperparameter sweep). All numeric arrays of a lane live in one arena; lane b sits `bstride` bytes
 // after lane 0, the task tables point into lane 0, and blockIdx.y selects the lane. One launch then advances every
@@ -339,6 +349,7 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     double *As = gemm_smem;
     double *Bs = gemm_smem + GEMM_STAGES * A_TILE;
 
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     GemmTask T = tasks[t];
     T.A = lane_ptr(T.A, bstride); T.B = lane_ptr(T.B, bstride); T.C = lane_ptr(T.C, bstride);
@@ -373,6 +384,7 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     TileLoader<BN, NT, TB, GEMM_KT> lb;
     la.init(T.A, T.lda, m0, T.m, a16, tid);
     lb.init(T.B, T.ldb, n0, T.n, b16, tid);
+    pdl_wait();            // (task search and tile bookkeeping above overlap the predecessor when launched programmatically)
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; s++) {
         if (s < nk) {
@@ -488,9 +500,11 @@ template <int NBT>
 __global__ void __launch_bounds__(256)
 potrf_inv_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col, long long bstride) {
     __shared__ double sA[NBT][NBT + 1];   // identity-padded beyond nb
+    pdl_launch_dependents();
     PanelTask T = tasks[blockIdx.x];
     T.D = lane_ptr(T.D, bstride); T.inv = lane_ptr(T.inv, bstride); fail_col = lane_ptr(fail_col, bstride);
     const int nb = T.nb, tid = threadIdx.x;
+    pdl_wait();
     for (int e = tid; e < NBT * NBT; e += 256) {
         const int i = e % NBT, j = e / NBT;
         double v = (i == j) ? 1.0 : 0.0;
@@ -553,9 +567,11 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
     __shared__ double srinv_all[N];                   // 1 / L_ii of every row, reused by the inversion
     __shared__ __align__(16) double spanel2[2][N][4];  // published column panel (rows 0..63 of the current 4 columns),
                                                        // double-buffered: step P+1 publishes while step P is still read
+    pdl_launch_dependents();
     PanelTask T = tasks[blockIdx.x];
     T.D = lane_ptr(T.D, bstride); T.inv = lane_ptr(T.inv, bstride); fail_col = lane_ptr(fail_col, bstride);
     const int nb = T.nb, tid = threadIdx.x;
+    pdl_wait();
     for (int e = tid; e < N * N; e += 256) {
         const int i = e % N, j = e / N;
         double v = (i == j) ? 1.0 : 0.0;
@@ -687,9 +703,11 @@ struct SplitTask {
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const SplitTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, long long bstride) {
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     SplitTask T = tasks[t];
     T.C = lane_ptr(T.C, bstride); T.part = lane_ptr(T.part, bstride);
+    pdl_wait();
     const int local = blockIdx.x - tile_prefix[t];
     const int mt = (T.m + 255) / 256;                 // a CTA owns 256 rows x 4 columns
     const int r = (local % mt) * 256 + threadIdx.x;
@@ -763,8 +781,10 @@ assemble_kernel(const AsmItem *__restrict__ items, const SuperMeta *__restrict__
                 double *__restrict__ Lx0, double *__restrict__ upd0, long long bstride) {
     double *__restrict__ Lx = lane_ptr_pinned(Lx0, bstride);
     double *__restrict__ upd = lane_ptr_pinned(upd0, bstride);
+    pdl_launch_dependents();
     const AsmItem it = items[blockIdx.x];
     const SuperMeta P = meta[it.super];
+    pdl_wait();
     const int c_lo = it.col0, c_hi = min(it.col0 + ASM_CW, P.nrow);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nr = P.nrow - P.ns;

@@ -20,6 +20,7 @@ namespace gmrf {
 
 constexpr int SOLVE_NB = 64;
 
+
 struct FwdStepTask {      // block column K_j = [k0, k1) of a supernode, x_j final in `x`
     const double *L;      // first row below the diagonal block: panel + k0*ld + k1
     const double *inv_next;   // inverse of the next diagonal block (nb_next x nb_next) or nullptr
@@ -171,6 +172,7 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
                        double *__restrict__ y, long long ldy, double *__restrict__ uvec, long long ldu) {
     __shared__ double sb[SOLVE_NB][1];
     __shared__ double sp[4][SOLVE_NB][1];
+    pdl_launch_dependents();
     const int s = supers[blockIdx.x];
     const SuperMeta P = meta[s];
     const int nr = P.nrow - P.ns;
@@ -179,6 +181,7 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
     const bool wide = P.wide != 0;           // long chains: the first 256-column block is solved by fwd_wide_diag_kernel
     double g[16];
     if (!wide) load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
+    pdl_wait();
     double *us = uvec + P.uvec_off + (long long)r * ldu;
     for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
     __syncthreads();
@@ -211,6 +214,7 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
     __shared__ double xs[SOLVE_NB][RB];
     __shared__ double part[8][SOLVE_NB][RB];
     __shared__ double sb[SOLVE_NB][RB];
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const FwdStepTask T = tasks[t];
     const int tile = blockIdx.x - tile_prefix[t];
@@ -230,6 +234,7 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
             l[i][h] = (kk < T.nb && r < T.m) ? T.L[r + (long long)kk * T.ld] : 0.0;
         }
     }
+    pdl_wait();        // (everything above reads only the factor and the task tables)
     for (int e = tid; e < SOLVE_NB * RB; e += 256) {
         const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
         xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(256)
 bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                   const double *__restrict__ xg, long long ldy) {
     __shared__ double st[SOLVE_NB][RB];
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const BwdGatherTask T = tasks[t];
     const int tile = T.tile0 + (blockIdx.x - tile_prefix[t]);
@@ -284,6 +290,7 @@ bwd_gather_kernel(const BwdGatherTask *__restrict__ tasks, const int *__restrict
     const bool tail = (tile == nblk - 1) && !T.pad_;      // pad_ = 1: long chain, bwd_wide_diag_kernel solves the last block
     double g[16];
     if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
+    pdl_wait();
     double acc[8][RB];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -349,6 +356,7 @@ __global__ void __launch_bounds__(256)
 bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                   long long ldy) {
     __shared__ double st[SOLVE_NB][RB];
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const BwdReduceTask T = tasks[t];
     const int tile = blockIdx.x - tile_prefix[t];
@@ -357,6 +365,7 @@ bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict
     const bool tail = (tile == nblk - 1) && !T.pad_;
     double g[16];
     if (tail) load_inv_lower_t(g, T.inv_last, T.nb_last, warp, lane);
+    pdl_wait();
     for (int e = tid; e < SOLVE_NB * RB; e += 256) {
         const int cl = e % SOLVE_NB, q = e / SOLVE_NB;
         const int c = tile * SOLVE_NB + cl;
@@ -381,6 +390,7 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
                 long long ldy) {
     __shared__ double xs[SOLVE_NB][RB];
     __shared__ double st[SOLVE_NB][RB];
+    pdl_launch_dependents();
     const int t = find_task(tile_prefix, ntasks, blockIdx.x);
     const BwdStepTask T = tasks[t];
     const int tile = blockIdx.x - tile_prefix[t];
@@ -398,6 +408,7 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
             const int r = lane + 32 * h;
             l[i][h] = (r < T.nb) ? T.L[r + (long long)(c0 + i) * T.ld] : 0.0;
         }
+    pdl_wait();        // (everything above reads only the factor and the task tables)
     for (int e = tid; e < SOLVE_NB * RB; e += 256) {
         const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
         xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
@@ -440,8 +451,12 @@ struct WideStepTask {     // forward: rows below block column K = [k0, k0 + nbw)
     const double *x;      // x_K (nbw entries per right-hand side, stride ldy)
     double *y;            // forward: own rows k1.. of the supernode;  backward: own columns 0.. of the supernode
     double *u;            // forward: update vector of the supernode (rows beyond ns)
+    const double *inv_head;   // look-ahead (hrows > 0): inverted 64 x 64 blocks of the NEXT diagonal block of the chain
     int ld, nbw;          // nbw <= 256
     int ms, m;            // forward: own rows below / all rows below;  backward: m = columns left of K (a multiple of 64 tiles)
+    int hrows, pad_;      // look-ahead: tile 0 of the task is a HEAD CTA that updates the hrows unknowns of the next diagonal
+                          // block (forward: the first hrows rows below K, backward: the 256 columns left of K) and solves that
+                          // block right away, so the chain needs one launch per 256 columns; the other tiles cover the rest
 };
 
 struct WideDiagTask {     // the 256 x 256 diagonal block D = L[K, K] with its (up to four) inverted 64 x 64 blocks
@@ -450,6 +465,108 @@ struct WideDiagTask {     // the 256 x 256 diagonal block D = L[K, K] with its (
     double *y;            // the nbw unknowns of K (stride ldy)
     int ld, nbw;
 };
+
+// x_K := L[K, K]^-1 y_K on the unknowns held in shared memory, block by block: x_b = inv_b y_b, then y_c -= L[c, b] x_b for
+// the later blocks c of K
+template <int RB>
+__device__ __forceinline__ void fwd_diag_solve_smem(double (*ys)[RB], double (*sp)[SOLVE_NB][RB], const double *__restrict__ D, int ld,
+                                                    const double *__restrict__ inv, int nbw, int tid) {
+    const int nblk = (nbw + SOLVE_NB - 1) / SOLVE_NB;
+    for (int b = 0; b < nblk; b++) {
+        const int c0 = b * SOLVE_NB, nb = min(SOLVE_NB, nbw - c0);
+        // the rows of the later blocks against this block's columns: issued now, used after the block solve
+        const int r = c0 + SOLVE_NB + tid;                     // one thread per later row (<= 192 of them)
+        double lrow[SOLVE_NB];
+        const bool has = r < nbw;
+#pragma unroll
+        for (int c = 0; c < SOLVE_NB; c++) lrow[c] = (has && c < nb) ? D[r + (long long)(c0 + c) * ld] : 0.0;
+        double g[16];
+        load_inv_lower(g, inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, tid);
+        {
+            const int rr = tid & 63, prt = tid >> 6;
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    s0 += g[i] * ys[c0 + prt * 16 + i][q];
+                    s1 += g[i + 1] * ys[c0 + prt * 16 + i + 1][q];
+                }
+                sp[prt][rr][q] = s0 + s1;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+            const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+            if (rr < nb) ys[c0 + rr][q] = (sp[0][rr][q] + sp[1][rr][q]) + (sp[2][rr][q] + sp[3][rr][q]);
+        }
+        __syncthreads();
+        if (has) {
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < SOLVE_NB; c += 2) { s0 += lrow[c] * ys[c0 + c][q]; s1 += lrow[c + 1] * ys[c0 + c + 1][q]; }
+                ys[r][q] -= s0 + s1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// x_K := L[K, K]^-T t_K on the unknowns held in shared memory, blocks in reverse: x_b = inv_b^T t_b, then
+// t_c -= L[b, c]^T x_b for the earlier blocks c of K
+template <int RB>
+__device__ __forceinline__ void bwd_diag_solve_smem(double (*ys)[RB], double (*st)[RB], const double *__restrict__ D, int ld,
+                                                    const double *__restrict__ inv, int nbw, int nrhs, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nblk = (nbw + SOLVE_NB - 1) / SOLVE_NB;
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int r0 = b * SOLVE_NB, nb = min(SOLVE_NB, nbw - r0);
+        // x_b = inv_b^T t_b: warp owns 8 columns of the inverse, lanes own rows lane, lane + 32
+        double g[16];
+        load_inv_lower_t(g, inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, warp, lane);
+        for (int e = tid; e < SOLVE_NB * RB; e += 256) st[e % SOLVE_NB][e / SOLVE_NB] = ys[r0 + e % SOLVE_NB][e / SOLVE_NB];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            if (q >= nrhs) break;
+            double p[8];
+            const double t0 = lane < nb ? st[lane][q] : 0.0, t1 = lane + 32 < nb ? st[lane + 32][q] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = g[2 * i] * t0 + g[2 * i + 1] * t1;
+            const double sum = warp_reduce8(p, lane);
+            const int c = warp * 8 + warp_reduce8_index(lane);
+            if ((lane & 3) == 0 && c < nb) ys[r0 + c][q] = sum;
+        }
+        __syncthreads();
+        if (b > 0) {
+            // t_c -= L[b-rows, c]^T x_b for the r0 earlier columns (r0 is a multiple of 64): 64 columns per pass, a warp
+            // takes 8 of them with two rows per lane -- 16 loads in flight, then the fixed 8-way shuffle tree
+            for (int cb = 0; cb < r0; cb += SOLVE_NB) {
+                double l[8][2];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const double *col = D + (long long)(cb + warp * 8 + i) * ld + r0;
+                    l[i][0] = lane < nb ? col[lane] : 0.0;
+                    l[i][1] = lane + 32 < nb ? col[lane + 32] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < RB; q++) {
+                    if (q >= nrhs) break;
+                    const double x0 = lane < nb ? ys[r0 + lane][q] : 0.0, x1 = lane + 32 < nb ? ys[r0 + lane + 32][q] : 0.0;
+                    double p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) p[i] = l[i][0] * x0 + l[i][1] * x1;
+                    const double sum = warp_reduce8(p, lane);
+                    const int c = cb + warp * 8 + warp_reduce8_index(lane);
+                    if ((lane & 3) == 0) ys[c][q] -= sum;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
 
 template <int RB>
 __global__ void __launch_bounds__(256)
@@ -461,7 +578,45 @@ fwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restri
     const WideStepTask T = tasks[t];
     const int tile = blockIdx.x - tile_prefix[t];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = tile * SOLVE_NB;
+    const int head = T.hrows > 0 ? 1 : 0;
+    if (head && tile == 0) {
+        // HEAD: the hrows unknowns of the next diagonal block. One thread per row streams the row's nbw entries (64 loads
+        // in flight per thread), then the block is solved in shared memory and published: the next launch finds x_{K+1}.
+        for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+            const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+            xs[kk][q] = (kk < T.nbw && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+        }
+        __syncthreads();
+        double acc0[RB], acc1[RB];
+#pragma unroll
+        for (int q = 0; q < RB; q++) acc0[q] = acc1[q] = 0.0;
+        const bool mine = tid < T.hrows;
+#pragma unroll 1
+        for (int b = 0; b < SOLVE_WB; b += SOLVE_NB) {
+            if (b >= T.nbw) break;
+            double lr[SOLVE_NB];
+#pragma unroll
+            for (int i = 0; i < SOLVE_NB; i++) lr[i] = (mine && b + i < T.nbw) ? T.L[tid + (long long)(b + i) * T.ld] : 0.0;
+#pragma unroll
+            for (int q = 0; q < RB; q++)
+#pragma unroll
+                for (int i = 0; i < SOLVE_NB; i += 2) {
+                    acc0[q] += lr[i] * xs[b + i][q];
+                    acc1[q] += lr[i + 1] * xs[b + i + 1][q];
+                }
+        }
+        double (*ys)[RB] = reinterpret_cast<double (*)[RB]>(&part[0][0][0]);                       // [256][RB]
+        double (*sp)[SOLVE_NB][RB] = reinterpret_cast<double (*)[SOLVE_NB][RB]>(&part[4][0][0]);   // [4][64][RB]
+#pragma unroll
+        for (int q = 0; q < RB; q++) ys[tid][q] = (mine && q < nrhs) ? T.y[tid + q * ldy] - (acc0[q] + acc1[q]) : 0.0;
+        __syncthreads();
+        fwd_diag_solve_smem<RB>(ys, sp, T.L + (long long)T.nbw * T.ld, T.ld, T.inv_head, T.hrows, tid);
+#pragma unroll
+        for (int q = 0; q < RB; q++)
+            if (mine && q < nrhs) T.y[tid + q * ldy] = ys[tid][q];
+        return;
+    }
+    const int row0 = T.hrows + (tile - head) * SOLVE_NB;
     // all 64 loads of the thread's 2 rows x 32 columns are issued before anything waits on them
     double l[4][8][2];
 #pragma unroll
@@ -507,7 +662,6 @@ fwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restri
     }
 }
 
-// x_K := L[K, K]^-1 y_K, block by block: x_b = inv_b y_b, then y_c -= L[c, b] x_b for the later blocks c of K
 template <int RB>
 __global__ void __launch_bounds__(256)
 fwd_wide_diag_kernel(const WideDiagTask *__restrict__ tasks, int nrhs, long long ldy) {
@@ -520,47 +674,7 @@ fwd_wide_diag_kernel(const WideDiagTask *__restrict__ tasks, int nrhs, long long
         ys[kk][q] = (kk < T.nbw && q < nrhs) ? T.y[kk + q * ldy] : 0.0;
     }
     __syncthreads();
-    const int nblk = (T.nbw + SOLVE_NB - 1) / SOLVE_NB;
-    for (int b = 0; b < nblk; b++) {
-        const int c0 = b * SOLVE_NB, nb = min(SOLVE_NB, T.nbw - c0);
-        // the rows of the later blocks against this block's columns: issued now, used after the block solve
-        const int r = c0 + SOLVE_NB + tid;                     // one thread per later row (<= 192 of them)
-        double lrow[SOLVE_NB];
-        const bool has = r < T.nbw;
-#pragma unroll
-        for (int c = 0; c < SOLVE_NB; c++) lrow[c] = (has && c < nb) ? T.D[r + (long long)(c0 + c) * T.ld] : 0.0;
-        double g[16];
-        load_inv_lower(g, T.inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, tid);
-        {
-            const int rr = tid & 63, prt = tid >> 6;
-#pragma unroll
-            for (int q = 0; q < RB; q++) {
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    s0 += g[i] * ys[c0 + prt * 16 + i][q];
-                    s1 += g[i + 1] * ys[c0 + prt * 16 + i + 1][q];
-                }
-                sp[prt][rr][q] = s0 + s1;
-            }
-        }
-        __syncthreads();
-        for (int e = tid; e < SOLVE_NB * RB; e += 256) {
-            const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
-            if (rr < nb) ys[c0 + rr][q] = (sp[0][rr][q] + sp[1][rr][q]) + (sp[2][rr][q] + sp[3][rr][q]);
-        }
-        __syncthreads();
-        if (has) {
-#pragma unroll
-            for (int q = 0; q < RB; q++) {
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < SOLVE_NB; c += 2) { s0 += lrow[c] * ys[c0 + c][q]; s1 += lrow[c + 1] * ys[c0 + c + 1][q]; }
-                ys[r][q] -= s0 + s1;
-            }
-        }
-        __syncthreads();
-    }
+    fwd_diag_solve_smem<RB>(ys, sp, T.D, T.ld, T.inv, T.nbw, tid);
     for (int e = tid; e < SOLVE_WB * RB; e += 256) {
         const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
         if (kk < T.nbw && q < nrhs) T.y[kk + q * ldy] = ys[kk][q];
@@ -576,14 +690,66 @@ bwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restri
     const WideStepTask T = tasks[t];
     const int tile = blockIdx.x - tile_prefix[t];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = tile * SOLVE_NB + warp * 8;
+    const int head = T.hrows > 0 ? 1 : 0;
+    if (head && tile == 0) {
+        // HEAD: the 256 unknowns of the previous diagonal block = columns [m - 256, m). Four passes of 64 columns (the
+        // ordinary tile code), then the transposed block solve in shared memory: the next launch finds x_{K-1}.
+        __shared__ double ys[SOLVE_WB][RB];
+        __shared__ double st[SOLVE_NB][RB];
+        for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+            const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+            xs[kk][q] = (kk < T.nbw && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
+            ys[kk][q] = 0.0;
+        }
+        __syncthreads();
+        const int cbase = T.m - SOLVE_WB;
+#pragma unroll 1
+        for (int cb = 0; cb < SOLVE_WB; cb += SOLVE_NB) {
+            const int cc = cbase + cb + warp * 8;
+            double lh[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const int r = lane + 32 * h;
+                    lh[i][h] = r < T.nbw ? T.L[r + (long long)(cc + i) * T.ld] : 0.0;
+                }
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                if (q >= nrhs) break;
+                double xv[8];
+#pragma unroll
+                for (int h = 0; h < 8; h++) xv[h] = xs[lane + 32 * h][q];
+                double p[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int h = 0; h < 8; h += 2) { s0 += lh[i][h] * xv[h]; s1 += lh[i][h + 1] * xv[h + 1]; }
+                    p[i] = s0 + s1;
+                }
+                const double sum = warp_reduce8(p, lane);
+                const int cl = cb + warp * 8 + warp_reduce8_index(lane);
+                if ((lane & 3) == 0) ys[cl][q] = T.y[cbase + cl + q * ldy] - sum;
+            }
+        }
+        __syncthreads();
+        bwd_diag_solve_smem<RB>(ys, st, T.L - SOLVE_WB + (long long)cbase * T.ld, T.ld, T.inv_head, SOLVE_WB, nrhs, tid);
+        for (int e = tid; e < SOLVE_WB * RB; e += 256) {
+            const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
+            if (q < nrhs) T.y[cbase + kk + q * ldy] = ys[kk][q];
+        }
+        return;
+    }
+    const int mcols = T.m - (head ? SOLVE_WB : 0);             // columns the ordinary tiles cover
+    const int c0 = (tile - head) * SOLVE_NB + warp * 8;
     double l[8][8];                                            // 8 columns x 8 rows (lane, lane + 32, ...)
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int h = 0; h < 8; h++) {
             const int r = lane + 32 * h;
-            l[i][h] = (r < T.nbw && c0 + i < T.m) ? T.L[r + (long long)(c0 + i) * T.ld] : 0.0;
+            l[i][h] = (r < T.nbw && c0 + i < mcols) ? T.L[r + (long long)(c0 + i) * T.ld] : 0.0;
         }
     for (int e = tid; e < SOLVE_WB * RB; e += 256) {
         const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
@@ -606,71 +772,24 @@ bwd_wide_step_kernel(const WideStepTask *__restrict__ tasks, const int *__restri
         }
         const double sum = warp_reduce8(p, lane);
         const int cl = warp * 8 + warp_reduce8_index(lane);
-        const int c = tile * SOLVE_NB + cl;
-        if ((lane & 3) == 0 && c < T.m) T.y[c + q * ldy] -= sum;
+        const int c = (tile - head) * SOLVE_NB + cl;
+        if ((lane & 3) == 0 && c < mcols) T.y[c + q * ldy] -= sum;
     }
 }
 
-// x_K := L[K, K]^-T t_K, blocks in reverse: x_b = inv_b^T t_b, then t_c -= L[b, c]^T x_b for the earlier blocks c of K
 template <int RB>
 __global__ void __launch_bounds__(256)
 bwd_wide_diag_kernel(const WideDiagTask *__restrict__ tasks, int nrhs, long long ldy) {
     __shared__ double ys[SOLVE_WB][RB];
     __shared__ double st[SOLVE_NB][RB];
     const WideDiagTask T = tasks[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     for (int e = tid; e < SOLVE_WB * RB; e += 256) {
         const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
         ys[kk][q] = (kk < T.nbw && q < nrhs) ? T.y[kk + q * ldy] : 0.0;
     }
     __syncthreads();
-    const int nblk = (T.nbw + SOLVE_NB - 1) / SOLVE_NB;
-    for (int b = nblk - 1; b >= 0; b--) {
-        const int r0 = b * SOLVE_NB, nb = min(SOLVE_NB, T.nbw - r0);
-        // x_b = inv_b^T t_b: warp owns 8 columns of the inverse, lanes own rows lane, lane + 32
-        double g[16];
-        load_inv_lower_t(g, T.inv + (long long)b * SOLVE_NB * SOLVE_NB, nb, warp, lane);
-        // rows r0.. of the earlier columns: warp w takes columns w, w + 8, ... of [0, r0), lanes the rows of the block
-        for (int e = tid; e < SOLVE_NB * RB; e += 256) st[e % SOLVE_NB][e / SOLVE_NB] = ys[r0 + e % SOLVE_NB][e / SOLVE_NB];
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < RB; q++) {
-            if (q >= nrhs) break;
-            double p[8];
-            const double t0 = lane < nb ? st[lane][q] : 0.0, t1 = lane + 32 < nb ? st[lane + 32][q] : 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) p[i] = g[2 * i] * t0 + g[2 * i + 1] * t1;
-            const double sum = warp_reduce8(p, lane);
-            const int c = warp * 8 + warp_reduce8_index(lane);
-            if ((lane & 3) == 0 && c < nb) ys[r0 + c][q] = sum;
-        }
-        __syncthreads();
-        if (b > 0) {
-            // t_c -= L[b-rows, c]^T x_b for the r0 earlier columns (r0 is a multiple of 64): 64 columns per pass, a warp
-            // takes 8 of them with two rows per lane -- 16 loads in flight, then the fixed 8-way shuffle tree
-            for (int cb = 0; cb < r0; cb += SOLVE_NB) {
-                double l[8][2];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const double *col = T.D + (long long)(cb + warp * 8 + i) * T.ld + r0;
-                    l[i][0] = lane < nb ? col[lane] : 0.0;
-                    l[i][1] = lane + 32 < nb ? col[lane + 32] : 0.0;
-                }
-#pragma unroll
-                for (int q = 0; q < RB; q++) {
-                    if (q >= nrhs) break;
-                    const double x0 = lane < nb ? ys[r0 + lane][q] : 0.0, x1 = lane + 32 < nb ? ys[r0 + lane + 32][q] : 0.0;
-                    double p[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) p[i] = l[i][0] * x0 + l[i][1] * x1;
-                    const double sum = warp_reduce8(p, lane);
-                    const int c = cb + warp * 8 + warp_reduce8_index(lane);
-                    if ((lane & 3) == 0) ys[c][q] -= sum;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bwd_diag_solve_smem<RB>(ys, st, T.D, T.ld, T.inv, T.nbw, nrhs, tid);
     for (int e = tid; e < SOLVE_WB * RB; e += 256) {
         const int kk = e % SOLVE_WB, q = e / SOLVE_WB;
         if (kk < T.nbw && q < nrhs) T.y[kk + q * ldy] = ys[kk][q];

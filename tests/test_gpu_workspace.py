@@ -422,10 +422,10 @@ def test_schedule_variants_agree():
                 # the three factorization paths: bulk only / fused chain steps everywhere / one-CTA fronts where they fit
                 {"fused_front": 0, "fused_chain": 0}, {"fused_front": 0, "chain_max_tiles": 1000000},
                 {"fused_chain": 0}, {"front_smem_kb": 60}, {"fused_front": 0, "chain_max_tiles": 40},
-                {"asm_gather": 0}, {"asm_gather": 0, "fused_front": 0, "fused_chain": 0}, {"syrk_gather": 1}, {"level_alap": 0}, {"wide_steps": 1},
+                {"asm_gather": 0}, {"asm_gather": 0, "fused_front": 0, "fused_chain": 0}, {"syrk_gather": 1}, {"level_alap": 0}, {"wide_steps": 1}, {"wide_steps": 2}, {"pdl": 0}, {"pdl": 0, "use_graph": 0},
                 {"syrk_gather": 1, "fused_front": 0, "fused_chain": 0}]
     defaults = {"splitk_min_k": 128, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1, "bwd_row_chunk": 2048,
-                "wide_rhs_min": 8, "fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "front_smem_kb": 200, "asm_gather": 1, "syrk_gather": 0, "level_alap": 1, "wide_steps": 0}
+                "wide_rhs_min": 8, "fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "front_smem_kb": 200, "asm_gather": 1, "syrk_gather": 0, "level_alap": 1, "wide_steps": 0, "pdl": 1}
     try:
         for v in variants:
             for k, val in {**defaults, **v}.items():
@@ -439,6 +439,43 @@ def test_schedule_variants_agree():
     finally:
         for k, val in defaults.items():
             _lib.set_option(k, val)
+
+
+def test_wide_solve_steps_agree():
+    """Few-RHS triangular solves on supernodes with more than 256 columns: the 64-column steps (default), the 256-column
+    steps with their own diagonal-block launches (wide_steps = 1) and the 256-column steps whose head CTA solves the next
+    diagonal block in the same launch (wide_steps = 2) are three schedules of the same sweeps. 23^3 vertices: the root
+    separator has 529 columns = two full 256-column blocks and a ragged one of 17."""
+    model = spde.MaternSPDE(*spde.mesh3d(22), 0)
+    Q = model.precision(1.1, 0.4)
+    n = Q.shape[0]
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((n, 8))
+    perm = spde.geometric_nd_perm((23, 23, 23), leaf=64, width=2)
+    res = {}
+    try:
+        for mode in (0, 1, 2, 3):               # 3: 64-column steps WITHOUT programmatic stream serialization
+            _lib.set_option("wide_steps", mode % 3)
+            _lib.set_option("pdl", 0 if mode == 3 else 1)
+            be = B200Backend(Q, ordering=perm, device=0)
+            assert be.info()["max_ns"] > 512
+            out = []
+            for m in (1, 2, 3, 8):
+                X = be.backend_solve(np.asfortranarray(B[:, :m]) if m > 1 else B[:, 0])
+                X = X.reshape(n, -1)
+                assert np.max(np.abs(Q @ X - B[:, :m])) <= 1e-10 * np.max(np.abs(B)), (mode, m)
+                out.append(X)
+            out.append(be.backend_backward_solve(B[:, 0]))
+            res[mode] = out
+            be.close()
+    finally:
+        _lib.set_option("wide_steps", 0)
+        _lib.set_option("pdl", 1)
+    for mode in (1, 2):
+        for a, c in zip(res[0], res[mode]):
+            assert _rel(c, a) <= 1e-11, mode
+    for a, c in zip(res[0], res[3]):          # same kernels, same order of operations: identical bits
+        assert np.array_equal(a, c)
 
 
 def test_run_to_run_bit_reproducible():
