@@ -1207,13 +1207,28 @@ void build_selinv_plan(gmrf_b200_handle *h, Builder &B) {
 // ------------------------------------------------------------------------------------------------
 // Launch dispatch
 // ------------------------------------------------------------------------------------------------
+// Kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may become resident while
+// its predecessor in the stream still runs and synchronizes itself with griddepcontrol.wait (kernels.cuh).
+template <typename... KA, typename... A>
+static inline void launch_k(bool pdl, void (*kern)(KA...), dim3 grid, int block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+
 template <int BM, int BN, int WGM, int WGN, bool TA, bool TB>
 void launch_gemm_t(const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st, int lanes, long long bstride,
-                   const GatherCtx *gctx = nullptr) {
+                   const GatherCtx *gctx = nullptr, bool pdl = false) {
     if (!TA && !TB && gctx)      // update-matrix products whose epilogue gathers the children's contributions
-        gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, 16, 3, true><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN>(), st>>>(tasks, prefix, ntasks, bstride, gctx);
+        launch_k(pdl, gemm_dmma_kernel<BM, BN, WGM, WGN, false, false, 16, 3, true>, dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN>(), st,
+                 tasks, prefix, ntasks, bstride, gctx);
     else
-        gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB><<<dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st>>>(tasks, prefix, ntasks, bstride);
+        launch_k(pdl, gemm_dmma_kernel<BM, BN, WGM, WGN, TA, TB>, dim3(grid, lanes), WGM * WGN * 32, gemm_smem_bytes<BM, BN, 16, 3, TA, TB>(), st,
+                 tasks, prefix, ntasks, bstride, (const GatherCtx *)nullptr);
 }
 
 // Opt in to > 48 KB dynamic shared memory for every GEMM instantiation (per device; must run outside stream capture).
@@ -1241,10 +1256,10 @@ cudaError_t configure_kernels(int front_smem = 0) {
 
 template <bool TA, bool TB>
 void launch_gemm(bool large, bool naive, const GemmTask *tasks, const int *prefix, int ntasks, int grid, cudaStream_t st,
-                 int lanes = 1, long long bstride = 0, const GatherCtx *gctx = nullptr) {
+                 int lanes = 1, long long bstride = 0, const GatherCtx *gctx = nullptr, bool pdl = false) {
     if (naive) gemm_naive_kernel<TA, TB><<<dim3(grid, lanes), 256, 0, st>>>(tasks, prefix, ntasks, bstride);
-    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx);
-    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx);
+    else if (large) launch_gemm_t<128, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx, pdl);
+    else launch_gemm_t<64, 64, 2, 2, TA, TB>(tasks, prefix, ntasks, grid, st, lanes, bstride, gctx, pdl);
 }
 
 struct TableSet {
@@ -1256,20 +1271,8 @@ struct TableSet {
     const RowGatherTask *rowgather = nullptr;
     double *y = nullptr, *u = nullptr;      // solve phases: permuted work array and update-vector pool
     int lanes = 1;                          // factorization: lanes advanced per launch (grid.y)
+    bool pdl = false;                       // launch the kernels that synchronize themselves (griddepcontrol.wait) programmatically
 };
-
-// Kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may become resident while
-// its predecessor in the stream still runs and synchronizes itself with griddepcontrol.wait (solve_kernels.cuh).
-template <typename... KA, typename... A>
-static inline void launch_k(bool pdl, void (*kern)(KA...), dim3 grid, cudaStream_t st, A... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, KA(args)...);
-}
 
 void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrhs, cudaStream_t stream_override = nullptr) {
     cudaStream_t st = stream_override ? stream_override : h->stream;
@@ -1279,40 +1282,40 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
     if (L.grid <= 0) return;
     switch (L.kind) {
         case K_ASSEMBLE:
-            assemble_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd, bstride);
+            launch_k(T.pdl, assemble_kernel, dim3(L.grid, T.lanes), 256, 0, st, T.items + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Lx, h->d_upd, bstride);
             break;
         case K_ASSEMBLE_G:
-            assemble_gather_kernel<<<dim3(L.grid, T.lanes), 256, AG_SMEM_BYTES, st>>>(h->d_asmtiles + L.task_off, h->d_meta, h->d_child, h->d_relidx,
-                                                                                    h->d_relpos, h->d_relpos_off, h->d_Lx, h->d_upd, bstride);
+            launch_k(T.pdl, assemble_gather_kernel, dim3(L.grid, T.lanes), 256, AG_SMEM_BYTES, st, h->d_asmtiles + L.task_off, h->d_meta, h->d_child,
+                     h->d_relidx, h->d_relpos, h->d_relpos_off, h->d_Lx, h->d_upd, bstride);
             break;
         case K_CHAIN:
-            chain_step_kernel<<<dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st>>>(h->d_chain + L.task_off, pf, L.ntasks, h->d_fail, bstride);
+            launch_k(T.pdl, chain_step_kernel, dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st, h->d_chain + L.task_off, pf, (int)L.ntasks, h->d_fail, bstride);
             break;
         case K_FRONT:
-            front_small_kernel<<<dim3(L.grid, T.lanes), 256, L.aux, st>>>(h->d_front + L.task_off, h->d_meta, h->d_child, h->d_relidx,
-                                                                          h->d_Lx, h->d_upd, h->d_fail, bstride);
+            launch_k(T.pdl, front_small_kernel, dim3(L.grid, T.lanes), 256, (size_t)L.aux, st, h->d_front + L.task_off, h->d_meta, h->d_child, h->d_relidx,
+                     h->d_Lx, h->d_upd, h->d_fail, bstride);
             break;
         case K_FINALIZE:
             chain_finalize_kernel<<<dim3(2 * L.grid, T.lanes), 256, FINALIZE_SMEM_BYTES, st>>>(h->d_final + L.task_off, bstride);
             break;
         case K_PANEL:
             switch (L.aux) {
-                case 8: potrf_inv_kernel<8><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
-                case 16: potrf_inv_kernel<16><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
-                case 32: potrf_inv_kernel<32><<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
-                default: potrf_inv64_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(h->d_panel + L.task_off, h->d_fail, bstride); break;
+                case 8: launch_k(T.pdl, potrf_inv_kernel<8>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
+                case 16: launch_k(T.pdl, potrf_inv_kernel<16>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
+                case 32: launch_k(T.pdl, potrf_inv_kernel<32>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
+                default: launch_k(T.pdl, potrf_inv64_kernel, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
             }
             break;
         case K_GEMM_NN_S: case K_GEMM_NN_L:
             launch_gemm<false, false>(L.kind == K_GEMM_NN_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride,
-                                      L.aux ? h->d_gctx : nullptr);
+                                      L.aux ? h->d_gctx : nullptr, T.pdl);
             break;
         case K_GEMM_NT_S: case K_GEMM_NT_L:
-            launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
+            launch_gemm<false, true>(L.kind == K_GEMM_NT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride, nullptr, T.pdl); break;
         case K_GEMM_TT_S: case K_GEMM_TT_L:
-            launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride); break;
+            launch_gemm<true, true>(L.kind == K_GEMM_TT_L, naive, T.gemm + L.task_off, pf, L.ntasks, L.grid, st, T.lanes, bstride, nullptr, T.pdl); break;
         case K_SPLIT_REDUCE:
-            splitk_reduce_kernel<<<dim3(L.grid, T.lanes), 256, 0, st>>>(T.split + L.task_off, pf, L.ntasks, bstride);
+            launch_k(T.pdl, splitk_reduce_kernel, dim3(L.grid, T.lanes), 256, 0, st, T.split + L.task_off, pf, (int)L.ntasks, bstride);
             break;
         case K_GATHER:
             selinv_gather_kernel<<<L.grid, 256, 0, st>>>(T.items + L.task_off, h->d_meta, h->d_relidx, h->d_Zx, h->d_zw);
@@ -1322,7 +1325,7 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_FWD_ASM: {
             dim3 g(L.grid, nrhs);
-            launch_k(h->opt.pdl != 0, fwd_assemble_x0_kernel, g, st, h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
+            launch_k(h->opt.pdl != 0, fwd_assemble_x0_kernel, g, 256, 0, st, h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
                      h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
             break;
         }
@@ -1349,10 +1352,10 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
 #define SOLVE_RB_DISPATCH_PDL(KERNEL, ...)                                                    \
     do {                                                                                       \
         const bool pdl = h->opt.pdl != 0;                                                      \
-        if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), st, __VA_ARGS__);                \
-        else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), st, __VA_ARGS__);           \
-        else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), st, __VA_ARGS__);           \
-        else launch_k(pdl, KERNEL<8>, dim3(L.grid), st, __VA_ARGS__);                          \
+        if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), 256, 0, st, __VA_ARGS__);                \
+        else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), 256, 0, st, __VA_ARGS__);           \
+        else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), 256, 0, st, __VA_ARGS__);           \
+        else launch_k(pdl, KERNEL<8>, dim3(L.grid), 256, 0, st, __VA_ARGS__);                          \
     } while (0)
         case K_FWD_STEP:
             SOLVE_RB_DISPATCH_PDL(fwd_step_kernel, (const FwdStepTask *)(h->d_fwd + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
@@ -1408,6 +1411,7 @@ void enqueue_factor(gmrf_b200_handle *h, int lanes = 1) {
     }
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
     T.lanes = lanes;
+    T.pdl = h->opt.pdl_factor != 0;
     // The finalize launches (block inverses for the solve / selected-inversion phases, parked diagonal squares -> panels)
     // feed nothing later in the factorization: they run on a side stream beside the upper tree levels, which leave
     // most SMs idle, and join before the log-determinant reads the diagonal.
@@ -1432,6 +1436,7 @@ void enqueue_factor(gmrf_b200_handle *h, int lanes = 1) {
 
 void enqueue_selinv(gmrf_b200_handle *h) {
     TableSet T{h->d_gemm_z, h->d_items_z, h->d_prefix_z, h->d_split_z};
+    T.pdl = h->opt.pdl_factor != 0;
     for (const Launch &L : h->selinv_plan.launches) run_launch(h, L, T, 0);
 }
 
@@ -1876,6 +1881,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "syrk_gather") o.syrk_gather = (int)value;
     else if (k == "wide_steps") o.wide_steps = (int)value;
     else if (k == "pdl") o.pdl = value != 0;
+    else if (k == "pdl_factor") o.pdl_factor = value != 0;
     else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;

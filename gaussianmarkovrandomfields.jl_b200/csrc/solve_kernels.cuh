@@ -208,7 +208,7 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
 // diagonal block then solves it (x_{j+1} = inv(L_{j+1,j+1}) b_{j+1}) and stores x in place of b.
 // ------------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RB == 1 ? 3 : 2)      // (one right-hand side: 3 CTAs per SM = at most 80 registers)
 fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                 long long ldy, long long ldu) {
     __shared__ double xs[SOLVE_NB][RB];
@@ -239,6 +239,14 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
         const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
         xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
     }
+    // the entries this thread will update at the end: fetched now, so that their L2 round trip overlaps the products
+    constexpr int NOUT = (SOLVE_NB * RB + 255) / 256;
+    double yold[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+        const int e = tid + 256 * k, rr = e % SOLVE_NB, q = e / SOLVE_NB, r = row0 + rr;
+        yold[k] = (e < SOLVE_NB * RB && r < T.m && q < nrhs) ? ((r < T.ms) ? T.y[r + q * ldy] : T.u[(r - T.ms) + q * ldu]) : 0.0;
+    }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < RB; q++) {
@@ -253,7 +261,10 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
         part[warp][lane + 32][q] = a1;
     }
     __syncthreads();
-    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+        const int e = tid + 256 * k;
+        if (e >= SOLVE_NB * RB) break;
         const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
         const int r = row0 + rr;
         if (head && rr >= T.nb_next) sb[rr][q] = 0.0;
@@ -262,7 +273,7 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
 #pragma unroll
         for (int w = 0; w < 8; w++) s += part[w][rr][q];
         double *dst = (r < T.ms) ? (T.y + r + q * ldy) : (T.u + (r - T.ms) + q * ldu);
-        const double v = *dst - s;
+        const double v = yold[k] - s;
         if (head && rr < T.nb_next) sb[rr][q] = v; else *dst = v;
     }
     if (!head) return;
@@ -385,7 +396,7 @@ bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict
 // holds block j-1 then solves it: x_{j-1} = inv(L_{j-1,j-1})' t_{j-1}.
 // ------------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RB == 1 ? 3 : 2)
 bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                 long long ldy) {
     __shared__ double xs[SOLVE_NB][RB];
@@ -413,6 +424,11 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
         const int kk = e % SOLVE_NB, q = e / SOLVE_NB;
         xs[kk][q] = (kk < T.nb && q < nrhs) ? T.x[kk + q * ldy] : 0.0;
     }
+    // the entries this thread will update at the end: fetched now, so that their L2 round trip overlaps the products
+    const int cl = warp * 8 + warp_reduce8_index(lane);
+    double yold[RB];
+#pragma unroll
+    for (int q = 0; q < RB; q++) yold[q] = ((lane & 3) == 0 && q < nrhs) ? T.y[(long long)tile * SOLVE_NB + cl + q * ldy] : 0.0;
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < RB; q++) {
@@ -422,10 +438,9 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
 #pragma unroll
         for (int i = 0; i < 8; i++) p[i] = l[i][0] * x0 + l[i][1] * x1;
         const double s = warp_reduce8(p, lane);
-        const int cl = warp * 8 + warp_reduce8_index(lane);
         if ((lane & 3) == 0) {
             double *dst = T.y + (long long)tile * SOLVE_NB + cl + q * ldy;
-            const double v = *dst - s;
+            const double v = yold[q] - s;
             if (tail) st[cl][q] = v; else *dst = v;
         }
     }
