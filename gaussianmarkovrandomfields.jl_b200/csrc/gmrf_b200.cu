@@ -887,7 +887,8 @@ void build_multi_plans(gmrf_b200_handle *h, Builder &B, int W, Plan &fwd_plan, P
     auto task = [](const double *A, int lda, const double *Bm, int ldb, double *C, int ldc, i64 m, i64 n, i64 k, int flags) {
         GemmTask g;
         g.A = A; g.B = Bm; g.C = C; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
-        g.m = (int)m; g.n = (int)n; g.k = (int)k; g.flags = flags; g.pad_ = 0;
+        g.m = (int)m; g.n = (int)n; g.k = (int)k; g.pad_ = 0;
+        g.flags = flags | GEMM_A_CONST;      // A is always a piece of the factor (panel or inverted diagonal block)
         return g;
     };
     // ---- forward: L y = b ------------------------------------------------------------------------------------
@@ -1599,6 +1600,7 @@ void enqueue_multi_sweeps(gmrf_b200_handle *h, int wi, int mode) {
     T.rowgather = M.d_rg;
     T.y = h->d_ym;
     T.u = h->d_um;
+    T.pdl = h->opt.pdl_multi != 0;
     const int W = 64 << wi;
     if (mode == 0)
         for (const Launch &L : M.fwd_plan.launches) run_launch(h, L, T, W);
@@ -1882,6 +1884,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "wide_steps") o.wide_steps = (int)value;
     else if (k == "pdl") o.pdl = value != 0;
     else if (k == "pdl_factor") o.pdl_factor = value != 0;
+    else if (k == "pdl_multi") o.pdl_multi = value != 0;
     else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;

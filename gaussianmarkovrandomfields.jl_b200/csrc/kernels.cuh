@@ -26,6 +26,8 @@ enum : int {
     GEMM_ADD_I = 8,      // add the identity on the local diagonal
     GEMM_GATHER = 16     // (GATHER instantiation, C = update matrix of supernode pad_ - 1) C = children's contributions - A B^T,
                          // written once: the extend-add of the update matrix happens in this epilogue
+    ,GEMM_A_CONST = 32   // operand A is not written by any kernel of the same graph (the factor during a triangular sweep): a
+                         // programmatically launched instance loads its first A tiles before waiting for the predecessor
 };
 
 struct GemmTask {        // C[m x n] (+)= alpha * Aop[m x k] * Bop[n x k]^T
@@ -384,13 +386,17 @@ gemm_dmma_kernel(const GemmTask *__restrict__ tasks, const int *__restrict__ til
     TileLoader<BN, NT, TB, GEMM_KT> lb;
     la.init(T.A, T.lda, m0, T.m, a16, tid);
     lb.init(T.B, T.ldb, n0, T.n, b16, tid);
-    pdl_wait();            // (task search and tile bookkeeping above overlap the predecessor when launched programmatically)
+    // A tiles of the first stages, then B tiles; the wait for a programmatic predecessor sits before the first operand it
+    // may have written (all A tiles join the first commit group: they were issued back to back anyway)
+    const bool a_ahead = (T.flags & GEMM_A_CONST) != 0;
+    if (!a_ahead) pdl_wait();
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++)
+        if (s < nk) la.load(as_base + s * A_TILE * 8, s * GEMM_KT, T.k);
+    if (a_ahead) pdl_wait();
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; s++) {
-        if (s < nk) {
-            la.load(as_base + s * A_TILE * 8, s * GEMM_KT, T.k);
-            lb.load(bs_base + s * B_TILE * 8, s * GEMM_KT, T.k);
-        }
+        if (s < nk) lb.load(bs_base + s * B_TILE * 8, s * GEMM_KT, T.k);
         cp_async_commit();
     }
     for (int kt = 0; kt < nk; kt++) {
