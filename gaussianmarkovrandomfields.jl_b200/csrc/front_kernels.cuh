@@ -45,23 +45,16 @@ constexpr int FSCRATCH = 2 * 3 * 4 * FPLD + FB;   // panel-step scratch: double-
 // FACTOR = false: sD already holds L (and srinv the reciprocal pivots); only the row tiles are solved.
 // `scratch`: panel_scratch_doubles(RT) doubles (FSCRATCH covers RT <= 2). Non-positive pivots: integer atomicMin of the 1-based column, NaNs propagate.
 // ------------------------------------------------------------------------------------------------
-// Cholesky of the 4 x 4 diagonal tile held by one thread (4 dependent rsqrt chains); publishes the tile (k-major) and
-// the reciprocal pivots.
+// Cholesky of the 4 x 4 diagonal tile held by one thread (chol4x4_lower: two rsqrt latencies); publishes the tile (k-major)
+// and the reciprocal pivots.
 __device__ __forceinline__ void factor_diag_tile(double (&a)[4][4], double *__restrict__ pb, double *__restrict__ srinv, int P, int nb,
                                                  int col0, int *fail_col, bool report) {
+    double ri[4], piv[4];
+    chol4x4_lower(a, ri, piv);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        const double d = a[c][c];
-        if (report && !(d > 0.0) && 4 * P + c < nb) atomicMin(fail_col, col0 + 4 * P + c + 1);
-        const double r = rsqrt(d);
-        a[c][c] = d * r;
-        srinv[4 * P + c] = r;
-#pragma unroll
-        for (int r2 = c + 1; r2 < 4; r2++) a[r2][c] *= r;
-#pragma unroll
-        for (int c2 = c + 1; c2 < 4; c2++)
-#pragma unroll
-            for (int r2 = c2; r2 < 4; r2++) a[r2][c2] -= a[r2][c] * a[c2][c];
+        if (report && !(piv[c] > 0.0) && 4 * P + c < nb) atomicMin(fail_col, col0 + 4 * P + c + 1);
+        srinv[4 * P + c] = ri[c];
     }
 #pragma unroll
     for (int c = 0; c < 4; c++)

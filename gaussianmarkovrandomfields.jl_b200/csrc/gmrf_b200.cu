@@ -2869,6 +2869,24 @@ int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv,
     if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
     return 0;
 }
+// y[i] = rsqrt_inline(x[i]) (the straight-line reciprocal square root of the 4 x 4 pivot tiles), for the accuracy test
+__global__ void test_rsqrt_kernel(const double *x, double *y, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) y[i] = rsqrt_inline(x[i]);
+}
+int gmrf_b200_test_rsqrt(int device, int n, const double *x, double *y) {
+    if (cudaSetDevice(device) != cudaSuccess) return test_fail("no device");
+    if (n < 1 || !x || !y) return GMRF_B200_ERR_ARG;
+    double *dx, *dy;
+    if (cudaMalloc(&dx, (size_t)n * 8) || cudaMalloc(&dy, (size_t)n * 8)) return test_fail("alloc");
+    cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice);
+    test_rsqrt_kernel<<<(n + 255) / 256, 256>>>(dx, dy, n);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dy);
+    if (e != cudaSuccess) return test_fail(cudaGetErrorString(e));
+    return 0;
+}
 int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info) {
     return gmrf_b200_test_potrf_inv(device, n, A, lda, nullptr, info);
 }

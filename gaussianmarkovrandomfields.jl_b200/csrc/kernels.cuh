@@ -76,6 +76,49 @@ struct GatherCtx {
 constexpr int GATHER_MAXC = 4;    // children whose inverse maps are resident at once
 
 // ------------------------------------------------------------------------------------------------
+// Cholesky of a 4 x 4 tile held in the registers of one thread (lower triangle of a[r][c], r >= c), the innermost serial
+// piece of every panel factorization: its latency is paid once per 4 columns on the critical path of the 2D configs.
+// Column by column it is four dependent rsqrt chains (~480 cycles each on sm_100a: MUFU seed + Newton steps + scale +
+// update). Here the tile is factored as two 2 x 2 blocks whose second pivot comes from the block's determinant,
+//     l00 = sqrt(a00),  l10 = a10 / l00,  l11 = sqrt(a00 a11 - a10^2) / sqrt(a00),
+// so both square roots of a block start together and the chain is two rsqrt latencies instead of four. The conditioning is
+// that of the ordinary recurrence (a11 - l10^2 = (a00 a11 - a10^2) / a00: the same cancellation). piv[c] gets a number with
+// the sign of the c-th pivot (for the not-positive-definite report), ri[c] = 1 / l_cc.
+// 1 / sqrt(x) as straight-line code: the hardware seed (rsqrt.approx.ftz.f64 -> MUFU.RSQ64H, ~20 good bits) and one
+// third-order correction y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2 (error after the step ~ e^3: below the rounding of the
+// five operations, max 1 ulp-ish measured against numpy in tests/test_gpu_kernels.py). The library rsqrt() carries a
+// slow-path branch for subnormal / special arguments, which keeps the compiler from interleaving two of them; pivots of a
+// factorization that is going to be used are normal positive numbers, and anything else (<= 0, NaN, inf) still comes out
+// as NaN / inf / 0 and is caught by the sign test on the pivot itself.
+__device__ __forceinline__ double rsqrt_inline(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
+
+__device__ __forceinline__ void chol4x4_lower(double (&a)[4][4], double (&ri)[4], double (&piv)[4]) {
+    const double a00 = a[0][0], a10 = a[1][0];
+    const double det1 = fma(a00, a[1][1], -(a10 * a10));
+    const double r0 = rsqrt_inline(a00), q1 = rsqrt_inline(det1);
+    const double l00 = a00 * r0, l10 = a10 * r0;
+    const double ri1 = l00 * q1;
+    const double l20 = a[2][0] * r0, l30 = a[3][0] * r0;
+    const double l21 = fma(-l20, l10, a[2][1]) * ri1, l31 = fma(-l30, l10, a[3][1]) * ri1;
+    const double s22 = fma(-l21, l21, fma(-l20, l20, a[2][2]));
+    const double s32 = fma(-l31, l21, fma(-l30, l20, a[3][2]));
+    const double s33 = fma(-l31, l31, fma(-l30, l30, a[3][3]));
+    const double det2 = fma(s22, s33, -(s32 * s32));
+    const double r2 = rsqrt_inline(s22), q3 = rsqrt_inline(det2);
+    const double l22 = s22 * r2;
+    piv[0] = a00; piv[1] = det1; piv[2] = s22; piv[3] = det2;
+    ri[0] = r0; ri[1] = ri1; ri[2] = r2; ri[3] = l22 * q3;
+    a[0][0] = l00; a[1][0] = l10; a[1][1] = det1 * q1 * r0;
+    a[2][0] = l20; a[2][1] = l21; a[3][0] = l30; a[3][1] = l31;
+    a[2][2] = l22; a[3][2] = s32 * r2; a[3][3] = det2 * q3 * r2;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Programmatic dependent launch (griddepcontrol). A kernel launched with the programmatic-stream-serialization attribute may
 // become resident while its predecessor in the stream still runs: it reads its task tables (and whatever else no kernel
 // of the same graph writes -- for the triangular sweeps that is the whole factor) and then waits for the predecessor's
@@ -596,20 +639,13 @@ potrf_inv64_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_c
     for (int P = 0; P < 16; P++) {
         double (*spanel)[4] = spanel2[P & 1];
         if (ty == P && tx == P) {
+            double ri[4], piv[4];
+            chol4x4_lower(a, ri, piv);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const double d = a[c][c];
-                if (!(d > 0.0) && 4 * P + c < nb) atomicMin(fail_col, T.col0 + 4 * P + c + 1);
-                const double r = rsqrt(d);
-                a[c][c] = d * r;
-                srinv[c] = r;
-                srinv_all[4 * P + c] = r;
-#pragma unroll
-                for (int r2 = c + 1; r2 < 4; r2++) a[r2][c] *= r;
-#pragma unroll
-                for (int c2 = c + 1; c2 < 4; c2++)
-#pragma unroll
-                    for (int r2 = c2; r2 < 4; r2++) a[r2][c2] -= a[r2][c] * a[c2][c];
+                if (!(piv[c] > 0.0) && 4 * P + c < nb) atomicMin(fail_col, T.col0 + 4 * P + c + 1);
+                srinv[c] = ri[c];
+                srinv_all[4 * P + c] = ri[c];
             }
 #pragma unroll
             for (int r = 0; r < 4; r++)

@@ -272,6 +272,8 @@ int gmrf_b200_set_option(const char *key, double value);
 int gmrf_b200_test_gemm(int device, int transa, int transb, int flags, int m, int n, int k,
                         const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
 int gmrf_b200_test_potrf(int device, int n, double *A, int lda, int *info);
+/* y[i] = the kernels' straight-line reciprocal square root of x[i] (pivot tiles of the panel factorizations). */
+int gmrf_b200_test_rsqrt(int device, int n, const double *x, double *y);
 /* same kernel, also returning inv(L) (n x n, leading dimension n, zeros above the diagonal) */
 int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv, int *info);
 /* Device-timed micro-benchmark of the library's own FP64 GEMM kernel (zero-filled device operands, best of

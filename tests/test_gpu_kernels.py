@@ -86,3 +86,22 @@ def test_potrf_diag(n):
         Ab = np.zeros((lda, n), order="F"); Ab[:n] = A2
         assert L.gmrf_b200_test_potrf(0, n, ptr(Ab), lda, ctypes.byref(info)) == 0
         assert info.value == 3
+
+
+def test_pivot_rsqrt_accuracy():
+    """The 4 x 4 pivot tiles use a straight-line 1/sqrt (hardware seed + one third-order step) instead of the library call:
+    it has to be as good as a correctly rounded one over the whole range a pivot can take."""
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([10.0 ** rng.uniform(-200, 200, 100000), 1.0 + rng.uniform(-1e-3, 1e-3, 20000), rng.uniform(0.5, 4.0, 80000),
+                        np.array([1.0, 2.0, 4.0, 0.25, 3.0, 1e-300, 1e300])])
+    y = np.empty_like(x)
+    assert L.gmrf_b200_test_rsqrt(0, x.size, ptr(x), ptr(y)) == 0
+    want = (1.0 / np.sqrt(x.astype(np.longdouble)))
+    rel = np.abs((y.astype(np.longdouble) - want) / want).astype(np.float64)
+    assert rel.max() <= 2.5e-16, rel.max()                      # ~ 1 ulp
+    # not-a-pivot arguments stay recognisable
+    bad = np.array([-1.0, 0.0, np.nan])
+    out = np.empty_like(bad)
+    assert L.gmrf_b200_test_rsqrt(0, bad.size, ptr(bad), ptr(out)) == 0
+    assert np.isnan(out[0]) and not np.isfinite(out[1]) and np.isnan(out[2])
