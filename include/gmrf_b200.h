@@ -262,7 +262,9 @@ int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
- * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather","syrk_gather","level_alap","wide_steps"}. */
+ * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather","syrk_gather","level_alap","wide_steps","syrk_split",
+ * "pdl" (few-RHS sweeps launched with programmatic stream serialization, default 1), "pdl_multi" (same for the wide right-hand-side
+ * GEMM sweeps, default 1), "pdl_factor" (same for the factorization / selected-inversion plans, default 0)}. */
 int gmrf_b200_set_option(const char *key, double value);
 
 /* Dense-kernel unit-test hooks (tests/ only). HOST pointers, column-major; operands are staged to `device`
