@@ -33,7 +33,7 @@ EXPORTS = [
     "gmrf_b200_selinv_dot", "gmrf_b200_selinv_dot_basis",
     "gmrf_b200_factor_nnz", "gmrf_b200_factor_pattern", "gmrf_b200_factor_values", "gmrf_b200_pattern_positions",
     "gmrf_b200_create_from_analysis", "gmrf_b200_analysis_export", "gmrf_b200_analysis_equal",
-    "gmrf_b200_test_rsqrt", "gmrf_b200_debug_chain_phases", "gmrf_b200_analysis_fingerprint", "gmrf_b200_adopt_factor_checked",
+    "gmrf_b200_test_rsqrt", "gmrf_b200_host_copy", "gmrf_b200_debug_chain_phases", "gmrf_b200_analysis_fingerprint", "gmrf_b200_adopt_factor_checked",
     "gmrf_b200_plan_launch_info", "gmrf_b200_set_hessian_pattern", "gmrf_b200_refactorize_base_minus_sparse", "gmrf_b200_selinv_quadform_rows",
 ]
 
@@ -153,6 +153,8 @@ def lib():
     L.gmrf_b200_adopt_factor.argtypes = [c_vp, ctypes.c_double, ctypes.c_int]
     L.gmrf_b200_host_register.restype = ctypes.c_int
     L.gmrf_b200_host_register.argtypes = [c_vp, c_i64]
+    L.gmrf_b200_host_copy.restype = ctypes.c_int
+    L.gmrf_b200_host_copy.argtypes = [c_vp, c_vp, c_i64]
     L.gmrf_b200_test_rsqrt.restype = ctypes.c_int
     L.gmrf_b200_test_rsqrt.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.gmrf_b200_debug_chain_phases.restype = ctypes.c_int
@@ -186,3 +188,15 @@ def set_option(key: str, value: float):
     rc = lib().gmrf_b200_set_option(key.encode(), float(value))
     if rc != 0:
         raise ValueError(f"unknown option {key!r}")
+
+
+def host_copy(dst, src):
+    """dst[:] = src for float64 arrays of equal size; large contiguous ones go through the library's threaded copy (the
+    host mirror `ws.Q.nzval .= nzval` of update_precision_values is 520 MB at 1 M dofs)."""
+    import numpy as np
+    if (dst.size >= (1 << 20) and isinstance(src, np.ndarray) and src.dtype == np.float64 and dst.dtype == np.float64
+            and src.size == dst.size and src.flags.c_contiguous and dst.flags.c_contiguous and not np.shares_memory(dst, src)):
+        rc = lib().gmrf_b200_host_copy(ptr(dst), ptr(src), dst.size)
+        if rc == 0:
+            return
+    dst[:] = src

@@ -11,6 +11,7 @@ from contextlib import contextmanager
 import numpy as np
 import scipy.sparse as sp
 
+from . import _lib
 from .backend import B200Backend, _csc, ordering_permutation
 
 __all__ = ["GMRFWorkspace", "WorkspacePool", "workspace_solve", "backward_solve", "logdet", "selinv", "selinv_diag",
@@ -64,7 +65,7 @@ class GMRFWorkspace:
         nzval = np.asarray(nzval, dtype=np.float64)
         if nzval.size != self.Q.data.size:
             raise ValueError(f"nzval length {nzval.size} does not match workspace Q nzval length {self.Q.data.size}")
-        self.Q.data[:] = nzval
+        _lib.host_copy(self.Q.data, nzval)
         self._invalidate()
         self.loaded_version = 0
 

@@ -260,6 +260,9 @@ int gmrf_b200_adopt_factor_checked(gmrf_b200_handle *h, uint64_t sender_fingerpr
  * gmrf_b200_refactorize moves it with an asynchronous DMA. Optional; ownership stays with the caller. */
 int gmrf_b200_host_register(void *ptr, int64_t bytes);
 int gmrf_b200_host_unregister(void *ptr);
+/* dst[0..n) = src[0..n) (doubles) with all host threads: the host mirror `ws.Q.nzval .= nzval` of update_precision_values
+ * (src/workspace/gmrf_workspace.jl:154-165) for callers without a threaded copy of their own. Regions must not overlap. */
+int gmrf_b200_host_copy(double *dst, const double *src, int64_t n);
 
 /* Tunables, set BEFORE create (process-wide defaults): key in {"relax_n0","relax_n1","relax_n2",
  * "relax_z0","relax_z1","relax_z2","use_graph","outer_block","naive_kernels","selinv_fast_root","splitk_min_k","wide_rhs_min","bwd_row_chunk","large_tile_mask","lanes","fused_front","fused_chain","chain_max_tiles","front_smem_kb","asm_gather","syrk_gather","level_alap","wide_steps","syrk_split",

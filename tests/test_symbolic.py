@@ -107,6 +107,24 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_lib.EXPORTS)
 
 
+def test_threaded_host_copy_matches_numpy():
+    """update_precision_values mirrors the caller's values into ws.Q.nzval; large arrays go through the library's threaded
+    copy (a host utility: no device involved)."""
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 1000, (1 << 20) + 12345, 3 * (1 << 20) + 7):
+        src = rng.standard_normal(n)
+        dst = np.full(n + 2, 7.0)
+        assert _lib.lib().gmrf_b200_host_copy(_lib.ptr(dst[1:]) if n else None, _lib.ptr(src) if n else None, n) == 0
+        assert np.array_equal(dst[1:n + 1], src) and dst[0] == 7.0 and dst[-1] == 7.0
+    big = rng.standard_normal((1 << 21) + 3)
+    out = np.zeros_like(big)
+    _lib.host_copy(out, big)
+    assert np.array_equal(out, big)
+    _lib.host_copy(out[::2], big[::2] * 2.0)            # strided views fall back to numpy
+    assert np.array_equal(out[::2], big[::2] * 2.0)
+    assert _lib.lib().gmrf_b200_host_copy(None, None, -1) != 0
+
+
 def test_amd_ordering_quality_and_speed():
     """Approximate minimum degree (supervariables, element absorption, mass elimination): a valid permutation whose
     fill stays within the usual AMD/ND band on a 2D mesh, in time near-linear in nnz(Q) (the exact-degree variant it
