@@ -1247,6 +1247,9 @@ cudaError_t configure_kernels(int front_smem = 0) {
     if ((e = configure_gemm_tile<128, 64, 2, 2>())) return e;
     if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
     if ((e = cudaFuncSetAttribute(chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
+    // (static + dynamic shared memory of the wider forward step kernels exceeds 48 KB)
+    if ((e = cudaFuncSetAttribute(fwd_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(fwd_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(assemble_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(chain_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FINALIZE_SMEM_BYTES))) return e;
     // (per device, sticky: handles of one process may need different sizes -> always opt in to the cap)
@@ -1350,25 +1353,25 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
     } while (0)
 // the kernels of the few-RHS sweeps: programmatic dependent launch (solve_kernels.cuh) -- the next step's CTAs may start
 // loading their factor tiles while this one finishes
-#define SOLVE_RB_DISPATCH_PDL(KERNEL, ...)                                                    \
+#define SOLVE_RB_DISPATCH_PDL(SMEM, KERNEL, ...)                                              \
     do {                                                                                       \
         const bool pdl = h->opt.pdl != 0;                                                      \
-        if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), 256, 0, st, __VA_ARGS__);                \
-        else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), 256, 0, st, __VA_ARGS__);           \
-        else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), 256, 0, st, __VA_ARGS__);           \
-        else launch_k(pdl, KERNEL<8>, dim3(L.grid), 256, 0, st, __VA_ARGS__);                          \
+        if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__);     \
+        else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__); \
+        else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__); \
+        else launch_k(pdl, KERNEL<8>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__);               \
     } while (0)
         case K_FWD_STEP:
-            SOLVE_RB_DISPATCH_PDL(fwd_step_kernel, (const FwdStepTask *)(h->d_fwd + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
+            SOLVE_RB_DISPATCH_PDL(STEP_SMEM_BYTES, fwd_step_kernel, (const FwdStepTask *)(h->d_fwd + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);
             break;
         case K_BWD_GATHER:
-            SOLVE_RB_DISPATCH_PDL(bwd_gather_kernel, h->d_bwdg + L.task_off, pf, (int)L.ntasks, nrhs, h->d_y, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(0, bwd_gather_kernel, h->d_bwdg + L.task_off, pf, (int)L.ntasks, nrhs, h->d_y, (long long)h->S.n);
             break;
         case K_BWD_REDUCE:
-            SOLVE_RB_DISPATCH_PDL(bwd_reduce_kernel, h->d_bwdr + L.task_off, pf, (int)L.ntasks, nrhs, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(0, bwd_reduce_kernel, h->d_bwdr + L.task_off, pf, (int)L.ntasks, nrhs, (long long)h->S.n);
             break;
         case K_BWD_STEP:
-            SOLVE_RB_DISPATCH_PDL(bwd_step_kernel, (const BwdStepTask *)(h->d_bwds + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n);
+            SOLVE_RB_DISPATCH_PDL(STEP_SMEM_BYTES, bwd_step_kernel, (const BwdStepTask *)(h->d_bwds + L.task_off), pf, (int)L.ntasks, nrhs, (long long)h->S.n);
             break;
         case K_FWD_WSTEP:
             SOLVE_RB_DISPATCH(fwd_wide_step_kernel, h->d_wstep + L.task_off, pf, L.ntasks, nrhs, (long long)h->S.n, (long long)h->S.uvec_total);

@@ -19,6 +19,7 @@
 namespace gmrf {
 
 constexpr int SOLVE_NB = 64;
+constexpr int STEP_SMEM_BYTES = SOLVE_NB * SOLVE_NB * 8;     // dynamic shared memory of the block-step kernels (staged inverse)
 
 
 struct FwdStepTask {      // block column K_j = [k0, k1) of a supernode, x_j final in `x`
@@ -160,6 +161,66 @@ __device__ __forceinline__ void apply_inv_lower_t(const double (&g)[16], int nb,
     }
 }
 
+// The block-step kernels keep the inverted diagonal block of their ONE look-ahead CTA in shared memory instead (cp.async,
+// no registers): with the 16 doubles per thread above, every CTA of the launch paid 32 registers for a block only one of
+// them applies, which capped the step kernels at 3 CTAs per SM (ncu, profiles/r02_ncu_full_fwd_step_3d48.txt: 33 % of the
+// warp slots, long-scoreboard stalls of 8-10 per issue, 1.2-2.4 TB/s per launch -- not enough loads in flight).
+__device__ __forceinline__ void stage_inv_block(double *__restrict__ sinv, const double *__restrict__ inv, int nb, int tid) {
+    for (int e = tid; e < nb * nb; e += 256) cp_async8(sinv + e, inv + e, 8);      // (8-byte granules: block bases may be odd)
+    cp_async_commit();
+}
+template <int RB>
+__device__ __forceinline__ void apply_inv_lower_smem(const double *__restrict__ sinv, int nb, const double (*sb)[RB],
+                                                     double (*sp)[SOLVE_NB][RB], double *__restrict__ out, long long ldo, int nrhs, int tid) {
+    const int r = tid & 63, part = tid >> 6;
+    double g[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int c = part * 16 + i;
+        g[i] = (r < nb && c <= r) ? sinv[r + c * nb] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            s0 += g[i] * sb[part * 16 + i][q];
+            s1 += g[i + 1] * sb[part * 16 + i + 1][q];
+        }
+        sp[part][r][q] = s0 + s1;
+    }
+    __syncthreads();
+    for (int e = tid; e < SOLVE_NB * RB; e += 256) {
+        const int rr = e % SOLVE_NB, q = e / SOLVE_NB;
+        if (rr < nb && q < nrhs) out[rr + q * ldo] = (sp[0][rr][q] + sp[1][rr][q]) + (sp[2][rr][q] + sp[3][rr][q]);
+    }
+}
+template <int RB>
+__device__ __forceinline__ void apply_inv_lower_t_smem(const double *__restrict__ sinv, int nb, const double (*st)[RB],
+                                                       double *__restrict__ out, long long ldo, int nrhs, int warp, int lane) {
+    double g[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = warp * 8 + i;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = lane + 32 * h;
+            g[2 * i + h] = (c < nb && r < nb && r >= c) ? sinv[r + c * nb] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RB; q++) {
+        if (q >= nrhs) break;
+        double p[8];
+        const double t0 = lane < nb ? st[lane][q] : 0.0, t1 = lane + 32 < nb ? st[lane + 32][q] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = g[2 * i] * t0 + g[2 * i + 1] * t1;
+        const double s = warp_reduce8(p, lane);
+        const int c = warp * 8 + warp_reduce8_index(lane);
+        if ((lane & 3) == 0 && c < nb) out[c + q * ldo] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Forward assembly of one level: supernode s pulls its children's update vectors (fixed order) into its own
 // rows of y and into u_s, then the first block of its chain is solved: x_0 = inv(L_00) b_0.
@@ -208,7 +269,7 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
 // diagonal block then solves it (x_{j+1} = inv(L_{j+1,j+1}) b_{j+1}) and stores x in place of b.
 // ------------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(256, RB == 1 ? 3 : 2)      // (one right-hand side: 3 CTAs per SM = at most 80 registers)
+__global__ void __launch_bounds__(256, RB == 1 ? 4 : 2)      // (one right-hand side: 4 CTAs per SM = at most 64 registers)
 fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                 long long ldy, long long ldu) {
     __shared__ double xs[SOLVE_NB][RB];
@@ -221,8 +282,8 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = tile * SOLVE_NB;
     const bool head = (tile == 0 && T.nb_next > 0);
-    double g[16];
-    if (head) load_inv_lower(g, T.inv_next, T.nb_next, tid);
+    extern __shared__ __align__(16) double step_sinv[];      // [64 x 64] inverse of the next diagonal block (look-ahead CTA only)
+    if (head) stage_inv_block(step_sinv, T.inv_next, T.nb_next, tid);
     // issue the tile loads first: 8 columns x 2 rows per thread
     double l[8][2];
 #pragma unroll
@@ -277,8 +338,9 @@ fwd_step_kernel(const FwdStepTask *__restrict__ tasks, const int *__restrict__ t
         if (head && rr < T.nb_next) sb[rr][q] = v; else *dst = v;
     }
     if (!head) return;
+    cp_async_wait<0>();
     __syncthreads();
-    apply_inv_lower<RB>(g, T.nb_next, sb, (double (*)[SOLVE_NB][RB])part, T.y, ldy, nrhs, tid);
+    apply_inv_lower_smem<RB>(step_sinv, T.nb_next, sb, (double (*)[SOLVE_NB][RB])part, T.y, ldy, nrhs, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,7 +458,7 @@ bwd_reduce_kernel(const BwdReduceTask *__restrict__ tasks, const int *__restrict
 // holds block j-1 then solves it: x_{j-1} = inv(L_{j-1,j-1})' t_{j-1}.
 // ------------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(256, RB == 1 ? 3 : 2)
+__global__ void __launch_bounds__(256, RB == 1 ? 4 : 2)
 bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int nrhs,
                 long long ldy) {
     __shared__ double xs[SOLVE_NB][RB];
@@ -409,8 +471,8 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
     const int c0 = tile * SOLVE_NB + warp * 8;
     const int ntiles = T.ncols / SOLVE_NB;
     const bool tail = (tile == ntiles - 1);
-    double g[16];
-    if (tail) load_inv_lower_t(g, T.inv_prev, SOLVE_NB, warp, lane);
+    extern __shared__ __align__(16) double step_sinv[];      // [64 x 64] inverse of the previous diagonal block (look-ahead CTA only)
+    if (tail) stage_inv_block(step_sinv, T.inv_prev, SOLVE_NB, tid);
     double l[8][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -445,8 +507,9 @@ bwd_step_kernel(const BwdStepTask *__restrict__ tasks, const int *__restrict__ t
         }
     }
     if (!tail) return;
+    cp_async_wait<0>();
     __syncthreads();
-    apply_inv_lower_t<RB>(g, SOLVE_NB, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
+    apply_inv_lower_t_smem<RB>(step_sinv, SOLVE_NB, st, T.y + (long long)tile * SOLVE_NB, ldy, nrhs, warp, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
