@@ -1329,7 +1329,7 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
             break;
         case K_FWD_ASM: {
             dim3 g(L.grid, nrhs);
-            launch_k(h->opt.pdl != 0, fwd_assemble_x0_kernel, g, 256, 0, st, h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
+            launch_k(T.pdl, fwd_assemble_x0_kernel, g, 256, 0, st, h->d_superlist + L.task_off, h->d_meta, h->d_child, h->d_relidx, h->d_Linv,
                      h->d_invbase, h->d_y, h->S.n, h->d_uvec, h->S.uvec_total);
             break;
         }
@@ -1355,7 +1355,7 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
 // loading their factor tiles while this one finishes
 #define SOLVE_RB_DISPATCH_PDL(SMEM, KERNEL, ...)                                              \
     do {                                                                                       \
-        const bool pdl = h->opt.pdl != 0;                                                      \
+        const bool pdl = T.pdl;                                                                \
         if (nrhs <= 1) launch_k(pdl, KERNEL<1>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__);     \
         else if (nrhs <= 2) launch_k(pdl, KERNEL<2>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__); \
         else if (nrhs <= 4) launch_k(pdl, KERNEL<4>, dim3(L.grid), 256, SMEM, st, __VA_ARGS__); \
@@ -1603,11 +1603,11 @@ void enqueue_multi_sweeps(gmrf_b200_handle *h, int wi, int mode) {
     T.rowgather = M.d_rg;
     T.y = h->d_ym;
     T.u = h->d_um;
-    T.pdl = h->opt.pdl_multi != 0;
+    T.pdl = false;               // (first kernel of a sweep: ordinary launch, see enqueue_sweeps)
     const int W = 64 << wi;
     if (mode == 0)
-        for (const Launch &L : M.fwd_plan.launches) run_launch(h, L, T, W);
-    for (const Launch &L : M.bwd_plan.launches) run_launch(h, L, T, W);
+        for (const Launch &L : M.fwd_plan.launches) { run_launch(h, L, T, W); T.pdl = h->opt.pdl_multi != 0; }
+    for (const Launch &L : M.bwd_plan.launches) { run_launch(h, L, T, W); T.pdl = h->opt.pdl_multi != 0; }
 }
 
 // Wide path: the right-hand sides go through the GEMM sweeps in blocks of 256, then 128, then 64 columns (the last
@@ -1679,9 +1679,11 @@ int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 
 // Enqueue the level-scheduled sweeps on the permuted work array d_y (mode 0: forward + backward, 1: backward only).
 void enqueue_sweeps(gmrf_b200_handle *h, int nb, int mode) {
     TableSet T{h->d_gemm, h->d_items, h->d_prefix, h->d_split};
+    // the first kernel of a sweep follows a copy / permutation that is not part of the plan: ordinary launch
+    T.pdl = false;
     if (mode == 0)
-        for (const Launch &L : h->fwd_plan.launches) run_launch(h, L, T, nb);
-    for (const Launch &L : h->bwd_plan.launches) run_launch(h, L, T, nb);
+        for (const Launch &L : h->fwd_plan.launches) { run_launch(h, L, T, nb); T.pdl = h->opt.pdl != 0; }
+    for (const Launch &L : h->bwd_plan.launches) { run_launch(h, L, T, nb); T.pdl = h->opt.pdl != 0; }
 }
 
 // X = Q^-1 B (mode 0) or X = P' L^-T Z (mode 1) on device buffers; nrhs processed in blocks of rhs_block.

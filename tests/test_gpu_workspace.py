@@ -454,9 +454,10 @@ def test_wide_solve_steps_agree():
     perm = spde.geometric_nd_perm((23, 23, 23), leaf=64, width=2)
     res = {}
     try:
-        for mode in (0, 1, 2, 3):               # 3: 64-column steps WITHOUT programmatic stream serialization
-            _lib.set_option("wide_steps", mode % 3)
+        for mode in (0, 1, 2, 3, 4):            # 3: 64-column steps WITHOUT programmatic stream serialization
+            _lib.set_option("wide_steps", mode % 3 if mode < 4 else 0)      # 4: programmatic launches on the stream, no graph
             _lib.set_option("pdl", 0 if mode == 3 else 1)
+            _lib.set_option("use_graph", 0 if mode == 4 else 1)
             be = B200Backend(Q, ordering=perm, device=0)
             assert be.info()["max_ns"] > 512
             out = []
@@ -471,11 +472,13 @@ def test_wide_solve_steps_agree():
     finally:
         _lib.set_option("wide_steps", 0)
         _lib.set_option("pdl", 1)
+        _lib.set_option("use_graph", 1)
     for mode in (1, 2):
         for a, c in zip(res[0], res[mode]):
             assert _rel(c, a) <= 1e-11, mode
-    for a, c in zip(res[0], res[3]):          # same kernels, same order of operations: identical bits
-        assert np.array_equal(a, c)
+    for other in (3, 4):
+        for a, c in zip(res[0], res[other]):  # same kernels, same order of operations: identical bits
+            assert np.array_equal(a, c), other
 
 
 def test_run_to_run_bit_reproducible():
