@@ -229,6 +229,156 @@ __device__ __forceinline__ void warp_dmma_32x16(const double *__restrict__ A, in
     }
 }
 
+// The same panel factorization, blocked: [D; rows of rt[0..RT)] (64 columns) is factored 16 columns at a time.
+//   * inside a 16-column sub-panel the rank-4 steps run on ONE 4 x 4 register tile per thread -- thread = (group g: D or a
+//     row tile, row tile ty, column tile ctl of the sub-panel), 64 (1 + RT) threads -- so the tile solves of a step are spread
+//     over 1 + RT half-warps instead of one, and the rank-4 updates touch 16 columns instead of up to 64;
+//   * the columns right of the sub-panel get ONE rank-16 update from shared memory on the FP64 tensor cores
+//     (warp_dmma_32x16, 8 warps).
+// panel_solve64<RT, true> updates every remaining column after every 4 columns from 4 x 4 register tiles (64 shared-memory
+// loads per thread for 192 FMAs) and its tile solves are done by a single warp holding 1 + RT tiles per thread.
+// Measured (clock64 stamps inside the kernel, profiles/r02_chain_phases.log): a rank-4 step of the sub-panel is ~1,400
+// cycles instead of ~2,400 -- the tile solves ~100, the 4 x 4 update of ONE tile per thread still ~750 (shared-memory
+// instruction throughput: 32 LDS.64 per thread, not bank conflicts -- a [k][r][row-tile] layout of the published panels
+// without any conflict measured slower), the look-ahead pivot tile ~450 -- but the rank-16 update costs ~9,200 cycles for the
+// first sub-panel: ~1,500 per 32 x 16 warp tile for 32 DMMAs (the SM's DMMA rate, equal to its DFMA rate) and ~2,000 for
+// reading and writing the 16 accumulators of C through shared memory. Net: the 192-row panel of a chain step is 10 %
+// slower (22 us against 20), the one-CTA fronts are faster; 2D factorizations gain 2-3 %, a 16-lane sweep 5 %.
+template <int RT>
+__device__ __forceinline__ void panel_factor64b(double *__restrict__ sD, double *__restrict__ scratch, const RowTile (&rt)[RT], int nb, int col0,
+                                                int *fail_col, bool report, long long *prof = nullptr) {
+    static_assert(RT >= 1 && RT <= 2, "row-tile groups");
+    constexpr int PB = (1 + RT) * 4 * FPLD;
+    double *srinv = scratch + 2 * PB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = tid >> 6;                            // 0: rows of the diagonal block, 1..RT: row tile g - 1
+    const int ty = tid & 15, ctl = (tid >> 4) & 3;     // row tile inside the group, column tile inside the sub-panel
+    const bool have = g <= RT;
+    const RowTile R = (g >= 1 && g <= RT) ? rt[g - 1] : RowTile{sD, FLD, FB};
+    const int nsteps = (nb + 3) >> 2;
+    for (int i = 4 * nsteps + tid; i < FB; i += 256) srinv[i] = 1.0;
+#pragma unroll 1
+    for (int s = 0; 4 * s < nsteps; s++) {
+        const int tx = 4 * s + ctl;
+        const bool act = have && tx < nsteps && (g > 0 || ty >= tx);
+        double a[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                a[r][c] = (act && 4 * ty + r < R.nr && (g == 0 || 4 * tx + c < nb)) ? R.p[(4 * tx + c) * R.ld + 4 * ty + r] : 0.0;
+        const int jmax = min(4, nsteps - 4 * s);
+        if (prof && s == 0 && tid == 0) prof[5] = clock64();
+#pragma unroll 1
+        for (int j = 0; j < jmax; j++) {
+            const int P = 4 * s + j;
+            double *pb = scratch + (P & 1) * PB;
+            const bool stamp = prof && P == 1 && tid == 34;          // (the look-ahead thread of step 1: g = 0, ty = 2, ctl = 2)
+            if (stamp) prof[0] = clock64();
+            if (j == 0) {          // (no look-ahead across sub-panels: this tile was final only after the rank-16 update)
+                if (g == 0 && ty == P && ctl == 0) factor_diag_tile(a, pb, srinv, P, nb, col0, fail_col, report);
+                __syncthreads();
+            }
+            if (act && ctl == j && (g > 0 || ty > P)) {
+                // X * L_PP^T = B on the 4 x 4 tile, column by column
+                double lpp[4][4], ri[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    ri[c] = srinv[4 * P + c];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) lpp[c][k] = pb[k * FPLD + 4 * P + c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        double sum = a[r][c];
+#pragma unroll
+                        for (int k = 0; k < c; k++) sum -= a[r][k] * lpp[c][k];
+                        a[r][c] = sum * ri[c];
+                    }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pb[(4 * g + c) * FPLD + 4 * ty + r] = a[r][c];
+            }
+            __syncthreads();
+            if (stamp) prof[1] = clock64();
+            if (act && ctl > j) {
+                double pc[4][4], pr[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) pc[c][k] = pb[k * FPLD + 4 * tx + c];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pr[r][k] = pb[(4 * g + k) * FPLD + 4 * ty + r];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) a[r][c] -= pr[r][k] * pc[c][k];
+                // look-ahead: the next diagonal tile of the sub-panel is final now
+                if (stamp) prof[2] = clock64() + (long long)(a[0][0] == 12345.678);      // (keeps the stamp behind the updates)
+                if (g == 0 && ty == P + 1 && ctl == j + 1) factor_diag_tile(a, scratch + ((P + 1) & 1) * PB, srinv, P + 1, nb, col0, fail_col, report);
+                if (stamp) prof[3] = clock64();
+            }
+            __syncthreads();
+            if (stamp) prof[4] = clock64();
+        }
+        if (prof && s == 0 && tid == 0) prof[6] = clock64();
+        // the sub-panel goes back to shared memory ...
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (4 * ty + r < R.nr && (g == 0 || 4 * tx + c < nb))
+                        R.p[(4 * tx + c) * R.ld + 4 * ty + r] = (g == 0 && 4 * tx + c > 4 * ty + r) ? 0.0 : a[r][c];
+        }
+        __syncthreads();
+        if (prof && s == 0 && tid == 0) prof[7] = clock64();
+        // ... and updates the columns to its right: C[r, c] -= sum_{k in sub-panel} L[r, k] L[c, k], 32 x 16 warp tiles
+        const int cbeg = 16 * (s + 1), cend = min(FB, (4 * nsteps + 15) & ~15);
+        if (cbeg < cend) {
+            const int ncb = (cend - cbeg) >> 4;
+            const int rb0 = (FB - cbeg + 31) >> 5;                 // 32-row blocks of the diagonal block (rows cbeg..63)
+            const int nrb = rb0 + 2 * RT;
+            for (int w = warp; w < nrb * ncb; w += 8) {
+                const int rb = w / ncb, cb = cbeg + 16 * (w - rb * ncb);
+                const int G = rb < rb0 ? 0 : 1 + ((rb - rb0) >> 1);
+                const RowTile C = G == 0 ? RowTile{sD, FLD, FB} : rt[G - 1];
+                const int r0 = G == 0 ? cbeg + 32 * rb : 32 * ((rb - rb0) & 1);
+                if (r0 >= C.nr) continue;
+                double acc[4][2][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+                const bool stamp2 = prof && s == 0 && w == 0 && lane == 0;
+                if (stamp2) prof[9] = clock64();
+                warp_dmma_32x16(C.p + 16 * s * C.ld, C.ld, r0, C.nr, sD + 16 * s * FLD, FLD, cb, FB, 16, acc);
+                if (stamp2) prof[10] = clock64() + (long long)(acc[0][0][0] == 12345.678);
+                const int grp = lane >> 2, tig = lane & 3;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = r0 + 8 * i + grp, c = cb + 8 * jj + 2 * tig + e;
+                            if (r < C.nr && (G == 0 ? r >= c : c < nb)) C.p[c * C.ld + r] -= acc[i][jj][e];
+                        }
+                if (stamp2) prof[11] = clock64();
+            }
+            __syncthreads();
+        }
+        if (prof && s == 0 && tid == 0) prof[8] = clock64();
+    }
+}
+
 // C[64 x 64] -= A[64 x 64] B[64 x 64]^T on column-major shared-memory tiles (leading dimension FLD), 8 warps x (32 x 16);
 // lower: warp tiles strictly above the diagonal are skipped (entries above the diagonal inside the others are computed
 // and ignored by the caller).
@@ -288,6 +438,7 @@ __device__ long long *g_chain_prof = nullptr;
 
 constexpr int CHAIN_SMEM_BYTES = (5 * FTILE + FSCRATCH) * (int)sizeof(double);
 
+template <bool BLK>
 __global__ void __launch_bounds__(256, 1)
 chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ tile_prefix, int ntasks, int *__restrict__ fail_col,
                   long long bstride) {
@@ -324,7 +475,8 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
     // ---- block 0: [D0; H; B0] is one 192 x 64 panel ----
     {
         const RowTile rt[2] = {{sH, FLD, T.nb1}, {sB0, FLD, nrv}};
-        panel_solve64<2, true>(sD0, scr, rt, T.nb0, T.col0, fail_col, diag);
+        if constexpr (BLK) panel_factor64b<2>(sD0, scr, rt, T.nb0, T.col0, fail_col, diag, (prof && tile == 1) ? prof + 8 : nullptr);
+        else panel_solve64<2, true>(sD0, scr, rt, T.nb0, T.col0, fail_col, diag);
     }
     CHAIN_STAMP(2);
     for (int e = tid; e < FB * FB; e += 256) {          // X0 -> HBM (coalesced along the rows)
@@ -338,7 +490,8 @@ chain_step_kernel(const ChainTask *__restrict__ tasks, const int *__restrict__ t
         __syncthreads();
         CHAIN_STAMP(4);
         const RowTile rt[1] = {{sB1, FLD, nrv}};
-        panel_solve64<1, true>(sD1, scr, rt, T.nb1, T.col0 + FB, fail_col, diag);
+        if constexpr (BLK) panel_factor64b<1>(sD1, scr, rt, T.nb1, T.col0 + FB, fail_col, diag);
+        else panel_solve64<1, true>(sD1, scr, rt, T.nb1, T.col0 + FB, fail_col, diag);
         CHAIN_STAMP(5);
         for (int e = tid; e < FB * FB; e += 256) {
             const int i = e & 63, j = e >> 6;
@@ -432,6 +585,7 @@ __host__ __device__ __forceinline__ int front_smem_doubles(int nrow, int ns) {
 }
 
 // (two CTAs per SM: the second one hides the barriers of the small panel steps)
+template <bool BLK>
 __global__ void __launch_bounds__(256, 2)
 front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restrict__ meta, const int *__restrict__ child_idx,
                    const int *__restrict__ relidx, double *__restrict__ Lx0, double *__restrict__ upd0, int *__restrict__ fail_col,
@@ -527,7 +681,8 @@ front_small_kernel(const FrontTask *__restrict__ tasks, const SuperMeta *__restr
         // the diagonal block together with the first 128 rows below it, then the remaining rows 128 at a time
         {
             const RowTile rt[2] = {{sP + k0 * ldp + k1, ldp, min(FB, nrow - k1)}, {sP + k0 * ldp + k1 + FB, ldp, max(0, min(FB, nrow - k1 - FB))}};
-            panel_solve64<2, true>(sD, scr, rt, nb, S.first + k0, fail_col, true);
+            if constexpr (BLK) panel_factor64b<2>(sD, scr, rt, nb, S.first + k0, fail_col, true);
+            else panel_solve64<2, true>(sD, scr, rt, nb, S.first + k0, fail_col, true);
         }
         for (int e = tid; e < nb * nb; e += 256) {
             const int i = e % nb, j = e / nb;

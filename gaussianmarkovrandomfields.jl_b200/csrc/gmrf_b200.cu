@@ -1246,7 +1246,8 @@ cudaError_t configure_kernels(int front_smem = 0) {
     cudaError_t e;
     if ((e = configure_gemm_tile<128, 64, 2, 2>())) return e;
     if ((e = configure_gemm_tile<64, 64, 2, 2>())) return e;
-    if ((e = cudaFuncSetAttribute(chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(chain_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(chain_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES))) return e;
     // (static + dynamic shared memory of the wider forward step kernels exceeds 48 KB)
     if ((e = cudaFuncSetAttribute(fwd_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(fwd_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES))) return e;
@@ -1254,7 +1255,8 @@ cudaError_t configure_kernels(int front_smem = 0) {
     if ((e = cudaFuncSetAttribute(chain_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FINALIZE_SMEM_BYTES))) return e;
     // (per device, sticky: handles of one process may need different sizes -> always opt in to the cap)
     const int fs = std::max(front_smem, 220 * 1024);
-    if ((e = cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs))) return e;
+    if ((e = cudaFuncSetAttribute(front_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs))) return e;
+    if ((e = cudaFuncSetAttribute(front_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs))) return e;
     return cudaSuccess;
 }
 
@@ -1293,11 +1295,18 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
                      h->d_relidx, h->d_relpos, h->d_relpos_off, h->d_Lx, h->d_upd, bstride);
             break;
         case K_CHAIN:
-            launch_k(T.pdl, chain_step_kernel, dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st, h->d_chain + L.task_off, pf, (int)L.ntasks, h->d_fail, bstride);
+            if (h->opt.panel_blocked >= 2)
+                launch_k(T.pdl, chain_step_kernel<true>, dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st, h->d_chain + L.task_off, pf, (int)L.ntasks, h->d_fail, bstride);
+            else
+                launch_k(T.pdl, chain_step_kernel<false>, dim3(L.grid, T.lanes), 256, CHAIN_SMEM_BYTES, st, h->d_chain + L.task_off, pf, (int)L.ntasks, h->d_fail, bstride);
             break;
         case K_FRONT:
-            launch_k(T.pdl, front_small_kernel, dim3(L.grid, T.lanes), 256, (size_t)L.aux, st, h->d_front + L.task_off, h->d_meta, h->d_child, h->d_relidx,
-                     h->d_Lx, h->d_upd, h->d_fail, bstride);
+            if (h->opt.panel_blocked)
+                launch_k(T.pdl, front_small_kernel<true>, dim3(L.grid, T.lanes), 256, (size_t)L.aux, st, h->d_front + L.task_off, h->d_meta, h->d_child,
+                         h->d_relidx, h->d_Lx, h->d_upd, h->d_fail, bstride);
+            else
+                launch_k(T.pdl, front_small_kernel<false>, dim3(L.grid, T.lanes), 256, (size_t)L.aux, st, h->d_front + L.task_off, h->d_meta, h->d_child,
+                         h->d_relidx, h->d_Lx, h->d_upd, h->d_fail, bstride);
             break;
         case K_FINALIZE:
             chain_finalize_kernel<<<dim3(2 * L.grid, T.lanes), 256, FINALIZE_SMEM_BYTES, st>>>(h->d_final + L.task_off, bstride);
@@ -1890,6 +1899,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "pdl") o.pdl = value != 0;
     else if (k == "pdl_factor") o.pdl_factor = value != 0;
     else if (k == "pdl_multi") o.pdl_multi = value != 0;
+    else if (k == "panel_blocked") o.panel_blocked = (int)value;
     else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
@@ -3069,19 +3079,20 @@ int gmrf_b200_debug_chain_phases(gmrf_b200_handle *h, int64_t *stamps, int n) {
     if (rc) return rc;
     if (!h->factored || !stamps || n < 7) { h->err = "debug_chain_phases: needs a factored handle and 7 slots"; return GMRF_B200_ERR_ARG; }
     long long *d = nullptr;
-    CUDA_TRY(h, cudaMalloc((void **)&d, 8 * sizeof(long long)));
-    cudaMemset(d, 0, 8 * sizeof(long long));
+    CUDA_TRY(h, cudaMalloc((void **)&d, 24 * sizeof(long long)));
+    cudaMemset(d, 0, 24 * sizeof(long long));
     CUDA_TRY(h, cudaMemcpyToSymbol(g_chain_prof, &d, sizeof(d)));
     const int ug = h->opt.use_graph;
     h->opt.use_graph = 0;
     rc = do_factor(h);
     h->opt.use_graph = ug;
-    long long host[8];
+    long long host[24];
     cudaMemcpy(host, d, sizeof(host), cudaMemcpyDeviceToHost);
     long long *null = nullptr;
     cudaMemcpyToSymbol(g_chain_prof, &null, sizeof(null));
     cudaFree(d);
     for (int i = 0; i < 7; i++) stamps[i] = host[i];
+    for (int i = 7; i < n && i < 24; i++) stamps[i] = host[i];        // [8..16]: inside the blocked panel (front_kernels.cuh)
     return rc < 0 ? rc : 0;
 }
 
