@@ -563,6 +563,42 @@ chain_finalize_kernel(const FinalizeTask *__restrict__ tasks, long long bstride)
 }
 
 // ------------------------------------------------------------------------------------------------
+// potrf + inverse of one 64 x 64 diagonal block per CTA (the bulk path's panel step), on the blocked panel code: the
+// identity rides along as a row tile, so ONE pass gives L and Y = I L^-T whose transpose is L^-1 -- the rank-4 steps are
+// latency bound and the extra group costs them nothing. potrf_inv64_kernel (kernels.cuh) factors without look-ahead
+// (three barriers per 4 columns with one active thread / warp between them) and then inverts with 64 threads by a fully
+// unrolled substitution while 192 threads wait: 30-37 us per launch, 7 barrier stalls per issue under ncu
+// (profiles/r02_ncu_full_potrf_3d48.txt).
+// ------------------------------------------------------------------------------------------------
+constexpr int POTRF_LA_SMEM_BYTES = (2 * FTILE + panel_scratch_doubles(1)) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256)
+potrf_inv64_la_kernel(const PanelTask *__restrict__ tasks, int *__restrict__ fail_col, long long bstride) {
+    extern __shared__ __align__(16) double fsm[];
+    double *sL = fsm, *sY = fsm + FTILE, *scr = fsm + 2 * FTILE;
+    pdl_launch_dependents();
+    PanelTask T = tasks[blockIdx.x];
+    T.D = lane_ptr(T.D, bstride); T.inv = lane_ptr(T.inv, bstride); fail_col = lane_ptr(fail_col, bstride);
+    const int nb = T.nb, tid = threadIdx.x;
+    pdl_wait();
+    for (int e = tid; e < FB * FB; e += 256) {
+        const int i = e & 63, j = e >> 6;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j <= i) v = T.D[i + (long long)j * T.ld];
+        sL[j * FLD + i] = v;
+        sY[j * FLD + i] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const RowTile rt[1] = {{sY, FLD, nb}};
+    panel_factor64b<1>(sL, scr, rt, nb, T.col0, fail_col, true);
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int i = e % nb, c = e / nb;
+        if (i >= c) T.D[i + (long long)c * T.ld] = sL[c * FLD + i];
+        T.inv[e] = (i >= c) ? sY[i * FLD + c] : 0.0;        // inv(i, c) = Y(c, i)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small fronts: one CTA per supernode; the nrow x ns panel lives in shared memory (column-major, leading dimension
 // ldp = nrow rounded up to odd). Extend-add is a GATHER: for every child the inverse of its relative-index list
 // (parent front row -> child update row, -1 if absent) is built in shared memory, and every entry of the parent front

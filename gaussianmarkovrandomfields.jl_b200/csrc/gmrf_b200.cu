@@ -1253,6 +1253,7 @@ cudaError_t configure_kernels(int front_smem = 0) {
     if ((e = cudaFuncSetAttribute(fwd_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(assemble_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM_BYTES))) return e;
     if ((e = cudaFuncSetAttribute(chain_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FINALIZE_SMEM_BYTES))) return e;
+    if ((e = cudaFuncSetAttribute(potrf_inv64_la_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_LA_SMEM_BYTES))) return e;
     // (per device, sticky: handles of one process may need different sizes -> always opt in to the cap)
     const int fs = std::max(front_smem, 220 * 1024);
     if ((e = cudaFuncSetAttribute(front_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs))) return e;
@@ -1316,7 +1317,12 @@ void run_launch(gmrf_b200_handle *h, const Launch &L, const TableSet &T, int nrh
                 case 8: launch_k(T.pdl, potrf_inv_kernel<8>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
                 case 16: launch_k(T.pdl, potrf_inv_kernel<16>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
                 case 32: launch_k(T.pdl, potrf_inv_kernel<32>, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
-                default: launch_k(T.pdl, potrf_inv64_kernel, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride); break;
+                default:
+                    if (h->opt.potrf_lookahead)
+                        launch_k(T.pdl, potrf_inv64_la_kernel, dim3(L.grid, T.lanes), 256, POTRF_LA_SMEM_BYTES, st, h->d_panel + L.task_off, h->d_fail, bstride);
+                    else
+                        launch_k(T.pdl, potrf_inv64_kernel, dim3(L.grid, T.lanes), 256, 0, st, h->d_panel + L.task_off, h->d_fail, bstride);
+                    break;
             }
             break;
         case K_GEMM_NN_S: case K_GEMM_NN_L:
@@ -1900,6 +1906,7 @@ int gmrf_b200_set_option(const char *key, double value) {
     else if (k == "pdl_factor") o.pdl_factor = value != 0;
     else if (k == "pdl_multi") o.pdl_multi = value != 0;
     else if (k == "panel_blocked") o.panel_blocked = (int)value;
+    else if (k == "potrf_lookahead") o.potrf_lookahead = value != 0;
     else if (k == "syrk_split") o.syrk_split = (int)value;
     else if (k == "fused_front") o.fused_front = (int)value;
     else if (k == "fused_chain") o.fused_chain = (int)value;
@@ -2873,7 +2880,10 @@ int gmrf_b200_test_potrf_inv(int device, int n, double *A, int lda, double *inv,
     if (n <= 8) potrf_inv_kernel<8><<<1, 256>>>(dT, dF, 0LL);
     else if (n <= 16) potrf_inv_kernel<16><<<1, 256>>>(dT, dF, 0LL);
     else if (n <= 32) potrf_inv_kernel<32><<<1, 256>>>(dT, dF, 0LL);
-    else potrf_inv64_kernel<<<1, 256>>>(dT, dF, 0LL);
+    else if (global_options().potrf_lookahead) {
+        if (configure_kernels() != cudaSuccess) return test_fail("kernel attributes");
+        potrf_inv64_la_kernel<<<1, 256, POTRF_LA_SMEM_BYTES>>>(dT, dF, 0LL);
+    } else potrf_inv64_kernel<<<1, 256>>>(dT, dF, 0LL);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(A, dA, (size_t)lda * n * 8, cudaMemcpyDeviceToHost);
     if (inv) cudaMemcpy(inv, dI, (size_t)n * n * 8, cudaMemcpyDeviceToHost);

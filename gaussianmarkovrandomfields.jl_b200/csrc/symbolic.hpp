@@ -38,6 +38,7 @@ struct Options {
     int pdl_factor = 0;       // same for the kernels of the factorization / selected inversion plans: only task tables and symbolic maps can be read ahead there, so it hides launch latency (2D configs), not HBM latency
     int pdl_multi = 1;        // same for the GEMM sweeps of the wide right-hand-side blocks: operand A of every product is a piece of the factor, its first tiles are loaded before the wait (64 columns: -12 % at 50 k dofs, -8 % at 117 k, -1.6 % at 1 M; bit-identical; profiles/r02_multi_pdl.log)
     int panel_blocked = 1;    // 1: the one-CTA front kernel factors its 64-column panels 16 columns at a time (rank-4 steps on one register tile per thread inside the sub-panel, one rank-16 DMMA update to its right); 2: the fused chain steps as well (measured slower there: the rank-16 update of a 192-row panel through shared memory costs more than it saves); 0: rank-4 updates of the whole panel after every 4 columns everywhere
+    int potrf_lookahead = 1;  // bulk path: 64 x 64 diagonal blocks factored AND inverted in one pass of the blocked panel code (identity as a row tile); 0 = the round-1 kernel (no look-ahead, 64-thread substitution for the inverse)
     int syrk_split = 0;       // allow split-K on the update-matrix products as well (few-tile launches at the top of 2D trees)
     int level_alap = 1;       // assembly-tree levels counted from the roots (as late as possible) instead of from the leaves
     int asm_gather = 1;       // extend-add as a gather through TMA-staged shared memory (0: the first, scatter-shaped kernel)

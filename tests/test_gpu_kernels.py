@@ -55,8 +55,16 @@ def test_gemm_variants(ta, tb, size, shape):
         assert np.abs(got - want).max() <= 1e-12 * scale * max(k, 1), (shape, flags, pads)
 
 
-@pytest.mark.parametrize("n", [1, 2, 7, 8, 31, 32, 33, 63, 64])
-def test_potrf_diag(n):
+@pytest.fixture(params=[1, 0], ids=["potrf_lookahead", "potrf_round1"])
+def potrf_variant(request):
+    """Both 64-column diagonal-block kernels: the blocked look-ahead one (default) and round 1's."""
+    _lib.set_option("potrf_lookahead", request.param)
+    yield request.param
+    _lib.set_option("potrf_lookahead", 1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 31, 32, 33, 47, 63, 64])
+def test_potrf_diag(n, potrf_variant):
     L = _lib.lib()
     rng = np.random.default_rng(n)
     M = rng.standard_normal((n, n))

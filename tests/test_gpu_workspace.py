@@ -422,10 +422,10 @@ def test_schedule_variants_agree():
                 # the three factorization paths: bulk only / fused chain steps everywhere / one-CTA fronts where they fit
                 {"fused_front": 0, "fused_chain": 0}, {"fused_front": 0, "chain_max_tiles": 1000000},
                 {"fused_chain": 0}, {"front_smem_kb": 60}, {"fused_front": 0, "chain_max_tiles": 40},
-                {"asm_gather": 0}, {"asm_gather": 0, "fused_front": 0, "fused_chain": 0}, {"syrk_gather": 1}, {"level_alap": 0}, {"wide_steps": 1}, {"wide_steps": 2}, {"pdl": 0}, {"pdl": 0, "use_graph": 0}, {"pdl_factor": 1}, {"panel_blocked": 0}, {"panel_blocked": 2}, {"panel_blocked": 2, "fused_front": 0, "chain_max_tiles": 1000000}, {"pdl_multi": 0, "wide_rhs_min": 1}, {"pdl_factor": 1, "use_graph": 0, "fused_front": 0, "fused_chain": 0, "asm_gather": 0},
+                {"asm_gather": 0}, {"asm_gather": 0, "fused_front": 0, "fused_chain": 0}, {"syrk_gather": 1}, {"level_alap": 0}, {"wide_steps": 1}, {"wide_steps": 2}, {"pdl": 0}, {"pdl": 0, "use_graph": 0}, {"pdl_factor": 1}, {"panel_blocked": 0}, {"panel_blocked": 2}, {"potrf_lookahead": 0}, {"potrf_lookahead": 1, "fused_front": 0, "fused_chain": 0}, {"panel_blocked": 2, "fused_front": 0, "chain_max_tiles": 1000000}, {"pdl_multi": 0, "wide_rhs_min": 1}, {"pdl_factor": 1, "use_graph": 0, "fused_front": 0, "fused_chain": 0, "asm_gather": 0},
                 {"syrk_gather": 1, "fused_front": 0, "fused_chain": 0}]
     defaults = {"splitk_min_k": 128, "outer_block": 256, "selinv_fast_root": 1, "use_graph": 1, "bwd_row_chunk": 2048,
-                "wide_rhs_min": 8, "fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "front_smem_kb": 200, "asm_gather": 1, "syrk_gather": 0, "level_alap": 1, "wide_steps": 0, "pdl": 1, "pdl_factor": 0, "pdl_multi": 1, "panel_blocked": 1}
+                "wide_rhs_min": 8, "fused_front": 1, "fused_chain": 1, "chain_max_tiles": 160, "front_smem_kb": 200, "asm_gather": 1, "syrk_gather": 0, "level_alap": 1, "wide_steps": 0, "pdl": 1, "pdl_factor": 0, "pdl_multi": 1, "panel_blocked": 1, "potrf_lookahead": 1}
     try:
         for v in variants:
             for k, val in {**defaults, **v}.items():
