@@ -742,7 +742,8 @@ void build_solve_plans(gmrf_b200_handle *h, Builder &B) {
     // forward: L y = b
     for (i64 l = 0; l < S.nlevels; l++) {
         const i64 *sb = S.level_idx.data() + S.level_ptr[l], *se = S.level_idx.data() + S.level_ptr[l + 1];
-        for (const i64 *sp = sb; sp < se; sp++) lst.push_back((int)*sp);
+        for (const i64 *sp = sb; sp < se; sp++)      // (one entry per FWD_ASM_ROWS front rows: fwd_assemble_x0_kernel)
+            for (i64 c = 0; c < std::max<i64>(1, cdiv(S.nrow(*sp), FWD_ASM_ROWS)); c++) lst.push_back((int)*sp);
         B.add_superlist(h->fwd_plan, lst, K_FWD_ASM);
         i64 maxsteps = 0, maxwide = 0;
         for (const i64 *sp = sb; sp < se; sp++) {

@@ -226,6 +226,8 @@ __device__ __forceinline__ void apply_inv_lower_t_smem(const double *__restrict_
 // rows of y and into u_s, then the first block of its chain is solved: x_0 = inv(L_00) b_0.
 // One CTA per (supernode, right-hand side).
 // ------------------------------------------------------------------------------------------------
+constexpr int FWD_ASM_ROWS = 4096;      // front rows per CTA: the top supernodes (30,000 rows) are split over several CTAs
+
 __global__ void __launch_bounds__(256)
 fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
                        const int *__restrict__ child_idx, const int *__restrict__ relidx,
@@ -235,16 +237,23 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
     __shared__ double sp[4][SOLVE_NB][1];
     pdl_launch_dependents();
     const int s = supers[blockIdx.x];
+    // a supernode with more than FWD_ASM_ROWS front rows appears once per row chunk in the list: this CTA's chunk is its
+    // position among the repeats. Every row has ONE owner CTA, which adds the children in their fixed order (the first
+    // version ran the root's 2 x 30,000 entries through one CTA: 233 us of serialized read-modify-writes per solve).
+    int first = blockIdx.x;
+    while (first > 0 && supers[first - 1] == s) first--;
+    const int chunk = blockIdx.x - first;
     const SuperMeta P = meta[s];
     const int nr = P.nrow - P.ns;
     const int r = blockIdx.y;
     const int nb0 = min(P.ns, SOLVE_NB);
-    const bool wide = P.wide != 0;           // long chains: the first 256-column block is solved by fwd_wide_diag_kernel
+    const int row_lo = chunk * FWD_ASM_ROWS, row_hi = min(P.nrow, row_lo + FWD_ASM_ROWS);
+    const bool solve0 = chunk == 0 && P.wide == 0;       // long chains: the first 256-column block is solved by fwd_wide_diag_kernel
     double g[16];
-    if (!wide) load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
+    if (solve0) load_inv_lower(g, Linv + inv_base[s], nb0, threadIdx.x);
     pdl_wait();
     double *us = uvec + P.uvec_off + (long long)r * ldu;
-    for (int i = threadIdx.x; i < nr; i += 256) us[i] = 0.0;
+    for (int i = max(row_lo, P.ns) - P.ns + threadIdx.x; i < row_hi - P.ns && i < nr; i += 256) us[i] = 0.0;
     __syncthreads();
     double *ys = y + P.first + (long long)r * ldy;
     for (int ci = P.child_begin; ci < P.child_end; ci++) {
@@ -252,13 +261,29 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
         const int cnr = C.nrow - C.ns;
         const int *rel = relidx + C.rowptr + C.ns;
         const double *uc = uvec + C.uvec_off + (long long)r * ldu;
-        for (int i = threadIdx.x; i < cnr; i += 256) {
-            const int p = rel[i];
-            if (p < P.ns) ys[p] += uc[i]; else us[p - P.ns] += uc[i];
+        // four entries per thread and pass, loads before stores: the rows of one child are distinct, so the four
+        // read-modify-writes are independent (written as a plain loop they serialize on possible aliasing)
+        for (int i0 = threadIdx.x; i0 < cnr; i0 += 4 * 256) {
+            double *dst[4];
+            double v[4], old[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 256 * u;
+                const int p = i < cnr ? rel[i] : -1;
+                ok[u] = p >= row_lo && p < row_hi;
+                dst[u] = p < P.ns ? ys + p : us + (p - P.ns);
+                v[u] = ok[u] ? uc[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) old[u] = ok[u] ? *dst[u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (ok[u]) *dst[u] = old[u] + v[u];
         }
         __syncthreads();
     }
-    if (wide) return;
+    if (!solve0) return;
     if (threadIdx.x < SOLVE_NB) sb[threadIdx.x][0] = threadIdx.x < nb0 ? ys[threadIdx.x] : 0.0;
     __syncthreads();
     apply_inv_lower<1>(g, nb0, sb, sp, ys, 0, 1, threadIdx.x);
