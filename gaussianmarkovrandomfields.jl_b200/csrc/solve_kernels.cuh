@@ -228,6 +228,22 @@ __device__ __forceinline__ void apply_inv_lower_t_smem(const double *__restrict_
 // ------------------------------------------------------------------------------------------------
 constexpr int FWD_ASM_ROWS = 4096;      // front rows per CTA: the top supernodes (30,000 rows) are split over several CTAs
 
+// First position of the sorted list rel[0..n) whose value is >= x, found by the whole CTA: 256 evenly spaced probes narrow
+// the window by a factor of 256 per round (two rounds for 65,000 entries). Uniform result; contains barriers.
+__device__ __forceinline__ int cta_lower_bound(const int *__restrict__ rel, int n, int x) {
+    int a = 0, b = n;                       // invariant: rel[i] < x for i < a, rel[i] >= x for i >= b
+    while (b - a > 0) {
+        const int stride = (b - a + 255) / 256;
+        const int i = a + (int)threadIdx.x * stride;
+        const int below = __syncthreads_count(i < b && rel[i] < x);       // probes a, a + stride, ...: a prefix of them is < x
+        if (below == 0) { b = a; break; }
+        const int na = a + (below - 1) * stride + 1;                      // the last probe < x
+        b = min(b, a + below * stride);                                   // the first probe >= x (or the old end)
+        a = na;
+    }
+    return b;
+}
+
 __global__ void __launch_bounds__(256)
 fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restrict__ meta,
                        const int *__restrict__ child_idx, const int *__restrict__ relidx,
@@ -261,16 +277,22 @@ fwd_assemble_x0_kernel(const int *__restrict__ supers, const SuperMeta *__restri
         const int cnr = C.nrow - C.ns;
         const int *rel = relidx + C.rowptr + C.ns;
         const double *uc = uvec + C.uvec_off + (long long)r * ldu;
+        // the child's rows that land in this chunk are a contiguous run of its (sorted) list
+        int run_lo = 0, run_hi = cnr;
+        if (P.nrow > FWD_ASM_ROWS) {
+            run_lo = cta_lower_bound(rel, cnr, row_lo);
+            run_hi = row_hi >= P.nrow ? cnr : cta_lower_bound(rel, cnr, row_hi);
+        }
         // four entries per thread and pass, loads before stores: the rows of one child are distinct, so the four
         // read-modify-writes are independent (written as a plain loop they serialize on possible aliasing)
-        for (int i0 = threadIdx.x; i0 < cnr; i0 += 4 * 256) {
+        for (int i0 = run_lo + threadIdx.x; i0 < run_hi; i0 += 4 * 256) {
             double *dst[4];
             double v[4], old[4];
             bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + 256 * u;
-                const int p = i < cnr ? rel[i] : -1;
+                const int p = i < run_hi ? rel[i] : -1;
                 ok[u] = p >= row_lo && p < row_hi;
                 dst[u] = p < P.ns ? ys + p : us + (p - P.ns);
                 v[u] = ok[u] ? uc[i] : 0.0;
