@@ -950,13 +950,19 @@ fwd_assemble_multi_kernel(const int *__restrict__ supers, const SuperMeta *__res
         const int cnr = C.nrow - C.ns;
         const int *rel = relidx + C.rowptr + C.ns;
         const double *uc = uvec + C.uvec_off + (long long)q0 * ldu;
+        // the rows of one child are distinct and so are the 8 columns: all loads of a pass are issued before its first
+        // store (as a plain `+=` loop the 8 read-modify-writes of an entry serialize on possible aliasing)
         for (int i = threadIdx.x; i < cnr; i += 256) {
             const int p = rel[i];
+            double *dst = (p < P.ns) ? (ys + p) : (us + (p - P.ns));
+            const long long ldd = (p < P.ns) ? ldy : ldu;
+            double v[MULTI_QB], old[MULTI_QB];
 #pragma unroll
-            for (int q = 0; q < MULTI_QB; q++) {
-                const double v = uc[i + q * ldu];
-                if (p < P.ns) ys[p + q * ldy] += v; else us[(p - P.ns) + q * ldu] += v;
-            }
+            for (int q = 0; q < MULTI_QB; q++) v[q] = uc[i + q * ldu];
+#pragma unroll
+            for (int q = 0; q < MULTI_QB; q++) old[q] = dst[q * ldd];
+#pragma unroll
+            for (int q = 0; q < MULTI_QB; q++) dst[q * ldd] = old[q] + v[q];
         }
         __syncthreads();
     }
