@@ -722,7 +722,17 @@ def run_gpu(args):
                          "peak_source": FP64_PEAK_SOURCE,
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": gemm_ms / sum(prof["ms"].values()) if sum(prof["ms"].values()) > 0 else None,
-                         "other_kernels_ms": {k: v for k, v in prof["ms"].items() if k != "gemm"}},
+                         "other_kernels_ms": {k: v for k, v in prof["ms"].items() if k != "gemm"},
+                         # the other two phases of the path against the roofline that bounds each (same numbers as the
+                         # top-level `selinv_ms` / `solves` keys, kept here so that they travel with the roofline record)
+                         "selinv": ({"bound": "tensor", "ms": selinv_ms, "achieved_equiv_2Fchol": 2.0 * flops / (selinv_ms * 1e-3) / 1e12,
+                                     "achieved_executed": 2.2 * flops / (selinv_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                     "frac_executed": (2.2 * flops / (selinv_ms * 1e-3) / 1e12) / peak if peak else None,
+                                     "note": "Takahashi recursion executes ~2.2 x F_chol flops (W L21 and G as full products)"}
+                                    if selinv_ms else None),
+                         "solve_1rhs": ({"bound": "hbm", "ms": solve["solve_1rhs_ms"], "achieved": solve["solve_1rhs_GBs"],
+                                         "peak": solve["hbm_peak_GBs"], "unit": "GB/s", "frac": solve["solve_1rhs_frac_of_hbm"],
+                                         "frac_algorithmic": solve["solve_1rhs_frac_of_hbm_algorithmic"]} if solve else None)},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "parity_check": parity,
