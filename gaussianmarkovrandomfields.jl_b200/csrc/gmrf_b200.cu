@@ -1631,6 +1631,7 @@ void enqueue_multi_sweeps(gmrf_b200_handle *h, int wi, int mode) {
 int do_solve_device(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs, int mode);
 
 int do_solve_device_wide(gmrf_b200_handle *h, const double *dB, double *dX, i64 ld, i64 nrhs_all, int mode) {
+    NvtxRange nvtx_("gmrf_b200:solve_wide");
     const Symbolic &S = h->S;
     int rc;
     cudaStream_t st = h->stream;

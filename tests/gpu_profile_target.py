@@ -1,5 +1,5 @@
 """Minimal target for ncu: analysis + 2 refactorizations (+ selinv, + solves) on one problem, graphs off so that
-every kernel shows up as its own launch.  python tests/gpu_profile_target.py 3d:48 [--selinv] [--solve] [--order=geo]"""
+every kernel shows up as its own launch.  python tests/gpu_profile_target.py 3d:48 [--selinv] [--solve] [--solve64] [--order=geo]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,3 +23,7 @@ if "--selinv" in sys.argv:
 if "--solve" in sys.argv:
     x = b.backend_solve(np.ones(Q.shape[0]))
     print("solve_ms", b.timings()["solve_ms"])
+if "--solve64" in sys.argv:
+    R = np.asfortranarray(np.random.default_rng(0).standard_normal((Q.shape[0], 64)))
+    X = b.backend_solve(R)
+    print("solve64_ms", b.timings()["solve_ms"], "residual", np.linalg.norm(Q @ X - R) / np.linalg.norm(R))
