@@ -491,3 +491,47 @@ def test_one_based_create_gives_the_same_analysis():
         if ordering is not None:
             assert np.array_equal(np.sort(p0), np.arange(60))
         h0.close(); h1.close()
+
+
+def test_pivot_tile_recurrence_restated_on_the_host():
+    """Host restatement of the two device routines under every panel factorization (csrc/kernels.cuh): `chol4x4_lower`
+    factors a 4 x 4 pivot tile as two 2 x 2 blocks whose second pivot comes from the block's determinant, and
+    `rsqrt_inline` refines a ~20-bit hardware seed with one third-order step. The claims made for them -- backward stable
+    like the column recurrence, 1 ulp-ish -- are checked here in plain numpy (the GPU suite checks the device code itself)."""
+    rng = np.random.default_rng(12)
+
+    def rsq(x):                       # seed rounded to 20 bits, then y (1 + e/2 + 3 e^2/8), e = 1 - x y^2
+        m, ex = np.frexp(1.0 / np.sqrt(x))
+        y = np.ldexp(np.round(m * 2.0 ** 20) / 2.0 ** 20, ex)
+        e = np.float64(1.0 - np.longdouble(x) * y * y)            # (fma on the device)
+        return y * (e * (0.375 * e + 0.5)) + y
+
+    xs = 10.0 ** rng.uniform(-150, 150, 20000)
+    exact = 1.0 / np.sqrt(xs.astype(np.longdouble))
+    assert np.max(np.abs((rsq(xs).astype(np.longdouble) - exact) / exact)) <= 2.5e-16
+
+    worst = 0.0
+    for _ in range(3000):
+        M = rng.standard_normal((4, 6))
+        A = M @ M.T + 10.0 ** rng.uniform(-9, 0) * np.eye(4)
+        a = np.tril(A)
+        det1 = a[0, 0] * a[1, 1] - a[1, 0] * a[1, 0]
+        r0, q1 = rsq(a[0, 0]), rsq(det1)
+        l00, l10 = a[0, 0] * r0, a[1, 0] * r0
+        ri1 = l00 * q1
+        l20, l30 = a[2, 0] * r0, a[3, 0] * r0
+        l21, l31 = (a[2, 1] - l20 * l10) * ri1, (a[3, 1] - l30 * l10) * ri1
+        s22 = a[2, 2] - l20 * l20 - l21 * l21
+        s32 = a[3, 2] - l30 * l20 - l31 * l21
+        s33 = a[3, 3] - l30 * l30 - l31 * l31
+        det2 = s22 * s33 - s32 * s32
+        r2, q3 = rsq(s22), rsq(det2)
+        L = np.array([[l00, 0, 0, 0], [l10, det1 * q1 * r0, 0, 0], [l20, l21, s22 * r2, 0], [l30, l31, s32 * r2, det2 * q3 * r2]])
+        ri = np.array([r0, ri1, r2, s22 * r2 * q3])
+        worst = max(worst, np.max(np.abs(L @ L.T - A)) / np.max(np.abs(A)))
+        assert np.allclose(ri * np.diag(L), 1.0, rtol=1e-13)        # the published reciprocal pivots
+        assert min(a[0, 0], det1, s22, det2) > 0                      # the four pivot-sign indicators
+    assert worst <= 4e-15                                             # backward error of the tile factorization
+    # an indefinite tile is flagged at the first failing column by the sign of the matching indicator
+    A = np.diag([2.0, 3.0, 4.0, 5.0]); A[1, 0] = A[0, 1] = 3.0        # a00 a11 - a10^2 = -3 < 0 -> column 2 (1-based)
+    assert A[0, 0] > 0 and A[0, 0] * A[1, 1] - A[1, 0] ** 2 < 0
